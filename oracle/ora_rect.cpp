@@ -1,0 +1,509 @@
+// ora_rect.cpp - CPU oracle, Stage B + D: restatement of oclrect.cl and of genGPUTask (oclrect.c:235-381).
+// TEST INFRASTRUCTURE ONLY (see rd_oracle.h).
+#include <vector>
+#include "ora_internal.h"
+
+namespace ora {
+
+// ---- oclrect.cl:74-95 ----
+static void k_simpleJunction(int32_t *out, const int32_t *in, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      out[p0] = 0;
+      if (x <= 0 || y <= 0 || x >= (iw - 1) || y >= (ih - 1)) continue;
+      if (!(in[p0] > 0)) continue;
+      int count = 1;
+      for (int i = 0; i < 8; i++)
+        if (in[p0 + RX[i] + RY[i] * iw] > 0) count++;
+      out[p0] = count == 1 ? 0 : count;
+    }
+}
+
+// ---- oclrect.cl:97-121 ----
+static void k_simpleConnect(int32_t *out, const int32_t *in, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      out[p0] = 0;
+      if (x <= 1 || y <= 1 || x >= (iw - 2) || y >= (ih - 2)) continue;
+      out[p0] = in[p0] != 0 ? 1 : 0;
+      if (in[p0] != 0) continue;
+      if (in[p0 - 1] == 2 && in[p0 + 1] != 0) out[p0] = 1;
+      if (in[p0 - 1] != 0 && in[p0 + 1] == 2) out[p0] = 1;
+      if (in[p0 - iw] == 2 && in[p0 + iw] != 0) out[p0] = 1;
+      if (in[p0 - iw] != 0 && in[p0 + iw] == 2) out[p0] = 1;
+      if (in[p0 - iw - 1] == 2 && in[p0 + iw + 1] == 2) out[p0] = 1;
+      if (in[p0 - iw + 1] == 2 && in[p0 + iw - 1] == 2) out[p0] = 1;
+      if (in[p0 + 1] == 2 && in[p0 + iw - 1] == 2) out[p0] = 1;
+      if (in[p0 - 1] == 2 && in[p0 + iw + 1] == 2) out[p0] = 1;
+      if (in[p0 - iw + 1] == 2 && in[p0 + iw] == 2) out[p0] = 1;
+      if (in[p0 - iw - 1] == 2 && in[p0 + iw] == 2) out[p0] = 1;
+    }
+}
+
+// ---- oclrect.cl:123-135 ----
+static void k_stringify(int32_t *out, const int32_t *in, int mod2, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      out[p0] = in[p0];
+      if (x <= 0 || y <= 0 || x >= (iw - 1) || y >= (ih - 1)) continue;
+      if (((x + y) & 1) != mod2) continue;
+      if (in[p0 - iw] != 0 && in[p0 - 1] != 0) out[p0] = 0;
+      if (in[p0 - iw] != 0 && in[p0 + 1] != 0) out[p0] = 0;
+      if (in[p0 + iw] != 0 && in[p0 - 1] != 0) out[p0] = 0;
+      if (in[p0 + iw] != 0 && in[p0 + 1] != 0) out[p0] = 0;
+    }
+}
+
+// ---- oclrect.cl:38-48 ----
+static inline uint32_t packlabbl(int l, int a, int b) {
+  uint32_t ret = (uint32_t)clampi(b, 0, 1023);
+  ret = (ret << 10) | (uint32_t)clampi(a, 0, 1023);
+  ret = (ret << 12) | (uint32_t)clampi(l, 0, 4095);
+  return ret;
+}
+
+#define BLBLURSIZE 4
+
+// ---- oclrect.cl:155-179 ----
+static void k_blblur0(uint32_t *out, const int8_t *edge, const uint32_t *in, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      int wsum = 0, oe = edge[y * iw + x] != 0;
+      int c0 = 0, c1 = 0, c2 = 0;
+      for (int xx = 0; xx >= -BLBLURSIZE; xx--) {
+        if (x + xx < 0) break;
+        if (x + xx > 0 && edge[y * iw + x + xx] != 0 && edge[y * iw + x + xx - 1] == 0) break;
+        if (x + xx > 0 && y < ih - 1 && edge[y * iw + x + xx] == 0 && edge[y * iw + x + xx - 1] != 0 && edge[(y + 1) * iw + x + xx] != 0) break;
+        wsum++;
+        uint32_t v = in[y * iw + x + xx];
+        c0 += v & 4095; c1 += (v >> 12) & 1023; c2 += (v >> 22) & 1023;
+      }
+      for (int xx = 0; xx <= BLBLURSIZE; xx++) {
+        if (x + xx > iw - 1) break;
+        if (x + xx < iw - 1 && edge[y * iw + x + xx] == 0 && edge[y * iw + x + xx + 1] != 0) break;
+        if (oe && edge[y * iw + x + xx] == 0) break;
+        wsum++;
+        uint32_t v = in[y * iw + x + xx];
+        c0 += v & 4095; c1 += (v >> 12) & 1023; c2 += (v >> 22) & 1023;
+      }
+      out[y * iw + x] = wsum == 0 ? in[y * iw + x] : packlabbl(c0 / wsum, c1 / wsum, c2 / wsum);
+    }
+}
+
+// ---- oclrect.cl:181-205 ----
+static void k_blblur1(uint32_t *out, const int8_t *edge, const uint32_t *in, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      int wsum = 0, oe = edge[y * iw + x] != 0;
+      int c0 = 0, c1 = 0, c2 = 0;
+      for (int yy = 0; yy >= -BLBLURSIZE; yy--) {
+        if (y + yy < 0) break;
+        if (y + yy > 0 && edge[(y + yy) * iw + x] != 0 && edge[(y + yy - 1) * iw + x] == 0) break;
+        if (y + yy > 0 && x < iw - 1 && edge[(y + yy) * iw + x] == 0 && edge[(y + yy - 1) * iw + x] != 0 && edge[(y + yy) * iw + x + 1] != 0) break;
+        wsum++;
+        uint32_t v = in[(y + yy) * iw + x];
+        c0 += v & 4095; c1 += (v >> 12) & 1023; c2 += (v >> 22) & 1023;
+      }
+      for (int yy = 0; yy <= BLBLURSIZE; yy++) {
+        if (y + yy > ih - 1) break;
+        if (y + yy < ih - 1 && edge[(y + yy) * iw + x] == 0 && edge[(y + yy + 1) * iw + x] != 0) break;
+        if (oe && edge[(y + yy) * iw + x] == 0) break;
+        wsum++;
+        uint32_t v = in[(y + yy) * iw + x];
+        c0 += v & 4095; c1 += (v >> 12) & 1023; c2 += (v >> 22) & 1023;
+      }
+      out[y * iw + x] = wsum == 0 ? in[y * iw + x] : packlabbl(c0 / wsum, c1 / wsum, c2 / wsum);
+    }
+}
+
+// ---- oclrect.cl:207-216 ----
+static void k_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int p0 = 0; p0 < iw * ih; p0++) {
+    float l, a, b;
+    unpacklab(in[p0], l, a, b);
+    out[p0] = packlab(roundf(l * n0) / (float)n0, roundf(a * n1) / (float)n1, roundf(b * n2) / (float)n2);
+  }
+}
+
+// ---- oclrect.cl:218-244 ----
+static void k_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      out[p0] = in[p0];
+      if (edge[p0] < 1e-6f) continue;
+      float dist = 1e+10f;
+      float l0, a0, b0;
+      unpacklab(in[p0], l0, a0, b0);
+      for (int yy = -1; yy <= 1; yy++)
+        for (int xx = -1; xx <= 1; xx++)
+          if (0 <= x + xx && x + xx < iw && 0 <= y + yy && y + yy < ih) {
+            const int p1 = (y + yy) * iw + x + xx;
+            if (edge[p1] >= 1e-6f) continue;
+            float l1, a1, b1;
+            unpacklab(in[p1], l1, a1, b1);
+            float d = distance3_c(l1 - l0, a1 - a0, b1 - b0);
+            if (d < dist) { out[p0] = in[p1]; dist = d; }
+          }
+    }
+}
+
+// ---- oclrect.cl:246-287 : scatter of constants, order independent ----
+static void k_mkMergeMask0(int32_t *out, const int32_t *junctionIn, int iw, int ih) {
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      if (junctionIn[y * iw + x] == 0) continue;
+      for (int yy = y - 6; yy <= y + 6; yy++)
+        for (int xx = x - 6; xx <= x + 6; xx++) {
+          if (xx < 0 || iw <= xx || yy < 0 || ih <= yy) continue;
+          int dsqu = (yy - y) * (yy - y) + (xx - x) * (xx - x);
+          if (16 <= dsqu && dsqu < 36) out[yy * iw + xx] = 1;
+        }
+    }
+}
+
+static void k_mkMergeMask1(int32_t *inout, const int32_t *junctionIn, int iw, int ih) {
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int j = junctionIn[y * iw + x];
+      if (j == 2) {
+        for (int yy = y - 8; yy <= y + 8; yy++)
+          for (int xx = x - 8; xx <= x + 8; xx++) {
+            if (xx < 0 || iw <= xx || yy < 0 || ih <= yy) continue;
+            int dsqu = (yy - y) * (yy - y) + (xx - x) * (xx - x);
+            if (dsqu < 64) inout[yy * iw + xx] = 0;
+          }
+      } else if (j != 0) {
+        for (int yy = y - 4; yy <= y + 4; yy++)
+          for (int xx = x - 4; xx <= x + 4; xx++) {
+            if (xx < 0 || iw <= xx || yy < 0 || ih <= yy) continue;
+            int dsqu = (yy - y) * (yy - y) + (xx - x) * (xx - x);
+            if (dsqu < 16) inout[yy * iw + xx] = 0;
+          }
+      }
+    }
+}
+
+// ---- oclrect.cl:289-334 + oclrect.c:325-331 : labelxPreprocess + 8 x labelMergeMain ----
+// The reference's result is schedule dependent: (i) 8 in-place passes need not converge, (ii) the
+// adopt rule `(pix equal || mask[adopter])` is asymmetric so even the fixed point depends on the order in
+// which trees merge, (iii) pixels of the 1-px image border never run the main pass.
+// CANONICAL: components of the graph made of
+//   - the labelxPreprocess links (every pixel: up neighbour if same colour, else left if same colour), and
+//   - every 4-neighbour pair (a, b) with b = a+1 or a+iw, at least one of the two not on the image border,
+//     with edge[b] <= 0 and (pix[a] == pix[b] || mask[a] != 0 || mask[b] != 0);
+// pixels not on the image border get the smallest index of their component, image-border pixels keep their
+// labelxPreprocess value (as they do in the reference unless an interior pixel happens to point at them).
+static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
+  const int n = iw * ih;
+  std::vector<int32_t> init(n);
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      if (y > 0 && pix[p0] == pix[p0 - iw]) init[p0] = p0 - iw;
+      else if (x > 0 && pix[p0] == pix[p0 - 1]) init[p0] = p0 - 1;
+      else init[p0] = p0;
+    }
+  for (int p = 0; p < n; p++) label[p] = p;
+  MinUF uf(label);
+  for (int p = 0; p < n; p++) if (init[p] != p) uf.unite(p, init[p]);
+  auto interior = [&](int x, int y) { return x > 0 && y > 0 && x < iw - 1 && y < ih - 1; };
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int a = y * iw + x;
+      if (x + 1 < iw && (interior(x, y) || interior(x + 1, y))) {
+        const int b = a + 1;
+        if (edge[b] <= 0 && (pix[a] == pix[b] || mask[a] != 0 || mask[b] != 0)) uf.unite(a, b);
+      }
+      if (y + 1 < ih && (interior(x, y) || interior(x, y + 1))) {
+        const int b = a + iw;
+        if (edge[b] <= 0 && (pix[a] == pix[b] || mask[a] != 0 || mask[b] != 0)) uf.unite(a, b);
+      }
+    }
+  std::vector<int32_t> root(n);
+  for (int p = 0; p < n; p++) root[p] = uf.find_compress(p);
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      label[p0] = interior(x, y) ? root[p0] : init[p0];
+    }
+}
+
+// ---- oclrect.cl:336-346 ----
+static void k_calcSize(int32_t *out, const int32_t *label, int iw, int ih) {
+  for (int p0 = 0; p0 < iw * ih; p0++) {
+    int l = label[p0];
+    if (l != -1) out[l]++;
+  }
+}
+
+// ---- oclrect.cl:348-371.  CANONICAL (Q3): Jacobi - every pixel reads the labels as they were at launch ----
+static void k_despeckle2(int32_t *labelinout, const int32_t *sizein, int thre, int iw, int ih) {
+  std::vector<int32_t> snap(labelinout, labelinout + (size_t)iw * ih);
+  const int32_t *L = snap.data();
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      if (sizein[L[p0]] > thre) continue;
+      int maxSize = 0, maxLabel = L[p0];
+      for (int yy = -1; yy <= 1; yy++)
+        for (int xx = -1; xx <= 1; xx++)
+          if (0 <= x + xx && x + xx < iw && 0 <= y + yy && y + yy < ih) {
+            const int p1 = (y + yy) * iw + x + xx;
+            if (sizein[L[p1]] > maxSize) { maxSize = sizein[L[p1]]; maxLabel = L[p1]; }
+          }
+      labelinout[p0] = maxLabel;
+    }
+}
+
+// ---- oclrect.cl:373-390 (the `edge` argument is unused by the kernel) ----
+static void k_markBoundary(int32_t *out, const int32_t *in, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      if (x <= 1 || y <= 1 || x >= iw - 2 || y >= ih - 2) { out[p0] = -1; continue; }
+      int nearEdge = 0;
+      const int c0 = in[p0];
+      for (int yy = -2; yy <= 2; yy++)
+        for (int xx = -2; xx <= 2; xx++)
+          if (in[p0 + yy * iw + xx] != c0) nearEdge = 1;
+      out[p0] = nearEdge ? in[p0] : -1;
+    }
+}
+
+// ---- oclrect.cl:427-464 : the vote table.  slot = ((lsid*bid) & 0x7fffffff) % nentry, no probing ----
+// CANONICAL (Q19): when several lsid want one slot the smallest lsid owns it (the reference: whoever's
+// atomic_cmpxchg lands first); every hit of the owner is recorded (the reference drops the one hit that
+// performed the claim, oclrect.cl:451-456, which is again arrival-order dependent).
+static void k_reduceLS(int32_t *out, const int32_t *boundaryin, const int32_t *lsidin, int iw, int ih, int nentry) {
+  // phase 1: owners
+  for (int y = 1; y < ih - 1; y++)
+    for (int x = 1; x < iw - 1; x++) {
+      const int lsid = lsidin[y * iw + x];
+      if (lsid <= 0) continue;
+      for (int yy = -3; yy <= 3; yy++) {
+        if (y + yy < 0 || ih <= y + yy) continue;
+        for (int xx = -3; xx <= 3; xx++) {
+          if (x + xx < 0 || iw <= x + xx) continue;
+          const int bid = boundaryin[(y + yy) * iw + x + xx];
+          if (bid <= 0) continue;
+          const int hash = (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry);
+          int cur = out[hash * 5 + 0];
+          if (cur == 0) { out[hash * 5 + 0] = lsid; g_stats.vote_slots++; }
+          else if (cur != lsid) {
+            g_stats.vote_collisions++;
+            if (lsid < cur) out[hash * 5 + 0] = lsid;
+          }
+        }
+      }
+    }
+  // phase 2: bounding boxes of where the owner touches the region
+  for (int y = 1; y < ih - 1; y++)
+    for (int x = 1; x < iw - 1; x++) {
+      const int lsid = lsidin[y * iw + x];
+      if (lsid <= 0) continue;
+      for (int yy = -3; yy <= 3; yy++) {
+        if (y + yy < 0 || ih <= y + yy) continue;
+        for (int xx = -3; xx <= 3; xx++) {
+          if (x + xx < 0 || iw <= x + xx) continue;
+          const int bid = boundaryin[(y + yy) * iw + x + xx];
+          if (bid <= 0) continue;
+          const int hash = (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry);
+          if (out[hash * 5 + 0] != lsid) continue;
+          int *e = &out[hash * 5];
+          if (iw - x > e[1]) e[1] = iw - x;
+          if (x > e[2]) e[2] = x;
+          if (ih - y > e[3]) e[3] = ih - y;
+          if (y > e[4]) e[4] = y;
+        }
+      }
+    }
+}
+
+}  // namespace ora
+
+using namespace ora;
+
+// =====================================================================================================
+// L3 object: same 6+6+2 planes and 2 bigs as oclrect_t (oclrect.c:51-53, 120-135), zero-initialised.
+// CANONICAL (Q1): device memory the reference never initialises reads as zero on the first frame.
+// =====================================================================================================
+struct ora_rect {
+  int iw, ih;
+  int32_t *buf[6], *tmp[6], *iobuf[2], *ioBig[2];
+  double t[5];
+};
+
+extern "C" {
+
+void ora_rect_simpleJunction(int32_t *out, const int32_t *in, int iw, int ih) { k_simpleJunction(out, in, iw, ih); }
+void ora_rect_simpleConnect(int32_t *out, const int32_t *in, int iw, int ih) { k_simpleConnect(out, in, iw, ih); }
+void ora_rect_stringify(int32_t *out, const int32_t *in, int mod2, int iw, int ih) { k_stringify(out, in, mod2, iw, ih); }
+void ora_rect_blblur0(uint32_t *out, const int8_t *edge, const uint32_t *in, int iw, int ih) { k_blblur0(out, edge, in, iw, ih); }
+void ora_rect_blblur1(uint32_t *out, const int8_t *edge, const uint32_t *in, int iw, int ih) { k_blblur1(out, edge, in, iw, ih); }
+void ora_rect_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2, int iw, int ih) { k_quantize(out, in, n0, n1, n2, iw, ih); }
+void ora_rect_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih) { k_despeckle(out, in, edge, iw, ih); }
+void ora_rect_mkMergeMask0(int32_t *out, const int32_t *junction, int iw, int ih) { k_mkMergeMask0(out, junction, iw, ih); }
+void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int ih) { k_mkMergeMask1(inout, junction, iw, ih); }
+void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { labelMerge(label, pix, mask, edge, iw, ih); }
+void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih) { k_calcSize(out, label, iw, ih); }
+void ora_rect_despeckle2(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih) { k_despeckle2(labelinout, size, thre, iw, ih); }
+void ora_rect_markBoundary(int32_t *out, const int32_t *in, int iw, int ih) { k_markBoundary(out, in, iw, ih); }
+void ora_rect_reduceLS(int32_t *out, const int32_t *boundary, const int32_t *lsid, int iw, int ih, int nentry) { k_reduceLS(out, boundary, lsid, iw, ih, nentry); }
+
+ora_rect *ora_rect_create(int iw, int ih) {
+  ora_rect *o = (ora_rect *)calloc(1, sizeof(ora_rect));
+  o->iw = iw; o->ih = ih;
+  const size_t P = (size_t)iw * ih * 4;
+  for (int i = 0; i < 6; i++) { o->buf[i] = (int32_t *)calloc(1, P); o->tmp[i] = (int32_t *)calloc(1, P); }
+  for (int i = 0; i < 2; i++) { o->iobuf[i] = (int32_t *)calloc(1, P); o->ioBig[i] = (int32_t *)calloc(1, 4 * P); }
+  return o;
+}
+
+void ora_rect_destroy(ora_rect *o) {
+  if (!o) return;
+  for (int i = 0; i < 6; i++) { free(o->buf[i]); free(o->tmp[i]); }
+  for (int i = 0; i < 2; i++) { free(o->iobuf[i]); free(o->ioBig[i]); }
+  free(o);
+}
+
+void *ora_rect_buffer(ora_rect *o, const char *name) {
+  if (!strncmp(name, "buf", 3) && name[3] >= '0' && name[3] < '6') return o->buf[name[3] - '0'];
+  if (!strncmp(name, "tmp", 3) && name[3] >= '0' && name[3] < '6') return o->tmp[name[3] - '0'];
+  if (!strncmp(name, "iobuf", 5) && name[5] >= '0' && name[5] < '2') return o->iobuf[name[5] - '0'];
+  if (!strncmp(name, "ioBig", 5) && name[5] >= '0' && name[5] < '2') return o->ioBig[name[5] - '0'];
+  return NULL;
+}
+
+void ora_rect_last_times(ora_rect *o, double out[5]) { for (int i = 0; i < 5; i++) out[i] = o->t[i]; }
+
+// genGPUTask, oclrect.c:235-381.  Step numbers are those of SURVEY.md section 10.1.
+void ora_rect_gpu_task(ora_rect *o, const uint8_t *img, int ws, int stop_step) {
+  const int iw = o->iw, ih = o->ih, n = iw * ih;
+  int32_t **buf = o->buf, **tmp = o->tmp, **iobuf = o->iobuf, **ioBig = o->ioBig;
+#define STEP(k) do { if ((k) > 0 && stop_step == (k)) return; } while (0)
+  double t0 = now_s();
+  o->t[0] = o->t[1] = o->t[2] = o->t[3] = 0;
+
+  // step 0 : memcpy + H2D of P bytes (oclrect.c:239-241); only ws*ih bytes carry the image
+  memcpy(iobuf[0], img, (size_t)ws * ih);
+  STEP(0);
+  // step 1 : bgr2plab
+  ora_convert_plab_bgr((uint32_t *)buf[0], (const uint8_t *)iobuf[0], iw, ih, ws);
+  STEP(1);
+  // step 2 : unpack
+  ora_unpack_f_f_f_plab((float *)tmp[0], (float *)tmp[1], (float *)tmp[2], (const uint32_t *)buf[0], iw, ih);
+  STEP(2);
+  // step 3 : 3 x iirblur r=2, scratch = first plane of ioBig[0], ioBig[1]
+  ora_iirblur_f_f((float *)tmp[3], (const float *)tmp[2], (float *)ioBig[0], (float *)ioBig[1], 2, iw, ih);
+  ora_iirblur_f_f((float *)tmp[2], (const float *)tmp[1], (float *)ioBig[0], (float *)ioBig[1], 2, iw, ih);
+  ora_iirblur_f_f((float *)tmp[1], (const float *)tmp[0], (float *)ioBig[0], (float *)ioBig[1], 2, iw, ih);
+  STEP(3);
+  // step 4 : pack
+  ora_pack_plab_f_f_f((uint32_t *)buf[1], (const float *)tmp[1], (const float *)tmp[2], (const float *)tmp[3], iw, ih);
+  STEP(4);
+  // step 5 : edgevec
+  ora_edgevec_f2_f((float *)ioBig[0], (const float *)tmp[1], iw, ih);
+  STEP(5);
+  // step 6 : edge magnitude
+  ora_edge_f_plab((float *)tmp[0], (const uint32_t *)buf[1], iw, ih);
+  STEP(6);
+  // step 7 : NMS thinning
+  ora_thinthres_f_f_f2((float *)buf[1], (const float *)tmp[0], (const float *)ioBig[0], iw, ih);
+  STEP(7);
+  // step 8 : threshold + cast -> edge bitmap #1
+  ora_threshold_f_f((float *)tmp[0], (const float *)buf[1], 0.0f, 0.0f, 1.0f, n);
+  ora_cast_i_f(tmp[1], (const float *)tmp[0], 1.0f, n);
+  STEP(8);
+  o->t[0] = now_s() - t0; t0 = now_s();
+
+  // step 9 : junction / connect / stringify x2 (oclrect.cl versions)
+  k_simpleJunction(buf[2], tmp[1], iw, ih);
+  k_simpleConnect(tmp[1], buf[2], iw, ih);
+  k_stringify(buf[2], tmp[1], 0, iw, ih);
+  k_stringify(tmp[1], buf[2], 1, iw, ih);
+  STEP(9);
+  // step 10 : label8x bgc=-1
+  label8x(buf[2], tmp[1], tmp[0], -1, iw, ih);
+  STEP(10);
+  // step 11 : calcStrength into buf[3] (NOT cleared: Q1) ; filterStrength 500
+  k_rect_calcStrength(buf[3], (const float *)buf[1], buf[2], iw, ih);
+  k_rect_filterStrength(buf[2], buf[3], 500, iw, ih);
+  STEP(11);
+  // step 12 : int edge mask -> i8 mask
+  ora_threshold_i_i(tmp[0], buf[2], 0, 0, 1, n);
+  ora_cast_c_i((int8_t *)tmp[1], tmp[0], n);
+  STEP(12);
+  // step 13 : 10 x (blblur0, blblur1)
+  k_blblur0((uint32_t *)tmp[0], (const int8_t *)tmp[1], (const uint32_t *)buf[0], iw, ih);
+  k_blblur1((uint32_t *)buf[4], (const int8_t *)tmp[1], (const uint32_t *)tmp[0], iw, ih);
+  for (int i = 0; i < 9; i++) {
+    k_blblur0((uint32_t *)tmp[0], (const int8_t *)tmp[1], (const uint32_t *)buf[4], iw, ih);
+    k_blblur1((uint32_t *)buf[4], (const int8_t *)tmp[1], (const uint32_t *)tmp[0], iw, ih);
+  }
+  STEP(13);
+  // step 14 : quantize 24^3 ; despeckle
+  k_quantize((uint32_t *)tmp[0], (const uint32_t *)buf[4], 24, 24, 24, iw, ih);
+  k_despeckle((uint32_t *)buf[4], (const uint32_t *)tmp[0], (const float *)buf[1], iw, ih);
+  STEP(14);
+  // step 15 : filterStrength 2500 ; threshold -> strong-edge bitmap in buf[3]
+  k_rect_filterStrength(buf[2], buf[3], 2500, iw, ih);
+  ora_threshold_i_i(buf[3], buf[2], 0, 0, 1, n);
+  STEP(15);
+  // step 16 : junction of strong edges ; merge mask
+  k_simpleJunction(tmp[0], buf[2], iw, ih);
+  k_clear(tmp[1], n);
+  k_mkMergeMask0(tmp[1], tmp[0], iw, ih);
+  k_mkMergeMask1(tmp[1], tmp[0], iw, ih);
+  STEP(16);
+  // step 17 : colour-region labels
+  labelMerge(buf[5], buf[4], tmp[1], buf[2], iw, ih);
+  STEP(17);
+  // step 18 : calcSize into tmp[0] which still holds the junction map (Q2) ; despeckle2
+  k_calcSize(tmp[0], buf[5], iw, ih);
+  k_despeckle2(buf[5], tmp[0], 16, iw, ih);
+  STEP(18);
+  // step 19 : boundary bands and their components -> segid map
+  k_markBoundary(tmp[1], buf[5], iw, ih);
+  label8x(iobuf[1], tmp[1], tmp[0], -1, iw, ih);
+  STEP(19);
+  o->t[1] = now_s() - t0; t0 = now_s();
+
+  // step 20 : polyline
+  ora_polyline_execute((ora_ls_t *)ioBig[0], iw * ih * 4 * 4, buf[0], buf[3], ioBig[1],
+                       tmp[0], tmp[1], tmp[2], tmp[3], tmp[4], tmp[5], 4.0f, 20, iw, ih, 0);
+  STEP(20);
+  o->t[2] = now_s() - t0; t0 = now_s();
+
+  // step 21 : vote table
+  k_clear(ioBig[1], n * 4);
+  k_reduceLS(ioBig[1], iobuf[1], buf[0], iw, ih, iw * ih * 4 / 5);
+  o->t[3] = now_s() - t0;
+#undef STEP
+}
+
+ora_rect_t *ora_rect_cpu_task(ora_rect *o, double tanAOV) {
+  double t0 = now_s();
+  ora_rect_t *r = ora_tail((const ora_ls_t *)o->ioBig[0], o->iobuf[1], o->ioBig[1], o->iw, o->ih, tanAOV);
+  o->t[4] = now_s() - t0;
+  return r;
+}
+
+ora_rect_t *ora_rect_execute_once(ora_rect *o, const uint8_t *img, int ws, double tanAOV) {
+  ora_rect_gpu_task(o, img, ws, 0);
+  return ora_rect_cpu_task(o, tanAOV);
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+/* rd_oracle.h - CPU oracle for the rectdetect hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is a CPU restatement of the reference's OpenCL kernels (oclimgutil.cl, oclrect.cl,
+ * oclpolyline.cl), of its launch schedules (oclrect.c:235-381 genGPUTask, oclpolyline.c:218-309
+ * oclpolyline_execute, oclimgutil.c:227-273, poly.cpp:104-123) and of its host tail
+ * (oclrect.c:385-1226 executeCPUTask).  It exists to check the CUDA path; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product library never links, imports or calls anything in this directory.
+ *
+ * PARITY STATUS: "parity unpinned".  The reference has no tests, golden vectors or fixtures
+ *  and cannot run in this image (no OpenCL ICD, no CL/cl.h), so
+ * this oracle is pinned only by (a) closed-form known-answer tests written for it
+ * (tests/test_oracle_kat.py), (b) the LUT check against the reference source/pinned digests
+ * (tools/gen_tables.py --check) and (c) an independent CCL cross-check (scipy).  Where the
+ * reference is schedule-dependent (data races, atomic arrival order, bounded label passes) the
+ * oracle fixes ONE canonical outcome; each such choice is marked "CANONICAL" in rd_oracle.cpp
+ * and listed in DESIGN.md section "Canonical semantics".
+ */
+#ifndef RD_ORACLE_H
+#define RD_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* == linesegment_t of the reference (oclpolyline.h:74-83) == */
+typedef struct ora_ls_t {
+  float x0, y0, x1, y1;
+  int32_t startIndex, endIndex, leftPtr, rightPtr, startCount, endCount, maxDist, polyid, npix, level;
+} ora_ls_t;
+
+/* == rect_t of the reference (oclrect.h:5-15): 176 bytes, element 0 is a header == */
+typedef struct ora_rect_t {
+  union {
+    struct { double c2[4][2]; double c3[4][3]; double value; uint32_t status; };
+    int nItems;
+  };
+} ora_rect_t;
+
+typedef struct ora_stats_t {
+  int label8x_seq_passes;      /* passes the reference's label8xMain needs under a sequential schedule (max over calls) */
+  int label8x_calls;
+  int labelpl_components;
+  int mkpl_ties;               /* exact arg-max ties seen in mkpl */
+  int mkpl_iterations_live;    /* how many of the 15 split iterations did work */
+  int vote_collisions;         /* reduceLS slots wanted by more than one lsid */
+  int vote_slots;              /* occupied slots */
+  int n_ls;                    /* lsList[0] count after polyline */
+  int ls_overflow;             /* "Too many linesegments" events */
+} ora_stats_t;
+
+void ora_set_threads(int n);
+int  ora_get_threads(void);
+void ora_get_stats(ora_stats_t *out);
+void ora_reset_stats(void);
+
+/* ---- Stage A operators: one function per oclimgutil_* wrapper (oclimgutil.c:140-319) ---- */
+void ora_clear(int32_t *out, int size_bytes);
+void ora_copy(int32_t *out, const int32_t *in, int size_bytes);
+void ora_cast_i_f(int32_t *out, const float *in, float scale, int size);
+void ora_cast_c_i(int8_t *out, const int32_t *in, int size);
+void ora_threshold_i_i(int32_t *out, const int32_t *in, int vlow, int threshold, int vhigh, int size);
+void ora_threshold_f_f(float *out, const float *in, float vlow, float threshold, float vhigh, int size);
+void ora_convert_plab_bgr(uint32_t *out, const uint8_t *in, int iw, int ih, int ws);   /* runs bgr2plab (Q9) */
+void ora_unpack_f_f_f_plab(float *o0, float *o1, float *o2, const uint32_t *in, int iw, int ih);
+void ora_pack_plab_f_f_f(uint32_t *out, const float *i0, const float *i1, const float *i2, int iw, int ih);
+void ora_iirblur_f_f(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih);
+void ora_edgevec_f2_f(float *out_xy, const float *in, int iw, int ih);
+void ora_edge_f_plab(float *out, const uint32_t *in, int iw, int ih);
+void ora_thinthres_f_f_f2(float *out, const float *in, const float *vxy, int iw, int ih);
+/* CANONICAL: converged labels.  Returns number of sequential passes the reference kernel needed. */
+int  ora_label8x_int_int(int32_t *out, const int32_t *in, int32_t *tmp, int bgc, int iw, int ih);
+void ora_calcStrength(int32_t *out, const float *edge, const int32_t *label, int iw, int ih);
+void ora_filterStrength(int32_t *labelinout, const int32_t *str, int thre, int iw, int ih);
+
+/* ---- Stage B kernels of oclrect.cl, exposed one by one for operator-level parity ---- */
+void ora_rect_simpleJunction(int32_t *out, const int32_t *in, int iw, int ih);
+void ora_rect_simpleConnect(int32_t *out, const int32_t *in, int iw, int ih);
+void ora_rect_stringify(int32_t *out, const int32_t *in, int mod2, int iw, int ih);
+void ora_rect_blblur0(uint32_t *out, const int8_t *edge, const uint32_t *in, int iw, int ih);
+void ora_rect_blblur1(uint32_t *out, const int8_t *edge, const uint32_t *in, int iw, int ih);
+void ora_rect_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2, int iw, int ih);
+void ora_rect_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih);
+void ora_rect_mkMergeMask0(int32_t *out, const int32_t *junction, int iw, int ih);
+void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int ih);
+/* labelxPreprocess + labelMergeMain x8 -> CANONICAL converged symmetric merge */
+void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);
+void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih);
+void ora_rect_despeckle2(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih);
+void ora_rect_markBoundary(int32_t *out, const int32_t *in, int iw, int ih);
+void ora_rect_reduceLS(int32_t *out, const int32_t *boundary, const int32_t *lsid, int iw, int ih, int nentry);
+
+/* ---- Stage C: oclpolyline_execute (oclpolyline.c:218), same argument order minus the CL handles.
+ *      stop_step: 0 = run everything, k>0 = return after step k of SURVEY.md 10.2 (for intermediates). ---- */
+void ora_polyline_execute(ora_ls_t *lsList, int lsListSize, int32_t *lsIdOut, const int32_t *in, int32_t *tmpBig,
+                          int32_t *tmp0, int32_t *tmp1, int32_t *tmp2, int32_t *tmp3, int32_t *tmp4, int32_t *tmp5,
+                          float minerror, int sizeThre, int iw, int ih, int stop_step);
+
+/* ---- L3: the oclrect_t object (oclrect.c:41-135) with the reference's buffer aliasing ---- */
+typedef struct ora_rect ora_rect;
+ora_rect *ora_rect_create(int iw, int ih);
+void      ora_rect_destroy(ora_rect *o);
+/* genGPUTask (oclrect.c:235-381).  stop_step: 0 = all, k>0 = return after step k of SURVEY.md 10.1 */
+void      ora_rect_gpu_task(ora_rect *o, const uint8_t *img, int ws, int stop_step);
+/* names: "buf0".."buf5", "tmp0".."tmp5", "iobuf0", "iobuf1", "ioBig0", "ioBig1" */
+void     *ora_rect_buffer(ora_rect *o, const char *name);
+/* executeCPUTask (oclrect.c:1049-1226) on the object's buffers; result is malloc()ed, element 0 = header */
+ora_rect_t *ora_rect_cpu_task(ora_rect *o, double tanAOV);
+/* oclrect_executeOnce (oclrect.c:1230) */
+ora_rect_t *ora_rect_execute_once(ora_rect *o, const uint8_t *img, int ws, double tanAOV);
+/* the host tail on caller-provided arrays (full-size vote table as the reference reads it back) */
+ora_rect_t *ora_tail(const ora_ls_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, double tanAOV);
+void ora_free(void *p);
+/* per-stage wall-clock of the last ora_rect_gpu_task / cpu_task, seconds: A, B, C, D, tail */
+void ora_rect_last_times(ora_rect *o, double out[5]);
+
+/* ---- poly.cpp:104-123 pipeline (config 1): fills lsId map (mem0) and LS list ---- */
+void ora_poly_frame(const uint8_t *img, int ws, int iw, int ih, float minerror, int sizeThre, int strengthThre,
+                    int32_t *lsIdOut, ora_ls_t *lsListOut /* iw*ih*16 bytes */, float *thinOut /* may be NULL */);
+
+/* ---- small pure functions exported for known-answer tests ---- */
+uint32_t ora_srgb2plab(int b, int g, int r);
+uint32_t ora_packlab(float l, float a, float b);
+void     ora_unpacklab(uint32_t plab, float out[3]);
+int      ora_mirror1(int x, int iw);
+int      ora_repeat1(int x, int iw);
+uint64_t ora_xrandom(uint64_t s);
+int32_t  ora_rand_at(int x, uint64_t seed);
+void     ora_clip_line(double x0, double y0, double x1, double y1, double xmin, double ymin, double xmax, double ymax, double out[4]);
+void     ora_intersection2(const double u[4], const double v[4], double out[2]);
+/* poseEstimation (oclrect.c:590) on 4 corner points given in image order */
+void     ora_pose(const double corners[4][2], int iw, int ih, double tanAOV, ora_rect_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
