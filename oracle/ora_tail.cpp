@@ -345,7 +345,7 @@ static V2 gv(const std::vector<Seg> &als) {        // oclrect.c:864-877
 static double sumLength(const std::vector<Seg> *als) {   // oclrect.c:879-884
   if (als == NULL) return 0;
   double ret = 0;
-  for (size_t i = 0; i < als->size(); i++) ret += sqrt(lsSquLen((*als)[i]));
+  for (size_t i = 0; i < als->size(); i++) ret += sqrt((double)lsSquLen((*als)[i]));   // C: sqrt(double) of the float-rounded square
   return ret;
 }
 

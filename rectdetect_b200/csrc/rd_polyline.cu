@@ -1,0 +1,628 @@
+// rd_polyline.cu - Stage C: edge-string tracing and polyline simplification (oclpolyline.h:85-88) on sm_100a.
+//
+// oclpolyline_execute keeps the reference's contract (oclpolyline.c:218-309): `in` is a 0/1 edge mask, the results
+// are the per-pixel segment-id map `lsIdOut` and the linesegment_t list `lsList` (element 0 = header).  The kernels
+// follow oclpolyline.cl one for one, except where the reference is schedule dependent; there the canonical outcome
+// of DESIGN.md is computed deterministically:
+//   - the three bounded label-propagation loops (label8x, labelpl) are exact connected components (rd_ccl.cu);
+//   - relabel_pass0 numbers strings in raster order of their root pixel by a block-count / scan / rank sequence
+//     instead of atomic_inc arrival order (Q4);
+//   - mkpl_pass2 picks the arg-max pixel with the smallest index and hands out new ids by a prefix sum over the
+//     parent id (Q4, Q8); because every split only rewrites fields of its own, its new and its right neighbour's
+//     entry, the 15 full-list copies of the reference (oclpolyline.c:207, 32 B/px each) are not needed at all;
+//   - refine_pass3 computes all shared vertices from the unmodified list before writing any (Q5).
+#include "rd_common.cuh"
+#include "rd_stageA.cuh"
+
+struct oclpolyline_t { uint32_t magic; int ordinal; };
+#define POLY_MAGIC 0x808eae03u
+
+typedef linesegment_t LS_t;
+struct LSX_t {                         // oclpolyline.cl:41-45
+  long long mx00, mx01, mx11, my0, my1;
+  short dirSEx, dirSEy, vDirSEx, vDirSEy;
+  int distSquSE, padding;
+};
+static_assert(sizeof(LS_t) == 56 && sizeof(LSX_t) == 56, "list entries are 56 bytes");
+
+#define MINEDGELEN 1
+#define MINNINDEX 4
+#define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
+#define IS_BORDER1 (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1)
+
+void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, cudaStream_t s);
+void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, cudaStream_t s);
+void rd_k_clear(int *out, int nints, cudaStream_t s);
+void rd_k_copy(int *out, const int *in, int nints, cudaStream_t s);
+void rd_k_rand(int *out, uint64_t seed, int n, cudaStream_t s);
+
+// ---------------------------------------------------------------------------- string clean-up (oclpolyline.cl:66-147)
+__global__ void kp_simpleJunction(int *out, const int *in, int iw, int ih) {
+  XY2D;
+  int r = 0;
+  if (!IS_BORDER1 && in[p0] != 0) {
+    int count = 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (in[p0 + RD_RX[i] + RD_RY[i] * iw] != 0) count++;
+    r = count == 1 ? 0 : count;
+  }
+  out[p0] = r;
+}
+// the 2-pixel frame of `out` is left untouched, as in the reference (oclpolyline.cl:91)
+__global__ void kp_simpleConnect(int *out, const int *in, int iw, int ih) {
+  XY2D;
+  if (x <= 1 || y <= 1 || x >= iw - 2 || y >= ih - 2) return;
+  int r = in[p0] != 0 ? 1 : 0;
+  if (!r) {
+    if (in[p0 - 2] != 0 && in[p0 - 1] == 2 && in[p0 + 1] == 2 && in[p0 + 2] != 0) r = 1;
+    if (in[p0 - iw * 2] != 0 && in[p0 - iw] == 2 && in[p0 + iw] == 2 && in[p0 + iw * 2] != 0) r = 1;
+    if (in[p0 - iw * 2 - 2] != 0 && in[p0 - iw - 1] == 2 && in[p0 + iw + 1] == 2 && in[p0 + iw * 2 + 2] != 0) r = 1;
+    if (in[p0 - iw * 2 + 2] != 0 && in[p0 - iw + 1] == 2 && in[p0 + iw - 1] == 2 && in[p0 + iw * 2 - 2] != 0) r = 1;
+    if (in[p0 + 2] != 0 && in[p0 + 1] == 2 && in[p0 + iw - 1] == 2 && in[p0 + iw - 2] != 0) r = 1;
+    if (in[p0 - 2] != 0 && in[p0 - 1] == 2 && in[p0 + iw + 1] == 2 && in[p0 + iw + 2] != 0) r = 1;
+    if (in[p0 - iw * 2 + 1] != 0 && in[p0 - iw + 1] == 2 && in[p0 + iw] == 2 && in[p0 + iw * 2] != 0) r = 1;
+    if (in[p0 - iw * 2 - 1] != 0 && in[p0 - iw - 1] == 2 && in[p0 + iw] == 2 && in[p0 + iw * 2] != 0) r = 1;
+  }
+  out[p0] = r;
+}
+__global__ void kp_stringify(int *out, const int *in, int mod2, int iw, int ih) {
+  XY2D;
+  int r = in[p0];
+  if (!IS_BORDER1 && ((x + y) & 1) == mod2) {
+    const bool n = in[p0 - iw] != 0, s = in[p0 + iw] != 0, w = in[p0 - 1] != 0, e = in[p0 + 1] != 0;
+    if ((n || s) && (w || e)) r = 0;
+  }
+  out[p0] = r;
+}
+__global__ void kp_removeBranch(int *out, const int *in, int iw, int ih) {
+  XY2D;
+  int r = 0;
+  if (!IS_BORDER1 && in[p0] != 0) {
+    int count = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (in[p0 + RD_RX[i] + RD_RY[i] * iw] != 0) count++;
+    r = count <= 2 ? 1 : 0;
+  }
+  out[p0] = r;
+}
+// oclpolyline.cl:149-167 ; the reference's non-atomic ++ is only ever compared with 0 (Q7)
+__global__ void kp_countEnds(int *out, const int *junction, const int *label, int iw, int ih) {
+  XY2D;
+  if (IS_BORDER1) return;
+  if (junction[p0] == 2) out[label[p0]] = 1;
+}
+__global__ void kp_breakLoops(int *edgeinout, int *labelinout, const int *nEnds, int iw, int ih) {
+  XY2D;
+  if (IS_BORDER1) return;
+  if (labelinout[p0] != p0) return;
+  if (nEnds[p0] == 0) { edgeinout[p0] = 0; labelinout[p0] = -1; }
+}
+
+// ---------------------------------------------------------------------------- end finding / numbering (oclpolyline.cl:169-310)
+__device__ __forceinline__ void getnp(const int *labelin, int p0, int iw, int &nx, int &ny) {
+  const int l = labelin[p0];
+  int i;
+  for (i = 0; i < 8; i++) if (labelin[p0 + RD_RX[i] + RD_RY[i] * iw] == l) break;
+  nx = i < 8 ? (p0 + RD_RX[i] + RD_RY[i] * iw) : p0;
+  for (i++; i < 8; i++) if (labelin[p0 + RD_RX[i] + RD_RY[i] * iw] == l) break;
+  ny = i < 8 ? (p0 + RD_RX[i] + RD_RY[i] * iw) : p0;
+}
+__global__ void kp_findEnds0(int *nextout, int *prevout, int *flagout, const int *labelin, int iw, int ih) {
+  XY2D;
+  int nx = -1, pv = -1, flag = -1;
+  if (!IS_BORDER1 && labelin[p0] != -1) {
+    int npx, npy, a, b;
+    getnp(labelin, p0, iw, npx, npy);
+    nx = npx; pv = npy; flag = 0;
+    if (npx != p0) { getnp(labelin, npx, iw, a, b); if (a == p0) flag |= 1; }
+    if (npy != p0) { getnp(labelin, npy, iw, a, b); if (b == p0) flag |= 2; }
+  }
+  nextout[p0] = nx; prevout[p0] = pv; flagout[p0] = flag;
+}
+// A launch reads one pair of flag bits of other pixels and rewrites only the other pair of its own pixel, so the
+// in-place update of flaginout is race free (the reads are volatile to keep them from being cached in registers).
+__global__ void kp_findEnds1(int *nextout, int *prevout, int *flaginout, const int *nextin, const int *previn, const int *labelin, int page, int iw, int ih) {
+  XY2D;
+  int nn = -1, pp = -1;
+  if (!IS_BORDER1 && labelin[p0] != -1) {
+    const volatile int *fl = flaginout;
+    const int f0 = fl[p0];
+    bool revn = page == 0 ? ((f0 & 1) != 0) : ((f0 & 4) != 0);
+    bool revp = page == 0 ? ((f0 & 2) != 0) : ((f0 & 8) != 0);
+    nn = nextin[p0]; pp = previn[p0];
+    for (int i = 0; i < 8; i++) {
+      const int nn2 = revn ? previn[nn] : nextin[nn];
+      const int pp2 = revp ? nextin[pp] : previn[pp];
+      int nflag = fl[nn], pflag = fl[pp];
+      if (page != 0) { nflag >>= 2; pflag >>= 2; }
+      revn = revn ? ((nflag & 2) == 0) : ((nflag & 1) != 0);
+      revp = revp ? ((pflag & 1) == 0) : ((pflag & 2) != 0);
+      nn = nn2; pp = pp2;
+    }
+    int f = f0;
+    if (page == 0) { f &= 3; f |= revn ? 4 : 0; f |= revp ? 8 : 0; }
+    else { f &= (3 << 2); f |= revn ? 1 : 0; f |= revp ? 2 : 0; }
+    flaginout[p0] = f;
+  }
+  nextout[p0] = nn; prevout[p0] = pp;
+}
+__global__ void kp_findEnds2(int *numout, int *linkout, const int *nextin, const int *previn, const int *labelin, int iw, int ih) {
+  XY2D;
+  int num = 0, link = -1;
+  if (!IS_BORDER1 && labelin[p0] != -1) {
+    int npx, npy;
+    getnp(labelin, p0, iw, npx, npy);
+    link = nextin[p0] < previn[p0] ? npx : npy;
+    num = link == p0 ? 0 : 1;
+  }
+  numout[p0] = num; linkout[p0] = link;
+}
+__global__ void kp_number(int *numout, int *linkout, const int *numin, const int *linkin, int iw, int ih) {
+  XY2D;
+  int no = 0, lo = -1;
+  if (!IS_BORDER1) {
+    const int l0 = linkin[p0];
+    if (l0 == -1) { no = numin[p0]; lo = -1; }
+    else {
+      int n = numin[p0], l = l0;
+      bool bail = false;
+      for (int i = 0; i < 32; i++) {
+        if (!(0 < l && l < iw * ih)) { bail = true; break; }
+        n += numin[l];
+        l = linkin[l];
+      }
+      if (!bail) { no = n; lo = l; }
+    }
+  }
+  numout[p0] = no; linkout[p0] = lo;
+}
+
+// ---------------------------------------------------------------------------- labelpl pre-step, sizes (oclpolyline.cl:312-378)
+__global__ void kp_plus1(int *out, const int *in, int n) {          // labelpl_preprocess: pix = number + 1 where number != 0
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int v = in[i]; out[i] = v == 0 ? 0 : v + 1; }
+}
+__global__ void kp_calcSize(int *out, const int *label, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = label[i];
+  if (b != 0) atomicAdd(out + b, 1);
+}
+__global__ void kp_filterSize(int *out, const int *labelin, const int *sizein, int sizethre, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = labelin[i];
+  out[i] = sizein[b] > sizethre ? b : 0;
+}
+
+// ---------------------------------------------------------------------------- relabel (oclpolyline.cl:380-420), raster-order ids
+// A root is an interior pixel whose label is its own index.  ids = 1 + number of roots before it in raster order.
+#define RL_BLOCK 1024
+__device__ __forceinline__ bool is_root(const int *label, int p, int iw, int ih) {
+  const int x = p % iw, y = p / iw;
+  if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return false;
+  const int g = label[p];
+  return g != 0 && g == p;
+}
+__global__ void kp_relabel_count(int *blockCount, const int *label, int iw, int ih) {
+  __shared__ int wsum[RL_BLOCK / 32];
+  const int p = blockIdx.x * RL_BLOCK + threadIdx.x;
+  const bool r = p < iw * ih && is_root(label, p, iw, ih);
+  const unsigned b = __ballot_sync(0xffffffffu, r);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = wsum[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) blockCount[blockIdx.x] = v;
+  }
+}
+// exclusive scan of blockCount in place (single CTA, chunked with a running carry); total -> *total
+__global__ void kp_scan_blocks(int *blockCount, int nblocks, int *total) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? blockCount[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wsum[threadIdx.x], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += t; }
+      wsum[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + wsum[threadIdx.x >> 5] + incl - v;
+    if (i < nblocks) blockCount[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void kp_relabel_rank(int *table, const int *blockOffset, const int *label, int iw, int ih) {
+  __shared__ int wsum[RL_BLOCK / 32];
+  const int p = blockIdx.x * RL_BLOCK + threadIdx.x;
+  const bool r = p < iw * ih && is_root(label, p, iw, ih);
+  const unsigned b = __ballot_sync(0xffffffffu, r);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) wsum[w] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = wsum[threadIdx.x], vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, vi, o); if (threadIdx.x >= o) vi += t; }
+    wsum[threadIdx.x] = vi - v;
+  }
+  __syncthreads();
+  if (r) table[p + 1] = blockOffset[blockIdx.x] + wsum[w] + __popc(b & ((1u << lane) - 1)) + 1;
+}
+__global__ void kp_relabel_pass1(int *labelinout, const int *tablein, int iw, int ih) {
+  XY2D;
+  if (x == 0 || y == 0 || x >= iw - 1 || y >= ih - 1) { labelinout[p0] = 0; return; }
+  const int g = labelinout[p0];
+  if (g == 0) return;
+  labelinout[p0] = tablein[g + 1];
+}
+
+// ---------------------------------------------------------------------------- mkpl (oclpolyline.cl:439-646)
+__device__ __forceinline__ bool ls_overflow(int g, int lsListSize) { return g < 0 || (size_t)lsListSize <= ((size_t)(g + 1)) * sizeof(LS_t); }
+
+__device__ __forceinline__ float distanceSqu(float vx, float vy, float wx, float wy) {
+  const float dx = __fsub_rn(vx, wx), dy = __fsub_rn(vy, wy);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+__device__ __forceinline__ void closestPoint(float vx, float vy, float wx, float wy, float px, float py, float &ox, float &oy) {
+  const float l2 = distanceSqu(vx, vy, wx, wy);
+  if (l2 <= 1e-4f) { ox = vx; oy = vy; return; }
+  const float t = __fdiv_rn(__fadd_rn(__fmul_rn(__fsub_rn(px, vx), __fsub_rn(wx, vx)), __fmul_rn(__fsub_rn(py, vy), __fsub_rn(wy, vy))), l2);
+  if (t < 0.0f) { ox = vx; oy = vy; return; }
+  if (t > 1.0f) { ox = wx; oy = wy; return; }
+  ox = __fadd_rn(vx, __fmul_rn(t, __fsub_rn(wx, vx)));
+  oy = __fadd_rn(vy, __fmul_rn(t, __fsub_rn(wy, vy)));
+}
+
+// pass0a: per-string start pixel (the LAST pixel in raster order whose number is 1, as a sequential sweep leaves it),
+// pixel count, largest number, and the list header (largest id).  aux[g] / aux[cap+g] : start / end pixel index.
+__global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int *flags, int maxIter, int iw, int ih) {
+  XY2D;
+  if (y == 0 && x < maxIter + 1) flags[x] = x == 0 ? 1 : 0;
+  if (IS_BORDER1) return;
+  const int g = labelin[p0], n = numberin[p0];
+  if (g == 0 || ls_overflow(g, lsListSize)) return;
+  if (n == 1) { atomicMax(aux + g, p0 + 1); atomicAdd(&gp[g].startCount, 1); }
+  atomicAdd(&gp[g].npix, 1);
+  atomicMax(&gp[g].endIndex, n);
+  atomicMax((int *)gp, g);
+}
+__global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int iw, int ih) {
+  XY2D;
+  if (IS_BORDER1) return;
+  const int g = labelin[p0], n = numberin[p0];
+  if (g == 0 || ls_overflow(g, lsListSize)) return;
+  if (n == gp[g].endIndex) {
+    if (gp[g].startCount == 1 && gp[g].npix >= 2) { atomicAdd(&gp[g].endCount, 1); atomicMin(aux + cap + g, p0); }
+    else aux[cap + g] = -1;                                      // polyid = 0
+  }
+}
+// one thread per list entry: turn the start / end pixel indices into coordinates
+__global__ void kp_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (g > *(const int *)gp || g >= cap) return;
+  const int sp = aux[g] - 1, ep = aux[cap + g];
+  if (sp >= 0) { gp[g].x0 = (float)(sp % iw); gp[g].y0 = (float)(sp / iw); gp[g].level = 0; }
+  if (ep >= 0 && ep != 0x7fffffff) { gp[g].x1 = (float)(ep % iw); gp[g].y1 = (float)(ep / iw); gp[g].polyid = g; }
+  else gp[g].polyid = 0;
+}
+__global__ void kp_fill(int *out, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+__global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *tmp, const int *labelin, const int *randin, const int *flags, int nIter, int iw, int ih) {
+  if (flags[nIter - 1] == 0) return;
+  XY2D;
+  const int g = labelin[p0];
+  if (g == 0 || ls_overflow(g, lsListSize)) return;
+  if (gp[g].polyid == 0) return;
+  const int x0 = (int)gp[g].x0, y0 = (int)gp[g].y0, x1 = (int)gp[g].x1, y1 = (int)gp[g].y1;
+  float cx, cy;
+  closestPoint((float)x0, (float)y0, (float)x1, (float)y1, (float)x, (float)y, cx, cy);
+  int dist = (int)__fmul_rn(rd_hypot(__fsub_rn(cx, (float)x), __fsub_rn(cy, (float)y)), 65536.0f);
+  dist ^= (randin[p0] & 0x1fff);
+  tmp[p0] = dist;
+  atomicMax(&gp[g].maxDist, dist);
+}
+// pass2a: winner[g] = smallest pixel index attaining maxDist
+__global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, const int *tmp, const int *labelin, const int *flags, int nIter, int iw, int ih) {
+  if (flags[nIter - 1] == 0) return;
+  XY2D;
+  const int g = labelin[p0];
+  if (g == 0 || ls_overflow(g, lsListSize)) return;
+  if (g > *(const int *)gp) return;
+  if (gp[g].polyid == 0) return;
+  if (tmp[p0] != gp[g].maxDist) return;
+  atomicMin(winner + g, p0);
+}
+// pass2b: single CTA; decides the splits of this iteration, numbers the new entries by a prefix sum over the
+// parent id and rewrites the list.  Also resets winner[] for the next iteration.
+__global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize, int *winner, const int *numberin, const int *flags, int nIter, float minerror, int iw) {
+  if (flags[nIter - 1] == 0) return;
+  __shared__ int wsum[32];
+  __shared__ int carry, total;
+  const int count = *(const int *)gp;
+  if (threadIdx.x == 0) carry = count;
+  __syncthreads();
+  for (int base = 1; base <= count; base += 1024) {
+    const int g = base + threadIdx.x;
+    bool split = false;
+    int px = 0, py = 0, n = 0, maxDist = 0, gr = 0, endIndex = 0, polyid = 0;
+    float x1 = 0, y1 = 0;
+    if (g <= count && !ls_overflow(g, lsListSize)) {
+      const int p0 = winner[g];
+      winner[g] = 0x7fffffff;
+      const LS_t o = gp[g];
+      if (p0 != 0x7fffffff && o.polyid != 0) {
+        px = p0 % iw; py = p0 / iw; n = numberin[p0];
+        maxDist = o.maxDist; gr = o.rightPtr; endIndex = o.endIndex; polyid = o.polyid; x1 = o.x1; y1 = o.y1;
+        split = true;
+        if (o.endIndex - o.startIndex < MINNINDEX - 1) split = false;
+        if (o.startCount > 1 || o.endCount > 1) split = false;
+        if (maxDist < ((int)__fmul_rn(minerror, 65536.0f))) split = false;
+        if (split && (float)maxDist < __fmul_rn(__fmul_rn(minerror, 3.0f), 65536.0f) &&
+            __fdiv_rn(__fmul_rn((float)maxDist, (float)maxDist), distanceSqu(o.x0, o.y0, o.x1, o.y1)) < 100000.0f) split = false;
+        if (distanceSqu((float)px, (float)py, o.x0, o.y0) < (float)(MINEDGELEN * MINEDGELEN)) split = false;
+        if (distanceSqu((float)px, (float)py, o.x1, o.y1) < (float)(MINEDGELEN * MINEDGELEN)) split = false;
+      }
+    }
+    // block-wide exclusive prefix sum of the split flags
+    const unsigned b = __ballot_sync(0xffffffffu, split);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int v = wsum[threadIdx.x];
+      int vi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, vi, o); if (threadIdx.x >= o) vi += t; }
+      wsum[threadIdx.x] = vi - v;
+      if (threadIdx.x == 31) total = vi;
+    }
+    __syncthreads();
+    const int rank = wsum[w] + __popc(b & ((1u << lane) - 1));
+    const int base_id = carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = base_id + total;
+    if (split) {
+      const int gn = base_id + rank + 1;
+      if (!ls_overflow(gn, lsListSize)) {
+        LS_t nw;
+        nw.x0 = (float)px; nw.y0 = (float)py; nw.x1 = x1; nw.y1 = y1;
+        nw.startIndex = n; nw.endIndex = endIndex; nw.leftPtr = g; nw.rightPtr = gr;
+        nw.startCount = 0; nw.endCount = 0; nw.maxDist = 0; nw.polyid = polyid; nw.npix = 0; nw.level = maxDist;
+        gp[gn] = nw;
+        gp[g].endIndex = n; gp[g].x1 = (float)px; gp[g].y1 = (float)py; gp[g].rightPtr = gn; gp[g].maxDist = 0;
+        if (gr != 0) gp[gr].leftPtr = gn;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *(int *)gp = carry;
+}
+__global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, int *flags, int nIter, int n) {
+  if (flags[nIter - 1] == 0) return;
+  const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p0 >= n) return;
+  const int g = labelinout[p0];
+  if (g == 0 || ls_overflow(g, lsListSize)) return;
+  if (gp[g].polyid == 0) return;
+  if (gp[g].endIndex < numberin[p0]) { labelinout[p0] = gp[g].rightPtr; flags[nIter] = 1; }
+}
+
+// ---------------------------------------------------------------------------- refine (oclpolyline.cl:680-809)
+__global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (g > *(const int *)ls) return;
+  if (ls[g].polyid == 0) return;
+  LSX_t v;
+  v.dirSEx = (short)(int)__fsub_rn(ls[g].x1, ls[g].x0);          // convert_short2: truncation (Q18)
+  v.dirSEy = (short)(int)__fsub_rn(ls[g].y1, ls[g].y0);
+  v.vDirSEx = (short)(-v.dirSEy);
+  v.vDirSEy = v.dirSEx;
+  v.mx00 = v.mx01 = v.mx11 = v.my0 = v.my1 = 0;
+  v.distSquSE = v.dirSEx * v.dirSEx + v.dirSEy * v.dirSEy;
+  v.padding = 0;
+  lsx[g] = v;
+}
+__global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, int iw, int ih) {
+  XY2D;
+  const int g = lsIdIn[p0];
+  if (g == 0) return;
+  if (g < 0 || *(const int *)ls < g) return;
+  const int vx = x - __float2int_rn(ls[g].x0), vy = y - __float2int_rn(ls[g].y0);   // convert_int2_rte
+  const int ay = vx * (int)lsx[g].vDirSEx + vy * (int)lsx[g].vDirSEy;
+  const int ax0 = vx * (int)lsx[g].dirSEx + vy * (int)lsx[g].dirSEy;
+  const int ax1 = lsx[g].distSquSE;
+  typedef unsigned long long ull;
+  atomicAdd((ull *)&lsx[g].mx00, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ax0)));   // convert_long_rte
+  atomicAdd((ull *)&lsx[g].mx01, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ax1)));
+  atomicAdd((ull *)&lsx[g].mx11, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ax1)));
+  atomicAdd((ull *)&lsx[g].my0, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ay)));
+  atomicAdd((ull *)&lsx[g].my1, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ay)));
+}
+__global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (g > *(const int *)ls) return;
+  if (ls[g].polyid == 0) return;
+  const float mx00 = (float)lsx[g].mx00, mx01 = (float)lsx[g].mx01, mx11 = (float)lsx[g].mx11, my0 = (float)lsx[g].my0, my1 = (float)lsx[g].my1;
+  float rdet = __fsub_rn(__fmul_rn(mx00, mx11), __fmul_rn(mx01, mx01));
+  if (rdet == 0) return;
+  rdet = (float)__ddiv_rn(1.0, (double)rdet);                   // `1.0 / rdet` divides in double (Q15)
+  const float as0 = __fmul_rn(__fsub_rn(__fmul_rn(mx11, my0), __fmul_rn(mx01, my1)), rdet);
+  const float as1 = __fmul_rn(__fsub_rn(__fmul_rn(mx00, my1), __fmul_rn(mx01, my0)), rdet);
+  const float vx = (float)lsx[g].vDirSEx, vy = (float)lsx[g].vDirSEy, as01 = __fadd_rn(as0, as1);
+  ls[g].x0 = __fadd_rn(ls[g].x0, __fmul_rn(vx, as1));
+  ls[g].y0 = __fadd_rn(ls[g].y0, __fmul_rn(vy, as1));
+  ls[g].x1 = __fadd_rn(ls[g].x1, __fmul_rn(vx, as01));
+  ls[g].y1 = __fadd_rn(ls[g].y1, __fmul_rn(vy, as01));
+}
+// pass3a computes the vertex g shares with its right neighbour from the unmodified list; pass3b writes it to both
+__global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (g > *(const int *)ls) return;
+  float2 r = make_float2(__int_as_float(0x7fc00000), 0.0f);     // NaN = nothing to write
+  if (ls[g].polyid != 0 && ls[g].rightPtr != 0) {
+    const int h = ls[g].rightPtr;
+    const float v0 = ls[g].x0, v1 = ls[g].y0, v2 = ls[g].x1, v3 = ls[g].y1;
+    const float u0 = ls[h].x0, u1 = ls[h].y0, u2 = ls[h].x1, u3 = ls[h].y1;
+    const float d = __fsub_rn(__fmul_rn(__fsub_rn(v2, v0), __fsub_rn(u3, u1)), __fmul_rn(__fsub_rn(v3, v1), __fsub_rn(u2, u0)));
+    const float mx = __fmul_rn(__fadd_rn(v2, u0), 0.5f), my = __fmul_rn(__fadd_rn(v3, u1), 0.5f);
+    if ((double)fabsf(d) < 1e-6) r = make_float2(mx, my);
+    else {
+      const float n = __fsub_rn(__fmul_rn(__fsub_rn(v1, u1), __fsub_rn(u2, u0)), __fmul_rn(__fsub_rn(v0, u0), __fsub_rn(u3, u1)));
+      const float q = __fdiv_rn(n, d);
+      const float wx = __fadd_rn(v0, __fmul_rn(q, __fsub_rn(v2, v0))), wy = __fadd_rn(v1, __fmul_rn(q, __fsub_rn(v3, v1)));
+      if (rd_hypot(__fsub_rn(wx, v2), __fsub_rn(wy, v3)) > 10.0f && rd_hypot(__fsub_rn(wx, u0), __fsub_rn(wy, u1)) > 10.0f) r = make_float2(mx, my);
+      else r = make_float2(wx, wy);
+    }
+  }
+  vtx[g] = r;
+}
+__global__ void kp_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (g > *(const int *)ls) return;
+  (void)rightPtrSnapshot;
+  const float2 r = vtx[g];
+  if (r.x != r.x) {
+    // distinguish "no right neighbour" from a genuinely NaN vertex: recompute the guard
+    if (ls[g].polyid == 0 || ls[g].rightPtr == 0) return;
+  }
+  const int h = ls[g].rightPtr;
+  ls[g].x1 = r.x; ls[g].y1 = r.y;
+  ls[h].x0 = r.x; ls[h].y0 = r.y;
+}
+
+// ---------------------------------------------------------------------------- the schedule (oclpolyline.c:218-309)
+static const dim3 PB(32, 8);
+#define G2 rd_grid2d(iw, ih, PB)
+
+void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *tmpBig, int *tmp0, int *tmp1, int *tmp2, int *tmp3,
+                     int *tmp4, int *tmp5, float minerror, int sizeThre, int iw, int ih, cudaStream_t s) {
+  const int n = iw * ih;
+  const int g1 = rd_cdiv(n, 256);
+  // step 1 : clean strings
+  RD_LAUNCH(kp_simpleJunction, G2, PB, 0, s, lsIdOut, in, iw, ih);
+  RD_LAUNCH(kp_simpleConnect, G2, PB, 0, s, tmp2, lsIdOut, iw, ih);
+  RD_LAUNCH(kp_stringify, G2, PB, 0, s, tmp1, tmp2, 0, iw, ih);
+  RD_LAUNCH(kp_stringify, G2, PB, 0, s, tmp2, tmp1, 1, iw, ih);
+  RD_LAUNCH(kp_removeBranch, G2, PB, 0, s, tmp1, tmp2, iw, ih);
+  // step 2 : string id = smallest pixel index
+  rd_label8x(lsIdOut, tmp1, tmp2, 0, iw, ih, s);
+  // step 3 : closed loops lose their root pixel
+  RD_LAUNCH(kp_simpleJunction, G2, PB, 0, s, tmp2, tmp1, iw, ih);
+  rd_k_clear(tmp3, n, s);
+  RD_LAUNCH(kp_countEnds, G2, PB, 0, s, tmp3, tmp2, lsIdOut, iw, ih);
+  RD_LAUNCH(kp_breakLoops, G2, PB, 0, s, tmp1, lsIdOut, tmp3, iw, ih);
+  // steps 4-6 : string ends by orientation-aware pointer jumping (8 hops x 4 launches)
+  RD_LAUNCH(kp_findEnds0, G2, PB, 0, s, tmp0, tmp2, tmpBig, lsIdOut, iw, ih);
+  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp3, tmp4, tmpBig, tmp0, tmp2, lsIdOut, 0, iw, ih);
+  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp0, tmp2, tmpBig, tmp3, tmp4, lsIdOut, 1, iw, ih);
+  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp3, tmp4, tmpBig, tmp0, tmp2, lsIdOut, 0, iw, ih);
+  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp0, tmp2, tmpBig, tmp3, tmp4, lsIdOut, 1, iw, ih);
+  RD_LAUNCH(kp_findEnds2, G2, PB, 0, s, tmpBig, tmp4, tmp0, tmp2, lsIdOut, iw, ih);
+  // step 7 : distance from the start by list ranking (32 hops x 3 launches)
+  RD_LAUNCH(kp_number, G2, PB, 0, s, tmp2, tmp3, tmpBig, tmp4, iw, ih);
+  RD_LAUNCH(kp_number, G2, PB, 0, s, tmpBig, tmp4, tmp2, tmp3, iw, ih);
+  RD_LAUNCH(kp_number, G2, PB, 0, s, tmp2, tmp3, tmpBig, tmp4, iw, ih);
+  // step 8 : split touching strings (numbers differing by more than 1 are not connected)
+  RD_LAUNCH(kp_plus1, g1, 256, 0, s, tmp1, tmp2, n);
+  rd_labelpl(tmpBig, tmp1, tmp3, iw, ih, s);
+  // step 9 : drop short strings
+  rd_k_clear(tmp1, n, s);
+  RD_LAUNCH(kp_calcSize, g1, 256, 0, s, tmp1, tmpBig, n);
+  RD_LAUNCH(kp_filterSize, g1, 256, 0, s, lsIdOut, tmpBig, tmp1, sizeThre, n);
+  // step 10 : compact ids 1..K in raster order of the root pixels.  table = tmpBig[0..n], block counts behind it
+  {
+    int *table = tmpBig, *blockCount = tmpBig + 2 * (size_t)n;
+    const int nb = rd_cdiv(n, RL_BLOCK);
+    rd_k_clear(tmpBig, n + 1, s);
+    RD_LAUNCH(kp_relabel_count, nb, RL_BLOCK, 0, s, blockCount, lsIdOut, iw, ih);
+    RD_LAUNCH(kp_scan_blocks, 1, 1024, 0, s, blockCount, nb, table);
+    RD_LAUNCH(kp_relabel_rank, nb, RL_BLOCK, 0, s, table, blockCount, lsIdOut, iw, ih);
+    RD_LAUNCH(kp_relabel_pass1, G2, PB, 0, s, lsIdOut, table, iw, ih);
+  }
+  // step 11 : mkpl.  aux (start / end pixel per string) and winner live in tmpBig; cap entries each
+  {
+    const int cap = lsListSize / (int)sizeof(LS_t);
+    int *aux = tmpBig, *winner = tmpBig + 2 * (size_t)cap;
+    int *flags = tmp4, *dist = tmp3, *rnd = tmp5;
+    const int N = 16;
+    rd_k_clear((int *)lsList, (lsListSize + 3) / 4, s);
+    rd_k_clear(aux, cap, s);
+    RD_LAUNCH(kp_fill, rd_cdiv(2 * cap, 256), 256, 0, s, aux + cap, 0x7fffffff, 2 * cap);      // end pixel (min) and winner (min)
+    RD_LAUNCH(kp_mkpl_pass0a, G2, PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, flags, N, iw, ih);
+    RD_LAUNCH(kp_mkpl_pass0b, G2, PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, iw, ih);
+    RD_LAUNCH(kp_mkpl_pass0c, rd_cdiv(cap, 256), 256, 0, s, lsList, aux, cap, iw);
+    rd_k_rand(rnd, 0, n, s);
+    for (int i = 0; i < N - 1; i++) {
+      RD_LAUNCH(kp_mkpl_pass1, G2, PB, 0, s, lsList, lsListSize, dist, lsIdOut, rnd, flags, i + 1, iw, ih);
+      RD_LAUNCH(kp_mkpl_pass2a, G2, PB, 0, s, lsList, lsListSize, winner, dist, lsIdOut, flags, i + 1, iw, ih);
+      RD_LAUNCH(kp_mkpl_pass2b, 1, 1024, 0, s, lsList, lsListSize, winner, tmp2, flags, i + 1, minerror, iw);
+      RD_LAUNCH(kp_mkpl_pass3, g1, 256, 0, s, lsList, lsListSize, tmp2, lsIdOut, flags, i + 1, n);
+    }
+  }
+  // step 12 : sub-pixel refinement.  LSX mirror of the list in tmpBig, shared vertices in tmp3
+  {
+    const int cap = lsListSize / (int)sizeof(LS_t);
+    LSX_t *lsx = (LSX_t *)tmpBig;
+    float2 *vtx = (float2 *)tmp3;                                 // the distance plane is dead after mkpl; 8 B x (count+1) <= P
+    const int gl = rd_cdiv(cap, 256);
+    RD_LAUNCH(kp_refine_pass0, gl, 256, 0, s, lsx, lsList);
+    RD_LAUNCH(kp_refine_pass1, G2, PB, 0, s, lsx, lsList, lsIdOut, iw, ih);
+    RD_LAUNCH(kp_refine_pass2, gl, 256, 0, s, lsx, lsList);
+    RD_LAUNCH(kp_refine_pass3a, gl, 256, 0, s, vtx, lsList);
+    RD_LAUNCH(kp_refine_pass3b, gl, 256, 0, s, vtx, lsList, (const int *)NULL);
+  }
+}
+
+extern "C" {
+
+oclpolyline_t *init_oclpolyline(cl_device_id device, cl_context) {          // oclpolyline.c:20-101
+  if (rd_device_count() <= 0) exitf(-1, "rectdetect_b200: no CUDA device; there is no CPU fallback\n");
+  oclpolyline_t *t = (oclpolyline_t *)calloc(1, sizeof(oclpolyline_t));
+  t->magic = POLY_MAGIC;
+  t->ordinal = device ? device->ordinal : 0;
+  return t;
+}
+void dispose_oclpolyline(oclpolyline_t *thiz) {
+  if (!thiz || thiz->magic != POLY_MAGIC) exitf(-1, "rectdetect_b200: bad oclpolyline_t\n");
+  thiz->magic = 0;
+  free(thiz);
+}
+
+cl_event oclpolyline_execute(oclpolyline_t *thiz, cl_mem lsList, int lsListSize, cl_mem lsIdOut, cl_mem in, cl_mem tmp0, cl_mem tmp1, cl_mem tmp2,
+                             cl_mem tmp3, cl_mem tmp4, cl_mem tmp5, cl_mem tmp6, float minerror, int sizeThre, int iw, int ih,
+                             cl_command_queue queue, const cl_event *events) {
+  if (!thiz || thiz->magic != POLY_MAGIC) exitf(-1, "rectdetect_b200: bad oclpolyline_t\n");
+  cudaStream_t s = rd_stream(queue);
+  rd_wait_events(s, events);
+  const size_t P = (size_t)iw * ih * 4;
+  rd_need(lsList, (size_t)lsListSize, "oclpolyline_execute lsList");
+  rd_need(lsIdOut, P, "oclpolyline_execute lsIdOut"); rd_need(in, P, "oclpolyline_execute in");
+  rd_need(tmp0, 4 * P, "oclpolyline_execute tmpBig");
+  cl_mem t[6] = {tmp1, tmp2, tmp3, tmp4, tmp5, tmp6};
+  for (int i = 0; i < 6; i++) rd_need(t[i], P, "oclpolyline_execute tmp");
+  if ((size_t)lsListSize > 4 * P) exitf(-1, "rectdetect_b200: oclpolyline_execute needs lsListSize <= iw*ih*16\n");
+  rd_polyline_run(rd_ptr<LS_t>(lsList), lsListSize, rd_ptr<int>(lsIdOut), rd_ptr<int>(in), rd_ptr<int>(tmp0), rd_ptr<int>(tmp1), rd_ptr<int>(tmp2),
+                  rd_ptr<int>(tmp3), rd_ptr<int>(tmp4), rd_ptr<int>(tmp5), rd_ptr<int>(tmp6), minerror, sizeThre, iw, ih, s);
+  return rd_make_event(s, events);
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// rd_shim.cu - the L1 surface of the reference (oclhelper.h:12-39, helper.h:12-31) and the handful of raw OpenCL
+// entry points its programs call (rect.cpp:60-64, poly.cpp:87-131, vidrect.cpp:120-127), on the CUDA runtime.
+// No OpenCL runtime, no program build, no work-group autotuner: kernels are compiled ahead of time for sm_100a.
+#include <stdarg.h>
+#include <time.h>
+#include <unistd.h>
+#include <vector>
+#include <mutex>
+#include "rd_common.cuh"
+
+std::atomic<int> g_rd_launches{0};
+
+extern "C" {
+
+// ---------------------------------------------------------------- helper.h
+void exitf(int code, const char *mes, ...) {             // helper.c:31
+  va_list ap;
+  va_start(ap, mes);
+  vfprintf(stderr, mes, ap);
+  va_end(ap);
+  fflush(stderr);
+  exit(code);
+}
+
+int64_t currentTimeMillis(void) {                         // helper.c:105
+  struct timespec ts;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  return (int64_t)ts.tv_sec * 1000 + ts.tv_nsec / 1000000;
+}
+
+void sleepMillis(int ms) {                                // helper.c:115
+  if (ms <= 0) return;
+  struct timespec ts = {ms / 1000, (long)(ms % 1000) * 1000000L};
+  nanosleep(&ts, NULL);
+}
+
+// uint64 -> void* map with 1024 buckets (helper.c:124-267).  Iteration order = bucket order, then insertion order
+// with swap-remove; the host tail's output order depends on it, so the structure is kept.
+struct ArrayMapNode { uint64_t key; void *value; };
+struct ArrayMap { std::vector<ArrayMapNode> bucket[1024]; int total; };
+static inline int am_hash(uint64_t key) { return (int)((key ^ (key >> 10) ^ (key >> 20) ^ (key >> 30)) & 1023); }
+
+ArrayMap *initArrayMap(void) { ArrayMap *m = new ArrayMap(); m->total = 0; return m; }
+void ArrayMap_dispose(ArrayMap *thiz) { delete thiz; }
+int ArrayMap_size(ArrayMap *thiz) { return thiz->total; }
+void *ArrayMap_remove(ArrayMap *thiz, uint64_t key) {
+  std::vector<ArrayMapNode> &b = thiz->bucket[am_hash(key)];
+  for (size_t i = 0; i < b.size(); i++)
+    if (b[i].key == key) {
+      void *old = b[i].value;
+      b[i] = b.back();
+      b.pop_back();
+      thiz->total--;
+      return old;
+    }
+  return NULL;
+}
+void *ArrayMap_put(ArrayMap *thiz, uint64_t key, void *value) {
+  if (value == NULL) return ArrayMap_remove(thiz, key);
+  std::vector<ArrayMapNode> &b = thiz->bucket[am_hash(key)];
+  for (size_t i = 0; i < b.size(); i++)
+    if (b[i].key == key) { void *old = b[i].value; b[i].value = value; return old; }
+  ArrayMapNode n = {key, value};
+  b.push_back(n);
+  thiz->total++;
+  return NULL;
+}
+void *ArrayMap_get(ArrayMap *thiz, uint64_t key) {
+  std::vector<ArrayMapNode> &b = thiz->bucket[am_hash(key)];
+  for (size_t i = 0; i < b.size(); i++) if (b[i].key == key) return b[i].value;
+  return NULL;
+}
+uint64_t *ArrayMap_keyArray(ArrayMap *thiz) {
+  uint64_t *a = (uint64_t *)malloc(sizeof(uint64_t) * (thiz->total > 0 ? thiz->total : 1));
+  int p = 0;
+  for (int j = 0; j < 1024; j++) for (size_t i = 0; i < thiz->bucket[j].size(); i++) a[p++] = thiz->bucket[j][i].key;
+  return a;
+}
+void **ArrayMap_valueArray(ArrayMap *thiz) {
+  void **a = (void **)malloc(sizeof(void *) * (thiz->total > 0 ? thiz->total : 1));
+  int p = 0;
+  for (int j = 0; j < 1024; j++) for (size_t i = 0; i < thiz->bucket[j].size(); i++) a[p++] = thiz->bucket[j][i].value;
+  return a;
+}
+
+// ---------------------------------------------------------------- oclhelper.h
+const char *clStrError(int c) {                           // oclhelper.c:31-111 (only the codes this library can produce)
+  switch (c) {
+    case CL_SUCCESS: return "CL_SUCCESS";
+    case CL_MEM_OBJECT_ALLOCATION_FAILURE: return "CL_MEM_OBJECT_ALLOCATION_FAILURE";
+    case CL_OUT_OF_RESOURCES: return "CL_OUT_OF_RESOURCES";
+    case CL_INVALID_VALUE: return "CL_INVALID_VALUE";
+    case CL_INVALID_COMMAND_QUEUE: return "CL_INVALID_COMMAND_QUEUE";
+    case CL_INVALID_MEM_OBJECT: return "CL_INVALID_MEM_OBJECT";
+    default: return "Unknown error";
+  }
+}
+cl_int checkError(cl_int ret, const char *s) {            // oclhelper.c:113-131
+  if (ret != CL_SUCCESS) exitf(-1, "%s : %s\n", s ? s : "error", clStrError(ret));
+  return ret;
+}
+cl_int ce(cl_int ret) { return checkError(ret, "Error"); } // oclhelper.c:133-138
+
+static std::mutex g_dev_mutex;
+static std::vector<rd_cl_device *> g_devices;
+static int probe_devices() {
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  if (!g_devices.empty()) return (int)g_devices.size();
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  for (int i = 0; i < n; i++) { rd_cl_device *d = new rd_cl_device; d->ordinal = i; g_devices.push_back(d); }
+  return n;
+}
+int rd_device_count(void) { return probe_devices(); }
+const char *rd_version(void) { return "rectdetect_b200 0.1 (sm_100a)"; }
+int rd_kernel_launches(void) { return g_rd_launches.load(); }
+
+char *getDeviceName(cl_device_id device) {                // oclhelper.c:140-169 : whitespace -> '_'
+  cudaDeviceProp p;
+  RD_CUDA(cudaGetDeviceProperties(&p, device->ordinal));
+  char *s = (char *)malloc(strlen(p.name) + 1);
+  strcpy(s, p.name);
+  for (char *c = s; *c; c++) if (*c == ' ' || *c == '\t') *c = '_';
+  return s;
+}
+int simpleGetDevices(cl_device_id *devices, int maxDevices) {
+  int n = probe_devices();
+  if (n > maxDevices) n = maxDevices;
+  for (int i = 0; i < n; i++) devices[i] = g_devices[i];
+  return n;
+}
+cl_device_id simpleGetDevice(int did) {                   // oclhelper.c:171-197
+  int n = probe_devices();
+  if (n == 0) exitf(-1, "No platform available\n");     // no CUDA device: there is no CPU fallback
+  if (did < 0 || did >= n) {
+    if (did >= 0) fprintf(stderr, "Device %d does not exist\n", did);
+    for (int i = 0; i < n; i++) { char *nm = getDeviceName(g_devices[i]); fprintf(stderr, "Device %d : %s\n", i, nm); free(nm); }
+    exit(-1);
+  }
+  return g_devices[did];
+}
+cl_context simpleCreateContext(cl_device_id device) {     // oclhelper.c:225-233
+  RD_CUDA(cudaSetDevice(device->ordinal));
+  RD_CUDA(cudaFree(0));
+  rd_cl_context *c = new rd_cl_context;
+  c->ordinal = device->ordinal;
+  return c;
+}
+void waitForEvent(cl_event ev) {                          // oclhelper.c:799-817, without the 15 ms poll (Q22)
+  if (!ev) return;
+  RD_CUDA(cudaEventSynchronize(ev->ev));
+}
+void clearPlan(void) {}
+int loadPlan(const char *, cl_device_id) { return 0; }
+void savePlan(const char *, cl_device_id) {}
+void startProfiling(size_t, size_t, size_t) {}
+void finishProfiling(void) {}
+void showPlan(void) {}
+static std::atomic<int> g_next_kid{0};
+int getNextKernelID(void) { return g_next_kid.fetch_add(1); }
+
+void *allocatePinnedMemory(size_t z, cl_context, cl_command_queue) {   // oclhelper.c:837-853
+  void *p = NULL;
+  RD_CUDA(cudaHostAlloc(&p, z ? z : 1, cudaHostAllocDefault));
+  return p;
+}
+void freePinnedMemory(void *p, cl_context, cl_command_queue) { if (p) RD_CUDA(cudaFreeHost(p)); }
+
+// ---------------------------------------------------------------- CL/cl.h compat
+cl_command_queue clCreateCommandQueue(cl_context context, cl_device_id device, cl_command_queue_properties, cl_int *errcode_ret) {
+  int ord = device ? device->ordinal : (context ? context->ordinal : 0);
+  RD_CUDA(cudaSetDevice(ord));
+  rd_cl_queue *q = new rd_cl_queue;
+  q->ordinal = ord;
+  q->owned = 1;
+  RD_CUDA(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+  if (errcode_ret) *errcode_ret = CL_SUCCESS;
+  return q;
+}
+cl_int clReleaseCommandQueue(cl_command_queue q) {
+  if (!q) return CL_INVALID_COMMAND_QUEUE;
+  if (q->owned) { RD_CUDA(cudaStreamSynchronize(q->stream)); RD_CUDA(cudaStreamDestroy(q->stream)); }
+  delete q;
+  return CL_SUCCESS;
+}
+cl_int clReleaseContext(cl_context c) { delete c; return CL_SUCCESS; }
+cl_int clFlush(cl_command_queue) { return CL_SUCCESS; }
+cl_int clFinish(cl_command_queue q) { RD_CUDA(cudaStreamSynchronize(rd_stream(q))); return CL_SUCCESS; }
+
+cl_mem clCreateBuffer(cl_context context, cl_mem_flags flags, size_t size, void *host_ptr, cl_int *errcode_ret) {
+  if (context) RD_CUDA(cudaSetDevice(context->ordinal));
+  rd_cl_mem *m = new rd_cl_mem;
+  m->bytes = size;
+  m->owned = 1;
+  cudaError_t e = cudaMalloc(&m->dptr, size ? size : 1);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete m;
+    if (errcode_ret) { *errcode_ret = CL_MEM_OBJECT_ALLOCATION_FAILURE; return NULL; }
+    exitf(-1, "clCreateBuffer : %s\n", cudaGetErrorString(e));
+  }
+  if ((flags & CL_MEM_COPY_HOST_PTR) && host_ptr) RD_CUDA(cudaMemcpy(m->dptr, host_ptr, size, cudaMemcpyHostToDevice));
+  if (errcode_ret) *errcode_ret = CL_SUCCESS;
+  return m;
+}
+cl_int clReleaseMemObject(cl_mem m) {
+  if (!m) return CL_INVALID_MEM_OBJECT;
+  if (m->owned) RD_CUDA(cudaFree(m->dptr));
+  delete m;
+  return CL_SUCCESS;
+}
+cl_int clRetainEvent(cl_event ev) { if (ev) ev->refs.fetch_add(1); return CL_SUCCESS; }
+cl_int clReleaseEvent(cl_event ev) {
+  if (ev && ev->refs.fetch_sub(1) == 1) { cudaEventDestroy(ev->ev); delete ev; }
+  return CL_SUCCESS;
+}
+cl_int clEnqueueReadBuffer(cl_command_queue queue, cl_mem buffer, cl_bool blocking, size_t offset, size_t size, void *ptr,
+                           cl_uint nwait, const cl_event *wait, cl_event *event) {
+  cudaStream_t s = rd_stream(queue);
+  for (cl_uint i = 0; i < nwait; i++) if (wait && wait[i]) RD_CUDA(cudaStreamWaitEvent(s, wait[i]->ev, 0));
+  if (!buffer || offset + size > buffer->bytes) return CL_INVALID_VALUE;
+  RD_CUDA(cudaMemcpyAsync(ptr, (char *)buffer->dptr + offset, size, cudaMemcpyDeviceToHost, s));
+  if (event) { cl_event one = NULL; *event = rd_make_event(s, &one); }
+  if (blocking) RD_CUDA(cudaStreamSynchronize(s));
+  return CL_SUCCESS;
+}
+cl_int clEnqueueWriteBuffer(cl_command_queue queue, cl_mem buffer, cl_bool blocking, size_t offset, size_t size, const void *ptr,
+                            cl_uint nwait, const cl_event *wait, cl_event *event) {
+  cudaStream_t s = rd_stream(queue);
+  for (cl_uint i = 0; i < nwait; i++) if (wait && wait[i]) RD_CUDA(cudaStreamWaitEvent(s, wait[i]->ev, 0));
+  if (!buffer || offset + size > buffer->bytes) return CL_INVALID_VALUE;
+  RD_CUDA(cudaMemcpyAsync((char *)buffer->dptr + offset, ptr, size, cudaMemcpyHostToDevice, s));
+  if (event) { cl_event one = NULL; *event = rd_make_event(s, &one); }
+  if (blocking) RD_CUDA(cudaStreamSynchronize(s));
+  return CL_SUCCESS;
+}
+
+// ---------------------------------------------------------------- extensions
+cl_mem rd_wrap_device_memory(void *dptr, size_t bytes) {
+  rd_cl_mem *m = new rd_cl_mem;
+  m->dptr = dptr; m->bytes = bytes; m->owned = 0;
+  return m;
+}
+void *rd_mem_device_ptr(cl_mem mem) { return mem ? mem->dptr : NULL; }
+size_t rd_mem_size(cl_mem mem) { return mem ? mem->bytes : 0; }
+cl_command_queue rd_wrap_stream(void *cuda_stream, int device) {
+  rd_cl_queue *q = new rd_cl_queue;
+  q->stream = (cudaStream_t)cuda_stream; q->ordinal = device; q->owned = 0;
+  return q;
+}
+void *rd_queue_stream(cl_command_queue queue) { return queue ? (void *)queue->stream : NULL; }
+void rd_free(void *p) { free(p); }
+
+}  // extern "C"
+
+cl_event rd_make_event(cudaStream_t s, const cl_event *events) {
+  if (events == NULL) return NULL;
+  rd_cl_event *e = new rd_cl_event;
+  e->refs.store(1);
+  RD_CUDA(cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming));
+  RD_CUDA(cudaEventRecord(e->ev, s));
+  return e;
+}
+
+void rd_wait_events(cudaStream_t s, const cl_event *events) {
+  if (events) for (int i = 0; events[i] != NULL; i++) RD_CUDA(cudaStreamWaitEvent(s, events[i]->ev, 0));
+}
