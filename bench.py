@@ -1,0 +1,283 @@
+#!/usr/bin/env python3
+"""bench.py - throughput of the rectangle-detection hot path on B200 (one process per GPU).
+
+metric  : Mpix/s = frames/s x iw x ih, BGR frame -> rect_t list (BASELINE.json)
+step    : one batch of --frames 1280x720 synthetic frames per GPU (config "vidrect 1280x720 synthetic stream, AOV 72,
+          batched on 1xB200"); frames of a batch are independent and are sharded across ranks (weak scaling, no data-path
+          collective; one gather of the rect lists to rank 0 per step).
+value   : frames already resident in HBM; every device stage, the compact read-back and the host tail run (rect lists
+          are produced on the host), plus the rect-list gather for N > 1.
+e2e     : the same through the C-ABI batch call with frames in pinned HOST memory (H2D copies inside the timed region).
+roofline: the kernel with the largest share of device time (per-kernel CUDA-event timing on the launching streams, in
+          the library, during the timed value steps) against the measured HBM copy bandwidth.
+--impl reference : the CPU oracle (restatement of the reference's OpenCL kernels and launch schedule; the reference itself
+          needs an OpenCL ICD + OpenCV that this image lacks) on all host cores, bounded sample per step.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mpix/s (frames/s x WxH) 1280x720 rect detect"
+TAN_AOV = math.tan(math.radians(36.0))
+
+# algorithmic (compulsory) bytes per pixel of each kernel: planes it must read + planes it must write, 4 B each unless
+# noted (DESIGN.md "Kernels").  Used for roofline.achieved of whichever kernel dominates the step.
+KERNEL_BYTES_PER_PX = {
+    "k_bgr2plab_unpack": 3 + 16, "k_iir_h": 12, "k_iir_v": 12, "k_iir_pass1": 16, "k_iir_pass3": 16, "k_pack_plab_r": 16,
+    "k_edgevec_r": 12, "k_edge_plab_r": 8, "k_thinthres_r": 16, "kr_threshold_cast": 12, "kr_simpleJunction": 8,
+    "kr_simpleConnect": 8, "kr_stringify": 8, "k_ccl_tile<LinkFn>": 9, "k_ccl_seams": 1, "k_ccl_flatten": 9,
+    "k_ccl_flatten_merge": 12, "kr_calcStrength": 8, "kr_filterStrength": 8, "kr_threshold_cast_c": 9, "kr_blblur<0>": 9,
+    "kr_blblur<1>": 9, "kr_quantize": 8, "kr_despeckle": 12, "kr_threshold_i_i": 8, "k_clear": 4, "k_copy": 8,
+    "kr_mkMergeMask0": 4, "kr_mkMergeMask1": 4, "kr_calcSize": 4, "kr_despeckle2": 8, "kr_markBoundary": 8,
+    "kp_simpleJunction": 8, "kp_simpleConnect": 8, "kp_stringify": 8, "kp_removeBranch": 8, "kp_countEnds": 8, "kp_breakLoops": 4,
+    "kp_findEnds0": 16, "kp_findEnds1": 24, "kp_findEnds2": 20, "kp_number": 16, "kp_plus1": 8, "kp_calcSize": 4,
+    "kp_filterSize": 12, "kp_relabel_count": 4, "kp_relabel_rank": 4, "kp_relabel_pass1": 8, "kp_mkpl_pass0a": 8,
+    "kp_mkpl_pass0b": 8, "kp_mkpl_pass1": 12, "kp_mkpl_pass2a": 8, "kp_mkpl_pass3": 8, "kp_refine_pass1": 4, "k_rand": 4,
+    "kr_reduceLS<0>": 8, "kr_reduceLS<1>": 8,
+}
+
+
+def synth_batch(iw, ih, first_seed, count, pinned):
+    import torch
+    from rectdetect_b200.synth import synth_frame
+    ws = 3 * iw
+    t = torch.empty((count, ih, ws), dtype=torch.uint8, pin_memory=pinned)
+    a = t.numpy()
+    for i in range(count):
+        synth_frame(iw, ih, first_seed + i, out=a[i])
+    return t
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)"""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_mpix(iw, ih, seeds, threads=None):
+    """CPU restatement of the reference schedule on `threads` host cores (all by default): -> (Mpix/s, cores, seconds)"""
+    import oracle_lib as ol
+    L = ol.oracle()
+    if threads:
+        L.ora_set_threads(threads)
+    cores = L.ora_get_threads()
+    o = ol.OracleRect(iw, ih)
+    frames = [ol.synth_frame(iw, ih, s) for s in seeds]
+    o.execute_once(frames[0], TAN_AOV)                 # warm-up (page faults, OpenMP pool)
+    t0 = time.perf_counter()
+    for f in frames:
+        o.execute_once(f, TAN_AOV)
+    dt = time.perf_counter() - t0
+    o.close()
+    return len(frames) * iw * ih / dt / 1e6, cores, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: rank 0 times the CPU oracle, the other ranks exit without work"""
+    if rank != 0:
+        return
+    iw, ih = args.w, args.h
+    sample = args.ref_frames
+    for _ in range(args.warmup):
+        cpu_oracle_mpix(iw, ih, [1000])
+    t0 = time.perf_counter()
+    vals = []
+    for s in range(args.steps):
+        v, cores, _ = cpu_oracle_mpix(iw, ih, [1000 + s * sample + i for i in range(sample)])
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32 (f64 host tail)",
+        "data": "synthetic",
+        "config": {"workload": "vidrect %dx%d synthetic stream, AOV 72, full imgutil->polyline->rect pipeline" % (iw, ih), "frames_per_step": sample,
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                         "sample": "%d frames of the workload per step (CPU oracle: OpenMP restatement of the reference's OpenCL schedule; the reference itself needs an OpenCL ICD + OpenCV, absent here)" % sample},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--w", type=int, default=1280)
+    ap.add_argument("--h", type=int, default=720)
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--nctx", type=int, default=8, help="pipeline objects (streams) per GPU")
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import rectdetect_b200 as rd
+    from rectdetect_b200 import dist as rdist
+
+    if not torch.cuda.is_available() or rd.device_count() <= local_rank:
+        raise SystemExit("bench.py: no CUDA device for rank %d; rectdetect_b200 has no CPU fallback" % rank)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    iw, ih, F = args.w, args.h, args.frames
+    ws = 3 * iw
+    total_frames = F * world
+    lo, hi = rdist.shard_range(total_frames, world, rank)
+    host_frames = synth_batch(iw, ih, 1000 + lo, hi - lo, pinned=True)           # seeds 1000+i (config 3)
+    dev_frames = host_frames.to("cuda", non_blocking=False)
+    frame_bytes = ih * ws
+    batch = rd.Batch(local_rank, iw, ih, nctx=args.nctx)
+    dev = "cuda"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(on_device):
+        ptr = dev_frames.data_ptr() if on_device else host_frames.data_ptr()
+        rects = batch.run(ptr, frame_bytes, ws, hi - lo, TAN_AOV, on_device=on_device)
+        return rdist.gather_rect_lists(lo, rects, total_frames, device=dev)
+
+    def timed(on_device, steps, profile=False):
+        barrier()
+        l0 = rd.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            rd.api.profile_start(None)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = step(on_device)
+        barrier()
+        e1.record()
+        torch.cuda.synchronize()
+        prof = rd.api.profile_stop() if profile else None
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        launches = torch.tensor([rd.kernel_launches() - l0], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        return float(t.item()), int(launches.item()), out, prof
+
+    for _ in range(args.warmup):
+        step(True)
+        step(False)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_val, launches, rects, _ = timed(True, args.steps)
+    ms_e2e, _, rects_e2e, _ = timed(False, args.steps)
+    clocks = sampler.finish() if sampler else None
+    # per-kernel device time (CUDA events on the launching streams) over the same steps, for the roofline of the top kernel;
+    # a separate pass so that the event records do not sit inside the headline timings
+    ms_prof, _, _, prof = timed(True, args.steps, profile=True)
+
+    pix_per_step = total_frames * iw * ih
+    value = pix_per_step * args.steps / (ms_val * 1e-3) / 1e6
+    e2e = pix_per_step * args.steps / (ms_e2e * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        top = max(prof.items(), key=lambda kv: kv[1][1])
+        tname, (tcnt, tms) = top
+        total_kernel_ms = sum(v[1] for v in prof.values())
+        bpp = KERNEL_BYTES_PER_PX.get(tname)
+        per_launch_ms = tms / tcnt
+        achieved = (bpp * iw * ih / (per_launch_ms * 1e-3) / 1e9) if bpp else None
+        roofline = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": (bpp * iw * ih) if bpp else None,
+                    "avg_launch_us": per_launch_ms * 1e3, "share_of_kernel_time": tms / total_kernel_ms,
+                    "top5": [[k, v[0], round(v[1], 3)] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:5]],
+                    "pipeline_algorithmic_bytes_per_px": 43, "pipeline_frac": (43.0 * value * 1e6 / 1e9) / peak}
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, cores, secs = cpu_oracle_mpix(iw, ih, [1000 + i for i in range(args.cpu_frames)])
+            cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                   "sample": "%d frames of the same stream, %.1f s (CPU oracle = OpenMP restatement of the reference's OpenCL kernels + schedule + host tail)" % (args.cpu_frames, secs)}
+        nrect = sum(len(r) for r in rects) if rects else 0
+        same = rects is not None and rects_e2e is not None and all(a.tobytes() == b.tobytes() for a, b in zip(rects, rects_e2e))
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i32 (f64 host tail)", "data": "synthetic",
+            "config": {"workload": "vidrect %dx%d synthetic stream (seeds 1000+i), AOV 72, full imgutil->polyline->rect pipeline, batched" % (iw, ih),
+                       "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "parallelism": "frames x%d" % world,
+                       "l2": "inputs larger than L2 (%d MB of frames + %d x 81 MB working sets per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx)},
+            "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": total_frames * 128 * 1024,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "rects_per_step": nrect, "value_and_e2e_rects_identical": bool(same), "profiled_pass_ms_per_step": ms_prof / args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

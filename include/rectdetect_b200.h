@@ -159,6 +159,11 @@ void  *rd_queue_stream(cl_command_queue queue);
 int    rd_device_count(void);                                    /* 0 when no CUDA device/driver is usable; never exits */
 const char *rd_version(void);
 int    rd_kernel_launches(void);                                 /* kernels launched by this library so far (process-wide counter) */
+/* per-kernel device time from CUDA events recorded on the launching stream around each launch.
+ * mode 1: every kernel, mode 2: only kernels whose name contains `select`.  rd_profile_stop waits for the device and
+ * returns one "kernel_name launches total_ms" line per kernel (string owned by the library, valid until the next call). */
+void   rd_profile_start(int mode, const char *select);
+const char *rd_profile_stop(void);
 
 /* Stage B / D operators, 1:1 with the __kernel functions of oclrect.cl (line numbers in parentheses) */
 void rd_rect_simpleJunction(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q);                    /* oclrect.cl:74  */

@@ -94,6 +94,7 @@ def lib():
         "rd_batch_create": (vp, [i, i, i, i, i]), "rd_batch_destroy": (None, [vp]),
         "rd_batch_run": (None, [vp, vp, sz, i, i, d, vp]), "rd_batch_run_device": (None, [vp, vp, sz, i, i, d, vp]),
         "rd_batch_stage_ms": (None, [vp, vp]),
+        "rd_profile_start": (None, [i, C.c_char_p]), "rd_profile_stop": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -116,6 +117,20 @@ def kernel_launches():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def profile_start(select=None):
+    """time every kernel (select=None) or only kernels whose name contains `select`, with CUDA events on their stream"""
+    lib().rd_profile_start(1 if select is None else 2, (select or "").encode())
+
+
+def profile_stop():
+    """-> {kernel name: (launches, total device ms)}"""
+    out = {}
+    for line in lib().rd_profile_stop().decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def rects_from_ptr(p):

@@ -36,11 +36,19 @@ extern std::atomic<int> g_rd_launches;
 // surface at the next synchronising call, which is also RD_CUDA-checked)
 #define RD_LAUNCH(kernel, grid, block, smem, stream, ...)                                                   \
   do {                                                                                                      \
+    const int ps_ = g_rd_prof_mode.load(std::memory_order_relaxed) ? rd_prof_begin(#kernel, (stream)) : -1; \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                             \
+    if (ps_ >= 0) rd_prof_end(ps_, (stream));                                                               \
     g_rd_launches.fetch_add(1, std::memory_order_relaxed);                                                  \
     cudaError_t e_ = cudaGetLastError();                                                                    \
     if (e_ != cudaSuccess) exitf(-1, "rectdetect_b200: launch of %s failed at %s:%d : %s\n", #kernel, __FILE__, __LINE__, cudaGetErrorString(e_)); \
   } while (0)
+
+// per-kernel device timing with CUDA events on the launching stream (rd_profile_* in rectdetect_b200.h).
+// mode 0: off (one relaxed load per launch), 1: every kernel, 2: only kernels whose name contains the selected string
+extern std::atomic<int> g_rd_prof_mode;
+int rd_prof_begin(const char *name, cudaStream_t s);
+void rd_prof_end(int slot, cudaStream_t s);
 
 static inline cudaStream_t rd_stream(cl_command_queue q) {
   if (!q) exitf(-1, "rectdetect_b200: NULL command queue\n");

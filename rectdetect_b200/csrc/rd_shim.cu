@@ -265,3 +265,69 @@ cl_event rd_make_event(cudaStream_t s, const cl_event *events) {
 void rd_wait_events(cudaStream_t s, const cl_event *events) {
   if (events) for (int i = 0; events[i] != NULL; i++) RD_CUDA(cudaStreamWaitEvent(s, events[i]->ev, 0));
 }
+
+// ---------------------------------------------------------------- per-kernel timing (used by bench.py for the roofline line)
+#include <map>
+#include <string>
+std::atomic<int> g_rd_prof_mode{0};
+namespace {
+struct ProfSlot { int name; cudaEvent_t a, b; };
+std::mutex g_prof_mutex;
+std::vector<ProfSlot> g_prof_slots;
+std::vector<std::string> g_prof_names;
+std::map<std::string, int> g_prof_index;
+std::string g_prof_select;
+std::string g_prof_report;
+}
+
+int rd_prof_begin(const char *name, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  if (g_rd_prof_mode.load() == 2 && strstr(name, g_prof_select.c_str()) == NULL) return -1;
+  auto it = g_prof_index.find(name);
+  int idx;
+  if (it == g_prof_index.end()) { idx = (int)g_prof_names.size(); g_prof_names.push_back(name); g_prof_index[name] = idx; }
+  else idx = it->second;
+  ProfSlot sl;
+  sl.name = idx;
+  RD_CUDA(cudaEventCreate(&sl.a));
+  RD_CUDA(cudaEventCreate(&sl.b));
+  RD_CUDA(cudaEventRecord(sl.a, s));
+  g_prof_slots.push_back(sl);
+  return (int)g_prof_slots.size() - 1;
+}
+void rd_prof_end(int slot, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  RD_CUDA(cudaEventRecord(g_prof_slots[slot].b, s));
+}
+
+extern "C" {
+// mode 0 off, 1 all kernels, 2 kernels whose name contains `select`
+void rd_profile_start(int mode, const char *select) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  g_prof_select = select ? select : "";
+  g_rd_prof_mode.store(mode);
+}
+// stops profiling, waits for the device and returns "name launches total_ms\n" lines (valid until the next call)
+const char *rd_profile_stop(void) {
+  g_rd_prof_mode.store(0);
+  RD_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  std::vector<double> ms(g_prof_names.size(), 0.0);
+  std::vector<int> cnt(g_prof_names.size(), 0);
+  for (ProfSlot &sl : g_prof_slots) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, sl.a, sl.b) == cudaSuccess) { ms[sl.name] += t; cnt[sl.name]++; } else cudaGetLastError();
+    cudaEventDestroy(sl.a);
+    cudaEventDestroy(sl.b);
+  }
+  g_prof_slots.clear();
+  g_prof_report.clear();
+  char line[256];
+  for (size_t i = 0; i < g_prof_names.size(); i++) {
+    if (!cnt[i]) continue;
+    snprintf(line, sizeof line, "%s %d %.6f\n", g_prof_names[i].c_str(), cnt[i], ms[i]);
+    g_prof_report += line;
+  }
+  return g_prof_report.c_str();
+}
+}

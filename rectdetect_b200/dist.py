@@ -1,0 +1,69 @@
+"""Frame-parallel sharding across GPUs (one process per GPU) and the single gather of the per-frame rectangle lists.
+
+The reference is single-device; frames are independent, so a batch of F frames is cut into
+contiguous shards, rank r owning frames [r*ceil(F/G), ...).  There is no data-path collective: the
+only exchange is one gather of the variable-length rect_t lists (176 B per rectangle) to rank 0, done as an
+all_gather of the per-rank sizes followed by an all_gather of size-padded byte tensors - over NCCL (NVLink/NVSwitch)
+when the tensors live on the GPU, over gloo in the CPU tests.
+"""
+import numpy as np
+
+from .api import RECT_DTYPE
+
+
+def shard_range(nframes, world_size, rank):
+    """contiguous shard [lo, hi) of rank `rank` for a batch of `nframes` frames"""
+    per = -(-nframes // world_size)
+    lo = min(rank * per, nframes)
+    return lo, min(lo + per, nframes)
+
+
+def pack_rect_lists(first_frame, rect_lists):
+    """per-frame rect arrays -> one uint8 blob: int64 header [nframes, first_frame], int64 counts, then the rect_t bytes"""
+    counts = np.array([len(r) for r in rect_lists], np.int64)
+    head = np.array([len(rect_lists), first_frame], np.int64)
+    body = np.concatenate([np.ascontiguousarray(r).view(np.uint8).reshape(-1) for r in rect_lists]) if len(rect_lists) and counts.sum() else np.zeros(0, np.uint8)
+    return np.concatenate([head.view(np.uint8), counts.view(np.uint8), body])
+
+
+def unpack_rect_lists(blob):
+    """inverse of pack_rect_lists -> (first_frame, [rect arrays])"""
+    blob = np.ascontiguousarray(blob, np.uint8)
+    nframes, first = (int(v) for v in blob[:16].view(np.int64))
+    counts = blob[16: 16 + 8 * nframes].view(np.int64)
+    off = 16 + 8 * nframes
+    out = []
+    for c in counts:
+        nb = int(c) * RECT_DTYPE.itemsize
+        out.append(blob[off: off + nb].view(RECT_DTYPE).copy())
+        off += nb
+    return first, out
+
+
+def gather_rect_lists(first_frame, rect_lists, nframes_total, device=None):
+    """gather every rank's per-frame rect lists; returns the full list (index = frame) on rank 0, None elsewhere.
+    Works without an initialised process group (single process)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return list(rect_lists)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    blob = torch.from_numpy(pack_rect_lists(first_frame, rect_lists)).to(dev)
+    size = torch.tensor([blob.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    mx = int(max(int(s.item()) for s in sizes))
+    padded = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    padded[: blob.numel()] = blob
+    parts = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    if rank != 0:
+        return None
+    full = [None] * nframes_total
+    for r in range(world):
+        first, lists = unpack_rect_lists(parts[r][: int(sizes[r].item())].cpu().numpy())
+        for i, rl in enumerate(lists):
+            full[first + i] = rl
+    return full

@@ -1,0 +1,394 @@
+"""Parity of the CUDA path against the CPU oracle, through the C-ABI (GPU only: pytest -m gpu).
+
+Bars (BASELINE.json north_star): integer edge / label / id maps bit-exact, float planes bit-exact as well (the
+canonical arithmetic is deterministic), rectangle corner coordinates within 1e-4 relative (they come out bit-exact
+in practice; the test prints which).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import parity
+from tools_path import ROOT
+
+pytestmark = pytest.mark.gpu
+L_ORA = ol.oracle()
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------- the loaded library is the product
+def test_cuda_library_is_the_path(rd, gpu_dev):
+    assert rd.device_count() >= 1
+    before = rd.kernel_launches()
+    g = rd.OclRect(gpu_dev, 320, 240)
+    g.execute_once(ol.synth_frame(320, 240, 3), parity.TAN_AOV)
+    assert rd.kernel_launches() - before > 50
+    g.close()
+    maps = open("/proc/self/maps").read()
+    assert "librectdetect_b200.so" in maps
+
+
+# ---------------------------------------------------------------------------------------------- every step of genGPUTask
+@pytest.mark.parametrize("iw,ih,seed", [(640, 480, 1), (333, 217, 7)])
+def test_every_pipeline_step_bit_exact(rd, gpu_dev, iw, ih, seed):
+    bad = [r for r in parity.compare_steps(iw, ih, seed, range(1, 22), rd, gpu_dev) if r[2] != 0]
+    assert not bad, bad
+
+
+def test_key_steps_bit_exact_720p(rd, gpu_dev):
+    # config 2 of BASELINE.json: one 1280x720 frame, seed 2.  edge bitmap, strong edges, region map, lsId map + list, votes
+    bad = [r for r in parity.compare_steps(1280, 720, 2, [8, 15, 19, 20, 21], rd, gpu_dev) if r[2] != 0]
+    assert not bad, bad
+
+
+def test_row_stride_wider_than_the_image(rd, gpu_dev):
+    iw, ih = 300, 200
+    bad = [r for r in parity.compare_steps(iw, ih, 11, [1, 8, 21], rd, gpu_dev, ws=4 * iw - 3) if r[2] != 0]
+    assert not bad, bad
+
+
+# ---------------------------------------------------------------------------------------------- public entry points
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_golden.json")))
+
+
+@pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%dx%d-s%d" % (g["iw"], g["ih"], g["seed"]))
+def test_execute_once_matches_golden_fixture(rd, gpu_dev, g):
+    # committed fixture (tools/make_golden.py): the CUDA path must reproduce the oracle's rectangles without the oracle running
+    img = ol.synth_frame(g["iw"], g["ih"], g["seed"])
+    o = rd.OclRect(gpu_dev, g["iw"], g["ih"])
+    rects = o.execute_once(img, parity.TAN_AOV)
+    assert len(rects) == g["n_rects"]
+    assert [int(s) for s in rects["status"]] == g["rect_status"]
+    assert np.allclose(rects["c2"], np.array(g["rect_c2"]).reshape(-1, 4, 2), rtol=1e-4, atol=1e-6)
+    import hashlib
+    assert hashlib.sha256(np.ascontiguousarray(o.buffer("buf0")).tobytes()).hexdigest() == g["lsid_sha"]
+    assert hashlib.sha256(np.ascontiguousarray(o.buffer("iobuf1")).tobytes()).hexdigest() == g["segid_sha"]
+    assert hashlib.sha256(np.ascontiguousarray(o.buffer("buf3")).tobytes()).hexdigest() == g["strong_edge_sha"]
+    assert hashlib.sha256(o.ls_list().tobytes()).hexdigest() == g["ls_sha"]
+    o.close()
+
+
+def test_stream_with_carry_over_and_pipelining(rd, gpu_dev):
+    # config 3 in miniature: vidrect's loop (vidrect.cpp:159-172) - enqueue N+1 before polling N.  Frames after the
+    # first see the previous strong-edge mask in the strength accumulator; the oracle object carries it too.
+    iw, ih, nf = 640, 360, 5
+    frames = [ol.synth_frame(iw, ih, 1000 + i) for i in range(nf)]
+    o = ol.OracleRect(iw, ih)
+    want = [o.execute_once(f, parity.TAN_AOV) for f in frames]
+    g = rd.OclRect(gpu_dev, iw, ih)
+    got = []
+    g.enqueue_task(frames[0])
+    for i in range(1, nf):
+        g.enqueue_task(frames[i])
+        got.append(g.poll_task(parity.TAN_AOV))
+    got.append(g.poll_task(parity.TAN_AOV))
+    for i in range(nf):
+        ok, why = parity.rects_close(want[i], got[i])
+        assert ok, (i, why)
+    assert np.array_equal(o.buffer("buf3"), g.buffer("buf3"))
+    g.close()
+
+
+def test_blank_and_tiny_frames(rd, gpu_dev):
+    for iw, ih in ((64, 48), (33, 17)):
+        img = np.full((ih, 3 * iw), 128, np.uint8)
+        g = rd.OclRect(gpu_dev, iw, ih)
+        o = ol.OracleRect(iw, ih)
+        assert len(g.execute_once(img, parity.TAN_AOV)) == 0 == len(o.execute_once(img, parity.TAN_AOV))
+        assert int(g.buffer("ioBig0")[0]) == 0                      # empty segment list
+        img = ol.synth_frame(iw, ih, 5)
+        ok, why = parity.rects_close(o.execute_once(img, parity.TAN_AOV), g.execute_once(img, parity.TAN_AOV))
+        assert ok, why
+        g.close()
+
+
+def test_batch_engine_matches_fresh_oracle_objects(rd, gpu_dev):
+    # every frame of a batch is processed as by a freshly created oclrect_t (no carry-over between frames)
+    iw, ih, nf = 640, 480, 12
+    frames = np.stack([ol.synth_frame(iw, ih, 2000 + i) for i in range(nf)])
+    b = rd.Batch(0, iw, ih, nctx=4)
+    got = b.run(frames.ctypes.data, frames[0].nbytes, 3 * iw, nf, parity.TAN_AOV)
+    again = b.run(frames.ctypes.data, frames[0].nbytes, 3 * iw, nf, parity.TAN_AOV)
+    b.close()
+    for i in range(nf):
+        o = ol.OracleRect(iw, ih)
+        want = o.execute_once(frames[i], parity.TAN_AOV)
+        ok, why = parity.rects_close(want, got[i])
+        assert ok, (i, why)
+        assert got[i].tobytes() == again[i].tobytes()
+        o.close()
+
+
+# ---------------------------------------------------------------------------------------------- operator level (L2)
+def test_imgutil_operators_individually(rd, gpu_dev):
+    # poly.cpp:104-121 : the same calls, one by one, on caller-owned buffers
+    L = rd.lib()
+    iw, ih = 320, 200
+    n = iw * ih
+    img = ol.synth_frame(iw, ih, 21)
+    iu = L.init_oclimgutil(gpu_dev.device, gpu_dev.context)
+    q = gpu_dev.queue
+    m = [gpu_dev.buffer(nbytes=4 * n) for _ in range(10)]
+    big = gpu_dev.buffer(nbytes=16 * n)
+    m[0].write(img)
+    L.oclimgutil_convert_plab_bgr(iu, m[4].h, m[0].h, iw, ih, 3 * iw, q, None)
+    plab = np.zeros(n, np.uint32)
+    L_ORA.ora_convert_plab_bgr(_p(plab), _p(img), iw, ih, 3 * iw)
+    assert np.array_equal(m[4].read(np.uint32), plab)
+
+    L.oclimgutil_unpack_f_f_f_plab(iu, m[1].h, m[2].h, m[3].h, m[4].h, iw, ih, q, None)
+    ch = [np.zeros(n, np.float32) for _ in range(3)]
+    L_ORA.ora_unpack_f_f_f_plab(_p(ch[0]), _p(ch[1]), _p(ch[2]), _p(plab), iw, ih)
+    for k in range(3):
+        assert np.array_equal(m[1 + k].read(np.float32).view(np.uint32), ch[k].view(np.uint32))
+
+    for r in (0, 2, 5):
+        L.oclimgutil_iirblur_f_f(iu, m[0].h, m[1].h, m[5].h, m[6].h, r, iw, ih, q, None)
+        want, t0, t1 = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        L_ORA.ora_iirblur_f_f(_p(want), _p(ch[0]), _p(t0), _p(t1), r, iw, ih)
+        assert np.array_equal(m[0].read(np.float32).view(np.uint32), want.view(np.uint32)), r
+    blurL = want  # r = 5
+
+    L.oclimgutil_edgevec_f2_f(iu, big.h, m[0].h, iw, ih, q, None)
+    vec = np.zeros(2 * n, np.float32)
+    L_ORA.ora_edgevec_f2_f(_p(vec), _p(blurL), iw, ih)
+    assert np.array_equal(big.read(np.float32, count=2 * n).view(np.uint32), vec.view(np.uint32))
+
+    L.oclimgutil_pack_plab_f_f_f(iu, m[7].h, m[0].h, m[2].h, m[3].h, iw, ih, q, None)
+    packed = np.zeros(n, np.uint32)
+    L_ORA.ora_pack_plab_f_f_f(_p(packed), _p(blurL), _p(ch[1]), _p(ch[2]), iw, ih)
+    assert np.array_equal(m[7].read(np.uint32), packed)
+
+    L.oclimgutil_edge_f_plab(iu, m[5].h, m[7].h, iw, ih, q, None)
+    mag = np.zeros(n, np.float32)
+    L_ORA.ora_edge_f_plab(_p(mag), _p(packed), iw, ih)
+    assert np.array_equal(m[5].read(np.float32).view(np.uint32), mag.view(np.uint32))
+
+    L.oclimgutil_thinthres_f_f_f2(iu, m[2].h, m[5].h, big.h, iw, ih, q, None)
+    thin = np.zeros(n, np.float32)
+    L_ORA.ora_thinthres_f_f_f2(_p(thin), _p(mag), _p(vec), iw, ih)
+    assert np.array_equal(m[2].read(np.float32).view(np.uint32), thin.view(np.uint32))
+
+    L.oclimgutil_threshold_f_f(iu, m[9].h, m[2].h, 0.0, 0.0, 1.0, n, q, None)
+    L.oclimgutil_cast_i_f(iu, m[8].h, m[9].h, 1.0, n, q, None)
+    edge = (thin > 0).astype(np.int32)
+    assert np.array_equal(m[8].read(np.int32), edge)
+
+    for bgc in (0, -1):
+        L.oclimgutil_label8x_int_int(iu, m[3].h, m[8].h, m[9].h, bgc, iw, ih, q, None)
+        lab, tmp = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        assert L_ORA.ora_label8x_int_int(_p(lab), _p(edge), _p(tmp), bgc, iw, ih) > 0
+        assert np.array_equal(m[3].read(np.int32), lab), bgc
+    # bgc = -1 labels from the last round: strengths and the strength filter (poly.cpp:118-121 uses bgc 0; both work)
+    L.oclimgutil_clear(iu, m[4].h, 4 * n, q, None)
+    L.oclimgutil_calcStrength(iu, m[4].h, m[2].h, m[3].h, iw, ih, q, None)
+    st = np.zeros(n, np.int32)
+    L_ORA.ora_calcStrength(_p(st), _p(thin), _p(lab), iw, ih)
+    assert np.array_equal(m[4].read(np.int32), st)
+    L.oclimgutil_filterStrength(iu, m[3].h, m[4].h, 500, iw, ih, q, None)
+    L_ORA.ora_filterStrength(_p(lab), _p(st), 500, iw, ih)
+    assert np.array_equal(m[3].read(np.int32), lab)
+    L.oclimgutil_threshold_i_i(iu, m[3].h, m[3].h, 0, 0, 1, n, q, None)
+    L.oclimgutil_cast_c_i(iu, m[6].h, m[3].h, n, q, None)
+    assert np.array_equal(m[6].read(np.int8, count=n), (lab > 0).astype(np.int8))
+    L.oclimgutil_copy(iu, m[5].h, m[3].h, 4 * n, q, None)
+    assert np.array_equal(m[5].read(np.int32), (lab > 0).astype(np.int32))
+    # events: non-NULL wait list -> an event comes back and can be waited on / released (oclhelper.c:719-745)
+    wait = (C.c_void_p * 1)(None)
+    ev = L.oclimgutil_clear(iu, m[5].h, 4 * n, q, wait)
+    assert ev is not None
+    L.waitForEvent(ev)
+    L.clReleaseEvent(ev)
+    assert not m[5].read(np.int32).any()
+    for b in m + [big]:
+        b.release()
+    L.dispose_oclimgutil(iu)
+
+
+def test_poly_pipeline_config1(rd, gpu_dev):
+    # config 1 of BASELINE.json: poly.cpp:104-123 on a 640x480 frame, seed 1, minerror 1, sizeThre 20, strength 500
+    L = rd.lib()
+    iw, ih, seed = 640, 480, 1
+    n = iw * ih
+    img = ol.synth_frame(iw, ih, seed)
+    want_id, want_ls, thin = np.zeros(n, np.int32), np.zeros(4 * n, np.int32), np.zeros(n, np.float32)
+    L_ORA.ora_poly_frame(_p(img), 3 * iw, iw, ih, 1.0, 20, 500, _p(want_id), _p(want_ls), _p(thin))
+
+    iu, pl, q = L.init_oclimgutil(gpu_dev.device, gpu_dev.context), L.init_oclpolyline(gpu_dev.device, gpu_dev.context), gpu_dev.queue
+    m = [gpu_dev.buffer(nbytes=4 * n) for _ in range(10)]
+    big, mls = gpu_dev.buffer(nbytes=16 * n), gpu_dev.buffer(nbytes=16 * n)
+    m[0].write(img)
+    L.oclimgutil_convert_plab_bgr(iu, m[4].h, m[0].h, iw, ih, 3 * iw, q, None)
+    L.oclimgutil_unpack_f_f_f_plab(iu, m[1].h, m[2].h, m[3].h, m[4].h, iw, ih, q, None)
+    L.oclimgutil_iirblur_f_f(iu, m[0].h, m[1].h, m[4].h, m[5].h, 2, iw, ih, q, None)
+    L.oclimgutil_iirblur_f_f(iu, m[1].h, m[2].h, m[4].h, m[5].h, 2, iw, ih, q, None)
+    L.oclimgutil_iirblur_f_f(iu, m[2].h, m[3].h, m[4].h, m[5].h, 2, iw, ih, q, None)
+    L.oclimgutil_pack_plab_f_f_f(iu, m[4].h, m[0].h, m[1].h, m[2].h, iw, ih, q, None)
+    L.oclimgutil_edgevec_f2_f(iu, big.h, m[0].h, iw, ih, q, None)
+    L.oclimgutil_edge_f_plab(iu, m[5].h, m[4].h, iw, ih, q, None)
+    L.oclimgutil_thinthres_f_f_f2(iu, m[2].h, m[5].h, big.h, iw, ih, q, None)
+    L.oclimgutil_threshold_f_f(iu, m[9].h, m[2].h, 0.0, 0.0, 1.0, n, q, None)
+    L.oclimgutil_cast_i_f(iu, m[8].h, m[9].h, 1.0, n, q, None)
+    L.oclimgutil_label8x_int_int(iu, m[3].h, m[8].h, m[9].h, 0, iw, ih, q, None)
+    L.oclimgutil_clear(iu, m[4].h, n * 4, q, None)
+    L.oclimgutil_calcStrength(iu, m[4].h, m[2].h, m[3].h, iw, ih, q, None)
+    L.oclimgutil_filterStrength(iu, m[3].h, m[4].h, 500, iw, ih, q, None)
+    L.oclimgutil_threshold_i_i(iu, m[3].h, m[3].h, 0, 0, 1, n, q, None)
+    L.oclpolyline_execute(pl, mls.h, 16 * n, m[0].h, m[3].h, big.h, m[4].h, m[5].h, m[6].h, m[7].h, m[8].h, m[9].h, 1.0, 20, iw, ih, q, None)
+    assert np.array_equal(m[2].read(np.float32).view(np.uint32), thin.view(np.uint32))
+    got_id, got_ls = m[0].read(np.int32), mls.read(np.int32)
+    cnt = int(want_ls[0])
+    assert cnt > 10 and int(got_ls[0]) == cnt
+    assert np.array_equal(got_id, want_id)
+    assert np.array_equal(got_ls[: 14 * (cnt + 1)], want_ls[: 14 * (cnt + 1)])
+    for b in m + [big, mls]:
+        b.release()
+    L.dispose_oclpolyline(pl)
+    L.dispose_oclimgutil(iu)
+
+
+def test_rect_operators_individually(rd, gpu_dev):
+    # Stage B / D kernels of oclrect.cl one by one on random inputs
+    L = rd.lib()
+    rng = np.random.default_rng(5)
+    iw, ih = 203, 131
+    n = iw * ih
+    q = gpu_dev.queue
+    buf = lambda a=None: gpu_dev.buffer(nbytes=4 * n, data=a)
+    edge01 = (rng.random(n) < 0.2).astype(np.int32)
+    out = np.zeros(n, np.int32)
+
+    a, b = buf(edge01), buf()
+    L.rd_rect_simpleJunction(b.h, a.h, iw, ih, q)
+    L_ORA.ora_rect_simpleJunction(_p(out), _p(edge01), iw, ih)
+    junction = out.copy()
+    assert np.array_equal(b.read(), junction)
+    L.rd_rect_simpleConnect(a.h, b.h, iw, ih, q)
+    L_ORA.ora_rect_simpleConnect(_p(out), _p(junction), iw, ih)
+    connect = out.copy()
+    assert np.array_equal(a.read(), connect)
+    for mod2 in (0, 1):
+        L.rd_rect_stringify(b.h, a.h, mod2, iw, ih, q)
+        L_ORA.ora_rect_stringify(_p(out), _p(connect), mod2, iw, ih)
+        assert np.array_equal(b.read(), out), mod2
+
+    plab = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    e8 = np.zeros(4 * n, np.int8)
+    e8[:n] = edge01
+    pin, pe, pout, want = buf(plab), buf(e8), buf(), np.zeros(n, np.uint32)
+    for fn, ofn in ((L.rd_rect_blblur0, L_ORA.ora_rect_blblur0), (L.rd_rect_blblur1, L_ORA.ora_rect_blblur1)):
+        fn(pout.h, pe.h, pin.h, iw, ih, q)
+        ofn(_p(want), _p(e8), _p(plab), iw, ih)
+        assert np.array_equal(pout.read(np.uint32), want)
+    L.rd_rect_quantize(pout.h, pin.h, 24, 24, 24, iw, ih, q)
+    L_ORA.ora_rect_quantize(_p(want), _p(plab), 24, 24, 24, iw, ih)
+    assert np.array_equal(pout.read(np.uint32), want)
+    strength = np.where(rng.random(n) < 0.3, rng.random(n), 0).astype(np.float32)
+    ps = buf(strength)
+    L.rd_rect_despeckle(pout.h, pin.h, ps.h, iw, ih, q)
+    L_ORA.ora_rect_despeckle(_p(want), _p(plab), _p(strength), iw, ih)
+    assert np.array_equal(pout.read(np.uint32), want)
+
+    sparse = np.where(rng.random(n) < 0.004, rng.integers(2, 5, n), 0).astype(np.int32)
+    pj, pm = buf(sparse), buf()
+    L.rd_rect_mkMergeMask0(pm.h, pj.h, iw, ih, q)
+    L.rd_rect_mkMergeMask1(pm.h, pj.h, iw, ih, q)
+    mask = np.zeros(n, np.int32)
+    L_ORA.ora_rect_mkMergeMask0(_p(mask), _p(sparse), iw, ih)
+    L_ORA.ora_rect_mkMergeMask1(_p(mask), _p(sparse), iw, ih)
+    assert np.array_equal(pm.read(), mask) and mask.any()
+
+    blocks = (rng.integers(0, 3, ((ih + 7) // 8, (iw + 7) // 8)).repeat(8, 0).repeat(8, 1)[:ih, :iw]).astype(np.uint32).reshape(-1)
+    edge_lbl = np.where(rng.random(n) < 0.05, 7, -1).astype(np.int32)
+    pp, pl_, pe2, plab_ = buf(blocks), buf(), buf(edge_lbl), buf(mask)
+    L.rd_rect_labelMerge(pl_.h, pp.h, plab_.h, pe2.h, iw, ih, q)
+    lab = np.zeros(n, np.int32)
+    L_ORA.ora_rect_labelMerge(_p(lab), _p(blocks.view(np.int32)), _p(mask), _p(edge_lbl), iw, ih)
+    assert np.array_equal(pl_.read(), lab)
+
+    size = np.zeros(n, np.int32)
+    psz = buf(size)
+    L.rd_rect_calcSize(psz.h, pl_.h, iw, ih, q)
+    L_ORA.ora_rect_calcSize(_p(size), _p(lab), iw, ih)
+    assert np.array_equal(psz.read(), size)
+    scratch = buf()
+    L.rd_rect_despeckle2(pl_.h, psz.h, scratch.h, 16, iw, ih, q)
+    L_ORA.ora_rect_despeckle2(_p(lab), _p(size), 16, iw, ih)
+    assert np.array_equal(pl_.read(), lab)
+    L.rd_rect_markBoundary(scratch.h, pl_.h, iw, ih, q)
+    L_ORA.ora_rect_markBoundary(_p(out), _p(lab), iw, ih)
+    assert np.array_equal(scratch.read(), out)
+
+    # vote table with deliberate slot collisions (tiny nentry): smallest lsid owns the slot
+    lsid = np.where(rng.random(n) < 0.03, rng.integers(1, 40, n), 0).astype(np.int32)
+    bnd = np.where(rng.random(n) < 0.1, rng.integers(1, 30, n), -1).astype(np.int32)
+    for nentry in (97, n * 4 // 5):
+        votes = np.zeros(4 * n, np.int32)
+        pv, pb, pi = gpu_dev.buffer(nbytes=16 * n), buf(bnd), buf(lsid)
+        L.rd_rect_reduceLS(pv.h, pb.h, pi.h, iw, ih, nentry, q)
+        L_ORA.ora_rect_reduceLS(_p(votes), _p(bnd), _p(lsid), iw, ih, nentry)
+        assert np.array_equal(pv.read(), votes), nentry
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("iw,ih,seed", [(1920, 1080, 2000), (3840, 2160, 5)])
+def test_full_size_invariants(rd, gpu_dev, iw, ih, seed):
+    # configs 4 and 5: too slow to replay step by step on the CPU for every run, so check what must hold at any size
+    img = ol.synth_frame(iw, ih, seed)
+    g = rd.OclRect(gpu_dev, iw, ih)
+    r1 = g.execute_once(img, parity.TAN_AOV)
+    n = iw * ih
+    seg, lsid, strong = g.buffer("iobuf1"), g.buffer("buf0"), g.buffer("buf3")
+    ls = g.ls_list()
+    cnt = len(ls) - 1
+    assert cnt > 0 and len(r1) > 0
+    # labels are the smallest index of their component: roots label themselves, labels never exceed the pixel index
+    idx = np.arange(n)
+    fg = seg >= 0
+    assert (seg[fg] <= idx[fg]).all() and (seg[seg[fg]] == seg[fg]).all()
+    # segment ids are 1..cnt, every live segment owns pixels, and ids only sit on strong-edge-derived pixels
+    assert lsid.min() == 0 and lsid.max() <= cnt
+    live = np.flatnonzero(ls["polyid"][1:] != 0) + 1
+    assert np.isin(live, np.unique(lsid)).sum() >= 0.9 * len(live)
+    assert set(np.unique(strong)) <= {0, 1}
+    # chains are consistent doubly-linked lists
+    for i in live:
+        r = ls["rightPtr"][i]
+        if r:
+            assert ls["leftPtr"][r] == i and ls["polyid"][r] == ls["polyid"][i]
+    # vote table: every occupied slot is owned by a segment id that hashes there with some region, boxes are inside the image
+    votes = g.buffer("ioBig1").reshape(-1, 5)[: n * 4 // 5]
+    occ = votes[votes[:, 0] != 0]
+    assert len(occ) > 0 and (occ[:, 0] >= 1).all() and (occ[:, 0] <= cnt).all()
+    assert (occ[:, 1] + occ[:, 2] >= iw).all() and (occ[:, 3] + occ[:, 4] >= ih).all()
+    # determinism / idempotence: a fresh object gives the same answer, and so does the oracle's host tail on these outputs
+    g2 = rd.OclRect(gpu_dev, iw, ih)
+    r2 = g2.execute_once(img, parity.TAN_AOV)
+    assert r1.tobytes() == r2.tobytes()
+    want = rd.rect_tail(ls, seg, g.buffer("ioBig1"), iw, ih, parity.TAN_AOV)
+    assert want.tobytes() == r1.tobytes()
+    g.close()
+    g2.close()
+
+
+def test_1080p_full_oracle_parity(rd, gpu_dev):
+    # one full CPU replay at the 8-GPU config's frame size
+    iw, ih, seed = 1920, 1080, 2001
+    img = ol.synth_frame(iw, ih, seed)
+    o = ol.OracleRect(iw, ih)
+    want = o.execute_once(img, parity.TAN_AOV)
+    g = rd.OclRect(gpu_dev, iw, ih)
+    got = g.execute_once(img, parity.TAN_AOV)
+    for name in ("buf3", "iobuf1", "buf0", "ioBig1"):
+        assert np.array_equal(o.buffer(name), g.buffer(name)), name
+    assert o.ls_list().tobytes() == g.ls_list().tobytes()
+    ok, why = parity.rects_close(want, got)
+    assert ok, why
+    g.close()
