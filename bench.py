@@ -150,7 +150,8 @@ def main():
     ap.add_argument("--w", type=int, default=1280)
     ap.add_argument("--h", type=int, default=720)
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--nctx", type=int, default=8, help="pipeline objects (streams) per GPU")
+    ap.add_argument("--nctx", type=int, default=4, help="pipeline objects (streams) per GPU")
+    ap.add_argument("--fpl", type=int, default=8, help="frames per kernel launch")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -181,7 +182,7 @@ def main():
     host_frames = synth_batch(iw, ih, 1000 + lo, hi - lo, pinned=True)           # seeds 1000+i (config 3)
     dev_frames = host_frames.to("cuda", non_blocking=False)
     frame_bytes = ih * ws
-    batch = rd.Batch(local_rank, iw, ih, nctx=args.nctx)
+    batch = rd.Batch(local_rank, iw, ih, nctx=args.nctx, frames_per_launch=args.fpl)
     dev = "cuda"
 
     def barrier():
@@ -265,8 +266,8 @@ def main():
             "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i32 (f64 host tail)", "data": "synthetic",
             "config": {"workload": "vidrect %dx%d synthetic stream (seeds 1000+i), AOV 72, full imgutil->polyline->rect pipeline, batched" % (iw, ih),
-                       "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "parallelism": "frames x%d" % world,
-                       "l2": "inputs larger than L2 (%d MB of frames + %d x 81 MB working sets per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx)},
+                       "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "frames_per_launch": args.fpl, "parallelism": "frames x%d" % world,
+                       "l2": "inputs larger than L2 (%d MB of frames + %d x 81 MB working sets per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx * args.fpl)},
             "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": total_frames * 128 * 1024,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -190,12 +190,13 @@ void   rd_oclrect_run_device(struct oclrect_t *thiz, const uint8_t *imgData, int
 rect_t *rd_rect_tail(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, double tanAOV);
 void   rd_free(void *p);
 
-/* Frame-batch engine: `nctx` independent frame contexts on one device, each with its own stream and buffers.
- * rd_batch_run detects rectangles in `nframes` host frames (BGR8, stride ws, frame i at frames + i*frame_stride)
- * and returns one malloc()ed rect_t list per frame in out[i] (same format as oclrect_executeOnce).  Each frame is
- * processed as by a freshly created oclrect_t (no state carried between frames). */
+/* Frame-batch engine: `nctx` pipeline objects on one device, each with its own stream, buffers for
+ * `frames_per_launch` frames and a host thread.  Every kernel launch processes up to frames_per_launch independent
+ * frames.  rd_batch_run detects rectangles in `nframes` host frames (BGR8, stride ws, frame i at frames +
+ * i*frame_stride) and returns one malloc()ed rect_t list per frame in out[i] (same format as oclrect_executeOnce).
+ * Each frame is processed as by a freshly created oclrect_t (no state carried between frames). */
 typedef struct rd_batch rd_batch;
-rd_batch *rd_batch_create(int device, int iw, int ih, int nctx, int tail_threads);
+rd_batch *rd_batch_create(int device, int iw, int ih, int nctx, int frames_per_launch);
 void rd_batch_destroy(rd_batch *b);
 void rd_batch_run(rd_batch *b, const uint8_t *frames, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out);
 /* device-resident variant: frames already in device memory (read in place).  out == NULL runs the device stages and the

@@ -247,11 +247,12 @@ class OclRect:
 
 
 class Batch:
-    """frame-batch engine: nctx pipeline objects on one device, frames are independent"""
+    """frame-batch engine: nctx pipeline objects (streams) on one device, each launch processes frames_per_launch frames;
+    frames are independent"""
 
-    def __init__(self, device, iw, ih, nctx=8):
+    def __init__(self, device, iw, ih, nctx=4, frames_per_launch=8):
         self.iw, self.ih = iw, ih
-        self.h = lib().rd_batch_create(device, iw, ih, nctx, 0)
+        self.h = lib().rd_batch_create(device, iw, ih, nctx, frames_per_launch)
 
     def run(self, frames_ptr, frame_stride, ws, nframes, tan_aov, on_device=False, want_rects=True):
         """frames_ptr: address of nframes BGR8 frames (host, ideally pinned, or device when on_device)"""

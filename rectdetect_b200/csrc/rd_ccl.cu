@@ -27,6 +27,7 @@
 // ---- link functors: which backward neighbours (W, NW, N, NE) of (x, y) belong to the same component ----
 struct Link8x {                       // label8xMain_int_int: equal value, value != bgc (oclimgutil.cl:511-538)
   const int *pix; int bgc, iw, ih;
+  __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix); }
   __device__ __forceinline__ unsigned operator()(int x, int y) const {
     const int p = y * iw + x, v = pix[p];
     if (v == bgc) return L_BG;
@@ -42,6 +43,7 @@ struct Link8x {                       // label8xMain_int_int: equal value, value
 };
 struct LinkPl {                       // labelpl_main: numbers (+1) both non-zero and differing by at most 1 (oclpolyline.cl:325-355)
   const int *num; int iw, ih;
+  __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, num); }
   __device__ __forceinline__ static bool con(int a, int b) { return b != 0 && abs(a - b) <= 1; }
   __device__ __forceinline__ unsigned operator()(int x, int y) const {
     const int p = y * iw + x, v = num[p];
@@ -58,6 +60,7 @@ struct LinkPl {                       // labelpl_main: numbers (+1) both non-zer
 };
 struct LinkMerge {                    // labelxPreprocess + labelMergeMain, canonical symmetric form (see rd_rect.cu / DESIGN.md)
   const uint32_t *pix; const int *mask; const int *edge; int iw, ih;
+  __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix, mask, edge); }
   __device__ __forceinline__ bool interior(int x, int y) const { return x > 0 && y > 0 && x < iw - 1 && y < ih - 1; }
   __device__ __forceinline__ unsigned operator()(int x, int y) const {
     const int b = y * iw + x;
@@ -100,7 +103,9 @@ __device__ __forceinline__ void sm_unite(int *L, int a, int b) {
 
 // local neighbour offsets for the four link bits (tile-local index = ly * TW + lx)
 template <class LinkFn>
-__global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *__restrict__ label, uint8_t *__restrict__ links, LinkFn f, int iw, int ih) {
+__global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *links, LinkFn f, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, label, links);
+  f.shift((size_t)blockIdx.z * fs);
   __shared__ int L[TW * TH];
   __shared__ uint8_t M[TW * TH];
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -151,7 +156,8 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *__restrict__ labe
 }
 
 // unions across tile seams.  One thread per pixel of the image; only seam pixels do work.
-__global__ void k_ccl_seams(int *label, const uint8_t *__restrict__ links, int iw, int ih) {
+__global__ void k_ccl_seams(int *label, const uint8_t *links, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, label, links);
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   const int lx = x & (TW - 1), ly = y & (TH - 1);
@@ -166,7 +172,8 @@ __global__ void k_ccl_seams(int *label, const uint8_t *__restrict__ links, int i
 }
 
 // final labels.  mode 0: background -> bgval, others -> root.
-__global__ void k_ccl_flatten(int *label, const uint8_t *__restrict__ links, int bgval, int n) {
+__global__ void k_ccl_flatten(int *label, const uint8_t *links, int bgval, int n, size_t fs) {
+  rd_batch_y(fs, label, links);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (links[p] & L_BG) { label[p] = bgval; return; }
@@ -176,7 +183,8 @@ __global__ void k_ccl_flatten(int *label, const uint8_t *__restrict__ links, int
 // the pixel (parents only ever move towards the root), so concurrent walks stay correct.
 
 // labelMerge: interior pixels get the root, image-border pixels keep their labelxPreprocess value (oclrect.cl:289-298)
-__global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *__restrict__ pix, int iw, int ih) {
+__global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *pix, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, label, pix);
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   const int p = y * iw + x;
@@ -189,28 +197,28 @@ __global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *
 }
 
 template <class LinkFn>
-static void ccl_core(int *label, uint8_t *links, LinkFn f, int iw, int ih, cudaStream_t s) {
-  RD_LAUNCH(k_ccl_tile<LinkFn>, dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH)), CCL_THREADS, 0, s, label, links, f, iw, ih);
+static void ccl_core(int *label, uint8_t *links, LinkFn f, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(k_ccl_tile<LinkFn>, rd_gz(dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH)), nb), CCL_THREADS, 0, s, label, links, f, iw, ih, fs);
   const dim3 b(32, 8);
-  RD_LAUNCH(k_ccl_seams, rd_grid2d(iw, ih, b), b, 0, s, label, links, iw, ih);
+  RD_LAUNCH(k_ccl_seams, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, label, links, iw, ih, fs);
 }
 
 // scratch: iw*ih bytes
-void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, cudaStream_t s) {
+void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   Link8x f = {pix, bgc, iw, ih};
-  ccl_core(label, (uint8_t *)scratch, f, iw, ih, s);
-  RD_LAUNCH(k_ccl_flatten, rd_cdiv(iw * ih, 256), 256, 0, s, label, (const uint8_t *)scratch, -1, iw * ih);
+  ccl_core(label, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  RD_LAUNCH(k_ccl_flatten, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, label, (const uint8_t *)scratch, -1, iw * ih, fs);
 }
 // labelpl (oclpolyline.c:170-184): `num` already holds number+1 (0 where the number is 0); zero pixels get label 0
-void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, cudaStream_t s) {
+void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   LinkPl f = {num, iw, ih};
-  ccl_core(label, (uint8_t *)scratch, f, iw, ih, s);
-  RD_LAUNCH(k_ccl_flatten, rd_cdiv(iw * ih, 256), 256, 0, s, label, (const uint8_t *)scratch, 0, iw * ih);
+  ccl_core(label, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  RD_LAUNCH(k_ccl_flatten, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, label, (const uint8_t *)scratch, 0, iw * ih, fs);
 }
 // labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331), converged.  work: iw*ih ints, scratch: iw*ih bytes; out may not alias work
-void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int iw, int ih, cudaStream_t s) {
+void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   LinkMerge f = {pix, mask, edge, iw, ih};
-  ccl_core(work, (uint8_t *)scratch, f, iw, ih, s);
+  ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
   const dim3 b(32, 8);
-  RD_LAUNCH(k_ccl_flatten_merge, rd_grid2d(iw, ih, b), b, 0, s, out, work, pix, iw, ih);
+  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, pix, iw, ih, fs);
 }

@@ -70,8 +70,20 @@ void rd_wait_events(cudaStream_t s, const cl_event *events);
 static inline int rd_cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline dim3 rd_grid2d(int iw, int ih, dim3 block) { return dim3(rd_cdiv(iw, block.x), rd_cdiv(ih, block.y)); }
 
+// ---- frame batching -------------------------------------------------------------------------------------------
+// Every kernel processes `nb` independent frames per launch.  All device buffers of one frame live in one arena and the
+// arenas of a batch are `fs` bytes apart, so the pointers of frame z are the pointers of frame 0 plus z*fs, whatever
+// they point at.  The frame index is blockIdx.z for 2-D kernels, blockIdx.y for 1-D kernels and blockIdx.x for the
+// single-CTA-per-frame kernels.  The operator-level API (one caller-owned buffer set) launches with nb = 1, fs = 0.
+static inline dim3 rd_gz(dim3 g, int nb) { g.z = nb; return g; }
+static inline dim3 rd_gy(dim3 g, int nb) { g.y = nb; return g; }
+
 // ---- device helpers shared by the three kernel families (oclimgutil.cl:28-63, identical copies in oclrect.cl:19-48) ----
 #ifdef __CUDACC__
+template <class... T> __device__ __forceinline__ void rd_batch_off(size_t o, T *&...p) { ((p = (T *)((char *)p + o)), ...); }
+template <class... T> __device__ __forceinline__ void rd_batch_z(size_t fs, T *&...p) { rd_batch_off((size_t)blockIdx.z * fs, p...); }
+template <class... T> __device__ __forceinline__ void rd_batch_y(size_t fs, T *&...p) { rd_batch_off((size_t)blockIdx.y * fs, p...); }
+template <class... T> __device__ __forceinline__ void rd_batch_x(size_t fs, T *&...p) { rd_batch_off((size_t)blockIdx.x * fs, p...); }
 __device__ __forceinline__ int rd_cl_clamp(int x, int lo, int hi) { return min(max(x, lo), hi); }
 __device__ __forceinline__ int rd_mirror1(int x, int iw) { return rd_cl_clamp(x, -x, iw * 2 - 2 - x); }
 __device__ __forceinline__ int rd_mirror(int x, int y, int iw, int ih) { return rd_mirror1(x, iw) + rd_mirror1(y, ih) * iw; }
@@ -121,7 +133,7 @@ __device__ __forceinline__ void rd_uf_unite(int *L, int a, int b) {
 
 // kernel families (host-side entry points used across translation units)
 // CCL: label = smallest linear index of the 8-connected equal-value component, bgc pixels -> -1
-void rd_label8x(int *label, const int *pix, void *scratch /* iw*ih bytes */, int bgc, int iw, int ih, cudaStream_t s);
+void rd_label8x(int *label, const int *pix, void *scratch /* iw*ih bytes */, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 
 // host tail (rd_tail.cpp) on the compact read-back record (see rd_rect.cu : tail_gather)
 struct rd_tail_sample { int32_t segid; int32_t vote[5]; };            // vote = the table entry the (ls,segid) pair hashes to

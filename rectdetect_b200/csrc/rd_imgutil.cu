@@ -15,56 +15,67 @@ struct oclimgutil_t { uint32_t magic; int ordinal; };
 static inline void chk(oclimgutil_t *t) { if (!t || t->magic != IMGUTIL_MAGIC) exitf(-1, "rectdetect_b200: bad oclimgutil_t\n"); }
 
 // ------------------------------------------------------------------------------------------ 1-D kernels
-__global__ void k_clear(int *out, int n) {                                   // oclimgutil.cl:197
+__global__ void k_clear(int *out, int n, size_t fs) {
+  rd_batch_y(fs, out);                                   // oclimgutil.cl:197
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = 0;
 }
-__global__ void k_copy(int *out, const int *in, int n) {                     // oclimgutil.cl:204
+__global__ void k_copy(int *out, const int *in, int n, size_t fs) {
+  rd_batch_y(fs, out, in);                     // oclimgutil.cl:204
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
 }
-__global__ void k_cast_i_f(int *out, const float *in, float scale, int n) {  // oclimgutil.cl:211
+__global__ void k_cast_i_f(int *out, const float *in, float scale, int n, size_t fs) {
+  rd_batch_y(fs, out, in);  // oclimgutil.cl:211
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int)__fmul_rn(in[i], scale);
 }
-__global__ void k_cast_c_i(int8_t *out, const int *in, int n) {              // oclimgutil.cl:218
+__global__ void k_cast_c_i(int8_t *out, const int *in, int n, size_t fs) {
+  rd_batch_y(fs, out, in);              // oclimgutil.cl:218
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int8_t)in[i];
 }
-__global__ void k_threshold_i_i(int *out, const int *in, int vlow, int thr, int vhigh, int n) {   // oclimgutil.cl:225
+__global__ void k_threshold_i_i(int *out, const int *in, int vlow, int thr, int vhigh, int n, size_t fs) {
+  rd_batch_y(fs, out, in);   // oclimgutil.cl:225
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] > thr ? vhigh : vlow;
 }
-__global__ void k_threshold_f_f(float *out, const float *in, float vlow, float thr, float vhigh, int n) {  // oclimgutil.cl:232
+__global__ void k_threshold_f_f(float *out, const float *in, float vlow, float thr, float vhigh, int n, size_t fs) {
+  rd_batch_y(fs, out, in);  // oclimgutil.cl:232
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] > thr ? vhigh : vlow;
 }
-__global__ void k_rand(int *out, uint64_t seed, int n) {                     // oclimgutil.cl:248
+__global__ void k_rand(int *out, uint64_t seed, int n, size_t fs) {
+  rd_batch_y(fs, out);                     // oclimgutil.cl:248
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = rd_rand_at(i, seed);
 }
 
 // ------------------------------------------------------------------------------------------ 2-D kernels
-__global__ void k_bgr2plab(uint32_t *out, const uint8_t *in, int iw, int ih, int ws) {   // oclimgutil.cl:256
+__global__ void k_bgr2plab(uint32_t *out, const uint8_t *in, int iw, int ih, int ws, size_t fs) {
+  rd_batch_z(fs, out, in);   // oclimgutil.cl:256
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   const uint8_t *p = in + (size_t)y * ws + x * 3;
   out[y * iw + x] = rd_srgb2plab(p[0], p[1], p[2], RD_S2L, RD_CFUNC, RD_CFUNC2);
 }
-__global__ void k_unpack_plab(float *o0, float *o1, float *o2, const uint32_t *in, int n) {   // oclimgutil.cl:333
+__global__ void k_unpack_plab(float *o0, float *o1, float *o2, const uint32_t *in, int n, size_t fs) {
+  rd_batch_y(fs, o0, o1, o2, in);   // oclimgutil.cl:333
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float l, a, b;
   rd_unpacklab(in[i], l, a, b);
   o0[i] = l; o1[i] = a; o2[i] = b;
 }
-__global__ void k_pack_plab(uint32_t *out, const float *i0, const float *i1, const float *i2, int n) {   // oclimgutil.cl:325
+__global__ void k_pack_plab(uint32_t *out, const float *i0, const float *i1, const float *i2, int n, size_t fs) {
+  rd_batch_y(fs, out, i0, i1, i2);   // oclimgutil.cl:325
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = rd_packlab(i0[i], i1[i], i2[i]);
 }
 
 // oclimgutil.cl:395-420 ; global-memory version of the 5x5 derivative pair (the rect pipeline uses the tiled one)
-__global__ void k_edgevec_f(float2 *dst, const float *in, int iw, int ih) {
+__global__ void k_edgevec_f(float2 *dst, const float *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, dst, in);
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   float vx = 0, vy = 0;
@@ -78,7 +89,8 @@ __global__ void k_edgevec_f(float2 *dst, const float *in, int iw, int ih) {
 }
 
 // oclimgutil.cl:422-437
-__global__ void k_edge_plab(float *out, const uint32_t *in, int iw, int ih) {
+__global__ void k_edge_plab(float *out, const uint32_t *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   out[y * iw + x] = rd_edge_plab_at(in[rd_mirror(x, y - 1, iw, ih)], in[rd_mirror(x - 1, y, iw, ih)], in[rd_mirror(x, y + 1, iw, ih)],
@@ -91,7 +103,8 @@ struct GlobalPlane {
   const float *p; int iw, ih;
   __device__ __forceinline__ float at(int x, int y) const { return p[rd_mirror(x, y, iw, ih)]; }
 };
-__global__ void k_thinthres(float *out, const float *in, const float2 *vec, int iw, int ih) {
+__global__ void k_thinthres(float *out, const float *in, const float2 *vec, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in, vec);
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   GlobalPlane pl = {in, iw, ih};
@@ -101,7 +114,8 @@ __global__ void k_thinthres(float *out, const float *in, const float2 *vec, int 
 // ---- recursive Gaussian, oclimgutil.cl:542-637.  One thread per row / column chain (the rect pipeline uses the
 // shared-memory-staged variant in rd_rect.cu).  The reference's warm-up stores for x < 0 / x >= iw land on elements
 // the same chain overwrites later, so only the in-range stores are issued. ----
-__global__ void k_iir_h(float *tmp0, float *tmp1, const float *ibuf, int r, int iw, int ih) {
+__global__ void k_iir_h(float *tmp0, float *tmp1, const float *ibuf, int r, int iw, int ih, size_t fs) {
+  rd_batch_y(fs, tmp0, tmp1, ibuf);
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int y = t >> 1, dir = t & 1;
   if (y >= ih) return;
@@ -119,7 +133,8 @@ __global__ void k_iir_h(float *tmp0, float *tmp1, const float *ibuf, int r, int 
     for (int x = iw + (r + 1 + 8); x >= 0; x--) { float d = tp.step(row[rd_mirror1(x, iw)], c); if (x < iw) o[x] = d; }
   }
 }
-__global__ void k_iir_v(float *tmp0, float *tmp1, const float *obuf, int r, int iw, int ih) {
+__global__ void k_iir_v(float *tmp0, float *tmp1, const float *obuf, int r, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, tmp0, tmp1, obuf);
   int x = blockIdx.x * blockDim.x + threadIdx.x, dir = blockIdx.y;
   if (x >= iw) return;
   const float *coef = RD_IIRCOEF[r];
@@ -133,17 +148,20 @@ __global__ void k_iir_v(float *tmp0, float *tmp1, const float *obuf, int r, int 
     for (int y = ih + (r + 1 + 8); y >= 0; y--) { float d = tp.step(obuf[x + (size_t)rd_mirror1(y, ih) * iw], c); if (y < ih) tmp1[x + (size_t)y * iw] = d; }
   }
 }
-__global__ void k_iir_pass1(float *obuf, const float *tmp0, const float *tmp1, const float *ibuf, int r, int n) {   // oclimgutil.cl:580
+__global__ void k_iir_pass1(float *obuf, const float *tmp0, const float *tmp1, const float *ibuf, int r, int n, size_t fs) {
+  rd_batch_y(fs, obuf, tmp0, tmp1, ibuf);   // oclimgutil.cl:580
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) obuf[i] = __fsub_rn(__fadd_rn(tmp1[i], tmp0[i]), __fmul_rn(ibuf[i], RD_IIRCOEF[r][0]));
 }
-__global__ void k_iir_pass3(float *obuf, const float *tmp0, const float *tmp1, int r, int n) {                     // oclimgutil.cl:629
+__global__ void k_iir_pass3(float *obuf, const float *tmp0, const float *tmp1, int r, int n, size_t fs) {
+  rd_batch_y(fs, obuf, tmp0, tmp1);                     // oclimgutil.cl:629
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) obuf[i] = __fsub_rn(__fadd_rn(tmp1[i], tmp0[i]), __fmul_rn(obuf[i], RD_IIRCOEF[r][0]));
 }
 
 // oclimgutil.cl:641-657 (identical to oclrect.cl:137-153) ; zero contributions are skipped (adding 0 is a no-op)
-__global__ void k_calcStrength(int *out, const float *edge, const int *label, int iw, int ih) {
+__global__ void k_calcStrength(int *out, const float *edge, const int *label, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, edge, label);
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return;
   int p0 = y * iw + x, l = label[p0];
@@ -152,7 +170,8 @@ __global__ void k_calcStrength(int *out, const float *edge, const int *label, in
   int v = (int)__fmul_rn(__fmul_rn(e, e), 10000.0f);
   if (v != 0) atomicAdd(out + l, v);
 }
-__global__ void k_filterStrength(int *labelinout, const int *str, int thre, int iw, int ih) {
+__global__ void k_filterStrength(int *labelinout, const int *str, int thre, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, labelinout, str);
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return;
   int p0 = y * iw + x, l = labelinout[p0];
@@ -163,15 +182,15 @@ __global__ void k_filterStrength(int *labelinout, const int *str, int thre, int 
 static const int B1 = 256;
 static const dim3 B2(32, 8);
 
-void rd_k_clear(int *out, int nints, cudaStream_t s) { if (nints > 0) RD_LAUNCH(k_clear, rd_cdiv(nints, B1), B1, 0, s, out, nints); }
-void rd_k_copy(int *out, const int *in, int nints, cudaStream_t s) { if (nints > 0) RD_LAUNCH(k_copy, rd_cdiv(nints, B1), B1, 0, s, out, in, nints); }
-void rd_k_rand(int *out, uint64_t seed, int n, cudaStream_t s) { if (n > 0) RD_LAUNCH(k_rand, rd_cdiv(n, B1), B1, 0, s, out, seed, n); }
-void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, cudaStream_t s) {
+void rd_k_clear(int *out, int nints, int nb, size_t fs, cudaStream_t s) { if (nints > 0) RD_LAUNCH(k_clear, rd_gy(rd_cdiv(nints, B1), nb), B1, 0, s, out, nints, fs); }
+void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream_t s) { if (nints > 0) RD_LAUNCH(k_copy, rd_gy(rd_cdiv(nints, B1), nb), B1, 0, s, out, in, nints, fs); }
+void rd_k_rand(int *out, uint64_t seed, int n, int nb, size_t fs, cudaStream_t s) { if (n > 0) RD_LAUNCH(k_rand, rd_gy(rd_cdiv(n, B1), nb), B1, 0, s, out, seed, n, fs); }
+void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   const int n = iw * ih;
-  RD_LAUNCH(k_iir_h, rd_cdiv(ih * 2, 64), 64, 0, s, tmp0, tmp1, ibuf, r, iw, ih);
-  RD_LAUNCH(k_iir_pass1, rd_cdiv(n, B1), B1, 0, s, obuf, tmp0, tmp1, ibuf, r, n);
-  RD_LAUNCH(k_iir_v, dim3(rd_cdiv(iw, 64), 2), 64, 0, s, tmp0, tmp1, obuf, r, iw, ih);
-  RD_LAUNCH(k_iir_pass3, rd_cdiv(n, B1), B1, 0, s, obuf, tmp0, tmp1, r, n);
+  RD_LAUNCH(k_iir_h, rd_gy(rd_cdiv(ih * 2, 64), nb), 64, 0, s, tmp0, tmp1, ibuf, r, iw, ih, fs);
+  RD_LAUNCH(k_iir_pass1, rd_gy(rd_cdiv(n, B1), nb), B1, 0, s, obuf, tmp0, tmp1, ibuf, r, n, fs);
+  RD_LAUNCH(k_iir_v, rd_gz(dim3(rd_cdiv(iw, 64), 2), nb), 64, 0, s, tmp0, tmp1, obuf, r, iw, ih, fs);
+  RD_LAUNCH(k_iir_pass3, rd_gy(rd_cdiv(n, B1), nb), B1, 0, s, obuf, tmp0, tmp1, r, n, fs);
 }
 
 extern "C" {
@@ -185,71 +204,71 @@ oclimgutil_t *init_oclimgutil(cl_device_id device, cl_context) {             // 
 }
 void dispose_oclimgutil(oclimgutil_t *thiz) { chk(thiz); thiz->magic = 0; free(thiz); }
 
-#define OP_PROLOGUE cudaStream_t s = rd_stream(queue); chk(thiz); rd_wait_events(s, events)
+#define OP_PROLOGUE cudaStream_t s = rd_stream(queue); chk(thiz); rd_wait_events(s, events); const int nb = 1; const size_t fs = 0; (void)nb; (void)fs
 
 cl_event oclimgutil_clear(oclimgutil_t *thiz, cl_mem out, int size, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   size = (size + 3) / 4;                                                      // bytes -> ints (oclimgutil.c:142)
   rd_need(out, (size_t)size * 4, "clear");
-  rd_k_clear(rd_ptr<int>(out), size, s);
+  rd_k_clear(rd_ptr<int>(out), size, 1, 0, s);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_copy(oclimgutil_t *thiz, cl_mem out, cl_mem in, int size, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   size = (size + 3) / 4;
   rd_need(out, (size_t)size * 4, "copy"); rd_need(in, (size_t)size * 4, "copy");
-  rd_k_copy(rd_ptr<int>(out), rd_ptr<int>(in), size, s);
+  rd_k_copy(rd_ptr<int>(out), rd_ptr<int>(in), size, 1, 0, s);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_cast_i_f(oclimgutil_t *thiz, cl_mem out, cl_mem in, float scale, int size, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   rd_need(out, (size_t)size * 4, "cast_i_f"); rd_need(in, (size_t)size * 4, "cast_i_f");
-  if (size > 0) RD_LAUNCH(k_cast_i_f, rd_cdiv(size, B1), B1, 0, s, rd_ptr<int>(out), rd_ptr<float>(in), scale, size);
+  if (size > 0) RD_LAUNCH(k_cast_i_f, rd_gy(rd_cdiv(size, B1), nb), B1, 0, s, rd_ptr<int>(out), rd_ptr<float>(in), scale, size, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_cast_c_i(oclimgutil_t *thiz, cl_mem out, cl_mem in, int size, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   rd_need(out, (size_t)size, "cast_c_i"); rd_need(in, (size_t)size * 4, "cast_c_i");
-  if (size > 0) RD_LAUNCH(k_cast_c_i, rd_cdiv(size, B1), B1, 0, s, rd_ptr<int8_t>(out), rd_ptr<int>(in), size);
+  if (size > 0) RD_LAUNCH(k_cast_c_i, rd_gy(rd_cdiv(size, B1), nb), B1, 0, s, rd_ptr<int8_t>(out), rd_ptr<int>(in), size, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_threshold_i_i(oclimgutil_t *thiz, cl_mem out, cl_mem in, int vlow, int threshold, int vhigh, int size, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   rd_need(out, (size_t)size * 4, "threshold_i_i"); rd_need(in, (size_t)size * 4, "threshold_i_i");
-  if (size > 0) RD_LAUNCH(k_threshold_i_i, rd_cdiv(size, B1), B1, 0, s, rd_ptr<int>(out), rd_ptr<int>(in), vlow, threshold, vhigh, size);
+  if (size > 0) RD_LAUNCH(k_threshold_i_i, rd_gy(rd_cdiv(size, B1), nb), B1, 0, s, rd_ptr<int>(out), rd_ptr<int>(in), vlow, threshold, vhigh, size, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_threshold_f_f(oclimgutil_t *thiz, cl_mem out, cl_mem in, float vlow, float threshold, float vhigh, int size, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   rd_need(out, (size_t)size * 4, "threshold_f_f"); rd_need(in, (size_t)size * 4, "threshold_f_f");
-  if (size > 0) RD_LAUNCH(k_threshold_f_f, rd_cdiv(size, B1), B1, 0, s, rd_ptr<float>(out), rd_ptr<float>(in), vlow, threshold, vhigh, size);
+  if (size > 0) RD_LAUNCH(k_threshold_f_f, rd_gy(rd_cdiv(size, B1), nb), B1, 0, s, rd_ptr<float>(out), rd_ptr<float>(in), vlow, threshold, vhigh, size, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_rand(oclimgutil_t *thiz, cl_mem out, int size, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   size = (size + 3) / 4;                                                      // oclimgutil.c:181 ; seed 0 (the reference passes none)
   rd_need(out, (size_t)size * 4, "rand");
-  rd_k_rand(rd_ptr<int>(out), 0, size, s);
+  rd_k_rand(rd_ptr<int>(out), 0, size, 1, 0, s);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_convert_plab_bgr(oclimgutil_t *thiz, cl_mem out, cl_mem in, int iw, int ih, int ws, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;                                                                // runs bgr2plab (Q9)
   rd_need(out, (size_t)iw * ih * 4, "convert_plab_bgr"); rd_need(in, (size_t)ws * (ih - 1) + (size_t)iw * 3, "convert_plab_bgr");
-  RD_LAUNCH(k_bgr2plab, rd_grid2d(iw, ih, B2), B2, 0, s, rd_ptr<uint32_t>(out), rd_ptr<uint8_t>(in), iw, ih, ws);
+  RD_LAUNCH(k_bgr2plab, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<uint32_t>(out), rd_ptr<uint8_t>(in), iw, ih, ws, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_unpack_f_f_f_plab(oclimgutil_t *thiz, cl_mem out0, cl_mem out1, cl_mem out2, cl_mem in, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   const size_t P = (size_t)iw * ih * 4;
   rd_need(out0, P, "unpack"); rd_need(out1, P, "unpack"); rd_need(out2, P, "unpack"); rd_need(in, P, "unpack");
-  RD_LAUNCH(k_unpack_plab, rd_cdiv(iw * ih, B1), B1, 0, s, rd_ptr<float>(out0), rd_ptr<float>(out1), rd_ptr<float>(out2), rd_ptr<uint32_t>(in), iw * ih);
+  RD_LAUNCH(k_unpack_plab, rd_gy(rd_cdiv(iw * ih, B1), nb), B1, 0, s, rd_ptr<float>(out0), rd_ptr<float>(out1), rd_ptr<float>(out2), rd_ptr<uint32_t>(in), iw * ih, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_pack_plab_f_f_f(oclimgutil_t *thiz, cl_mem out, cl_mem in0, cl_mem in1, cl_mem in2, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   const size_t P = (size_t)iw * ih * 4;
   rd_need(out, P, "pack"); rd_need(in0, P, "pack"); rd_need(in1, P, "pack"); rd_need(in2, P, "pack");
-  RD_LAUNCH(k_pack_plab, rd_cdiv(iw * ih, B1), B1, 0, s, rd_ptr<uint32_t>(out), rd_ptr<float>(in0), rd_ptr<float>(in1), rd_ptr<float>(in2), iw * ih);
+  RD_LAUNCH(k_pack_plab, rd_gy(rd_cdiv(iw * ih, B1), nb), B1, 0, s, rd_ptr<uint32_t>(out), rd_ptr<float>(in0), rd_ptr<float>(in1), rd_ptr<float>(in2), iw * ih, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_iirblur_f_f(oclimgutil_t *thiz, cl_mem obuf, cl_mem ibuf, cl_mem tmp0, cl_mem tmp1, int r, int iw, int ih, cl_command_queue queue, const cl_event *events) {
@@ -257,45 +276,45 @@ cl_event oclimgutil_iirblur_f_f(oclimgutil_t *thiz, cl_mem obuf, cl_mem ibuf, cl
   const size_t P = (size_t)iw * ih * 4;
   rd_need(obuf, P, "iirblur"); rd_need(ibuf, P, "iirblur"); rd_need(tmp0, P, "iirblur"); rd_need(tmp1, P, "iirblur");
   if (r < 0 || r >= 32) exitf(-1, "rectdetect_b200: iirblur radius %d out of range\n", r);
-  rd_k_iirblur(rd_ptr<float>(obuf), rd_ptr<float>(ibuf), rd_ptr<float>(tmp0), rd_ptr<float>(tmp1), r, iw, ih, s);
+  rd_k_iirblur(rd_ptr<float>(obuf), rd_ptr<float>(ibuf), rd_ptr<float>(tmp0), rd_ptr<float>(tmp1), r, iw, ih, 1, 0, s);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_edgevec_f2_f(oclimgutil_t *thiz, cl_mem out, cl_mem in, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   rd_need(out, (size_t)iw * ih * 8, "edgevec"); rd_need(in, (size_t)iw * ih * 4, "edgevec");
-  RD_LAUNCH(k_edgevec_f, rd_grid2d(iw, ih, B2), B2, 0, s, rd_ptr<float2>(out), rd_ptr<float>(in), iw, ih);
+  RD_LAUNCH(k_edgevec_f, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<float2>(out), rd_ptr<float>(in), iw, ih, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_edge_f_plab(oclimgutil_t *thiz, cl_mem out, cl_mem in, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   rd_need(out, (size_t)iw * ih * 4, "edge_f_plab"); rd_need(in, (size_t)iw * ih * 4, "edge_f_plab");
-  RD_LAUNCH(k_edge_plab, rd_grid2d(iw, ih, B2), B2, 0, s, rd_ptr<float>(out), rd_ptr<uint32_t>(in), iw, ih);
+  RD_LAUNCH(k_edge_plab, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<float>(out), rd_ptr<uint32_t>(in), iw, ih, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_thinthres_f_f_f2(oclimgutil_t *thiz, cl_mem out, cl_mem in, cl_mem vec, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   rd_need(out, (size_t)iw * ih * 4, "thinthres"); rd_need(in, (size_t)iw * ih * 4, "thinthres"); rd_need(vec, (size_t)iw * ih * 8, "thinthres");
-  RD_LAUNCH(k_thinthres, rd_grid2d(iw, ih, B2), B2, 0, s, rd_ptr<float>(out), rd_ptr<float>(in), rd_ptr<float2>(vec), iw, ih);
+  RD_LAUNCH(k_thinthres, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<float>(out), rd_ptr<float>(in), rd_ptr<float2>(vec), iw, ih, fs);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_label8x_int_int(oclimgutil_t *thiz, cl_mem out, cl_mem in, cl_mem tmp, int bgc, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;                                                                // converged labels; tmp holds the per-pixel link bytes
   rd_need(out, (size_t)iw * ih * 4, "label8x"); rd_need(in, (size_t)iw * ih * 4, "label8x"); rd_need(tmp, (size_t)iw * ih, "label8x tmp");
-  rd_label8x(rd_ptr<int>(out), rd_ptr<int>(in), tmp->dptr, bgc, iw, ih, s);
+  rd_label8x(rd_ptr<int>(out), rd_ptr<int>(in), tmp->dptr, bgc, iw, ih, 1, 0, s);
   return rd_make_event(s, events);
 }
 cl_event oclimgutil_calcStrength(oclimgutil_t *thiz, cl_mem out, cl_mem edge, cl_mem label, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   const size_t P = (size_t)iw * ih * 4;
   rd_need(out, P, "calcStrength"); rd_need(edge, P, "calcStrength"); rd_need(label, P, "calcStrength");
-  RD_LAUNCH(k_calcStrength, rd_grid2d(iw, ih, B2), B2, 0, s, rd_ptr<int>(out), rd_ptr<float>(edge), rd_ptr<int>(label), iw, ih);
+  RD_LAUNCH(k_calcStrength, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<int>(out), rd_ptr<float>(edge), rd_ptr<int>(label), iw, ih, fs);
   return NULL;                                                                // oclimgutil.c:311-314 always passes NULL events
 }
 cl_event oclimgutil_filterStrength(oclimgutil_t *thiz, cl_mem labelinout, cl_mem str, int thre, int iw, int ih, cl_command_queue queue, const cl_event *events) {
   OP_PROLOGUE;
   const size_t P = (size_t)iw * ih * 4;
   rd_need(labelinout, P, "filterStrength"); rd_need(str, P, "filterStrength");
-  RD_LAUNCH(k_filterStrength, rd_grid2d(iw, ih, B2), B2, 0, s, rd_ptr<int>(labelinout), rd_ptr<int>(str), thre, iw, ih);
+  RD_LAUNCH(k_filterStrength, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<int>(labelinout), rd_ptr<int>(str), thre, iw, ih, fs);
   return NULL;
 }
 

@@ -30,14 +30,15 @@ static_assert(sizeof(LS_t) == 56 && sizeof(LSX_t) == 56, "list entries are 56 by
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
 #define IS_BORDER1 (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1)
 
-void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, cudaStream_t s);
-void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, cudaStream_t s);
-void rd_k_clear(int *out, int nints, cudaStream_t s);
-void rd_k_copy(int *out, const int *in, int nints, cudaStream_t s);
-void rd_k_rand(int *out, uint64_t seed, int n, cudaStream_t s);
+void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_k_clear(int *out, int nints, int nb, size_t fs, cudaStream_t s);
+void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream_t s);
+void rd_k_rand(int *out, uint64_t seed, int n, int nb, size_t fs, cudaStream_t s);
 
 // ---------------------------------------------------------------------------- string clean-up (oclpolyline.cl:66-147)
-__global__ void kp_simpleJunction(int *out, const int *in, int iw, int ih) {
+__global__ void kp_simpleJunction(int *out, const int *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   int r = 0;
   if (!IS_BORDER1 && in[p0] != 0) {
@@ -49,7 +50,8 @@ __global__ void kp_simpleJunction(int *out, const int *in, int iw, int ih) {
   out[p0] = r;
 }
 // the 2-pixel frame of `out` is left untouched, as in the reference (oclpolyline.cl:91)
-__global__ void kp_simpleConnect(int *out, const int *in, int iw, int ih) {
+__global__ void kp_simpleConnect(int *out, const int *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   if (x <= 1 || y <= 1 || x >= iw - 2 || y >= ih - 2) return;
   int r = in[p0] != 0 ? 1 : 0;
@@ -65,7 +67,8 @@ __global__ void kp_simpleConnect(int *out, const int *in, int iw, int ih) {
   }
   out[p0] = r;
 }
-__global__ void kp_stringify(int *out, const int *in, int mod2, int iw, int ih) {
+__global__ void kp_stringify(int *out, const int *in, int mod2, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   int r = in[p0];
   if (!IS_BORDER1 && ((x + y) & 1) == mod2) {
@@ -74,7 +77,8 @@ __global__ void kp_stringify(int *out, const int *in, int mod2, int iw, int ih) 
   }
   out[p0] = r;
 }
-__global__ void kp_removeBranch(int *out, const int *in, int iw, int ih) {
+__global__ void kp_removeBranch(int *out, const int *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   int r = 0;
   if (!IS_BORDER1 && in[p0] != 0) {
@@ -86,12 +90,14 @@ __global__ void kp_removeBranch(int *out, const int *in, int iw, int ih) {
   out[p0] = r;
 }
 // oclpolyline.cl:149-167 ; the reference's non-atomic ++ is only ever compared with 0 (Q7)
-__global__ void kp_countEnds(int *out, const int *junction, const int *label, int iw, int ih) {
+__global__ void kp_countEnds(int *out, const int *junction, const int *label, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, junction, label);
   XY2D;
   if (IS_BORDER1) return;
   if (junction[p0] == 2) out[label[p0]] = 1;
 }
-__global__ void kp_breakLoops(int *edgeinout, int *labelinout, const int *nEnds, int iw, int ih) {
+__global__ void kp_breakLoops(int *edgeinout, int *labelinout, const int *nEnds, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, edgeinout, labelinout, nEnds);
   XY2D;
   if (IS_BORDER1) return;
   if (labelinout[p0] != p0) return;
@@ -107,7 +113,8 @@ __device__ __forceinline__ void getnp(const int *labelin, int p0, int iw, int &n
   for (i++; i < 8; i++) if (labelin[p0 + RD_RX[i] + RD_RY[i] * iw] == l) break;
   ny = i < 8 ? (p0 + RD_RX[i] + RD_RY[i] * iw) : p0;
 }
-__global__ void kp_findEnds0(int *nextout, int *prevout, int *flagout, const int *labelin, int iw, int ih) {
+__global__ void kp_findEnds0(int *nextout, int *prevout, int *flagout, const int *labelin, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, nextout, prevout, flagout, labelin);
   XY2D;
   int nx = -1, pv = -1, flag = -1;
   if (!IS_BORDER1 && labelin[p0] != -1) {
@@ -121,7 +128,8 @@ __global__ void kp_findEnds0(int *nextout, int *prevout, int *flagout, const int
 }
 // A launch reads one pair of flag bits of other pixels and rewrites only the other pair of its own pixel, so the
 // in-place update of flaginout is race free (the reads are volatile to keep them from being cached in registers).
-__global__ void kp_findEnds1(int *nextout, int *prevout, int *flaginout, const int *nextin, const int *previn, const int *labelin, int page, int iw, int ih) {
+__global__ void kp_findEnds1(int *nextout, int *prevout, int *flaginout, const int *nextin, const int *previn, const int *labelin, int page, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, nextout, prevout, flaginout, nextin, previn, labelin);
   XY2D;
   int nn = -1, pp = -1;
   if (!IS_BORDER1 && labelin[p0] != -1) {
@@ -146,7 +154,8 @@ __global__ void kp_findEnds1(int *nextout, int *prevout, int *flaginout, const i
   }
   nextout[p0] = nn; prevout[p0] = pp;
 }
-__global__ void kp_findEnds2(int *numout, int *linkout, const int *nextin, const int *previn, const int *labelin, int iw, int ih) {
+__global__ void kp_findEnds2(int *numout, int *linkout, const int *nextin, const int *previn, const int *labelin, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, numout, linkout, nextin, previn, labelin);
   XY2D;
   int num = 0, link = -1;
   if (!IS_BORDER1 && labelin[p0] != -1) {
@@ -157,7 +166,8 @@ __global__ void kp_findEnds2(int *numout, int *linkout, const int *nextin, const
   }
   numout[p0] = num; linkout[p0] = link;
 }
-__global__ void kp_number(int *numout, int *linkout, const int *numin, const int *linkin, int iw, int ih) {
+__global__ void kp_number(int *numout, int *linkout, const int *numin, const int *linkin, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, numout, linkout, numin, linkin);
   XY2D;
   int no = 0, lo = -1;
   if (!IS_BORDER1) {
@@ -178,17 +188,20 @@ __global__ void kp_number(int *numout, int *linkout, const int *numin, const int
 }
 
 // ---------------------------------------------------------------------------- labelpl pre-step, sizes (oclpolyline.cl:312-378)
-__global__ void kp_plus1(int *out, const int *in, int n) {          // labelpl_preprocess: pix = number + 1 where number != 0
+__global__ void kp_plus1(int *out, const int *in, int n, size_t fs) {
+  rd_batch_y(fs, out, in);          // labelpl_preprocess: pix = number + 1 where number != 0
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const int v = in[i]; out[i] = v == 0 ? 0 : v + 1; }
 }
-__global__ void kp_calcSize(int *out, const int *label, int n) {
+__global__ void kp_calcSize(int *out, const int *label, int n, size_t fs) {
+  rd_batch_y(fs, out, label);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int b = label[i];
   if (b != 0) atomicAdd(out + b, 1);
 }
-__global__ void kp_filterSize(int *out, const int *labelin, const int *sizein, int sizethre, int n) {
+__global__ void kp_filterSize(int *out, const int *labelin, const int *sizein, int sizethre, int n, size_t fs) {
+  rd_batch_y(fs, out, labelin, sizein);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int b = labelin[i];
@@ -204,7 +217,8 @@ __device__ __forceinline__ bool is_root(const int *label, int p, int iw, int ih)
   const int g = label[p];
   return g != 0 && g == p;
 }
-__global__ void kp_relabel_count(int *blockCount, const int *label, int iw, int ih) {
+__global__ void kp_relabel_count(int *blockCount, const int *label, int iw, int ih, size_t fs) {
+  rd_batch_y(fs, blockCount, label);
   __shared__ int wsum[RL_BLOCK / 32];
   const int p = blockIdx.x * RL_BLOCK + threadIdx.x;
   const bool r = p < iw * ih && is_root(label, p, iw, ih);
@@ -219,7 +233,8 @@ __global__ void kp_relabel_count(int *blockCount, const int *label, int iw, int 
   }
 }
 // exclusive scan of blockCount in place (single CTA, chunked with a running carry); total -> *total
-__global__ void kp_scan_blocks(int *blockCount, int nblocks, int *total) {
+__global__ void kp_scan_blocks(int *blockCount, int nblocks, int *total, size_t fs) {
+  rd_batch_x(fs, blockCount, total);
   __shared__ int wsum[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -247,7 +262,8 @@ __global__ void kp_scan_blocks(int *blockCount, int nblocks, int *total) {
   }
   if (threadIdx.x == 0) *total = carry;
 }
-__global__ void kp_relabel_rank(int *table, const int *blockOffset, const int *label, int iw, int ih) {
+__global__ void kp_relabel_rank(int *table, const int *blockOffset, const int *label, int iw, int ih, size_t fs) {
+  rd_batch_y(fs, table, blockOffset, label);
   __shared__ int wsum[RL_BLOCK / 32];
   const int p = blockIdx.x * RL_BLOCK + threadIdx.x;
   const bool r = p < iw * ih && is_root(label, p, iw, ih);
@@ -264,7 +280,8 @@ __global__ void kp_relabel_rank(int *table, const int *blockOffset, const int *l
   __syncthreads();
   if (r) table[p + 1] = blockOffset[blockIdx.x] + wsum[w] + __popc(b & ((1u << lane) - 1)) + 1;
 }
-__global__ void kp_relabel_pass1(int *labelinout, const int *tablein, int iw, int ih) {
+__global__ void kp_relabel_pass1(int *labelinout, const int *tablein, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, labelinout, tablein);
   XY2D;
   if (x == 0 || y == 0 || x >= iw - 1 || y >= ih - 1) { labelinout[p0] = 0; return; }
   const int g = labelinout[p0];
@@ -291,7 +308,8 @@ __device__ __forceinline__ void closestPoint(float vx, float vy, float wx, float
 
 // pass0a: per-string start pixel (the LAST pixel in raster order whose number is 1, as a sequential sweep leaves it),
 // pixel count, largest number, and the list header (largest id).  aux[g] / aux[cap+g] : start / end pixel index.
-__global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int *flags, int maxIter, int iw, int ih) {
+__global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int *flags, int maxIter, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, gp, aux, numberin, labelin, flags);
   XY2D;
   if (y == 0 && x < maxIter + 1) flags[x] = x == 0 ? 1 : 0;
   if (IS_BORDER1) return;
@@ -302,7 +320,8 @@ __global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, cons
   atomicMax(&gp[g].endIndex, n);
   atomicMax((int *)gp, g);
 }
-__global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int iw, int ih) {
+__global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, gp, aux, numberin, labelin);
   XY2D;
   if (IS_BORDER1) return;
   const int g = labelin[p0], n = numberin[p0];
@@ -313,7 +332,8 @@ __global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, cons
   }
 }
 // one thread per list entry: turn the start / end pixel indices into coordinates
-__global__ void kp_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw) {
+__global__ void kp_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw, size_t fs) {
+  rd_batch_y(fs, gp, aux);
   const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
   if (g > *(const int *)gp || g >= cap) return;
   const int sp = aux[g] - 1, ep = aux[cap + g];
@@ -321,12 +341,14 @@ __global__ void kp_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw) {
   if (ep >= 0 && ep != 0x7fffffff) { gp[g].x1 = (float)(ep % iw); gp[g].y1 = (float)(ep / iw); gp[g].polyid = g; }
   else gp[g].polyid = 0;
 }
-__global__ void kp_fill(int *out, int v, int n) {
+__global__ void kp_fill(int *out, int v, int n, size_t fs) {
+  rd_batch_y(fs, out);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = v;
 }
 
-__global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *tmp, const int *labelin, const int *randin, const int *flags, int nIter, int iw, int ih) {
+__global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *tmp, const int *labelin, const int *randin, const int *flags, int nIter, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, gp, tmp, labelin, randin, flags);
   if (flags[nIter - 1] == 0) return;
   XY2D;
   const int g = labelin[p0];
@@ -341,7 +363,8 @@ __global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *tmp, const int *lab
   atomicMax(&gp[g].maxDist, dist);
 }
 // pass2a: winner[g] = smallest pixel index attaining maxDist
-__global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, const int *tmp, const int *labelin, const int *flags, int nIter, int iw, int ih) {
+__global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, const int *tmp, const int *labelin, const int *flags, int nIter, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, gp, winner, tmp, labelin, flags);
   if (flags[nIter - 1] == 0) return;
   XY2D;
   const int g = labelin[p0];
@@ -353,7 +376,8 @@ __global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, cons
 }
 // pass2b: single CTA; decides the splits of this iteration, numbers the new entries by a prefix sum over the
 // parent id and rewrites the list.  Also resets winner[] for the next iteration.
-__global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize, int *winner, const int *numberin, const int *flags, int nIter, float minerror, int iw) {
+__global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize, int *winner, const int *numberin, const int *flags, int nIter, float minerror, int iw, size_t fs) {
+  rd_batch_x(fs, gp, winner, numberin, flags);
   if (flags[nIter - 1] == 0) return;
   __shared__ int wsum[32];
   __shared__ int carry, total;
@@ -416,7 +440,8 @@ __global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize,
   }
   if (threadIdx.x == 0) *(int *)gp = carry;
 }
-__global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, int *flags, int nIter, int n) {
+__global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, int *flags, int nIter, int n, size_t fs) {
+  rd_batch_y(fs, gp, numberin, labelinout, flags);
   if (flags[nIter - 1] == 0) return;
   const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (p0 >= n) return;
@@ -427,7 +452,8 @@ __global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberi
 }
 
 // ---------------------------------------------------------------------------- refine (oclpolyline.cl:680-809)
-__global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls) {
+__global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls, size_t fs) {
+  rd_batch_y(fs, lsx, ls);
   const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
   if (g > *(const int *)ls) return;
   if (ls[g].polyid == 0) return;
@@ -441,7 +467,8 @@ __global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls) {
   v.padding = 0;
   lsx[g] = v;
 }
-__global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, int iw, int ih) {
+__global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, lsx, ls, lsIdIn);
   XY2D;
   const int g = lsIdIn[p0];
   if (g == 0) return;
@@ -457,7 +484,8 @@ __global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, i
   atomicAdd((ull *)&lsx[g].my0, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ay)));
   atomicAdd((ull *)&lsx[g].my1, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ay)));
 }
-__global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls) {
+__global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls, size_t fs) {
+  rd_batch_y(fs, lsx, ls);
   const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
   if (g > *(const int *)ls) return;
   if (ls[g].polyid == 0) return;
@@ -474,7 +502,8 @@ __global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls) {
   ls[g].y1 = __fadd_rn(ls[g].y1, __fmul_rn(vy, as01));
 }
 // pass3a computes the vertex g shares with its right neighbour from the unmodified list; pass3b writes it to both
-__global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls) {
+__global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls, size_t fs) {
+  rd_batch_y(fs, vtx, ls);
   const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
   if (g > *(const int *)ls) return;
   float2 r = make_float2(__int_as_float(0x7fc00000), 0.0f);     // NaN = nothing to write
@@ -495,7 +524,8 @@ __global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls) {
   }
   vtx[g] = r;
 }
-__global__ void kp_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot) {
+__global__ void kp_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot, size_t fs) {
+  rd_batch_y(fs, vtx, ls, rightPtrSnapshot);
   const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
   if (g > *(const int *)ls) return;
   (void)rightPtrSnapshot;
@@ -514,49 +544,49 @@ static const dim3 PB(32, 8);
 #define G2 rd_grid2d(iw, ih, PB)
 
 void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *tmpBig, int *tmp0, int *tmp1, int *tmp2, int *tmp3,
-                     int *tmp4, int *tmp5, float minerror, int sizeThre, int iw, int ih, cudaStream_t s) {
+                     int *tmp4, int *tmp5, float minerror, int sizeThre, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   const int n = iw * ih;
   const int g1 = rd_cdiv(n, 256);
   // step 1 : clean strings
-  RD_LAUNCH(kp_simpleJunction, G2, PB, 0, s, lsIdOut, in, iw, ih);
-  RD_LAUNCH(kp_simpleConnect, G2, PB, 0, s, tmp2, lsIdOut, iw, ih);
-  RD_LAUNCH(kp_stringify, G2, PB, 0, s, tmp1, tmp2, 0, iw, ih);
-  RD_LAUNCH(kp_stringify, G2, PB, 0, s, tmp2, tmp1, 1, iw, ih);
-  RD_LAUNCH(kp_removeBranch, G2, PB, 0, s, tmp1, tmp2, iw, ih);
+  RD_LAUNCH(kp_simpleJunction, rd_gz(G2, nb), PB, 0, s, lsIdOut, in, iw, ih, fs);
+  RD_LAUNCH(kp_simpleConnect, rd_gz(G2, nb), PB, 0, s, tmp2, lsIdOut, iw, ih, fs);
+  RD_LAUNCH(kp_stringify, rd_gz(G2, nb), PB, 0, s, tmp1, tmp2, 0, iw, ih, fs);
+  RD_LAUNCH(kp_stringify, rd_gz(G2, nb), PB, 0, s, tmp2, tmp1, 1, iw, ih, fs);
+  RD_LAUNCH(kp_removeBranch, rd_gz(G2, nb), PB, 0, s, tmp1, tmp2, iw, ih, fs);
   // step 2 : string id = smallest pixel index
-  rd_label8x(lsIdOut, tmp1, tmp2, 0, iw, ih, s);
+  rd_label8x(lsIdOut, tmp1, tmp2, 0, iw, ih, nb, fs, s);
   // step 3 : closed loops lose their root pixel
-  RD_LAUNCH(kp_simpleJunction, G2, PB, 0, s, tmp2, tmp1, iw, ih);
-  rd_k_clear(tmp3, n, s);
-  RD_LAUNCH(kp_countEnds, G2, PB, 0, s, tmp3, tmp2, lsIdOut, iw, ih);
-  RD_LAUNCH(kp_breakLoops, G2, PB, 0, s, tmp1, lsIdOut, tmp3, iw, ih);
+  RD_LAUNCH(kp_simpleJunction, rd_gz(G2, nb), PB, 0, s, tmp2, tmp1, iw, ih, fs);
+  rd_k_clear(tmp3, n, nb, fs, s);
+  RD_LAUNCH(kp_countEnds, rd_gz(G2, nb), PB, 0, s, tmp3, tmp2, lsIdOut, iw, ih, fs);
+  RD_LAUNCH(kp_breakLoops, rd_gz(G2, nb), PB, 0, s, tmp1, lsIdOut, tmp3, iw, ih, fs);
   // steps 4-6 : string ends by orientation-aware pointer jumping (8 hops x 4 launches)
-  RD_LAUNCH(kp_findEnds0, G2, PB, 0, s, tmp0, tmp2, tmpBig, lsIdOut, iw, ih);
-  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp3, tmp4, tmpBig, tmp0, tmp2, lsIdOut, 0, iw, ih);
-  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp0, tmp2, tmpBig, tmp3, tmp4, lsIdOut, 1, iw, ih);
-  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp3, tmp4, tmpBig, tmp0, tmp2, lsIdOut, 0, iw, ih);
-  RD_LAUNCH(kp_findEnds1, G2, PB, 0, s, tmp0, tmp2, tmpBig, tmp3, tmp4, lsIdOut, 1, iw, ih);
-  RD_LAUNCH(kp_findEnds2, G2, PB, 0, s, tmpBig, tmp4, tmp0, tmp2, lsIdOut, iw, ih);
+  RD_LAUNCH(kp_findEnds0, rd_gz(G2, nb), PB, 0, s, tmp0, tmp2, tmpBig, lsIdOut, iw, ih, fs);
+  RD_LAUNCH(kp_findEnds1, rd_gz(G2, nb), PB, 0, s, tmp3, tmp4, tmpBig, tmp0, tmp2, lsIdOut, 0, iw, ih, fs);
+  RD_LAUNCH(kp_findEnds1, rd_gz(G2, nb), PB, 0, s, tmp0, tmp2, tmpBig, tmp3, tmp4, lsIdOut, 1, iw, ih, fs);
+  RD_LAUNCH(kp_findEnds1, rd_gz(G2, nb), PB, 0, s, tmp3, tmp4, tmpBig, tmp0, tmp2, lsIdOut, 0, iw, ih, fs);
+  RD_LAUNCH(kp_findEnds1, rd_gz(G2, nb), PB, 0, s, tmp0, tmp2, tmpBig, tmp3, tmp4, lsIdOut, 1, iw, ih, fs);
+  RD_LAUNCH(kp_findEnds2, rd_gz(G2, nb), PB, 0, s, tmpBig, tmp4, tmp0, tmp2, lsIdOut, iw, ih, fs);
   // step 7 : distance from the start by list ranking (32 hops x 3 launches)
-  RD_LAUNCH(kp_number, G2, PB, 0, s, tmp2, tmp3, tmpBig, tmp4, iw, ih);
-  RD_LAUNCH(kp_number, G2, PB, 0, s, tmpBig, tmp4, tmp2, tmp3, iw, ih);
-  RD_LAUNCH(kp_number, G2, PB, 0, s, tmp2, tmp3, tmpBig, tmp4, iw, ih);
+  RD_LAUNCH(kp_number, rd_gz(G2, nb), PB, 0, s, tmp2, tmp3, tmpBig, tmp4, iw, ih, fs);
+  RD_LAUNCH(kp_number, rd_gz(G2, nb), PB, 0, s, tmpBig, tmp4, tmp2, tmp3, iw, ih, fs);
+  RD_LAUNCH(kp_number, rd_gz(G2, nb), PB, 0, s, tmp2, tmp3, tmpBig, tmp4, iw, ih, fs);
   // step 8 : split touching strings (numbers differing by more than 1 are not connected)
-  RD_LAUNCH(kp_plus1, g1, 256, 0, s, tmp1, tmp2, n);
-  rd_labelpl(tmpBig, tmp1, tmp3, iw, ih, s);
+  RD_LAUNCH(kp_plus1, rd_gy(g1, nb), 256, 0, s, tmp1, tmp2, n, fs);
+  rd_labelpl(tmpBig, tmp1, tmp3, iw, ih, nb, fs, s);
   // step 9 : drop short strings
-  rd_k_clear(tmp1, n, s);
-  RD_LAUNCH(kp_calcSize, g1, 256, 0, s, tmp1, tmpBig, n);
-  RD_LAUNCH(kp_filterSize, g1, 256, 0, s, lsIdOut, tmpBig, tmp1, sizeThre, n);
+  rd_k_clear(tmp1, n, nb, fs, s);
+  RD_LAUNCH(kp_calcSize, rd_gy(g1, nb), 256, 0, s, tmp1, tmpBig, n, fs);
+  RD_LAUNCH(kp_filterSize, rd_gy(g1, nb), 256, 0, s, lsIdOut, tmpBig, tmp1, sizeThre, n, fs);
   // step 10 : compact ids 1..K in raster order of the root pixels.  table = tmpBig[0..n], block counts behind it
   {
     int *table = tmpBig, *blockCount = tmpBig + 2 * (size_t)n;
-    const int nb = rd_cdiv(n, RL_BLOCK);
-    rd_k_clear(tmpBig, n + 1, s);
-    RD_LAUNCH(kp_relabel_count, nb, RL_BLOCK, 0, s, blockCount, lsIdOut, iw, ih);
-    RD_LAUNCH(kp_scan_blocks, 1, 1024, 0, s, blockCount, nb, table);
-    RD_LAUNCH(kp_relabel_rank, nb, RL_BLOCK, 0, s, table, blockCount, lsIdOut, iw, ih);
-    RD_LAUNCH(kp_relabel_pass1, G2, PB, 0, s, lsIdOut, table, iw, ih);
+    const int nblk = rd_cdiv(n, RL_BLOCK);
+    rd_k_clear(tmpBig, n + 1, nb, fs, s);
+    RD_LAUNCH(kp_relabel_count, rd_gy(nblk, nb), RL_BLOCK, 0, s, blockCount, lsIdOut, iw, ih, fs);
+    RD_LAUNCH(kp_scan_blocks, dim3(nb), 1024, 0, s, blockCount, nblk, table, fs);
+    RD_LAUNCH(kp_relabel_rank, rd_gy(nblk, nb), RL_BLOCK, 0, s, table, blockCount, lsIdOut, iw, ih, fs);
+    RD_LAUNCH(kp_relabel_pass1, rd_gz(G2, nb), PB, 0, s, lsIdOut, table, iw, ih, fs);
   }
   // step 11 : mkpl.  aux (start / end pixel per string) and winner live in tmpBig; cap entries each
   {
@@ -564,18 +594,18 @@ void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, 
     int *aux = tmpBig, *winner = tmpBig + 2 * (size_t)cap;
     int *flags = tmp4, *dist = tmp3, *rnd = tmp5;
     const int N = 16;
-    rd_k_clear((int *)lsList, (lsListSize + 3) / 4, s);
-    rd_k_clear(aux, cap, s);
-    RD_LAUNCH(kp_fill, rd_cdiv(2 * cap, 256), 256, 0, s, aux + cap, 0x7fffffff, 2 * cap);      // end pixel (min) and winner (min)
-    RD_LAUNCH(kp_mkpl_pass0a, G2, PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, flags, N, iw, ih);
-    RD_LAUNCH(kp_mkpl_pass0b, G2, PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, iw, ih);
-    RD_LAUNCH(kp_mkpl_pass0c, rd_cdiv(cap, 256), 256, 0, s, lsList, aux, cap, iw);
-    rd_k_rand(rnd, 0, n, s);
+    rd_k_clear((int *)lsList, (lsListSize + 3) / 4, nb, fs, s);
+    rd_k_clear(aux, cap, nb, fs, s);
+    RD_LAUNCH(kp_fill, rd_gy(rd_cdiv(2 * cap, 256), nb), 256, 0, s, aux + cap, 0x7fffffff, 2 * cap, fs);      // end pixel (min) and winner (min)
+    RD_LAUNCH(kp_mkpl_pass0a, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, flags, N, iw, ih, fs);
+    RD_LAUNCH(kp_mkpl_pass0b, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, iw, ih, fs);
+    RD_LAUNCH(kp_mkpl_pass0c, rd_gy(rd_cdiv(cap, 256), nb), 256, 0, s, lsList, aux, cap, iw, fs);
+    rd_k_rand(rnd, 0, n, nb, fs, s);
     for (int i = 0; i < N - 1; i++) {
-      RD_LAUNCH(kp_mkpl_pass1, G2, PB, 0, s, lsList, lsListSize, dist, lsIdOut, rnd, flags, i + 1, iw, ih);
-      RD_LAUNCH(kp_mkpl_pass2a, G2, PB, 0, s, lsList, lsListSize, winner, dist, lsIdOut, flags, i + 1, iw, ih);
-      RD_LAUNCH(kp_mkpl_pass2b, 1, 1024, 0, s, lsList, lsListSize, winner, tmp2, flags, i + 1, minerror, iw);
-      RD_LAUNCH(kp_mkpl_pass3, g1, 256, 0, s, lsList, lsListSize, tmp2, lsIdOut, flags, i + 1, n);
+      RD_LAUNCH(kp_mkpl_pass1, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, dist, lsIdOut, rnd, flags, i + 1, iw, ih, fs);
+      RD_LAUNCH(kp_mkpl_pass2a, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, winner, dist, lsIdOut, flags, i + 1, iw, ih, fs);
+      RD_LAUNCH(kp_mkpl_pass2b, dim3(nb), 1024, 0, s, lsList, lsListSize, winner, tmp2, flags, i + 1, minerror, iw, fs);
+      RD_LAUNCH(kp_mkpl_pass3, rd_gy(g1, nb), 256, 0, s, lsList, lsListSize, tmp2, lsIdOut, flags, i + 1, n, fs);
     }
   }
   // step 12 : sub-pixel refinement.  LSX mirror of the list in tmpBig, shared vertices in tmp3
@@ -584,11 +614,11 @@ void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, 
     LSX_t *lsx = (LSX_t *)tmpBig;
     float2 *vtx = (float2 *)tmp3;                                 // the distance plane is dead after mkpl; 8 B x (count+1) <= P
     const int gl = rd_cdiv(cap, 256);
-    RD_LAUNCH(kp_refine_pass0, gl, 256, 0, s, lsx, lsList);
-    RD_LAUNCH(kp_refine_pass1, G2, PB, 0, s, lsx, lsList, lsIdOut, iw, ih);
-    RD_LAUNCH(kp_refine_pass2, gl, 256, 0, s, lsx, lsList);
-    RD_LAUNCH(kp_refine_pass3a, gl, 256, 0, s, vtx, lsList);
-    RD_LAUNCH(kp_refine_pass3b, gl, 256, 0, s, vtx, lsList, (const int *)NULL);
+    RD_LAUNCH(kp_refine_pass0, rd_gy(gl, nb), 256, 0, s, lsx, lsList, fs);
+    RD_LAUNCH(kp_refine_pass1, rd_gz(G2, nb), PB, 0, s, lsx, lsList, lsIdOut, iw, ih, fs);
+    RD_LAUNCH(kp_refine_pass2, rd_gy(gl, nb), 256, 0, s, lsx, lsList, fs);
+    RD_LAUNCH(kp_refine_pass3a, rd_gy(gl, nb), 256, 0, s, vtx, lsList, fs);
+    RD_LAUNCH(kp_refine_pass3b, rd_gy(gl, nb), 256, 0, s, vtx, lsList, (const int *)NULL, fs);
   }
 }
 
@@ -621,7 +651,7 @@ cl_event oclpolyline_execute(oclpolyline_t *thiz, cl_mem lsList, int lsListSize,
   for (int i = 0; i < 6; i++) rd_need(t[i], P, "oclpolyline_execute tmp");
   if ((size_t)lsListSize > 4 * P) exitf(-1, "rectdetect_b200: oclpolyline_execute needs lsListSize <= iw*ih*16\n");
   rd_polyline_run(rd_ptr<LS_t>(lsList), lsListSize, rd_ptr<int>(lsIdOut), rd_ptr<int>(in), rd_ptr<int>(tmp0), rd_ptr<int>(tmp1), rd_ptr<int>(tmp2),
-                  rd_ptr<int>(tmp3), rd_ptr<int>(tmp4), rd_ptr<int>(tmp5), rd_ptr<int>(tmp6), minerror, sizeThre, iw, ih, s);
+                  rd_ptr<int>(tmp3), rd_ptr<int>(tmp4), rd_ptr<int>(tmp5), rd_ptr<int>(tmp6), minerror, sizeThre, iw, ih, 1, 0, s);
   return rd_make_event(s, events);
 }
 

@@ -17,13 +17,13 @@
 
 typedef linesegment_t LS_t;
 
-void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, cudaStream_t s);
-void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int iw, int ih, cudaStream_t s);
-void rd_k_clear(int *out, int nints, cudaStream_t s);
-void rd_k_copy(int *out, const int *in, int nints, cudaStream_t s);
-void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, cudaStream_t s);
+void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_k_clear(int *out, int nints, int nb, size_t fs, cudaStream_t s);
+void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream_t s);
+void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *tmpBig, int *tmp0, int *tmp1, int *tmp2, int *tmp3,
-                     int *tmp4, int *tmp5, float minerror, int sizeThre, int iw, int ih, cudaStream_t s);
+                     int *tmp4, int *tmp5, float minerror, int sizeThre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_tail_gather_host(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, rd_tail_sample *out);
 
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
@@ -31,7 +31,8 @@ static const dim3 RB(32, 8);
 #define G2 rd_grid2d(iw, ih, RB)
 
 // ---------------------------------------------------------------------------- oclrect.cl:74-135
-__global__ void kr_simpleJunction(int *out, const int *in, int iw, int ih) {
+__global__ void kr_simpleJunction(int *out, const int *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   int r = 0;
   if (!(x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) && in[p0] > 0) {
@@ -42,7 +43,8 @@ __global__ void kr_simpleJunction(int *out, const int *in, int iw, int ih) {
   }
   out[p0] = r;
 }
-__global__ void kr_simpleConnect(int *out, const int *in, int iw, int ih) {
+__global__ void kr_simpleConnect(int *out, const int *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   int r = 0;
   if (!(x <= 1 || y <= 1 || x >= iw - 2 || y >= ih - 2)) {
@@ -64,7 +66,8 @@ __global__ void kr_simpleConnect(int *out, const int *in, int iw, int ih) {
   }
   out[p0] = r;
 }
-__global__ void kr_stringify(int *out, const int *in, int mod2, int iw, int ih) {
+__global__ void kr_stringify(int *out, const int *in, int mod2, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   int r = in[p0];
   if (!(x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) && ((x + y) & 1) == mod2) {
@@ -75,7 +78,8 @@ __global__ void kr_stringify(int *out, const int *in, int mod2, int iw, int ih) 
 }
 
 // ---------------------------------------------------------------------------- oclrect.cl:137-153 (same code as oclimgutil.cl:641-657)
-__global__ void kr_calcStrength(int *out, const float *edge, const int *label, int iw, int ih) {
+__global__ void kr_calcStrength(int *out, const float *edge, const int *label, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, edge, label);
   XY2D;
   if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return;
   const int l = label[p0];
@@ -84,24 +88,28 @@ __global__ void kr_calcStrength(int *out, const float *edge, const int *label, i
   const int v = (int)__fmul_rn(__fmul_rn(e, e), 10000.0f);
   if (v != 0) atomicAdd(out + l, v);
 }
-__global__ void kr_filterStrength(int *labelinout, const int *str, int thre, int iw, int ih) {
+__global__ void kr_filterStrength(int *labelinout, const int *str, int thre, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, labelinout, str);
   XY2D;
   if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return;
   const int l = labelinout[p0];
   if (l <= 0 || str[l] < thre) labelinout[p0] = -1;
 }
-__global__ void kr_threshold_i_i(int *out, const int *in, int vlow, int thr, int vhigh, int n) {
+__global__ void kr_threshold_i_i(int *out, const int *in, int vlow, int thr, int vhigh, int n, size_t fs) {
+  rd_batch_y(fs, out, in);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] > thr ? vhigh : vlow;
 }
-__global__ void kr_threshold_cast(float *outf, int *outi, const float *in, int n) {     // threshold_f_f(0,0,1) + cast_i_f(1.0), oclrect.c:262-263
+__global__ void kr_threshold_cast(float *outf, int *outi, const float *in, int n, size_t fs) {
+  rd_batch_y(fs, outf, outi, in);     // threshold_f_f(0,0,1) + cast_i_f(1.0), oclrect.c:262-263
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float t = in[i] > 0.0f ? 1.0f : 0.0f;
   outf[i] = t;
   outi[i] = (int)t;
 }
-__global__ void kr_threshold_cast_c(int *outi, int8_t *outc, const int *in, int n) {    // threshold_i_i(0,0,1) + cast_c_i, oclrect.c:282-284
+__global__ void kr_threshold_cast_c(int *outi, int8_t *outc, const int *in, int n, size_t fs) {
+  rd_batch_y(fs, outi, outc, in);    // threshold_i_i(0,0,1) + cast_c_i, oclrect.c:282-284
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int t = in[i] > 0 ? 1 : 0;
@@ -120,7 +128,8 @@ __device__ __forceinline__ uint32_t packlabbl(int l, int a, int b) {
 // DIR 0: along x (blblur0), DIR 1: along y (blblur1).  `step` is the stride of the walk, `side` the stride of the
 // perpendicular neighbour the second stop rule looks at (row below for blblur0, column to the right for blblur1).
 template <int DIR>
-__global__ void kr_blblur(uint32_t *out, const int8_t *__restrict__ edge, const uint32_t *__restrict__ in, int iw, int ih) {
+__global__ void kr_blblur(uint32_t *out, const int8_t *edge, const uint32_t *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, edge, in);
   XY2D;
   const int pos = DIR == 0 ? x : y, len = DIR == 0 ? iw : ih;
   const int step = DIR == 0 ? 1 : iw, side = DIR == 0 ? iw : 1;
@@ -149,7 +158,8 @@ __global__ void kr_blblur(uint32_t *out, const int8_t *__restrict__ edge, const 
 }
 
 // ---------------------------------------------------------------------------- oclrect.cl:207-244
-__global__ void kr_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2, int n) {
+__global__ void kr_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2, int n, size_t fs) {
+  rd_batch_y(fs, out, in);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float l, a, b;
@@ -157,7 +167,8 @@ __global__ void kr_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, i
   out[i] = rd_packlab(__fdiv_rn(roundf(__fmul_rn(l, (float)n0)), (float)n0), __fdiv_rn(roundf(__fmul_rn(a, (float)n1)), (float)n1),
                       __fdiv_rn(roundf(__fmul_rn(b, (float)n2)), (float)n2));
 }
-__global__ void kr_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih) {
+__global__ void kr_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in, edge);
   XY2D;
   uint32_t r = in[p0];
   if (!(edge[p0] < 1e-6f)) {
@@ -179,7 +190,8 @@ __global__ void kr_despeckle(uint32_t *out, const uint32_t *in, const float *edg
 }
 
 // ---------------------------------------------------------------------------- oclrect.cl:246-287 : scatters of constants (order independent)
-__global__ void kr_mkMergeMask0(int *out, const int *junctionIn, int iw, int ih) {
+__global__ void kr_mkMergeMask0(int *out, const int *junctionIn, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, junctionIn);
   XY2D;
   if (junctionIn[p0] == 0) return;
   for (int yy = max(y - 6, 0); yy <= min(y + 6, ih - 1); yy++)
@@ -188,7 +200,8 @@ __global__ void kr_mkMergeMask0(int *out, const int *junctionIn, int iw, int ih)
       if (16 <= dsqu && dsqu < 36) out[yy * iw + xx] = 1;
     }
 }
-__global__ void kr_mkMergeMask1(int *inout, const int *junctionIn, int iw, int ih) {
+__global__ void kr_mkMergeMask1(int *inout, const int *junctionIn, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, inout, junctionIn);
   XY2D;
   const int j = junctionIn[p0];
   if (j == 0) return;
@@ -201,14 +214,16 @@ __global__ void kr_mkMergeMask1(int *inout, const int *junctionIn, int iw, int i
 }
 
 // ---------------------------------------------------------------------------- oclrect.cl:336-390
-__global__ void kr_calcSize(int *out, const int *label, int n) {
+__global__ void kr_calcSize(int *out, const int *label, int n, size_t fs) {
+  rd_batch_y(fs, out, label);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int l = label[i];
   if (l != -1) atomicAdd(out + l, 1);
 }
 // Jacobi form of despeckle2: reads the labels as they were at launch (`snap`), writes `out`
-__global__ void kr_despeckle2(int *out, const int *snap, const int *sizein, int thre, int iw, int ih) {
+__global__ void kr_despeckle2(int *out, const int *snap, const int *sizein, int thre, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, snap, sizein);
   XY2D;
   const int l0 = snap[p0];
   int res = l0;
@@ -224,7 +239,8 @@ __global__ void kr_despeckle2(int *out, const int *snap, const int *sizein, int 
   }
   out[p0] = res;
 }
-__global__ void kr_markBoundary(int *out, const int *in, int iw, int ih) {
+__global__ void kr_markBoundary(int *out, const int *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   int r = -1;
   if (!(x <= 1 || y <= 1 || x >= iw - 2 || y >= ih - 2)) {
@@ -243,7 +259,8 @@ __global__ void kr_markBoundary(int *out, const int *in, int iw, int ih) {
 // slot = ((lsid*bid) & 0x7fffffff) % nentry, no probing.  Canonical: the smallest lsid that wants a slot
 // owns it and all of its hits are recorded.  Phase 0 claims, phase 1 accumulates the four maxima.
 template <int PHASE>
-__global__ void kr_reduceLS(int *out, const int *__restrict__ boundaryin, const int *__restrict__ lsidin, int iw, int ih, int nentry) {
+__global__ void kr_reduceLS(int *out, const int *boundaryin, const int *lsidin, int iw, int ih, int nentry, size_t fs) {
+  rd_batch_z(fs, out, boundaryin, lsidin);
   XY2D;
   if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return;
   const int lsid = lsidin[p0];
@@ -279,7 +296,8 @@ __global__ void kr_reduceLS(int *out, const int *__restrict__ boundaryin, const 
 // ---------------------------------------------------------------------------- read-back record for the host tail
 // Blob layout: [0] int n, [1] int n_gathered, ... 64-byte header; LS_t[n_g+1] at byte 64; rd_tail_sample[(n_g+1)*15] behind it
 // (8-byte aligned).  n_g = min(n, maxLS).  Double arithmetic exactly as oclrect.c:1069-1084 (no FMA, IEEE sqrt/div).
-__global__ void k_tail_gather(unsigned char *blob, int maxLS, const LS_t *ls, const int *segidMap, const int *votes, int iw, int ih, int nentry) {
+__global__ void k_tail_gather(unsigned char *blob, int maxLS, const LS_t *ls, const int *segidMap, const int *votes, int iw, int ih, int nentry, size_t fs) {
+  rd_batch_y(fs, blob, ls, segidMap, votes);
   const int n = *(const int *)ls;
   const int ng = min(max(n, 0), maxLS);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,21 +333,25 @@ __global__ void k_tail_gather(unsigned char *blob, int maxLS, const LS_t *ls, co
 }
 
 // ============================================================================ the oclrect_t object
+// One object owns `nb` frame arenas (nb = 1 for the reference's single-frame API, oclrect.h:17-23; more for the batch
+// engine).  An arena holds every device buffer of one frame with the reference's buffer plan (oclrect.c:120-135):
+// buf0..5, tmp0..5, iobuf0..1 (planes of P = iw*ih*4 bytes), ioBig0..1 (4P each) and the read-back record.
 #define RECT_MAGIC 0x808eae02u
 struct oclrect_t {
   uint32_t magic;
-  int iw, ih, ordinal;
+  int iw, ih, ordinal, nb;
   cl_command_queue queue;
-  cl_mem buf[6], tmp[6], iobuf[2], ioBig[2];
-  unsigned char *dblob;                 // device read-back record
+  unsigned char *dbase;                 // nb arenas, fs bytes apart
+  size_t fs;
+  cl_mem buf[6], tmp[6], iobuf[2], ioBig[2];   // non-owning handles on the buffers of arena 0
+  unsigned char *dblob;                 // read-back record of arena 0
   size_t blobBytes;
   int maxLS;
-  uint8_t *hostImg[2];                  // pinned: frame staging (hostiobuf[page][0] of the reference)
-  unsigned char *hostBlob[2];           // pinned: read-back record
+  uint8_t *hostImg[2];                  // pinned: frame staging, nb x P per page (hostiobuf[page][0] of the reference)
+  unsigned char *hostBlob[2];           // pinned: read-back records, nb x blobBytes per page
   int nextPageToEnqueue, nextPageToPoll;
   cudaEvent_t events[2];
-  int pending[2];
-  int ws[2];
+  int pending[2];                       // number of frames in flight on the page
 };
 #define FIRST_CHUNK ((size_t)128 * 1024)
 
@@ -337,109 +359,110 @@ static inline int *PI(cl_mem m) { return (int *)m->dptr; }
 static inline float *PF(cl_mem m) { return (float *)m->dptr; }
 static inline uint32_t *PU(cl_mem m) { return (uint32_t *)m->dptr; }
 
-extern "C" cl_event oclimgutil_convert_plab_bgr(oclimgutil_t *, cl_mem, cl_mem, int, int, int, cl_command_queue, const cl_event *);
-
-__global__ void k_bgr2plab_unpack(uint32_t *plab, float *o0, float *o1, float *o2, const uint8_t *in, int iw, int ih, int ws);
-__global__ void k_pack_plab_r(uint32_t *out, const float *i0, const float *i1, const float *i2, int n);
-__global__ void k_edgevec_r(float2 *dst, const float *in, int iw, int ih);
-__global__ void k_edge_plab_r(float *out, const uint32_t *in, int iw, int ih);
-__global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, int iw, int ih);
+__global__ void k_bgr2plab_unpack(uint32_t *plab, float *o0, float *o1, float *o2, const uint8_t *in, size_t in_fs, int iw, int ih, int ws, size_t fs);
+__global__ void k_pack_plab_r(uint32_t *out, const float *i0, const float *i1, const float *i2, int n, size_t fs);
+__global__ void k_edgevec_r(float2 *dst, const float *in, int iw, int ih, size_t fs);
+__global__ void k_edge_plab_r(float *out, const uint32_t *in, int iw, int ih, size_t fs);
+__global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, int iw, int ih, size_t fs);
 
 // genGPUTask (oclrect.c:235-381) without the copies.  Step numbers follow SURVEY.md section 10.1; stop_step = k > 0
 // returns after step k (for the intermediate-parity tests), 0 runs everything.
-static void gpu_task(oclrect_t *o, int ws, int stop_step, cudaStream_t s) {
+static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int stop_step, int nb, cudaStream_t s) {
   const int iw = o->iw, ih = o->ih, n = iw * ih, g1 = rd_cdiv(n, 256);
+  const size_t fs = o->fs;
   cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
 #define STEP(k) do { if (stop_step == (k)) return; } while (0)
   // steps 1-2 : BGR -> packed Lab (kept in buf0) and its three float channels
-  RD_LAUNCH(k_bgr2plab_unpack, G2, RB, 0, s, PU(buf[0]), PF(tmp[0]), PF(tmp[1]), PF(tmp[2]), (const uint8_t *)iobuf[0]->dptr, iw, ih, ws);
+  RD_LAUNCH(k_bgr2plab_unpack, rd_gz(G2, nb), RB, 0, s, PU(buf[0]), PF(tmp[0]), PF(tmp[1]), PF(tmp[2]), din, din_fs, iw, ih, ws, fs);
   STEP(1); STEP(2);
   // step 3 : recursive Gaussian r=2 on b, a, L
-  rd_k_iirblur(PF(tmp[3]), PF(tmp[2]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, s);
-  rd_k_iirblur(PF(tmp[2]), PF(tmp[1]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, s);
-  rd_k_iirblur(PF(tmp[1]), PF(tmp[0]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, s);
+  rd_k_iirblur(PF(tmp[3]), PF(tmp[2]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, nb, fs, s);
+  rd_k_iirblur(PF(tmp[2]), PF(tmp[1]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, nb, fs, s);
+  rd_k_iirblur(PF(tmp[1]), PF(tmp[0]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, nb, fs, s);
   STEP(3);
   // steps 4-7 : blurred plab, unit gradient, edge magnitude, NMS thinning (thinned strength stays in buf1)
-  RD_LAUNCH(k_pack_plab_r, g1, 256, 0, s, PU(buf[1]), PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), n);
+  RD_LAUNCH(k_pack_plab_r, rd_gy(g1, nb), 256, 0, s, PU(buf[1]), PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), n, fs);
   STEP(4);
-  RD_LAUNCH(k_edgevec_r, G2, RB, 0, s, (float2 *)ioBig[0]->dptr, PF(tmp[1]), iw, ih);
+  RD_LAUNCH(k_edgevec_r, rd_gz(G2, nb), RB, 0, s, (float2 *)ioBig[0]->dptr, PF(tmp[1]), iw, ih, fs);
   STEP(5);
-  RD_LAUNCH(k_edge_plab_r, G2, RB, 0, s, PF(tmp[0]), PU(buf[1]), iw, ih);
+  RD_LAUNCH(k_edge_plab_r, rd_gz(G2, nb), RB, 0, s, PF(tmp[0]), PU(buf[1]), iw, ih, fs);
   STEP(6);
-  RD_LAUNCH(k_thinthres_r, G2, RB, 0, s, PF(buf[1]), PF(tmp[0]), (const float2 *)ioBig[0]->dptr, iw, ih);
+  RD_LAUNCH(k_thinthres_r, rd_gz(G2, nb), RB, 0, s, PF(buf[1]), PF(tmp[0]), (const float2 *)ioBig[0]->dptr, iw, ih, fs);
   STEP(7);
   // step 8 : edge bitmap #1
-  RD_LAUNCH(kr_threshold_cast, g1, 256, 0, s, PF(tmp[0]), PI(tmp[1]), PF(buf[1]), n);
+  RD_LAUNCH(kr_threshold_cast, rd_gy(g1, nb), 256, 0, s, PF(tmp[0]), PI(tmp[1]), PF(buf[1]), n, fs);
   STEP(8);
   // step 9 : junction / connect / stringify x2
-  RD_LAUNCH(kr_simpleJunction, G2, RB, 0, s, PI(buf[2]), PI(tmp[1]), iw, ih);
-  RD_LAUNCH(kr_simpleConnect, G2, RB, 0, s, PI(tmp[1]), PI(buf[2]), iw, ih);
-  RD_LAUNCH(kr_stringify, G2, RB, 0, s, PI(buf[2]), PI(tmp[1]), 0, iw, ih);
-  RD_LAUNCH(kr_stringify, G2, RB, 0, s, PI(tmp[1]), PI(buf[2]), 1, iw, ih);
+  RD_LAUNCH(kr_simpleJunction, rd_gz(G2, nb), RB, 0, s, PI(buf[2]), PI(tmp[1]), iw, ih, fs);
+  RD_LAUNCH(kr_simpleConnect, rd_gz(G2, nb), RB, 0, s, PI(tmp[1]), PI(buf[2]), iw, ih, fs);
+  RD_LAUNCH(kr_stringify, rd_gz(G2, nb), RB, 0, s, PI(buf[2]), PI(tmp[1]), 0, iw, ih, fs);
+  RD_LAUNCH(kr_stringify, rd_gz(G2, nb), RB, 0, s, PI(tmp[1]), PI(buf[2]), 1, iw, ih, fs);
   STEP(9);
   // step 10 : components of the 0/1 string image (background included, bgc = -1)
-  rd_label8x(PI(buf[2]), PI(tmp[1]), tmp[0]->dptr, -1, iw, ih, s);
+  rd_label8x(PI(buf[2]), PI(tmp[1]), tmp[0]->dptr, -1, iw, ih, nb, fs, s);
   STEP(10);
   // step 11 : strengths accumulate into buf3 (not cleared: Q1), weak components die
-  RD_LAUNCH(kr_calcStrength, G2, RB, 0, s, PI(buf[3]), PF(buf[1]), PI(buf[2]), iw, ih);
-  RD_LAUNCH(kr_filterStrength, G2, RB, 0, s, PI(buf[2]), PI(buf[3]), 500, iw, ih);
+  RD_LAUNCH(kr_calcStrength, rd_gz(G2, nb), RB, 0, s, PI(buf[3]), PF(buf[1]), PI(buf[2]), iw, ih, fs);
+  RD_LAUNCH(kr_filterStrength, rd_gz(G2, nb), RB, 0, s, PI(buf[2]), PI(buf[3]), 500, iw, ih, fs);
   STEP(11);
   // step 12 : int and i8 edge masks
-  RD_LAUNCH(kr_threshold_cast_c, g1, 256, 0, s, PI(tmp[0]), (int8_t *)tmp[1]->dptr, PI(buf[2]), n);
+  RD_LAUNCH(kr_threshold_cast_c, rd_gy(g1, nb), 256, 0, s, PI(tmp[0]), (int8_t *)tmp[1]->dptr, PI(buf[2]), n, fs);
   STEP(12);
   // step 13 : 10 x (blblur0, blblur1)
-  RD_LAUNCH(kr_blblur<0>, G2, RB, 0, s, PU(tmp[0]), (const int8_t *)tmp[1]->dptr, PU(buf[0]), iw, ih);
-  RD_LAUNCH(kr_blblur<1>, G2, RB, 0, s, PU(buf[4]), (const int8_t *)tmp[1]->dptr, PU(tmp[0]), iw, ih);
+  RD_LAUNCH(kr_blblur<0>, rd_gz(G2, nb), RB, 0, s, PU(tmp[0]), (const int8_t *)tmp[1]->dptr, PU(buf[0]), iw, ih, fs);
+  RD_LAUNCH(kr_blblur<1>, rd_gz(G2, nb), RB, 0, s, PU(buf[4]), (const int8_t *)tmp[1]->dptr, PU(tmp[0]), iw, ih, fs);
   for (int i = 0; i < 9; i++) {
-    RD_LAUNCH(kr_blblur<0>, G2, RB, 0, s, PU(tmp[0]), (const int8_t *)tmp[1]->dptr, PU(buf[4]), iw, ih);
-    RD_LAUNCH(kr_blblur<1>, G2, RB, 0, s, PU(buf[4]), (const int8_t *)tmp[1]->dptr, PU(tmp[0]), iw, ih);
+    RD_LAUNCH(kr_blblur<0>, rd_gz(G2, nb), RB, 0, s, PU(tmp[0]), (const int8_t *)tmp[1]->dptr, PU(buf[4]), iw, ih, fs);
+    RD_LAUNCH(kr_blblur<1>, rd_gz(G2, nb), RB, 0, s, PU(buf[4]), (const int8_t *)tmp[1]->dptr, PU(tmp[0]), iw, ih, fs);
   }
   STEP(13);
   // step 14 : quantize 24^3, despeckle
-  RD_LAUNCH(kr_quantize, g1, 256, 0, s, PU(tmp[0]), PU(buf[4]), 24, 24, 24, n);
-  RD_LAUNCH(kr_despeckle, G2, RB, 0, s, PU(buf[4]), PU(tmp[0]), PF(buf[1]), iw, ih);
+  RD_LAUNCH(kr_quantize, rd_gy(g1, nb), 256, 0, s, PU(tmp[0]), PU(buf[4]), 24, 24, 24, n, fs);
+  RD_LAUNCH(kr_despeckle, rd_gz(G2, nb), RB, 0, s, PU(buf[4]), PU(tmp[0]), PF(buf[1]), iw, ih, fs);
   STEP(14);
   // step 15 : strong-edge bitmap -> buf3
-  RD_LAUNCH(kr_filterStrength, G2, RB, 0, s, PI(buf[2]), PI(buf[3]), 2500, iw, ih);
-  RD_LAUNCH(kr_threshold_i_i, g1, 256, 0, s, PI(buf[3]), PI(buf[2]), 0, 0, 1, n);
+  RD_LAUNCH(kr_filterStrength, rd_gz(G2, nb), RB, 0, s, PI(buf[2]), PI(buf[3]), 2500, iw, ih, fs);
+  RD_LAUNCH(kr_threshold_i_i, rd_gy(g1, nb), 256, 0, s, PI(buf[3]), PI(buf[2]), 0, 0, 1, n, fs);
   STEP(15);
   // step 16 : junctions of the strong edges, merge mask
-  RD_LAUNCH(kr_simpleJunction, G2, RB, 0, s, PI(tmp[0]), PI(buf[2]), iw, ih);
-  rd_k_clear(PI(tmp[1]), n, s);
-  RD_LAUNCH(kr_mkMergeMask0, G2, RB, 0, s, PI(tmp[1]), PI(tmp[0]), iw, ih);
-  RD_LAUNCH(kr_mkMergeMask1, G2, RB, 0, s, PI(tmp[1]), PI(tmp[0]), iw, ih);
+  RD_LAUNCH(kr_simpleJunction, rd_gz(G2, nb), RB, 0, s, PI(tmp[0]), PI(buf[2]), iw, ih, fs);
+  rd_k_clear(PI(tmp[1]), n, nb, fs, s);
+  RD_LAUNCH(kr_mkMergeMask0, rd_gz(G2, nb), RB, 0, s, PI(tmp[1]), PI(tmp[0]), iw, ih, fs);
+  RD_LAUNCH(kr_mkMergeMask1, rd_gz(G2, nb), RB, 0, s, PI(tmp[1]), PI(tmp[0]), iw, ih, fs);
   STEP(16);
   // step 17 : colour regions (work plane tmp4, link bytes tmp5: both dead until the polyline stage rewrites them)
-  rd_labelMerge(PI(buf[5]), PI(tmp[4]), PU(buf[4]), PI(tmp[1]), PI(buf[2]), tmp[5]->dptr, iw, ih, s);
+  rd_labelMerge(PI(buf[5]), PI(tmp[4]), PU(buf[4]), PI(tmp[1]), PI(buf[2]), tmp[5]->dptr, iw, ih, nb, fs, s);
   STEP(17);
   // step 18 : region sizes on top of the junction map (Q2), small regions absorbed (Jacobi: snapshot in tmp4)
-  RD_LAUNCH(kr_calcSize, g1, 256, 0, s, PI(tmp[0]), PI(buf[5]), n);
-  rd_k_copy(PI(tmp[4]), PI(buf[5]), n, s);
-  RD_LAUNCH(kr_despeckle2, G2, RB, 0, s, PI(buf[5]), PI(tmp[4]), PI(tmp[0]), 16, iw, ih);
+  RD_LAUNCH(kr_calcSize, rd_gy(g1, nb), 256, 0, s, PI(tmp[0]), PI(buf[5]), n, fs);
+  rd_k_copy(PI(tmp[4]), PI(buf[5]), n, nb, fs, s);
+  RD_LAUNCH(kr_despeckle2, rd_gz(G2, nb), RB, 0, s, PI(buf[5]), PI(tmp[4]), PI(tmp[0]), 16, iw, ih, fs);
   STEP(18);
   // step 19 : boundary bands and their components -> segid map
-  RD_LAUNCH(kr_markBoundary, G2, RB, 0, s, PI(tmp[1]), PI(buf[5]), iw, ih);
-  rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[0]->dptr, -1, iw, ih, s);
+  RD_LAUNCH(kr_markBoundary, rd_gz(G2, nb), RB, 0, s, PI(tmp[1]), PI(buf[5]), iw, ih, fs);
+  rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[0]->dptr, -1, iw, ih, nb, fs, s);
   STEP(19);
   // step 20 : polyline
   rd_polyline_run((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(buf[3]), PI(ioBig[1]), PI(tmp[0]), PI(tmp[1]), PI(tmp[2]), PI(tmp[3]), PI(tmp[4]),
-                  PI(tmp[5]), 4.0f, 20, iw, ih, s);
+                  PI(tmp[5]), 4.0f, 20, iw, ih, nb, fs, s);
   STEP(20);
   // step 21 : vote table
   const int nentry = n * 4 / 5;
-  rd_k_clear(PI(ioBig[1]), n * 4, s);
-  RD_LAUNCH(kr_reduceLS<0>, G2, RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry);
-  RD_LAUNCH(kr_reduceLS<1>, G2, RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry);
+  rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
+  RD_LAUNCH(kr_reduceLS<0>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS<1>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
   STEP(21);
   // step 22 : compact read-back record instead of the reference's three big copies (oclrect.c:371-376)
-  RD_LAUNCH(k_tail_gather, rd_cdiv(o->maxLS + 1, 128), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry);
+  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
 #undef STEP
 }
 
 // ---- fused / specialised Stage A kernels of the rect pipeline ----
 #define RD_TABLE_QUAL static __device__ const
 #include "rd_tables.inc"
-__global__ void k_bgr2plab_unpack(uint32_t *plab, float *o0, float *o1, float *o2, const uint8_t *in, int iw, int ih, int ws) {
+__global__ void k_bgr2plab_unpack(uint32_t *plab, float *o0, float *o1, float *o2, const uint8_t *in, size_t in_fs, int iw, int ih, int ws, size_t fs) {
+  rd_batch_z(fs, plab, o0, o1, o2);
+  rd_batch_z(in_fs, in);
   XY2D;
   const uint8_t *p = in + (size_t)y * ws + x * 3;
   const uint32_t v = rd_srgb2plab(p[0], p[1], p[2], RD_S2L, RD_CFUNC, RD_CFUNC2);
@@ -448,11 +471,13 @@ __global__ void k_bgr2plab_unpack(uint32_t *plab, float *o0, float *o1, float *o
   rd_unpacklab(v, l, a, b);
   o0[p0] = l; o1[p0] = a; o2[p0] = b;
 }
-__global__ void k_pack_plab_r(uint32_t *out, const float *i0, const float *i1, const float *i2, int n) {
+__global__ void k_pack_plab_r(uint32_t *out, const float *i0, const float *i1, const float *i2, int n, size_t fs) {
+  rd_batch_y(fs, out, i0, i1, i2);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = rd_packlab(i0[i], i1[i], i2[i]);
 }
-__global__ void k_edgevec_r(float2 *dst, const float *in, int iw, int ih) {
+__global__ void k_edgevec_r(float2 *dst, const float *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, dst, in);
   XY2D;
   float vx = 0, vy = 0;
   for (int yy = -2; yy <= 2; yy++)
@@ -463,7 +488,8 @@ __global__ void k_edgevec_r(float2 *dst, const float *in, int iw, int ih) {
     }
   dst[p0] = rd_edgevec_normalise(vx, vy);
 }
-__global__ void k_edge_plab_r(float *out, const uint32_t *in, int iw, int ih) {
+__global__ void k_edge_plab_r(float *out, const uint32_t *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
   XY2D;
   out[p0] = rd_edge_plab_at(in[rd_mirror(x, y - 1, iw, ih)], in[rd_mirror(x - 1, y, iw, ih)], in[rd_mirror(x, y + 1, iw, ih)],
                             in[rd_mirror(x + 1, y, iw, ih)], in[rd_mirror(x - 1, y - 1, iw, ih)], in[rd_mirror(x + 1, y + 1, iw, ih)],
@@ -473,7 +499,8 @@ struct RPlane {
   const float *p; int iw, ih;
   __device__ __forceinline__ float at(int x, int y) const { return p[rd_mirror(x, y, iw, ih)]; }
 };
-__global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, int iw, int ih) {
+__global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in, vec);
   XY2D;
   RPlane pl = {in, iw, ih};
   out[p0] = rd_thinthres_at(pl, x, y, vec[p0]);
@@ -481,108 +508,130 @@ __global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, in
 
 static void chk(oclrect_t *t) { if (!t || t->magic != RECT_MAGIC) exitf(-1, "rectdetect_b200: bad oclrect_t\n"); }
 
-// copy frame -> pinned page -> device, run the schedule, queue the first chunk of the read-back record.
-// src_kind 0: pageable host memory (staged through the pinned page, oclrect.c:1235/1256), 1: pinned host memory
-// (copied to the device directly), 2: device memory (the schedule reads it in place).  fresh != 0 clears the one
-// buffer that carries state from the previous frame (buf3) so the frame is processed as by a new object.
-static void enqueue_page(oclrect_t *o, const uint8_t *img, int ws, int page, int src_kind, int fresh) {
-  const int iw = o->iw, ih = o->ih;
-  if (ws < 3 * iw || (size_t)ws * ih > (size_t)iw * ih * 4) exitf(-1, "rectdetect_b200: row stride %d not in [3*iw, 4*iw]\n", ws);
-  cudaStream_t s = rd_stream(o->queue);
-  RD_CUDA(cudaSetDevice(o->ordinal));
-  void *keep = o->iobuf[0]->dptr;
-  if (src_kind == 0) {
-    memcpy(o->hostImg[page], img, (size_t)ws * ih);
-    RD_CUDA(cudaMemcpyAsync(o->iobuf[0]->dptr, o->hostImg[page], (size_t)ws * ih, cudaMemcpyHostToDevice, s));   // oclrect.c:241
-  } else if (src_kind == 1) {
-    RD_CUDA(cudaMemcpyAsync(o->iobuf[0]->dptr, img, (size_t)ws * ih, cudaMemcpyHostToDevice, s));
-  } else {
-    o->iobuf[0]->dptr = (void *)img;
-  }
-  if (fresh) RD_CUDA(cudaMemsetAsync(o->buf[3]->dptr, 0, (size_t)iw * ih * 4, s));
-  gpu_task(o, ws, 0, s);
-  o->iobuf[0]->dptr = keep;
-  RD_CUDA(cudaMemcpyAsync(o->hostBlob[page], o->dblob, o->blobBytes < FIRST_CHUNK ? o->blobBytes : FIRST_CHUNK, cudaMemcpyDeviceToHost, s));
-  RD_CUDA(cudaEventRecord(o->events[page], s));
-  o->pending[page] = 1;
-  o->ws[page] = ws;
-}
-
 static size_t blob_need(int ng) { return 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7) + (size_t)(ng + 1) * RD_TAIL_NSAMPLE * sizeof(rd_tail_sample); }
 
-// executeCPUTask (oclrect.c:1049) on the read-back record of `page`
-static rect_t *finish_page(oclrect_t *o, int page, double tanAOV, int run_tail = 1) {
-  cudaStream_t s = rd_stream(o->queue);
-  RD_CUDA(cudaSetDevice(o->ordinal));
-  RD_CUDA(cudaEventSynchronize(o->events[page]));
-  o->pending[page] = 0;
-  if (!run_tail) return NULL;
-  const int n = ((int *)o->hostBlob[page])[0], ng = ((int *)o->hostBlob[page])[1];
-  if (n > ng) {
-    // more segments than the compact record holds: read back what the reference reads back and gather on the host
-    const size_t P = (size_t)o->iw * o->ih * 4;
-    std::vector<unsigned char> ls((size_t)(n + 1) * sizeof(LS_t)), seg(P), votes(4 * P);
-    RD_CUDA(cudaMemcpyAsync(ls.data(), o->ioBig[0]->dptr, ls.size(), cudaMemcpyDeviceToHost, s));
-    RD_CUDA(cudaMemcpyAsync(seg.data(), o->iobuf[1]->dptr, P, cudaMemcpyDeviceToHost, s));
-    RD_CUDA(cudaMemcpyAsync(votes.data(), o->ioBig[1]->dptr, 4 * P, cudaMemcpyDeviceToHost, s));
-    RD_CUDA(cudaStreamSynchronize(s));
-    return rd_rect_tail((const linesegment_t *)ls.data(), (const int32_t *)seg.data(), (const int32_t *)votes.data(), o->iw, o->ih, tanAOV);
-  }
-  const size_t need = blob_need(ng);
-  if (need > FIRST_CHUNK) {
-    RD_CUDA(cudaMemcpyAsync(o->hostBlob[page] + FIRST_CHUNK, o->dblob + FIRST_CHUNK, need - FIRST_CHUNK, cudaMemcpyDeviceToHost, s));
-    RD_CUDA(cudaStreamSynchronize(s));
-  }
-  const linesegment_t *ls = (const linesegment_t *)(o->hostBlob[page] + 64);
-  const rd_tail_sample *sm = (const rd_tail_sample *)(o->hostBlob[page] + 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7));
-  return rd_tail_compact(ls, sm, o->iw, o->ih, tanAOV);
-}
-
-extern "C" {
-
-struct oclrect_t *init_oclrect(oclimgutil_t *, oclpolyline_t *, cl_device_id device, cl_context context, cl_command_queue queue, int iw, int ih) {
+static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int ih, int nb) {
   if (rd_device_count() <= 0) exitf(-1, "rectdetect_b200: no CUDA device; there is no CPU fallback\n");
   if (iw < 8 || ih < 8) exitf(-1, "rectdetect_b200: frame %dx%d too small\n", iw, ih);
   if (!queue) exitf(-1, "rectdetect_b200: init_oclrect needs a command queue\n");
+  if (nb < 1) nb = 1;
   oclrect_t *o = (oclrect_t *)calloc(1, sizeof(oclrect_t));
   o->magic = RECT_MAGIC;
-  o->iw = iw; o->ih = ih;
-  o->ordinal = device ? device->ordinal : queue->ordinal;
+  o->iw = iw; o->ih = ih; o->nb = nb;
+  o->ordinal = ordinal;
   o->queue = queue;
   RD_CUDA(cudaSetDevice(o->ordinal));
-  const size_t P = (size_t)iw * ih * 4;
-  // CANONICAL (Q1): memory the reference never initialises reads as zero on the first frame
-  for (int i = 0; i < 6; i++) {
-    o->buf[i] = clCreateBuffer(context, CL_MEM_HOST_NO_ACCESS, P, NULL, NULL); RD_CUDA(cudaMemset(o->buf[i]->dptr, 0, P));
-    o->tmp[i] = clCreateBuffer(context, CL_MEM_HOST_NO_ACCESS, P, NULL, NULL); RD_CUDA(cudaMemset(o->tmp[i]->dptr, 0, P));
-  }
-  for (int i = 0; i < 2; i++) {
-    o->iobuf[i] = clCreateBuffer(context, CL_MEM_READ_WRITE, P, NULL, NULL); RD_CUDA(cudaMemset(o->iobuf[i]->dptr, 0, P));
-    o->ioBig[i] = clCreateBuffer(context, CL_MEM_READ_WRITE, 4 * P, NULL, NULL); RD_CUDA(cudaMemset(o->ioBig[i]->dptr, 0, 4 * P));
-  }
+  const size_t P = (((size_t)iw * ih * 4) + 255) & ~(size_t)255;
   size_t bb = (size_t)iw * ih * 2;
   if (bb < ((size_t)1 << 20)) bb = (size_t)1 << 20;
-  o->maxLS = (int)((bb - 128) / (sizeof(LS_t) + RD_TAIL_NSAMPLE * sizeof(rd_tail_sample))) - 1;
-  const int cap = (int)(4 * P / sizeof(LS_t)) - 1;
-  if (o->maxLS > cap) o->maxLS = cap;
+  bb = (bb + 255) & ~(size_t)255;
   o->blobBytes = bb;
-  RD_CUDA(cudaMalloc((void **)&o->dblob, bb));
-  RD_CUDA(cudaMemset(o->dblob, 0, bb));
+  o->maxLS = (int)((bb - 128) / (sizeof(LS_t) + RD_TAIL_NSAMPLE * sizeof(rd_tail_sample))) - 1;
+  const int cap = (int)((size_t)iw * ih * 16 / sizeof(LS_t)) - 1;
+  if (o->maxLS > cap) o->maxLS = cap;
+  o->fs = 22 * P + bb;
+  RD_CUDA(cudaMalloc((void **)&o->dbase, o->fs * nb));
+  // CANONICAL (Q1): memory the reference never initialises reads as zero on the first frame
+  RD_CUDA(cudaMemset(o->dbase, 0, o->fs * nb));
+  unsigned char *q = o->dbase;
+  for (int i = 0; i < 6; i++) { o->buf[i] = rd_wrap_device_memory(q, P); q += P; }
+  for (int i = 0; i < 6; i++) { o->tmp[i] = rd_wrap_device_memory(q, P); q += P; }
+  for (int i = 0; i < 2; i++) { o->iobuf[i] = rd_wrap_device_memory(q, P); q += P; }
+  for (int i = 0; i < 2; i++) { o->ioBig[i] = rd_wrap_device_memory(q, 4 * P); q += 4 * P; }
+  o->dblob = q;
   for (int p = 0; p < 2; p++) {
-    o->hostImg[p] = (uint8_t *)allocatePinnedMemory(P, context, queue);
-    o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(bb, context, queue);
+    o->hostImg[p] = (uint8_t *)allocatePinnedMemory((size_t)iw * ih * 4 * nb, NULL, NULL);
+    o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(bb * nb, NULL, NULL);
     RD_CUDA(cudaEventCreateWithFlags(&o->events[p], cudaEventDisableTiming));
   }
   RD_CUDA(cudaDeviceSynchronize());
   return o;
 }
 
+// `count` frames (<= nb), frame i at img + i*frame_stride -> device, run the schedule, queue the first chunk of every
+// read-back record.  src_kind 0: pageable host memory (staged through the pinned page, oclrect.c:1235/1256),
+// 1: pinned host memory (copied to the device directly), 2: device memory (the schedule reads it in place).
+// fresh != 0 clears the one buffer that carries state from the previous frame (buf3) so that every frame is
+// processed as by a newly created object.
+static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, int ws, int page, int src_kind, int fresh, int count) {
+  const int iw = o->iw, ih = o->ih;
+  if (ws < 3 * iw || (size_t)ws * ih > (size_t)iw * ih * 4) exitf(-1, "rectdetect_b200: row stride %d not in [3*iw, 4*iw]\n", ws);
+  if (count < 1 || count > o->nb) exitf(-1, "rectdetect_b200: %d frames do not fit an object built for %d\n", count, o->nb);
+  cudaStream_t s = rd_stream(o->queue);
+  RD_CUDA(cudaSetDevice(o->ordinal));
+  const size_t fbytes = (size_t)ws * ih;
+  const uint8_t *din = (const uint8_t *)o->iobuf[0]->dptr;
+  size_t din_fs = o->fs;
+  if (src_kind == 0) {
+    const size_t hstride = (size_t)iw * ih * 4;
+    for (int i = 0; i < count; i++) memcpy(o->hostImg[page] + i * hstride, img + i * frame_stride, fbytes);
+    RD_CUDA(cudaMemcpy2DAsync(o->iobuf[0]->dptr, o->fs, o->hostImg[page], hstride, fbytes, count, cudaMemcpyHostToDevice, s));   // oclrect.c:241
+  } else if (src_kind == 1) {
+    RD_CUDA(cudaMemcpy2DAsync(o->iobuf[0]->dptr, o->fs, img, count > 1 ? frame_stride : fbytes, fbytes, count, cudaMemcpyHostToDevice, s));
+  } else {
+    din = img;
+    din_fs = frame_stride;
+  }
+  if (fresh) RD_CUDA(cudaMemset2DAsync(o->buf[3]->dptr, o->fs, 0, (size_t)iw * ih * 4, count, s));
+  gpu_task(o, din, din_fs, ws, 0, count, s);
+  const size_t chunk = o->blobBytes < FIRST_CHUNK ? o->blobBytes : FIRST_CHUNK;
+  RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], o->blobBytes, o->dblob, o->fs, chunk, count, cudaMemcpyDeviceToHost, s));
+  RD_CUDA(cudaEventRecord(o->events[page], s));
+  o->pending[page] = count;
+}
+
+// executeCPUTask (oclrect.c:1049) on the read-back records of `page`; out[i] receives the list of frame i
+static void finish_page(oclrect_t *o, int page, double tanAOV, rect_t **out, int run_tail) {
+  cudaStream_t s = rd_stream(o->queue);
+  RD_CUDA(cudaSetDevice(o->ordinal));
+  RD_CUDA(cudaEventSynchronize(o->events[page]));
+  const int count = o->pending[page];
+  o->pending[page] = 0;
+  if (!run_tail) { for (int i = 0; i < count; i++) if (out) out[i] = NULL; return; }
+  bool more = false;
+  for (int i = 0; i < count; i++) {
+    unsigned char *hb = o->hostBlob[page] + (size_t)i * o->blobBytes;
+    const int n = ((int *)hb)[0], ng = ((int *)hb)[1];
+    const size_t need = blob_need(ng);
+    if (n <= ng && need > FIRST_CHUNK) {
+      RD_CUDA(cudaMemcpyAsync(hb + FIRST_CHUNK, o->dblob + (size_t)i * o->fs + FIRST_CHUNK, need - FIRST_CHUNK, cudaMemcpyDeviceToHost, s));
+      more = true;
+    }
+  }
+  if (more) RD_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < count; i++) {
+    unsigned char *hb = o->hostBlob[page] + (size_t)i * o->blobBytes;
+    const int n = ((int *)hb)[0], ng = ((int *)hb)[1];
+    if (n > ng) {
+      // more segments than the compact record holds: read back what the reference reads back and gather on the host
+      const size_t P = (size_t)o->iw * o->ih * 4, off = (size_t)i * o->fs;
+      std::vector<unsigned char> ls((size_t)(n + 1) * sizeof(LS_t)), seg(P), votes(4 * P);
+      RD_CUDA(cudaMemcpyAsync(ls.data(), (char *)o->ioBig[0]->dptr + off, ls.size(), cudaMemcpyDeviceToHost, s));
+      RD_CUDA(cudaMemcpyAsync(seg.data(), (char *)o->iobuf[1]->dptr + off, P, cudaMemcpyDeviceToHost, s));
+      RD_CUDA(cudaMemcpyAsync(votes.data(), (char *)o->ioBig[1]->dptr + off, 4 * P, cudaMemcpyDeviceToHost, s));
+      RD_CUDA(cudaStreamSynchronize(s));
+      out[i] = rd_rect_tail((const linesegment_t *)ls.data(), (const int32_t *)seg.data(), (const int32_t *)votes.data(), o->iw, o->ih, tanAOV);
+      continue;
+    }
+    const linesegment_t *ls = (const linesegment_t *)(hb + 64);
+    const rd_tail_sample *sm = (const rd_tail_sample *)(hb + 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7));
+    out[i] = rd_tail_compact(ls, sm, o->iw, o->ih, tanAOV);
+  }
+}
+
+extern "C" {
+
+struct oclrect_t *init_oclrect(oclimgutil_t *, oclpolyline_t *, cl_device_id device, cl_context, cl_command_queue queue, int iw, int ih) {
+  return rect_create(queue, device ? device->ordinal : (queue ? queue->ordinal : 0), iw, ih, 1);
+}
+
 void dispose_oclrect(struct oclrect_t *o) {
   chk(o);
+  RD_CUDA(cudaSetDevice(o->ordinal));
   RD_CUDA(cudaStreamSynchronize(rd_stream(o->queue)));
   for (int i = 0; i < 6; i++) { clReleaseMemObject(o->buf[i]); clReleaseMemObject(o->tmp[i]); }
   for (int i = 0; i < 2; i++) { clReleaseMemObject(o->iobuf[i]); clReleaseMemObject(o->ioBig[i]); }
-  RD_CUDA(cudaFree(o->dblob));
+  RD_CUDA(cudaFree(o->dbase));
   for (int p = 0; p < 2; p++) { freePinnedMemory(o->hostImg[p], NULL, NULL); freePinnedMemory(o->hostBlob[p], NULL, NULL); RD_CUDA(cudaEventDestroy(o->events[p])); }
   o->magic = 0;
   free(o);
@@ -591,8 +640,10 @@ void dispose_oclrect(struct oclrect_t *o) {
 rect_t *oclrect_executeOnce(struct oclrect_t *o, uint8_t *imgData, int ws, const double tanAOV) {   // oclrect.c:1230
   chk(o);
   if (o->pending[0]) exitf(-1, "rectdetect_b200: oclrect_executeOnce while a task is pending on page 0\n");
-  enqueue_page(o, imgData, ws, 0, 0, 0);
-  return finish_page(o, 0, tanAOV);
+  enqueue_page(o, imgData, 0, ws, 0, 0, 0, 1);
+  rect_t *r = NULL;
+  finish_page(o, 0, tanAOV, &r, 1);
+  return r;
 }
 
 void oclrect_enqueueTask(struct oclrect_t *o, uint8_t *imgData, int ws) {                            // oclrect.c:1248
@@ -600,7 +651,7 @@ void oclrect_enqueueTask(struct oclrect_t *o, uint8_t *imgData, int ws) {       
   const int page = 1 & o->nextPageToEnqueue;
   o->nextPageToEnqueue++;
   if (o->pending[page]) exitf(-1, "rectdetect_b200: oclrect_enqueueTask with two tasks already in flight\n");   // assert(events[page]==NULL)
-  enqueue_page(o, imgData, ws, page, 0, 0);
+  enqueue_page(o, imgData, 0, ws, page, 0, 0, 1);
 }
 
 rect_t *oclrect_pollTask(struct oclrect_t *o, const double tanAOV) {                                // oclrect.c:1263
@@ -608,7 +659,9 @@ rect_t *oclrect_pollTask(struct oclrect_t *o, const double tanAOV) {            
   const int page = 1 & o->nextPageToPoll;
   o->nextPageToPoll++;
   if (!o->pending[page]) exitf(-1, "rectdetect_b200: oclrect_pollTask without a pending task\n");
-  return finish_page(o, page, tanAOV);
+  rect_t *r = NULL;
+  finish_page(o, page, tanAOV, &r, 1);
+  return r;
 }
 
 cl_mem rd_oclrect_buffer(struct oclrect_t *o, const char *name) {
@@ -624,53 +677,56 @@ void rd_oclrect_run_device(struct oclrect_t *o, const uint8_t *imgData, int ws, 
   chk(o);
   cudaStream_t s = rd_stream(o->queue);
   RD_CUDA(cudaMemcpyAsync(o->iobuf[0]->dptr, imgData, (size_t)ws * o->ih, cudaMemcpyHostToDevice, s));
-  if (stop_step != -1) gpu_task(o, ws, stop_step, s);
+  if (stop_step != -1) gpu_task(o, (const uint8_t *)o->iobuf[0]->dptr, o->fs, ws, stop_step, 1, s);
   RD_CUDA(cudaStreamSynchronize(s));
 }
 
 // ---- Stage B / D operators, one per __kernel of oclrect.cl ----
-#define QS cudaStream_t s = rd_stream(q)
-void rd_rect_simpleJunction(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_simpleJunction, G2, RB, 0, s, PI(out), PI(in), iw, ih); }
-void rd_rect_simpleConnect(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_simpleConnect, G2, RB, 0, s, PI(out), PI(in), iw, ih); }
-void rd_rect_stringify(cl_mem out, cl_mem in, int mod2, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_stringify, G2, RB, 0, s, PI(out), PI(in), mod2, iw, ih); }
-void rd_rect_blblur0(cl_mem out, cl_mem e, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_blblur<0>, G2, RB, 0, s, PU(out), (const int8_t *)e->dptr, PU(in), iw, ih); }
-void rd_rect_blblur1(cl_mem out, cl_mem e, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_blblur<1>, G2, RB, 0, s, PU(out), (const int8_t *)e->dptr, PU(in), iw, ih); }
-void rd_rect_quantize(cl_mem out, cl_mem in, int n0, int n1, int n2, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_quantize, rd_cdiv(iw * ih, 256), 256, 0, s, PU(out), PU(in), n0, n1, n2, iw * ih); }
-void rd_rect_despeckle(cl_mem out, cl_mem in, cl_mem edge, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_despeckle, G2, RB, 0, s, PU(out), PU(in), PF(edge), iw, ih); }
-void rd_rect_mkMergeMask0(cl_mem out, cl_mem j, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_mkMergeMask0, G2, RB, 0, s, PI(out), PI(j), iw, ih); }
-void rd_rect_mkMergeMask1(cl_mem io, cl_mem j, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_mkMergeMask1, G2, RB, 0, s, PI(io), PI(j), iw, ih); }
+#define QS cudaStream_t s = rd_stream(q); const int nb = 1; const size_t fs = 0
+void rd_rect_simpleJunction(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_simpleJunction, rd_gz(G2, nb), RB, 0, s, PI(out), PI(in), iw, ih, fs); }
+void rd_rect_simpleConnect(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_simpleConnect, rd_gz(G2, nb), RB, 0, s, PI(out), PI(in), iw, ih, fs); }
+void rd_rect_stringify(cl_mem out, cl_mem in, int mod2, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_stringify, rd_gz(G2, nb), RB, 0, s, PI(out), PI(in), mod2, iw, ih, fs); }
+void rd_rect_blblur0(cl_mem out, cl_mem e, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_blblur<0>, rd_gz(G2, nb), RB, 0, s, PU(out), (const int8_t *)e->dptr, PU(in), iw, ih, fs); }
+void rd_rect_blblur1(cl_mem out, cl_mem e, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_blblur<1>, rd_gz(G2, nb), RB, 0, s, PU(out), (const int8_t *)e->dptr, PU(in), iw, ih, fs); }
+void rd_rect_quantize(cl_mem out, cl_mem in, int n0, int n1, int n2, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_quantize, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, PU(out), PU(in), n0, n1, n2, iw * ih, fs); }
+void rd_rect_despeckle(cl_mem out, cl_mem in, cl_mem edge, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_despeckle, rd_gz(G2, nb), RB, 0, s, PU(out), PU(in), PF(edge), iw, ih, fs); }
+void rd_rect_mkMergeMask0(cl_mem out, cl_mem j, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_mkMergeMask0, rd_gz(G2, nb), RB, 0, s, PI(out), PI(j), iw, ih, fs); }
+void rd_rect_mkMergeMask1(cl_mem io, cl_mem j, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_mkMergeMask1, rd_gz(G2, nb), RB, 0, s, PI(io), PI(j), iw, ih, fs); }
 void rd_rect_labelMerge(cl_mem label, cl_mem pix, cl_mem mask, cl_mem edge, int iw, int ih, cl_command_queue q) {
   QS;
   int *work = NULL; void *links = NULL;
   RD_CUDA(cudaMallocAsync((void **)&work, (size_t)iw * ih * 4, s));
   RD_CUDA(cudaMallocAsync(&links, (size_t)iw * ih, s));
-  rd_labelMerge(PI(label), work, PU(pix), PI(mask), PI(edge), links, iw, ih, s);
+  rd_labelMerge(PI(label), work, PU(pix), PI(mask), PI(edge), links, iw, ih, 1, 0, s);
   RD_CUDA(cudaFreeAsync(work, s));
   RD_CUDA(cudaFreeAsync(links, s));
 }
-void rd_rect_calcSize(cl_mem out, cl_mem label, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_calcSize, rd_cdiv(iw * ih, 256), 256, 0, s, PI(out), PI(label), iw * ih); }
+void rd_rect_calcSize(cl_mem out, cl_mem label, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_calcSize, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, PI(out), PI(label), iw * ih, fs); }
 void rd_rect_despeckle2(cl_mem io, cl_mem size, cl_mem scratch, int thre, int iw, int ih, cl_command_queue q) {
   QS;
-  rd_k_copy(PI(scratch), PI(io), iw * ih, s);
-  RD_LAUNCH(kr_despeckle2, G2, RB, 0, s, PI(io), PI(scratch), PI(size), thre, iw, ih);
+  rd_k_copy(PI(scratch), PI(io), iw * ih, 1, 0, s);
+  RD_LAUNCH(kr_despeckle2, rd_gz(G2, nb), RB, 0, s, PI(io), PI(scratch), PI(size), thre, iw, ih, fs);
 }
-void rd_rect_markBoundary(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_markBoundary, G2, RB, 0, s, PI(out), PI(in), iw, ih); }
+void rd_rect_markBoundary(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_markBoundary, rd_gz(G2, nb), RB, 0, s, PI(out), PI(in), iw, ih, fs); }
 void rd_rect_reduceLS(cl_mem out, cl_mem boundary, cl_mem lsid, int iw, int ih, int nentry, cl_command_queue q) {
   QS;
-  RD_LAUNCH(kr_reduceLS<0>, G2, RB, 0, s, PI(out), PI(boundary), PI(lsid), iw, ih, nentry);
-  RD_LAUNCH(kr_reduceLS<1>, G2, RB, 0, s, PI(out), PI(boundary), PI(lsid), iw, ih, nentry);
+  RD_LAUNCH(kr_reduceLS<0>, rd_gz(G2, nb), RB, 0, s, PI(out), PI(boundary), PI(lsid), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS<1>, rd_gz(G2, nb), RB, 0, s, PI(out), PI(boundary), PI(lsid), iw, ih, nentry, fs);
 }
+
 
 
 // ============================================================================ frame-batch engine
-// nctx independent pipeline objects, each with its own stream, driven by one host thread each.  A worker keeps two
-// frames in flight on its object (enqueue N+1 before polling N, vidrect.cpp:159-172), so the device stages of one
-// frame overlap the host tail of the previous one, and the nctx streams overlap each other on the GPU.
+// nctx pipeline objects, each with its own stream and room for `fpl` frames per launch, each driven by one host
+// thread.  Every kernel launch processes a chunk of up to fpl independent frames (blockIdx.z / .y = frame), which
+// amortises launch latency and fills the 148 SMs even where one frame offers little parallelism (the recursive-
+// Gaussian scans have 2 chains per row).  A worker keeps two chunks in flight on its object (enqueue N+1 before
+// polling N, vidrect.cpp:159-172), so the device stages overlap the host tails, and the nctx streams overlap each other.
 }  // extern "C" (reopened below)
 
 #include <thread>
 struct rd_batch {
-  int device, iw, ih, nctx;
+  int device, iw, ih, nctx, fpl;
   std::vector<oclrect_t *> ctx;
   std::vector<cl_command_queue> queues;
   double stage_ms[5];
@@ -687,28 +743,38 @@ static int host_ptr_kind(const void *p) {
 static void batch_worker(rd_batch *b, int c, const uint8_t *frames, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out, int kind, int run_tail) {
   oclrect_t *o = b->ctx[c];
   RD_CUDA(cudaSetDevice(b->device));
+  const int nchunks = (nframes + b->fpl - 1) / b->fpl;
   int prev = -1, prevPage = 0, page = 0;
-  for (int f = c; f < nframes; f += b->nctx) {
-    enqueue_page(o, frames + (size_t)f * frame_stride, ws, page, kind, 1);
-    if (prev >= 0) { rect_t *r = finish_page(o, prevPage, tanAOV, run_tail); if (out) out[prev] = r; else free(r); }
-    prev = f; prevPage = page; page ^= 1;
+  std::vector<rect_t *> tmp(b->fpl);
+  auto finish = [&](int chunk, int pg) {
+    const int f0 = chunk * b->fpl;
+    finish_page(o, pg, tanAOV, tmp.data(), run_tail);
+    const int cnt = (nframes - f0) < b->fpl ? (nframes - f0) : b->fpl;
+    for (int i = 0; i < cnt; i++) { if (out) out[f0 + i] = tmp[i]; else free(tmp[i]); }
+  };
+  for (int ch = c; ch < nchunks; ch += b->nctx) {
+    const int f0 = ch * b->fpl;
+    const int cnt = (nframes - f0) < b->fpl ? (nframes - f0) : b->fpl;
+    enqueue_page(o, frames + (size_t)f0 * frame_stride, frame_stride, ws, page, kind, 1, cnt);
+    if (prev >= 0) finish(prev, prevPage);
+    prev = ch; prevPage = page; page ^= 1;
   }
-  if (prev >= 0) { rect_t *r = finish_page(o, prevPage, tanAOV, run_tail); if (out) out[prev] = r; else free(r); }
+  if (prev >= 0) finish(prev, prevPage);
 }
 
 extern "C" {
 
-rd_batch *rd_batch_create(int device, int iw, int ih, int nctx, int tail_threads) {
-  (void)tail_threads;
+rd_batch *rd_batch_create(int device, int iw, int ih, int nctx, int frames_per_launch) {
   if (rd_device_count() <= device || device < 0) exitf(-1, "rectdetect_b200: rd_batch_create: no CUDA device %d; there is no CPU fallback\n", device);
   if (nctx < 1) nctx = 1;
+  if (frames_per_launch < 1) frames_per_launch = 1;
   rd_batch *b = new rd_batch();
-  b->device = device; b->iw = iw; b->ih = ih; b->nctx = nctx;
+  b->device = device; b->iw = iw; b->ih = ih; b->nctx = nctx; b->fpl = frames_per_launch;
   cl_device_id dev = simpleGetDevice(device);
   for (int c = 0; c < nctx; c++) {
     cl_command_queue q = clCreateCommandQueue(NULL, dev, 0, NULL);
     b->queues.push_back(q);
-    b->ctx.push_back(init_oclrect(NULL, NULL, dev, NULL, q, iw, ih));
+    b->ctx.push_back(rect_create(q, device, iw, ih, frames_per_launch));
   }
   for (int i = 0; i < 5; i++) b->stage_ms[i] = 0;
   return b;
@@ -721,7 +787,8 @@ void rd_batch_destroy(rd_batch *b) {
 }
 
 static void batch_run(rd_batch *b, const uint8_t *frames, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out, int kind, int run_tail) {
-  const int nw = b->nctx < nframes ? b->nctx : nframes;
+  const int nchunks = (nframes + b->fpl - 1) / b->fpl;
+  const int nw = b->nctx < nchunks ? b->nctx : nchunks;
   std::vector<std::thread> th;
   for (int c = 1; c < nw; c++) th.emplace_back(batch_worker, b, c, frames, frame_stride, ws, nframes, tanAOV, out, kind, run_tail);
   if (nw > 0) batch_worker(b, 0, frames, frame_stride, ws, nframes, tanAOV, out, kind, run_tail);
@@ -739,4 +806,5 @@ void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, 
 }
 
 void rd_batch_stage_ms(rd_batch *b, double out_ms[5]) { for (int i = 0; i < 5; i++) out_ms[i] = b->stage_ms[i]; }
+
 }  // extern "C"

@@ -111,9 +111,9 @@ def test_blank_and_tiny_frames(rd, gpu_dev):
 
 def test_batch_engine_matches_fresh_oracle_objects(rd, gpu_dev):
     # every frame of a batch is processed as by a freshly created oclrect_t (no carry-over between frames)
-    iw, ih, nf = 640, 480, 12
+    iw, ih, nf = 640, 480, 13                     # 13 frames over 2 objects x 3 frames per launch: ragged last chunk
     frames = np.stack([ol.synth_frame(iw, ih, 2000 + i) for i in range(nf)])
-    b = rd.Batch(0, iw, ih, nctx=4)
+    b = rd.Batch(0, iw, ih, nctx=2, frames_per_launch=3)
     got = b.run(frames.ctypes.data, frames[0].nbytes, 3 * iw, nf, parity.TAN_AOV)
     again = b.run(frames.ctypes.data, frames[0].nbytes, 3 * iw, nf, parity.TAN_AOV)
     b.close()
