@@ -24,61 +24,66 @@
 #define L_NE 8
 #define L_BG 0x80
 
-// ---- link functors: which backward neighbours (W, NW, N, NE) of (x, y) belong to the same component ----
+// ---- link functors.  load(x, y) reads what the predicate needs to know about ONE pixel (each pixel of the tile and
+// of its one-pixel apron above / beside is loaded once into shared memory); link(...) then decides, from the staged
+// values of a pixel (c) and of its W, NW, N, NE neighbours, which of the four belong to the same component. ----
 struct Link8x {                       // label8xMain_int_int: equal value, value != bgc (oclimgutil.cl:511-538)
+  typedef int V;
   const int *pix; int bgc, iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix); }
-  __device__ __forceinline__ unsigned operator()(int x, int y) const {
-    const int p = y * iw + x, v = pix[p];
-    if (v == bgc) return L_BG;
+  __device__ __forceinline__ V load(int x, int y) const { return pix[(size_t)y * iw + x]; }
+  __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
+    if (c == bgc) return L_BG;
     unsigned m = 0;
-    if (x > 0 && pix[p - 1] == v) m |= L_W;
+    if (x > 0 && w == c) m |= L_W;
     if (y > 0) {
-      if (pix[p - iw] == v) m |= L_N;
-      if (x > 0 && pix[p - iw - 1] == v) m |= L_NW;
-      if (x < iw - 1 && pix[p - iw + 1] == v) m |= L_NE;
+      if (n == c) m |= L_N;
+      if (x > 0 && nw == c) m |= L_NW;
+      if (x < iw - 1 && ne == c) m |= L_NE;
     }
     return m;
   }
 };
 struct LinkPl {                       // labelpl_main: numbers (+1) both non-zero and differing by at most 1 (oclpolyline.cl:325-355)
+  typedef int V;
   const int *num; int iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, num); }
+  __device__ __forceinline__ V load(int x, int y) const { return num[(size_t)y * iw + x]; }
   __device__ __forceinline__ static bool con(int a, int b) { return b != 0 && abs(a - b) <= 1; }
-  __device__ __forceinline__ unsigned operator()(int x, int y) const {
-    const int p = y * iw + x, v = num[p];
-    if (v == 0) return L_BG;
+  __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
+    if (c == 0) return L_BG;
     unsigned m = 0;
-    if (x > 0 && con(v, num[p - 1])) m |= L_W;
+    if (x > 0 && con(c, w)) m |= L_W;
     if (y > 0) {
-      if (con(v, num[p - iw])) m |= L_N;
-      if (x > 0 && con(v, num[p - iw - 1])) m |= L_NW;
-      if (x < iw - 1 && con(v, num[p - iw + 1])) m |= L_NE;
+      if (con(c, n)) m |= L_N;
+      if (x > 0 && con(c, nw)) m |= L_NW;
+      if (x < iw - 1 && con(c, ne)) m |= L_NE;
     }
     return m;
   }
 };
 struct LinkMerge {                    // labelxPreprocess + labelMergeMain, canonical symmetric form (see rd_rect.cu / DESIGN.md)
+  struct V { uint32_t pix; uint32_t fl; };        // fl bit 0: mask != 0, bit 1: edge <= 0
   const uint32_t *pix; const int *mask; const int *edge; int iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix, mask, edge); }
+  __device__ __forceinline__ V load(int x, int y) const {
+    const size_t p = (size_t)y * iw + x;
+    V v; v.pix = pix[p]; v.fl = (mask[p] != 0 ? 1u : 0u) | (edge[p] <= 0 ? 2u : 0u);
+    return v;
+  }
   __device__ __forceinline__ bool interior(int x, int y) const { return x > 0 && y > 0 && x < iw - 1 && y < ih - 1; }
-  __device__ __forceinline__ unsigned operator()(int x, int y) const {
-    const int b = y * iw + x;
-    const uint32_t v = pix[b];
+  __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
     unsigned m = 0;
-    const bool upSame = y > 0 && pix[b - iw] == v;
-    const bool e = edge[b] <= 0;
-    const bool mb = mask[b] != 0;
+    const bool upSame = y > 0 && n.pix == c.pix;
+    const bool e = (c.fl & 2) != 0, mb = (c.fl & 1) != 0;
     if (y > 0) {
-      const int a = b - iw;
       if (upSame) m |= L_N;                                                     // preprocess link
-      else if ((interior(x, y) || interior(x, y - 1)) && e && (mb || mask[a] != 0)) m |= L_N;
+      else if ((interior(x, y) || interior(x, y - 1)) && e && (mb || (n.fl & 1))) m |= L_N;
     }
     if (x > 0) {
-      const int a = b - 1;
-      const bool same = pix[a] == v;
+      const bool same = w.pix == c.pix;
       if (same && !upSame) m |= L_W;                                            // preprocess link (left only when up differs)
-      else if ((interior(x, y) || interior(x - 1, y)) && e && (same || mb || mask[a] != 0)) m |= L_W;
+      else if ((interior(x, y) || interior(x - 1, y)) && e && (same || mb || (w.fl & 1))) m |= L_W;
     }
     return m;
   }
@@ -101,22 +106,33 @@ __device__ __forceinline__ void sm_unite(int *L, int a, int b) {
   }
 }
 
-// local neighbour offsets for the four link bits (tile-local index = ly * TW + lx)
+// One CTA per 32x32 tile, one warp per tile row at a time (8 warps x 4 rows).  Horizontal runs are resolved with a
+// warp ballot: every pixel starts out pointing at the first pixel of its run (depth 1), so the union-find only has
+// to stitch runs of adjacent rows together.
 template <class LinkFn>
 __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *links, LinkFn f, int iw, int ih, size_t fs) {
   rd_batch_z(fs, label, links);
   f.shift((size_t)blockIdx.z * fs);
+  typedef typename LinkFn::V V;
   __shared__ int L[TW * TH];
   __shared__ uint8_t M[TW * TH];
+  __shared__ V T[(TH + 1) * (TW + 2)];                            // tile + the row above + a column on each side
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;        // 8 warps, each warp owns rows wy, wy+8, wy+16, wy+24
   const int x = x0 + lx;
+  for (int i = threadIdx.x; i < (TH + 1) * (TW + 2); i += CCL_THREADS) {
+    const int tx = i % (TW + 2), ty = i / (TW + 2);
+    const int gx = x0 - 1 + tx, gy = y0 - 1 + ty;
+    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) T[i] = f.load(gx, gy);   // positions outside the image are never consulted
+  }
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int ly = wy + k * 8, y = y0 + ly, i = ly * TW + lx;
     unsigned m = L_BG, full = L_BG;
     if (x < iw && y < ih) {
-      full = f(x, y);
+      const V *c = T + (ly + 1) * (TW + 2) + lx + 1;
+      full = f.link(c[0], c[-1], c[-(TW + 2) - 1], c[-(TW + 2)], c[-(TW + 2) + 1], x, y);
       links[(size_t)y * iw + x] = (uint8_t)full;
       m = full;
       if (lx == 0) m &= ~(L_W | L_NW);                             // neighbours outside the tile are the seam kernel's business
@@ -124,51 +140,68 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
       if (ly == 0) m &= ~(L_NW | L_N | L_NE);
     }
     M[i] = (uint8_t)m;
-    int l = i;                                                     // smallest connected backward neighbour: NW < N < NE < W
-    if (m & L_W) l = i - 1;
-    if (m & L_NE) l = i - TW + 1;
-    if (m & L_N) l = i - TW;
-    if (m & L_NW) l = i - TW - 1;
-    L[i] = l;
+    const unsigned starts = ~__ballot_sync(0xffffffffu, (m & L_W) != 0);      // bit j set: pixel j starts a run
+    const int first = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));        // nearest run start at or left of lx (bit 0 is always set)
+    L[i] = ly * TW + first;
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) { const int i = (wy + k * 8) * TW + lx; L[i] = sm_find(L, i); }
-  __syncthreads();
+  // Stitch the runs of adjacent rows.  A union is skipped when a neighbouring link already implies it: the link to N is
+  // implied when the W neighbour has it too and both pairs are W-linked; the links to NW / NE are implied by the link to N
+  // when N is W-linked to them.  (Each skipped union follows from links that are themselves processed, so the components
+  // are unchanged - also for predicates that are not transitive.)  A uniform tile needs 31 unions instead of ~3000.
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int i = (wy + k * 8) * TW + lx;
     const unsigned m = M[i];
-    if (m & L_W) sm_unite(L, i, i - 1);
-    if (m & L_NW) sm_unite(L, i, i - TW - 1);
-    if (m & L_N) sm_unite(L, i, i - TW);
-    if (m & L_NE) sm_unite(L, i, i - TW + 1);
+    if (m & (L_NW | L_N | L_NE)) {
+      const unsigned mn = M[i - TW];
+      if ((m & L_N) && !((m & L_W) && (M[i - 1] & L_N) && (mn & L_W))) sm_unite(L, i, i - TW);
+      if ((m & L_NW) && !((m & L_N) && (mn & L_W))) sm_unite(L, i, i - TW - 1);
+      if ((m & L_NE) && !((m & L_N) && (M[i - TW + 1] & L_W))) sm_unite(L, i, i - TW + 1);
+    }
+  }
+  __syncthreads();
+  // run starts look up their root first, then every pixel reads it through its run start (two hops)
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int i = (wy + k * 8) * TW + lx;
+    if (!(M[i] & L_W)) L[i] = sm_find(L, i);
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int ly = wy + k * 8, y = y0 + ly, i = ly * TW + lx;
     if (x < iw && y < ih) {
-      const int r = sm_find(L, i);
+      const int r = L[L[i]];
       label[(size_t)y * iw + x] = (y0 + (r >> 5)) * iw + x0 + (r & 31);
     }
   }
 }
 
-// unions across tile seams.  One thread per pixel of the image; only seam pixels do work.
-__global__ void k_ccl_seams(int *label, const uint8_t *links, int iw, int ih, size_t fs) {
+// unions across tile seams: one CTA of 96 threads per tile - warp 0 walks the top row (links to the tile row above),
+// warp 1 the left column (W / NW links to the tile on the left), warp 2 the right column (NE links to the tile on the right).
+__global__ void __launch_bounds__(96) k_ccl_seams(int *label, const uint8_t *links, int iw, int ih, size_t fs) {
   rd_batch_z(fs, label, links);
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x, y;
+  if (w == 0) { x = x0 + lane; y = y0; }
+  else if (w == 1) { x = x0; y = y0 + lane; }
+  else { x = x0 + TW - 1; y = y0 + lane; }
   if (x >= iw || y >= ih) return;
-  const int lx = x & (TW - 1), ly = y & (TH - 1);
-  if (lx != 0 && lx != TW - 1 && ly != 0) return;
   const int p = y * iw + x;
   const unsigned m = links[p];
   if (m & L_BG) return;
-  if ((m & L_W) && lx == 0) rd_uf_unite(label, p, p - 1);
-  if ((m & L_NW) && (lx == 0 || ly == 0)) rd_uf_unite(label, p, p - iw - 1);
-  if ((m & L_N) && ly == 0) rd_uf_unite(label, p, p - iw);
-  if ((m & L_NE) && (lx == TW - 1 || ly == 0)) rd_uf_unite(label, p, p - iw + 1);
+  if (w == 0) {
+    if (m & L_NW) rd_uf_unite(label, p, p - iw - 1);
+    if (m & L_N) rd_uf_unite(label, p, p - iw);
+    if (m & L_NE) rd_uf_unite(label, p, p - iw + 1);
+  } else if (w == 1) {
+    if (m & L_W) rd_uf_unite(label, p, p - 1);
+    if ((m & L_NW) && lane != 0) rd_uf_unite(label, p, p - iw - 1);            // lane 0 is the corner pixel, done by warp 0
+  } else {
+    if ((m & L_NE) && lane != 0) rd_uf_unite(label, p, p - iw + 1);
+  }
 }
 
 // final labels.  mode 0: background -> bgval, others -> root.
@@ -199,8 +232,7 @@ __global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *
 template <class LinkFn>
 static void ccl_core(int *label, uint8_t *links, LinkFn f, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   RD_LAUNCH(k_ccl_tile<LinkFn>, rd_gz(dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH)), nb), CCL_THREADS, 0, s, label, links, f, iw, ih, fs);
-  const dim3 b(32, 8);
-  RD_LAUNCH(k_ccl_seams, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, label, links, iw, ih, fs);
+  RD_LAUNCH(k_ccl_seams, dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH), nb), 96, 0, s, label, links, iw, ih, fs);
 }
 
 // scratch: iw*ih bytes

@@ -1,0 +1,408 @@
+// rd_fast.cu - the tuned kernels of the rect pipeline's device schedule (rd_rect.cu : gpu_task).
+//
+// The operator-level kernels in rd_imgutil.cu / rd_rect.cu follow the reference one launch per __kernel.  The
+// schedule replaces the expensive groups by the kernels below, which compute bit-identical results:
+//   rd_blblur_run     : the 10 x (blblur0, blblur1) edge-stopped box blurs (oclrect.cl:155-205, oclrect.c:286-296).
+//                       The stop rules only look at the edge mask, which is the same for all 20 passes, so the walk
+//                       extents of every pixel are computed once (1 B/px per direction) and each iteration becomes
+//                       one shared-memory-tiled kernel doing the x pass and the y pass back to back.
+//   rd_calcSize_run   : region histogram (oclrect.cl:336) with warp- and CTA-level aggregation in front of the
+//                       global atomics (one region can own half a frame).
+//   rd_iirblur3_run   : the three recursive-Gaussian blurs of oclrect.c:248-250 (oclimgutil.cl:542-637) straight
+//                       from the packed Lab plane: one thread runs the three channel chains of a row (column)
+//                       and direction, the pass1 / pass3 combinations are folded into the consumers.
+#include "rd_common.cuh"
+#include "rd_stageA.cuh"
+#define RD_TABLE_QUAL static __device__ const
+#include "rd_tables.inc"
+
+// =============================================================================================== blblur
+#define BLB 4
+// walk extents of pixel (pos along the walk, p0) : nl = pixels taken walking back (0..5), nr = walking forward (0..5)
+template <int DIR, class E>
+__device__ __forceinline__ unsigned blb_extent(const E &e, int x, int y, int iw, int ih) {
+  const int pos = DIR == 0 ? x : y, len = DIR == 0 ? iw : ih;
+  const bool hasSide = DIR == 0 ? (y < ih - 1) : (x < iw - 1);
+  const int oe = e.at(x, y) != 0;
+  int nl = 0, nr = 0;
+  for (int d = 0; d >= -BLB; d--) {
+    if (pos + d < 0) break;
+    const int qx = DIR == 0 ? x + d : x, qy = DIR == 0 ? y : y + d;
+    const int bx = DIR == 0 ? qx - 1 : qx, by = DIR == 0 ? qy : qy - 1;          // previous pixel of the walk
+    const int sx = DIR == 0 ? qx : qx + 1, sy = DIR == 0 ? qy + 1 : qy;          // perpendicular neighbour
+    if (pos + d > 0 && e.at(qx, qy) != 0 && e.at(bx, by) == 0) break;
+    if (pos + d > 0 && hasSide && e.at(qx, qy) == 0 && e.at(bx, by) != 0 && e.at(sx, sy) != 0) break;
+    nl++;
+  }
+  for (int d = 0; d <= BLB; d++) {
+    if (pos + d > len - 1) break;
+    const int qx = DIR == 0 ? x + d : x, qy = DIR == 0 ? y : y + d;
+    const int fx = DIR == 0 ? qx + 1 : qx, fy = DIR == 0 ? qy : qy + 1;          // next pixel of the walk
+    if (pos + d < len - 1 && e.at(qx, qy) == 0 && e.at(fx, fy) != 0) break;
+    if (oe && e.at(qx, qy) == 0) break;
+    nr++;
+  }
+  return (unsigned)nl | ((unsigned)nr << 4);
+}
+
+#define EX_TX 64
+#define EX_TY 16
+#define EX_H 5
+struct SmemEdge {
+  const int8_t *t; int x0, y0;           // tile origin (image coords of t[0]) ; row pitch EX_TX + 2*EX_H
+  __device__ __forceinline__ int at(int x, int y) const { return t[(y - y0) * (EX_TX + 2 * EX_H) + (x - x0)]; }
+};
+__global__ void __launch_bounds__(256) kf_blb_extents(uint8_t *extH, uint8_t *extV, const int8_t *edge, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, extH, extV, edge);
+  __shared__ int8_t tile[(EX_TY + 2 * EX_H) * (EX_TX + 2 * EX_H)];
+  const int x0 = blockIdx.x * EX_TX - EX_H, y0 = blockIdx.y * EX_TY - EX_H;
+  for (int i = threadIdx.x; i < (EX_TY + 2 * EX_H) * (EX_TX + 2 * EX_H); i += 256) {
+    const int tx = i % (EX_TX + 2 * EX_H), ty = i / (EX_TX + 2 * EX_H);
+    const int gx = x0 + tx, gy = y0 + ty;
+    tile[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih) ? edge[(size_t)gy * iw + gx] : (int8_t)0;   // never read when outside
+  }
+  __syncthreads();
+  SmemEdge e = {tile, x0, y0};
+#pragma unroll
+  for (int k = 0; k < (EX_TX * EX_TY) / 256; k++) {
+    const int i = threadIdx.x + k * 256;
+    const int x = blockIdx.x * EX_TX + (i % EX_TX), y = blockIdx.y * EX_TY + (i / EX_TX);
+    if (x < iw && y < ih) {
+      extH[(size_t)y * iw + x] = (uint8_t)blb_extent<0>(e, x, y, iw, ih);
+      extV[(size_t)y * iw + x] = (uint8_t)blb_extent<1>(e, x, y, iw, ih);
+    }
+  }
+}
+
+// floor(c / w) for 0 <= c < 2^16, 1 <= w <= 10 : one multiply-high by ceil(2^32 / w)
+__constant__ const unsigned BLB_RCP[11] = {0u, 0u, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u, 0x1c71c71du, 0x1999999au};
+__device__ __forceinline__ unsigned blb_div(unsigned c, unsigned w) { return w == 1 ? c : __umulhi(c, BLB_RCP[w]); }
+__device__ __forceinline__ uint32_t blb_mean(unsigned c0, unsigned c1, unsigned c2, unsigned w) {
+  // packlabbl(csum / wsum): the quotients cannot leave their fields (means of in-range values), so no clamp is needed
+  return (blb_div(c2, w) << 22) | (blb_div(c1, w) << 12) | blb_div(c0, w);
+}
+
+#define IT_TX 64
+#define IT_TY 32
+#define IT_PW (IT_TX + 2 * BLB)        // input tile pitch
+// Shared-memory tiles hold the three channels spread out in one 64-bit word (L at bit 0, a at bit 20, b at bit 40), so
+// a walk is a chain of plain 64-bit adds (at most 10 terms of at most 12 bits each: no field can overflow into the next).
+typedef unsigned long long blb_w;
+__device__ __forceinline__ blb_w blb_spread(uint32_t v) { return (blb_w)(v & 4095u) | ((blb_w)((v >> 12) & 1023u) << 20) | ((blb_w)(v >> 22) << 40); }
+__device__ __forceinline__ uint32_t blb_pack(blb_w w) { return (uint32_t)(w & 4095u) | ((uint32_t)((w >> 20) & 1023u) << 12) | ((uint32_t)(w >> 40) << 22); }
+// sum of c[-(nb_-1)..0] and c[0..nf_-1] (the centre counts once per walk that reaches it), then the packed mean
+__device__ __forceinline__ uint32_t blb_walk(const blb_w *c, int stride, int nb_, int nf_) {
+  blb_w acc = 0;
+#pragma unroll
+  for (int d = 0; d <= BLB; d++) {
+    if (d < nb_) acc += c[-d * stride];
+    if (d < nf_) acc += c[d * stride];
+  }
+  const unsigned w = nb_ + nf_;
+  if (w == 0) return blb_pack(c[0]);
+  return blb_mean((unsigned)(acc & 0xfffffu), (unsigned)((acc >> 20) & 0xfffffu), (unsigned)(acc >> 40), w);
+}
+// one iteration = blblur0 then blblur1.  Input tile (TY+8) x (TX+8) -> x pass on (TY+8) x TX -> y pass on TY x TX.
+// CTA = 64 x 4 threads; everything the two passes need (pixels and walk extents) is staged in shared memory first.
+__global__ void __launch_bounds__(256) kf_blb_iter(uint32_t *out, const uint32_t *in, const uint8_t *extH, const uint8_t *extV, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in, extH, extV);
+  __shared__ blb_w tin[(IT_TY + 2 * BLB) * IT_PW];
+  __shared__ blb_w th[(IT_TY + 2 * BLB) * IT_TX];
+  __shared__ uint8_t eh[(IT_TY + 2 * BLB) * IT_TX];
+  __shared__ uint8_t ev[IT_TY * IT_TX];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int bx = blockIdx.x * IT_TX, by = blockIdx.y * IT_TY;
+  const int gx = bx + tx;
+#pragma unroll
+  for (int r = ty; r < IT_TY + 2 * BLB; r += 4) {
+    const int gy = by - BLB + r;
+    const bool rowok = gy >= 0 && gy < ih;
+    const size_t rb = (size_t)gy * iw;
+    const int gl = bx - BLB + tx;                                   // tile column tx
+    tin[r * IT_PW + tx] = blb_spread((rowok && gl >= 0 && gl < iw) ? in[rb + gl] : 0u);
+    if (tx < 2 * BLB) { const int g2 = gl + IT_TX; tin[r * IT_PW + IT_TX + tx] = blb_spread((rowok && g2 < iw) ? in[rb + g2] : 0u); }
+    eh[r * IT_TX + tx] = (rowok && gx < iw) ? extH[rb + gx] : (uint8_t)0;
+    if (r < IT_TY) { const int g3 = by + r; ev[r * IT_TX + tx] = (g3 < ih && gx < iw) ? extV[(size_t)g3 * iw + gx] : (uint8_t)0; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < IT_TY + 2 * BLB; r += 4) {
+    const unsigned e = eh[r * IT_TX + tx];
+    th[r * IT_TX + tx] = blb_spread(blb_walk(tin + r * IT_PW + tx + BLB, 1, e & 15, e >> 4));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < IT_TY; r += 4) {
+    const int gy = by + r;
+    const unsigned e = ev[r * IT_TX + tx];
+    const uint32_t v = blb_walk(th + (r + BLB) * IT_TX + tx, IT_TX, e & 15, e >> 4);
+    if (gx < iw && gy < ih) out[(size_t)gy * iw + gx] = v;
+  }
+}
+
+// steps 13 of genGPUTask: src -> 10 iterations -> dst, ping-ponging through `pong`; ext: 2*iw*ih bytes of scratch
+void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int8_t *edge, uint8_t *ext, int iters, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  uint8_t *extH = ext, *extV = ext + (size_t)iw * ih;
+  RD_LAUNCH(kf_blb_extents, dim3(rd_cdiv(iw, EX_TX), rd_cdiv(ih, EX_TY), nb), 256, 0, s, extH, extV, edge, iw, ih, fs);
+  const dim3 g(rd_cdiv(iw, IT_TX), rd_cdiv(ih, IT_TY), nb);
+  const uint32_t *cur = src;
+  for (int i = 0; i < iters; i++) {
+    uint32_t *o = ((iters - i) & 1) ? dst : pong;       // the last iteration lands in dst
+    RD_LAUNCH(kf_blb_iter, g, dim3(IT_TX, 4), 0, s, o, cur, extH, extV, iw, ih, fs);
+    cur = o;
+  }
+}
+
+// =============================================================================================== calcSize
+#define CS_SLOTS 64
+__global__ void __launch_bounds__(256) kf_calcSize(int *out, const int *label, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, label);
+  __shared__ int keys[CS_SLOTS];
+  __shared__ int cnts[CS_SLOTS];
+  if (threadIdx.x < CS_SLOTS) { keys[threadIdx.x] = -1; cnts[threadIdx.x] = 0; }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + lx;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int y = blockIdx.y * 32 + wy + k * 8;
+    const bool ok = x < iw && y < ih;
+    const int l = ok ? label[(size_t)y * iw + x] : -1;
+    const unsigned act = __ballot_sync(0xffffffffu, l != -1);
+    if (l == -1) continue;
+    const unsigned peers = __match_any_sync(act, l);
+    if ((int)(__ffs(peers) - 1) != lx) continue;
+    const int c = __popc(peers);
+    unsigned h = ((unsigned)l * 2654435761u) >> 26;           // 6-bit hash
+    bool done = false;
+    for (int probe = 0; probe < 8 && !done; probe++, h = (h + 1) & (CS_SLOTS - 1)) {
+      const int prev = atomicCAS(&keys[h], -1, l);
+      if (prev == -1 || prev == l) { atomicAdd(&cnts[h], c); done = true; }
+    }
+    if (!done) atomicAdd(out + l, c);                         // crowded tile: straight to global
+  }
+  __syncthreads();
+  if (threadIdx.x < CS_SLOTS && keys[threadIdx.x] != -1) atomicAdd(out + keys[threadIdx.x], cnts[threadIdx.x]);
+}
+void rd_calcSize_run(int *out, const int *label, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(kf_calcSize, dim3(rd_cdiv(iw, 32), rd_cdiv(ih, 32), nb), 256, 0, s, out, label, iw, ih, fs);
+}
+
+// =============================================================================================== recursive Gaussian x3
+// Horizontal: one thread per (row, direction) runs the L, a and b chains of that row straight from the packed Lab
+// plane (the unpack of oclimgutil.cl:333 is three ALU ops) and stores the raw causal / anti-causal responses.
+// Each lane walks its own row with 128-bit loads / stores; the L1 keeps the other half of each sector for the next step.
+// unpack one channel of a packed Lab word (oclimgutil.cl:36-39)
+template <int CH> __device__ __forceinline__ float unpack_ch(uint32_t plab) {
+  const int sh = CH == 0 ? 0 : (CH == 1 ? 12 : 22);
+  const unsigned mask = CH == 0 ? 4095u : 1023u;
+  const float sc = CH == 0 ? 1.0f / 4096 : 1.0f / 1024, of = CH == 0 ? 0.5f / 4096 : 0.5f / 1024;
+  return __fadd_rn(__fmul_rn((float)(int)((plab >> sh) & mask), sc), of);
+}
+// The recurrence (oclimgutil.cl:549-558) eight steps at a time.  The taps are the previous seven inputs and outputs; with
+// the loop fully unrolled they are plain registers named at compile time, so no tap is ever moved (the straightforward
+// form shifts 14 registers per step, which doubled the instruction count).  pi / po: the last eight inputs / outputs,
+// index 7 = newest.  Order of operations per step is that of rd_iir_taps::step.
+struct Chain8 {
+  float pi[8], po[8];
+  __device__ __forceinline__ Chain8() {
+#pragma unroll
+    for (int i = 0; i < 8; i++) pi[i] = po[i] = 0.0f;
+  }
+  __device__ __forceinline__ float step1(float in, const float *c) {          // warm-up / ragged tail: one step, taps shifted
+    float d = __fmul_rn(in, c[0]);
+    float a = __fmul_rn(c[1], pi[7]);
+#pragma unroll
+    for (int j = 2; j <= 7; j++) a = __fadd_rn(a, __fmul_rn(c[j], pi[8 - j]));
+    d = __fadd_rn(d, a);
+    float b = __fmul_rn(c[8], po[7]);
+#pragma unroll
+    for (int j = 1; j <= 6; j++) b = __fadd_rn(b, __fmul_rn(c[8 + j], po[7 - j]));
+    d = __fadd_rn(d, b);
+#pragma unroll
+    for (int i = 0; i < 7; i++) { pi[i] = pi[i + 1]; po[i] = po[i + 1]; }
+    pi[7] = in; po[7] = d;
+    return d;
+  }
+  __device__ __forceinline__ void step8(const float (&in)[8], float (&out)[8], const float *c) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      // X(j): input j steps into this block (j >= 0) or from the previous block (j < 0); O(j) likewise for outputs
+#define X_(j) ((j) >= 0 ? in[(j) < 0 ? 0 : (j)] : pi[(j) < 0 ? 8 + (j) : 0])
+#define O_(j) ((j) >= 0 ? out[(j) < 0 ? 0 : (j)] : po[(j) < 0 ? 8 + (j) : 0])
+      float d = __fmul_rn(in[k], c[0]);
+      float a = __fmul_rn(c[1], X_(k - 1));
+#pragma unroll
+      for (int j = 2; j <= 7; j++) a = __fadd_rn(a, __fmul_rn(c[j], X_(k - j)));
+      d = __fadd_rn(d, a);
+      float b = __fmul_rn(c[8], O_(k - 1));
+#pragma unroll
+      for (int j = 1; j <= 6; j++) b = __fadd_rn(b, __fmul_rn(c[8 + j], O_(k - 1 - j)));
+      d = __fadd_rn(d, b);
+      out[k] = d;
+#undef X_
+#undef O_
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { pi[i] = in[i]; po[i] = out[i]; }
+  }
+};
+
+// Horizontal pass: thread t -> channel t % 3, direction (t / 3) & 1, row t / 6 (the six chains of a row sit in
+// neighbouring lanes).  Each lane streams its row with 128-bit loads (next eight pixels prefetched) and 128-bit stores.
+template <int CH, int DIR>
+__device__ __forceinline__ void iir_h_chain(float *q, const uint32_t *row, const float *c, int warm, int iw) {
+  Chain8 st;
+  if (DIR == 0) for (int x = -warm; x < 0; x++) st.step1(unpack_ch<CH>(row[rd_mirror1(x, iw)]), c);
+  else for (int x = iw + warm; x >= iw; x--) st.step1(unpack_ch<CH>(row[rd_mirror1(x, iw)]), c);
+  if ((iw & 7) == 0) {
+    const int nblk = iw >> 3;
+    // block b covers pixels [8b, 8b+8) walking forward, [iw-8-8b, iw-8b) walking backward
+    const uint4 *src = (const uint4 *)row;
+    uint4 v0 = src[DIR == 0 ? 0 : 2 * nblk - 2], v1 = src[DIR == 0 ? 1 : 2 * nblk - 1];
+    for (int b = 0; b < nblk; b++) {
+      const int base = DIR == 0 ? 2 * b : 2 * (nblk - 1 - b);
+      const uint4 c0 = v0, c1 = v1;
+      if (b + 1 < nblk) { const int nb2 = DIR == 0 ? base + 2 : base - 2; v0 = src[nb2]; v1 = src[nb2 + 1]; }
+      const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      float in[8], out[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) in[k] = unpack_ch<CH>(w[DIR == 0 ? k : 7 - k]);
+      st.step8(in, out, c);
+      float4 *dst = (float4 *)q + base;
+      if (DIR == 0) { dst[0] = make_float4(out[0], out[1], out[2], out[3]); dst[1] = make_float4(out[4], out[5], out[6], out[7]); }
+      else { dst[0] = make_float4(out[7], out[6], out[5], out[4]); dst[1] = make_float4(out[3], out[2], out[1], out[0]); }
+    }
+  } else {
+    if (DIR == 0) for (int x = 0; x < iw; x++) q[x] = st.step1(unpack_ch<CH>(row[x]), c);
+    else for (int x = iw - 1; x >= 0; x--) q[x] = st.step1(unpack_ch<CH>(row[x]), c);
+  }
+}
+// CTA = 6 warps over 32 rows: warp w runs channel w / 2 in direction w % 2 (no divergence inside a warp), lane = row.
+__global__ void __launch_bounds__(192) kf_iir_h3(float *f0, float *f1, float *f2, float *b0, float *b1, float *b2, const uint32_t *plab, int r, int iw, int ih, size_t fs) {
+  rd_batch_y(fs, f0, f1, f2, b0, b1, b2, plab);
+  const int w = threadIdx.x >> 5, y = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (y >= ih) return;
+  float c[15];
+#pragma unroll
+  for (int i = 0; i < 15; i++) c[i] = RD_IIRCOEF[r][i];
+  const uint32_t *row = plab + (size_t)y * iw;
+  const size_t ro = (size_t)y * iw;
+  const int warm = r + 1 + 8;
+  switch (w) {
+    case 0: iir_h_chain<0, 0>(f0 + ro, row, c, warm, iw); break;
+    case 1: iir_h_chain<0, 1>(b0 + ro, row, c, warm, iw); break;
+    case 2: iir_h_chain<1, 0>(f1 + ro, row, c, warm, iw); break;
+    case 3: iir_h_chain<1, 1>(b1 + ro, row, c, warm, iw); break;
+    case 4: iir_h_chain<2, 0>(f2 + ro, row, c, warm, iw); break;
+    default: iir_h_chain<2, 1>(b2 + ro, row, c, warm, iw); break;
+  }
+}
+// pass1 (oclimgutil.cl:580) for the three channels: h = bwd + fwd - in*coef0, in place of the forward planes
+__global__ void kf_iir_mid3(float *f0, float *f1, float *f2, const float *b0, const float *b1, const float *b2, const uint32_t *plab, int r, int n, size_t fs) {
+  rd_batch_y(fs, f0, f1, f2, b0, b1, b2, plab);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c0 = RD_IIRCOEF[r][0];
+  float l, a, b;
+  rd_unpacklab(plab[i], l, a, b);
+  f0[i] = __fsub_rn(__fadd_rn(b0[i], f0[i]), __fmul_rn(l, c0));
+  f1[i] = __fsub_rn(__fadd_rn(b1[i], f1[i]), __fmul_rn(a, c0));
+  f2[i] = __fsub_rn(__fadd_rn(b2[i], f2[i]), __fmul_rn(b, c0));
+}
+// Vertical: one thread per (column, channel, direction), coalesced across the warp; the rows of the next eight steps are
+// loaded while the current eight are computed.
+__global__ void __launch_bounds__(128) kf_iir_v3(float *vf0, float *vf1, float *vf2, float *vb0, float *vb1, float *vb2,
+                                                 const float *h0, const float *h1, const float *h2, int r, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, vf0, vf1, vf2, vb0, vb1, vb2, h0, h1, h2);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y >> 1, dir = blockIdx.y & 1;
+  if (x >= iw) return;
+  float c[15];
+#pragma unroll
+  for (int i = 0; i < 15; i++) c[i] = RD_IIRCOEF[r][i];
+  const float *__restrict__ h = (ch == 0 ? h0 : (ch == 1 ? h1 : h2)) + x;
+  float *__restrict__ o = (dir == 0 ? (ch == 0 ? vf0 : (ch == 1 ? vf1 : vf2)) : (ch == 0 ? vb0 : (ch == 1 ? vb1 : vb2))) + x;
+  Chain8 st;
+  const int warm = r + 1 + 8;
+  const int sgn = dir == 0 ? 1 : -1;
+  if (dir == 0) for (int y = -warm; y < 0; y++) st.step1(h[(size_t)rd_mirror1(y, ih) * iw], c);
+  else for (int y = ih + warm; y >= ih; y--) st.step1(h[(size_t)rd_mirror1(y, ih) * iw], c);
+  const int y0 = dir == 0 ? 0 : ih - 1;                          // first real row; row k of the walk is y0 + k*sgn
+  const int nblk = ih >> 3;
+  float cur[8], nxt[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cur[j] = j < ih ? h[(size_t)(y0 + j * sgn) * iw] : 0.0f;
+  for (int b = 0; b < nblk; b++) {
+    const int k0 = b * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { const int k = k0 + 8 + j; nxt[j] = k < ih ? h[(size_t)(y0 + k * sgn) * iw] : 0.0f; }
+    float out[8];
+    st.step8(cur, out, c);
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[(size_t)(y0 + (k0 + j) * sgn) * iw] = out[j];
+#pragma unroll
+    for (int j = 0; j < 8; j++) cur[j] = nxt[j];
+  }
+  for (int k = nblk * 8, j = 0; k < ih; k++, j++) {               // ragged tail (ih % 8 rows): cur[] holds them
+    float v = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) if (q == j) v = cur[q];
+    o[(size_t)(y0 + k * sgn) * iw] = st.step1(v, c);
+  }
+}
+// pass3 (oclimgutil.cl:629) for the three channels + pack_plab (oclimgutil.cl:325): blurred L plane and blurred packed Lab
+__global__ void kf_iir_fin3(float *outL, float *outA, float *outB, uint32_t *outPlab, const float *vf0, const float *vf1, const float *vf2, const float *vb0,
+                            const float *vb1, const float *vb2, const float *h0, const float *h1, const float *h2, int r, int n, size_t fs) {
+  rd_batch_y(fs, outL, outA, outB, outPlab, vf0, vf1, vf2, vb0, vb1, vb2, h0, h1, h2);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c0 = RD_IIRCOEF[r][0];
+  const float l = __fsub_rn(__fadd_rn(vb0[i], vf0[i]), __fmul_rn(h0[i], c0));
+  const float a = __fsub_rn(__fadd_rn(vb1[i], vf1[i]), __fmul_rn(h1[i], c0));
+  const float b = __fsub_rn(__fadd_rn(vb2[i], vf2[i]), __fmul_rn(h2[i], c0));
+  outL[i] = l; outA[i] = a; outB[i] = b;
+  outPlab[i] = rd_packlab(l, a, b);
+}
+
+// =============================================================================================== BGR8 -> packed Lab
+// bgr2plab (oclimgutil.cl:256) four pixels per thread: three 32-bit loads bring 12 bytes, one 128-bit store leaves.
+__global__ void __launch_bounds__(256) kf_bgr2plab4(uint32_t *out, const uint8_t *in, size_t in_fs, int iw, int ih, int ws, size_t fs) {
+  rd_batch_z(fs, out);
+  rd_batch_z(in_fs, in);
+  const int x4 = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x4 * 4 >= iw || y >= ih) return;
+  const uint32_t *p = (const uint32_t *)(in + (size_t)y * ws) + x4 * 3;
+  const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+  uint4 r;
+  r.x = rd_srgb2plab(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255, RD_S2L, RD_CFUNC, RD_CFUNC2);
+  r.y = rd_srgb2plab(w0 >> 24, w1 & 255, (w1 >> 8) & 255, RD_S2L, RD_CFUNC, RD_CFUNC2);
+  r.z = rd_srgb2plab((w1 >> 16) & 255, w1 >> 24, w2 & 255, RD_S2L, RD_CFUNC, RD_CFUNC2);
+  r.w = rd_srgb2plab((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24, RD_S2L, RD_CFUNC, RD_CFUNC2);
+  *(uint4 *)(out + (size_t)y * iw + x4 * 4) = r;
+}
+__global__ void kf_bgr2plab1(uint32_t *out, const uint8_t *in, size_t in_fs, int iw, int ih, int ws, size_t fs) {
+  rd_batch_z(fs, out);
+  rd_batch_z(in_fs, in);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const uint8_t *p = in + (size_t)y * ws + x * 3;
+  out[(size_t)y * iw + x] = rd_srgb2plab(p[0], p[1], p[2], RD_S2L, RD_CFUNC, RD_CFUNC2);
+}
+void rd_bgr2plab_run(uint32_t *out, const uint8_t *in, size_t in_fs, int iw, int ih, int ws, int nb, size_t fs, cudaStream_t s) {
+  const dim3 b(32, 8);
+  if ((iw & 3) == 0 && (ws & 3) == 0 && (in_fs & 3) == 0 && ((uintptr_t)in & 3) == 0)
+    RD_LAUNCH(kf_bgr2plab4, dim3(rd_cdiv(iw / 4, 32), rd_cdiv(ih, 8), nb), b, 0, s, out, in, in_fs, iw, ih, ws, fs);
+  else
+    RD_LAUNCH(kf_bgr2plab1, dim3(rd_cdiv(iw, 32), rd_cdiv(ih, 8), nb), b, 0, s, out, in, in_fs, iw, ih, ws, fs);
+}
+
+// steps 2-4 of genGPUTask: outL/outA/outB = blurred channels (also the forward scratch), outPlab = blurred packed Lab;
+// sb / sf : three scratch planes each (plane pitch `pp` floats)
+void rd_iirblur3_run(float *outL, float *outA, float *outB, uint32_t *outPlab, const uint32_t *plab, float *sb, float *sf, size_t pp, int r, int iw, int ih,
+                     int nb, size_t fs, cudaStream_t s) {
+  const int n = iw * ih;
+  RD_LAUNCH(kf_iir_h3, dim3(rd_cdiv(ih, 32), nb), 192, 0, s, outL, outA, outB, sb, sb + pp, sb + 2 * pp, plab, r, iw, ih, fs);
+  RD_LAUNCH(kf_iir_mid3, dim3(rd_cdiv(n, 256), nb), 256, 0, s, outL, outA, outB, sb, sb + pp, sb + 2 * pp, plab, r, n, fs);
+  RD_LAUNCH(kf_iir_v3, dim3(rd_cdiv(iw, 128), 6, nb), 128, 0, s, sf, sf + pp, sf + 2 * pp, sb, sb + pp, sb + 2 * pp, outL, outA, outB, r, iw, ih, fs);
+  RD_LAUNCH(kf_iir_fin3, dim3(rd_cdiv(n, 256), nb), 256, 0, s, outL, outA, outB, outPlab, sf, sf + pp, sf + 2 * pp, sb, sb + pp, sb + 2 * pp, outL, outA, outB, r, n, fs);
+}

@@ -20,6 +20,16 @@ __global__ void k_clear(int *out, int n, size_t fs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = 0;
 }
+__global__ void k_clear4(int4 *out, int n4, size_t fs) {                     // 128-bit stores, 4 ints per thread
+  rd_batch_y(fs, out);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) out[i] = make_int4(0, 0, 0, 0);
+}
+__global__ void k_copy4(int4 *out, const int4 *in, int n4, size_t fs) {
+  rd_batch_y(fs, out, in);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) out[i] = in[i];
+}
 __global__ void k_copy(int *out, const int *in, int n, size_t fs) {
   rd_batch_y(fs, out, in);                     // oclimgutil.cl:204
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,8 +192,18 @@ __global__ void k_filterStrength(int *labelinout, const int *str, int thre, int 
 static const int B1 = 256;
 static const dim3 B2(32, 8);
 
-void rd_k_clear(int *out, int nints, int nb, size_t fs, cudaStream_t s) { if (nints > 0) RD_LAUNCH(k_clear, rd_gy(rd_cdiv(nints, B1), nb), B1, 0, s, out, nints, fs); }
-void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream_t s) { if (nints > 0) RD_LAUNCH(k_copy, rd_gy(rd_cdiv(nints, B1), nb), B1, 0, s, out, in, nints, fs); }
+void rd_k_clear(int *out, int nints, int nb, size_t fs, cudaStream_t s) {
+  if (nints <= 0) return;
+  const int n4 = (((uintptr_t)out & 15) == 0 && (fs & 15) == 0) ? nints / 4 : 0;
+  if (n4 > 0) RD_LAUNCH(k_clear4, rd_gy(rd_cdiv(n4, B1), nb), B1, 0, s, (int4 *)out, n4, fs);
+  if (nints - n4 * 4 > 0) RD_LAUNCH(k_clear, rd_gy(rd_cdiv(nints - n4 * 4, B1), nb), B1, 0, s, out + n4 * 4, nints - n4 * 4, fs);
+}
+void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream_t s) {
+  if (nints <= 0) return;
+  const int n4 = (((uintptr_t)out & 15) == 0 && ((uintptr_t)in & 15) == 0 && (fs & 15) == 0) ? nints / 4 : 0;
+  if (n4 > 0) RD_LAUNCH(k_copy4, rd_gy(rd_cdiv(n4, B1), nb), B1, 0, s, (int4 *)out, (const int4 *)in, n4, fs);
+  if (nints - n4 * 4 > 0) RD_LAUNCH(k_copy, rd_gy(rd_cdiv(nints - n4 * 4, B1), nb), B1, 0, s, out + n4 * 4, in + n4 * 4, nints - n4 * 4, fs);
+}
 void rd_k_rand(int *out, uint64_t seed, int n, int nb, size_t fs, cudaStream_t s) { if (n > 0) RD_LAUNCH(k_rand, rd_gy(rd_cdiv(n, B1), nb), B1, 0, s, out, seed, n, fs); }
 void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   const int n = iw * ih;

@@ -29,6 +29,10 @@ static_assert(sizeof(LS_t) == 56 && sizeof(LSX_t) == 56, "list entries are 56 by
 #define MINNINDEX 4
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
 #define IS_BORDER1 (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1)
+// kernels over the compact list of labelled pixels: grid-stride loop, `continue` instead of `return`
+#define PLIST_LOOP const int pcount_ = plist[0]; for (int k_ = blockIdx.x * blockDim.x + threadIdx.x; k_ < pcount_; k_ += gridDim.x * blockDim.x)
+#define PLIST_XY const int p0 = plist[k_ + 1]; const int x = p0 % iw, y = p0 / iw; (void)x; (void)y
+#define LIST_BLOCKS 32
 
 void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
@@ -233,8 +237,9 @@ __global__ void kp_relabel_count(int *blockCount, const int *label, int iw, int 
   }
 }
 // exclusive scan of blockCount in place (single CTA, chunked with a running carry); total -> *total
-__global__ void kp_scan_blocks(int *blockCount, int nblocks, int *total, size_t fs) {
-  rd_batch_x(fs, blockCount, total);
+__global__ void kp_scan_blocks(int *blockCount, int nblocks, int *total, int *plist, size_t fs) {
+  rd_batch_x(fs, blockCount, total, plist);
+  if (threadIdx.x == 0) plist[0] = 0;
   __shared__ int wsum[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -280,13 +285,28 @@ __global__ void kp_relabel_rank(int *table, const int *blockOffset, const int *l
   __syncthreads();
   if (r) table[p + 1] = blockOffset[blockIdx.x] + wsum[w] + __popc(b & ((1u << lane) - 1)) + 1;
 }
-__global__ void kp_relabel_pass1(int *labelinout, const int *tablein, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, labelinout, tablein);
-  XY2D;
-  if (x == 0 || y == 0 || x >= iw - 1 || y >= ih - 1) { labelinout[p0] = 0; return; }
-  const int g = labelinout[p0];
-  if (g == 0) return;
-  labelinout[p0] = tablein[g + 1];
+// relabel_pass1 (oclpolyline.cl:400) + compaction: every pixel that ends up with a segment id is appended to plist
+// (plist[0] = count, entries from 1; order is irrelevant to the consumers, which only use commutative atomics).
+__global__ void kp_relabel_pass1(int *labelinout, const int *tablein, int *plist, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, labelinout, tablein, plist);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const bool in = x < iw && y < ih;
+  const int p0 = y * iw + x;
+  int g = 0;
+  if (in) {
+    if (x == 0 || y == 0 || x >= iw - 1 || y >= ih - 1) labelinout[p0] = 0;
+    else {
+      g = labelinout[p0];
+      if (g != 0) { g = tablein[g + 1]; labelinout[p0] = g; }
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, g != 0);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(plist, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (g != 0) plist[1 + base + __popc(m & ((1u << lane) - 1))] = p0;
 }
 
 // ---------------------------------------------------------------------------- mkpl (oclpolyline.cl:439-646)
@@ -306,40 +326,54 @@ __device__ __forceinline__ void closestPoint(float vx, float vy, float wx, float
   oy = __fadd_rn(vy, __fmul_rn(t, __fsub_rn(wy, vy)));
 }
 
+// init: zero the list entries of the K initial strings (K = table[0], oclpolyline.c:192 clears the whole list), reset
+// the per-string start / end pixel slots and the arg-max slots, and arm the iteration flags (oclpolyline.cl:442-444)
+__global__ void kp_mkpl_init(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const int *table, int *flags, int maxIter, size_t fs) {
+  rd_batch_y(fs, gp, aux, winner, table, flags);
+  const int cap2 = min(cap, lsListSize / (int)sizeof(LS_t));
+  const int K = min(table[0], cap2 - 1);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (t < maxIter + 1) flags[t] = t == 0 ? 1 : 0;
+  int *raw = (int *)gp;
+  for (int i = t; i < (K + 1) * 14; i += nt) raw[i] = 0;
+  for (int g = t; g <= K; g += nt) { aux[g] = 0; aux[cap + g] = 0x7fffffff; winner[g] = 0x7fffffff; }
+}
 // pass0a: per-string start pixel (the LAST pixel in raster order whose number is 1, as a sequential sweep leaves it),
 // pixel count, largest number, and the list header (largest id).  aux[g] / aux[cap+g] : start / end pixel index.
-__global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int *flags, int maxIter, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, gp, aux, numberin, labelin, flags);
-  XY2D;
-  if (y == 0 && x < maxIter + 1) flags[x] = x == 0 ? 1 : 0;
-  if (IS_BORDER1) return;
-  const int g = labelin[p0], n = numberin[p0];
-  if (g == 0 || ls_overflow(g, lsListSize)) return;
-  if (n == 1) { atomicMax(aux + g, p0 + 1); atomicAdd(&gp[g].startCount, 1); }
-  atomicAdd(&gp[g].npix, 1);
-  atomicMax(&gp[g].endIndex, n);
-  atomicMax((int *)gp, g);
+__global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, const int *plist, int iw, size_t fs) {
+  rd_batch_y(fs, gp, aux, numberin, labelin, plist);
+  PLIST_LOOP {
+    PLIST_XY;
+    const int g = labelin[p0], n = numberin[p0];
+    if (g == 0 || ls_overflow(g, lsListSize)) continue;
+    if (n == 1) { atomicMax(aux + g, p0 + 1); atomicAdd(&gp[g].startCount, 1); }
+    atomicAdd(&gp[g].npix, 1);
+    atomicMax(&gp[g].endIndex, n);
+    atomicMax((int *)gp, g);
+  }
 }
-__global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, gp, aux, numberin, labelin);
-  XY2D;
-  if (IS_BORDER1) return;
-  const int g = labelin[p0], n = numberin[p0];
-  if (g == 0 || ls_overflow(g, lsListSize)) return;
-  if (n == gp[g].endIndex) {
-    if (gp[g].startCount == 1 && gp[g].npix >= 2) { atomicAdd(&gp[g].endCount, 1); atomicMin(aux + cap + g, p0); }
-    else aux[cap + g] = -1;                                      // polyid = 0
+__global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, const int *plist, int iw, size_t fs) {
+  rd_batch_y(fs, gp, aux, numberin, labelin, plist);
+  PLIST_LOOP {
+    PLIST_XY;
+    const int g = labelin[p0], n = numberin[p0];
+    if (g == 0 || ls_overflow(g, lsListSize)) continue;
+    if (n == gp[g].endIndex) {
+      if (gp[g].startCount == 1 && gp[g].npix >= 2) { atomicAdd(&gp[g].endCount, 1); atomicMin(aux + cap + g, p0); }
+      else aux[cap + g] = -1;                                      // polyid = 0
+    }
   }
 }
 // one thread per list entry: turn the start / end pixel indices into coordinates
 __global__ void kp_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw, size_t fs) {
   rd_batch_y(fs, gp, aux);
-  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (g > *(const int *)gp || g >= cap) return;
-  const int sp = aux[g] - 1, ep = aux[cap + g];
-  if (sp >= 0) { gp[g].x0 = (float)(sp % iw); gp[g].y0 = (float)(sp / iw); gp[g].level = 0; }
-  if (ep >= 0 && ep != 0x7fffffff) { gp[g].x1 = (float)(ep % iw); gp[g].y1 = (float)(ep / iw); gp[g].polyid = g; }
-  else gp[g].polyid = 0;
+  const int count = min(*(const int *)gp, cap - 1);
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count; g += gridDim.x * blockDim.x) {
+    const int sp = aux[g] - 1, ep = aux[cap + g];
+    if (sp >= 0) { gp[g].x0 = (float)(sp % iw); gp[g].y0 = (float)(sp / iw); gp[g].level = 0; }
+    if (ep >= 0 && ep != 0x7fffffff) { gp[g].x1 = (float)(ep % iw); gp[g].y1 = (float)(ep / iw); gp[g].polyid = g; }
+    else gp[g].polyid = 0;
+  }
 }
 __global__ void kp_fill(int *out, int v, int n, size_t fs) {
   rd_batch_y(fs, out);
@@ -347,32 +381,39 @@ __global__ void kp_fill(int *out, int v, int n, size_t fs) {
   if (i < n) out[i] = v;
 }
 
-__global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *tmp, const int *labelin, const int *randin, const int *flags, int nIter, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, gp, tmp, labelin, randin, flags);
+// pass1 (oclpolyline.cl:509): distance of every labelled pixel to the chord of its segment, xor-ed with 13 bits of the
+// per-pixel hash (oclpolyline.cl:883, seed 0, evaluated in place instead of being read from a plane), kept per list
+// slot, and the per-segment maximum.
+__global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *dist, const int *labelin, const int *plist, const int *flags, int nIter, int iw, size_t fs) {
+  rd_batch_y(fs, gp, dist, labelin, plist, flags);
   if (flags[nIter - 1] == 0) return;
-  XY2D;
-  const int g = labelin[p0];
-  if (g == 0 || ls_overflow(g, lsListSize)) return;
-  if (gp[g].polyid == 0) return;
-  const int x0 = (int)gp[g].x0, y0 = (int)gp[g].y0, x1 = (int)gp[g].x1, y1 = (int)gp[g].y1;
-  float cx, cy;
-  closestPoint((float)x0, (float)y0, (float)x1, (float)y1, (float)x, (float)y, cx, cy);
-  int dist = (int)__fmul_rn(rd_hypot(__fsub_rn(cx, (float)x), __fsub_rn(cy, (float)y)), 65536.0f);
-  dist ^= (randin[p0] & 0x1fff);
-  tmp[p0] = dist;
-  atomicMax(&gp[g].maxDist, dist);
+  PLIST_LOOP {
+    PLIST_XY;
+    const int g = labelin[p0];
+    if (g == 0 || ls_overflow(g, lsListSize)) continue;
+    if (gp[g].polyid == 0) continue;
+    const int x0 = (int)gp[g].x0, y0 = (int)gp[g].y0, x1 = (int)gp[g].x1, y1 = (int)gp[g].y1;
+    float cx, cy;
+    closestPoint((float)x0, (float)y0, (float)x1, (float)y1, (float)x, (float)y, cx, cy);
+    int d = (int)__fmul_rn(rd_hypot(__fsub_rn(cx, (float)x), __fsub_rn(cy, (float)y)), 65536.0f);
+    d ^= (rd_rand_at(p0, 0) & 0x1fff);
+    dist[k_] = d;
+    atomicMax(&gp[g].maxDist, d);
+  }
 }
 // pass2a: winner[g] = smallest pixel index attaining maxDist
-__global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, const int *tmp, const int *labelin, const int *flags, int nIter, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, gp, winner, tmp, labelin, flags);
+__global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, const int *dist, const int *labelin, const int *plist, const int *flags, int nIter, int iw, size_t fs) {
+  rd_batch_y(fs, gp, winner, dist, labelin, plist, flags);
   if (flags[nIter - 1] == 0) return;
-  XY2D;
-  const int g = labelin[p0];
-  if (g == 0 || ls_overflow(g, lsListSize)) return;
-  if (g > *(const int *)gp) return;
-  if (gp[g].polyid == 0) return;
-  if (tmp[p0] != gp[g].maxDist) return;
-  atomicMin(winner + g, p0);
+  PLIST_LOOP {
+    PLIST_XY;
+    const int g = labelin[p0];
+    if (g == 0 || ls_overflow(g, lsListSize)) continue;
+    if (g > *(const int *)gp) continue;
+    if (gp[g].polyid == 0) continue;
+    if (dist[k_] != gp[g].maxDist) continue;
+    atomicMin(winner + g, p0);
+  }
 }
 // pass2b: single CTA; decides the splits of this iteration, numbers the new entries by a prefix sum over the
 // parent id and rewrites the list.  Also resets winner[] for the next iteration.
@@ -432,6 +473,7 @@ __global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize,
         nw.startIndex = n; nw.endIndex = endIndex; nw.leftPtr = g; nw.rightPtr = gr;
         nw.startCount = 0; nw.endCount = 0; nw.maxDist = 0; nw.polyid = polyid; nw.npix = 0; nw.level = maxDist;
         gp[gn] = nw;
+        winner[gn] = 0x7fffffff;
         gp[g].endIndex = n; gp[g].x1 = (float)px; gp[g].y1 = (float)py; gp[g].rightPtr = gn; gp[g].maxDist = 0;
         if (gr != 0) gp[gr].leftPtr = gn;
       }
@@ -440,23 +482,24 @@ __global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize,
   }
   if (threadIdx.x == 0) *(int *)gp = carry;
 }
-__global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, int *flags, int nIter, int n, size_t fs) {
-  rd_batch_y(fs, gp, numberin, labelinout, flags);
+__global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, const int *plist, int *flags, int nIter, int iw, size_t fs) {
+  rd_batch_y(fs, gp, numberin, labelinout, plist, flags);
   if (flags[nIter - 1] == 0) return;
-  const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p0 >= n) return;
-  const int g = labelinout[p0];
-  if (g == 0 || ls_overflow(g, lsListSize)) return;
-  if (gp[g].polyid == 0) return;
-  if (gp[g].endIndex < numberin[p0]) { labelinout[p0] = gp[g].rightPtr; flags[nIter] = 1; }
+  PLIST_LOOP {
+    PLIST_XY;
+    const int g = labelinout[p0];
+    if (g == 0 || ls_overflow(g, lsListSize)) continue;
+    if (gp[g].polyid == 0) continue;
+    if (gp[g].endIndex < numberin[p0]) { labelinout[p0] = gp[g].rightPtr; flags[nIter] = 1; }
+  }
 }
 
 // ---------------------------------------------------------------------------- refine (oclpolyline.cl:680-809)
 __global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls, size_t fs) {
   rd_batch_y(fs, lsx, ls);
-  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (g > *(const int *)ls) return;
-  if (ls[g].polyid == 0) return;
+  const int count_ = *(const int *)ls;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
+  if (ls[g].polyid == 0) continue;
   LSX_t v;
   v.dirSEx = (short)(int)__fsub_rn(ls[g].x1, ls[g].x0);          // convert_short2: truncation (Q18)
   v.dirSEy = (short)(int)__fsub_rn(ls[g].y1, ls[g].y0);
@@ -466,32 +509,35 @@ __global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls, size_t fs) {
   v.distSquSE = v.dirSEx * v.dirSEx + v.dirSEy * v.dirSEy;
   v.padding = 0;
   lsx[g] = v;
+  }
 }
-__global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, lsx, ls, lsIdIn);
-  XY2D;
-  const int g = lsIdIn[p0];
-  if (g == 0) return;
-  if (g < 0 || *(const int *)ls < g) return;
-  const int vx = x - __float2int_rn(ls[g].x0), vy = y - __float2int_rn(ls[g].y0);   // convert_int2_rte
-  const int ay = vx * (int)lsx[g].vDirSEx + vy * (int)lsx[g].vDirSEy;
-  const int ax0 = vx * (int)lsx[g].dirSEx + vy * (int)lsx[g].dirSEy;
-  const int ax1 = lsx[g].distSquSE;
-  typedef unsigned long long ull;
-  atomicAdd((ull *)&lsx[g].mx00, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ax0)));   // convert_long_rte
-  atomicAdd((ull *)&lsx[g].mx01, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ax1)));
-  atomicAdd((ull *)&lsx[g].mx11, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ax1)));
-  atomicAdd((ull *)&lsx[g].my0, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ay)));
-  atomicAdd((ull *)&lsx[g].my1, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ay)));
+__global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, const int *plist, int iw, size_t fs) {
+  rd_batch_y(fs, lsx, ls, lsIdIn, plist);
+  PLIST_LOOP {
+    PLIST_XY;
+    const int g = lsIdIn[p0];
+    if (g == 0) continue;
+    if (g < 0 || *(const int *)ls < g) continue;
+    const int vx = x - __float2int_rn(ls[g].x0), vy = y - __float2int_rn(ls[g].y0);   // convert_int2_rte
+    const int ay = vx * (int)lsx[g].vDirSEx + vy * (int)lsx[g].vDirSEy;
+    const int ax0 = vx * (int)lsx[g].dirSEx + vy * (int)lsx[g].dirSEy;
+    const int ax1 = lsx[g].distSquSE;
+    typedef unsigned long long ull;
+    atomicAdd((ull *)&lsx[g].mx00, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ax0)));   // convert_long_rte
+    atomicAdd((ull *)&lsx[g].mx01, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ax1)));
+    atomicAdd((ull *)&lsx[g].mx11, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ax1)));
+    atomicAdd((ull *)&lsx[g].my0, (ull)__float2ll_rn(__fmul_rn((float)ax0, (float)ay)));
+    atomicAdd((ull *)&lsx[g].my1, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ay)));
+  }
 }
 __global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls, size_t fs) {
   rd_batch_y(fs, lsx, ls);
-  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (g > *(const int *)ls) return;
-  if (ls[g].polyid == 0) return;
+  const int count_ = *(const int *)ls;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
+  if (ls[g].polyid == 0) continue;
   const float mx00 = (float)lsx[g].mx00, mx01 = (float)lsx[g].mx01, mx11 = (float)lsx[g].mx11, my0 = (float)lsx[g].my0, my1 = (float)lsx[g].my1;
   float rdet = __fsub_rn(__fmul_rn(mx00, mx11), __fmul_rn(mx01, mx01));
-  if (rdet == 0) return;
+  if (rdet == 0) continue;
   rdet = (float)__ddiv_rn(1.0, (double)rdet);                   // `1.0 / rdet` divides in double (Q15)
   const float as0 = __fmul_rn(__fsub_rn(__fmul_rn(mx11, my0), __fmul_rn(mx01, my1)), rdet);
   const float as1 = __fmul_rn(__fsub_rn(__fmul_rn(mx00, my1), __fmul_rn(mx01, my0)), rdet);
@@ -500,12 +546,13 @@ __global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls, size_t fs) {
   ls[g].y0 = __fadd_rn(ls[g].y0, __fmul_rn(vy, as1));
   ls[g].x1 = __fadd_rn(ls[g].x1, __fmul_rn(vx, as01));
   ls[g].y1 = __fadd_rn(ls[g].y1, __fmul_rn(vy, as01));
+  }
 }
 // pass3a computes the vertex g shares with its right neighbour from the unmodified list; pass3b writes it to both
 __global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls, size_t fs) {
   rd_batch_y(fs, vtx, ls);
-  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (g > *(const int *)ls) return;
+  const int count_ = *(const int *)ls;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
   float2 r = make_float2(__int_as_float(0x7fc00000), 0.0f);     // NaN = nothing to write
   if (ls[g].polyid != 0 && ls[g].rightPtr != 0) {
     const int h = ls[g].rightPtr;
@@ -523,24 +570,26 @@ __global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls, size_t fs) {
     }
   }
   vtx[g] = r;
+  }
 }
 __global__ void kp_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot, size_t fs) {
   rd_batch_y(fs, vtx, ls, rightPtrSnapshot);
-  const int g = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (g > *(const int *)ls) return;
+  const int count_ = *(const int *)ls;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
   (void)rightPtrSnapshot;
   const float2 r = vtx[g];
   if (r.x != r.x) {
     // distinguish "no right neighbour" from a genuinely NaN vertex: recompute the guard
-    if (ls[g].polyid == 0 || ls[g].rightPtr == 0) return;
+    if (ls[g].polyid == 0 || ls[g].rightPtr == 0) continue;
   }
   const int h = ls[g].rightPtr;
   ls[g].x1 = r.x; ls[g].y1 = r.y;
   ls[h].x0 = r.x; ls[h].y0 = r.y;
+  }
 }
 
 // ---------------------------------------------------------------------------- the schedule (oclpolyline.c:218-309)
-static const dim3 PB(32, 8);
+static const dim3 PB(32, getenv("RD_BY") ? atoi(getenv("RD_BY")) : 8);
 #define G2 rd_grid2d(iw, ih, PB)
 
 void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *tmpBig, int *tmp0, int *tmp1, int *tmp2, int *tmp3,
@@ -578,48 +627,47 @@ void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, 
   rd_k_clear(tmp1, n, nb, fs, s);
   RD_LAUNCH(kp_calcSize, rd_gy(g1, nb), 256, 0, s, tmp1, tmpBig, n, fs);
   RD_LAUNCH(kp_filterSize, rd_gy(g1, nb), 256, 0, s, lsIdOut, tmpBig, tmp1, sizeThre, n, fs);
-  // step 10 : compact ids 1..K in raster order of the root pixels.  table = tmpBig[0..n], block counts behind it
+  // step 10 : compact ids 1..K in raster order of the root pixels (table = tmpBig[0..n], block counts behind it) and
+  // gather the labelled pixels into a compact list (plist = tmp1, dead after filterSize): everything downstream only
+  // touches those ~2 % of the frame.
+  int *table = tmpBig, *blockCount = tmpBig + 2 * (size_t)n, *plist = tmp1;
   {
-    int *table = tmpBig, *blockCount = tmpBig + 2 * (size_t)n;
     const int nblk = rd_cdiv(n, RL_BLOCK);
     rd_k_clear(tmpBig, n + 1, nb, fs, s);
     RD_LAUNCH(kp_relabel_count, rd_gy(nblk, nb), RL_BLOCK, 0, s, blockCount, lsIdOut, iw, ih, fs);
-    RD_LAUNCH(kp_scan_blocks, dim3(nb), 1024, 0, s, blockCount, nblk, table, fs);
+    RD_LAUNCH(kp_scan_blocks, dim3(nb), 1024, 0, s, blockCount, nblk, table, plist, fs);
     RD_LAUNCH(kp_relabel_rank, rd_gy(nblk, nb), RL_BLOCK, 0, s, table, blockCount, lsIdOut, iw, ih, fs);
-    RD_LAUNCH(kp_relabel_pass1, rd_gz(G2, nb), PB, 0, s, lsIdOut, table, iw, ih, fs);
+    RD_LAUNCH(kp_relabel_pass1, rd_gz(G2, nb), PB, 0, s, lsIdOut, table, plist, iw, ih, fs);
   }
-  // step 11 : mkpl.  aux (start / end pixel per string) and winner live in tmpBig; cap entries each
+  const int cap = lsListSize / (int)sizeof(LS_t);
+  const dim3 lg(LIST_BLOCKS, nb), sg(4, nb);
+  // step 11 : mkpl.  aux (start / end pixel per string) and winner (arg-max pixel per segment) sit behind the table
   {
-    const int cap = lsListSize / (int)sizeof(LS_t);
-    int *aux = tmpBig, *winner = tmpBig + 2 * (size_t)cap;
-    int *flags = tmp4, *dist = tmp3, *rnd = tmp5;
+    int *aux = tmpBig + n + 8, *winner = aux + 2 * (size_t)cap;
+    int *flags = tmp4, *dist = tmp3;
     const int N = 16;
-    rd_k_clear((int *)lsList, (lsListSize + 3) / 4, nb, fs, s);
-    rd_k_clear(aux, cap, nb, fs, s);
-    RD_LAUNCH(kp_fill, rd_gy(rd_cdiv(2 * cap, 256), nb), 256, 0, s, aux + cap, 0x7fffffff, 2 * cap, fs);      // end pixel (min) and winner (min)
-    RD_LAUNCH(kp_mkpl_pass0a, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, flags, N, iw, ih, fs);
-    RD_LAUNCH(kp_mkpl_pass0b, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, iw, ih, fs);
-    RD_LAUNCH(kp_mkpl_pass0c, rd_gy(rd_cdiv(cap, 256), nb), 256, 0, s, lsList, aux, cap, iw, fs);
-    rd_k_rand(rnd, 0, n, nb, fs, s);
+    RD_LAUNCH(kp_mkpl_init, rd_gy(8, nb), 256, 0, s, lsList, lsListSize, aux, winner, cap, table, flags, N, fs);
+    RD_LAUNCH(kp_mkpl_pass0a, lg, 256, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, plist, iw, fs);
+    RD_LAUNCH(kp_mkpl_pass0b, lg, 256, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, plist, iw, fs);
+    RD_LAUNCH(kp_mkpl_pass0c, sg, 256, 0, s, lsList, aux, cap, iw, fs);
     for (int i = 0; i < N - 1; i++) {
-      RD_LAUNCH(kp_mkpl_pass1, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, dist, lsIdOut, rnd, flags, i + 1, iw, ih, fs);
-      RD_LAUNCH(kp_mkpl_pass2a, rd_gz(G2, nb), PB, 0, s, lsList, lsListSize, winner, dist, lsIdOut, flags, i + 1, iw, ih, fs);
+      RD_LAUNCH(kp_mkpl_pass1, lg, 256, 0, s, lsList, lsListSize, dist, lsIdOut, plist, flags, i + 1, iw, fs);
+      RD_LAUNCH(kp_mkpl_pass2a, lg, 256, 0, s, lsList, lsListSize, winner, dist, lsIdOut, plist, flags, i + 1, iw, fs);
       RD_LAUNCH(kp_mkpl_pass2b, dim3(nb), 1024, 0, s, lsList, lsListSize, winner, tmp2, flags, i + 1, minerror, iw, fs);
-      RD_LAUNCH(kp_mkpl_pass3, rd_gy(g1, nb), 256, 0, s, lsList, lsListSize, tmp2, lsIdOut, flags, i + 1, n, fs);
+      RD_LAUNCH(kp_mkpl_pass3, lg, 256, 0, s, lsList, lsListSize, tmp2, lsIdOut, plist, flags, i + 1, iw, fs);
     }
   }
   // step 12 : sub-pixel refinement.  LSX mirror of the list in tmpBig, shared vertices in tmp3
   {
-    const int cap = lsListSize / (int)sizeof(LS_t);
     LSX_t *lsx = (LSX_t *)tmpBig;
-    float2 *vtx = (float2 *)tmp3;                                 // the distance plane is dead after mkpl; 8 B x (count+1) <= P
-    const int gl = rd_cdiv(cap, 256);
-    RD_LAUNCH(kp_refine_pass0, rd_gy(gl, nb), 256, 0, s, lsx, lsList, fs);
-    RD_LAUNCH(kp_refine_pass1, rd_gz(G2, nb), PB, 0, s, lsx, lsList, lsIdOut, iw, ih, fs);
-    RD_LAUNCH(kp_refine_pass2, rd_gy(gl, nb), 256, 0, s, lsx, lsList, fs);
-    RD_LAUNCH(kp_refine_pass3a, rd_gy(gl, nb), 256, 0, s, vtx, lsList, fs);
-    RD_LAUNCH(kp_refine_pass3b, rd_gy(gl, nb), 256, 0, s, vtx, lsList, (const int *)NULL, fs);
+    float2 *vtx = (float2 *)tmp3;                                 // the distance slots are dead after mkpl; 8 B x (count+1) <= P
+    RD_LAUNCH(kp_refine_pass0, sg, 256, 0, s, lsx, lsList, fs);
+    RD_LAUNCH(kp_refine_pass1, lg, 256, 0, s, lsx, lsList, lsIdOut, plist, iw, fs);
+    RD_LAUNCH(kp_refine_pass2, sg, 256, 0, s, lsx, lsList, fs);
+    RD_LAUNCH(kp_refine_pass3a, sg, 256, 0, s, vtx, lsList, fs);
+    RD_LAUNCH(kp_refine_pass3b, sg, 256, 0, s, vtx, lsList, (const int *)NULL, fs);
   }
+  (void)tmp5;
 }
 
 extern "C" {

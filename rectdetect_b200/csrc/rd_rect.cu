@@ -24,10 +24,15 @@ void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream
 void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *tmpBig, int *tmp0, int *tmp1, int *tmp2, int *tmp3,
                      int *tmp4, int *tmp5, float minerror, int sizeThre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_bgr2plab_run(uint32_t *out, const uint8_t *in, size_t in_fs, int iw, int ih, int ws, int nb, size_t fs, cudaStream_t s);
+void rd_iirblur3_run(float *outL, float *outA, float *outB, uint32_t *outPlab, const uint32_t *plab, float *sb, float *sf, size_t pp, int r, int iw, int ih,
+                     int nb, size_t fs, cudaStream_t s);
+void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int8_t *edge, uint8_t *ext, int iters, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_calcSize_run(int *out, const int *label, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_tail_gather_host(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, rd_tail_sample *out);
 
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
-static const dim3 RB(32, 8);
+static const dim3 RB(32, getenv("RD_BY") ? atoi(getenv("RD_BY")) : 8);
 #define G2 rd_grid2d(iw, ih, RB)
 
 // ---------------------------------------------------------------------------- oclrect.cl:74-135
@@ -342,7 +347,7 @@ struct oclrect_t {
   int iw, ih, ordinal, nb;
   cl_command_queue queue;
   unsigned char *dbase;                 // nb arenas, fs bytes apart
-  size_t fs;
+  size_t fs, P;                         // arena stride, plane pitch (bytes)
   cl_mem buf[6], tmp[6], iobuf[2], ioBig[2];   // non-owning handles on the buffers of arena 0
   unsigned char *dblob;                 // read-back record of arena 0
   size_t blobBytes;
@@ -372,17 +377,12 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   const size_t fs = o->fs;
   cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
 #define STEP(k) do { if (stop_step == (k)) return; } while (0)
-  // steps 1-2 : BGR -> packed Lab (kept in buf0) and its three float channels
-  RD_LAUNCH(k_bgr2plab_unpack, rd_gz(G2, nb), RB, 0, s, PU(buf[0]), PF(tmp[0]), PF(tmp[1]), PF(tmp[2]), din, din_fs, iw, ih, ws, fs);
-  STEP(1); STEP(2);
-  // step 3 : recursive Gaussian r=2 on b, a, L
-  rd_k_iirblur(PF(tmp[3]), PF(tmp[2]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, nb, fs, s);
-  rd_k_iirblur(PF(tmp[2]), PF(tmp[1]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, nb, fs, s);
-  rd_k_iirblur(PF(tmp[1]), PF(tmp[0]), PF(ioBig[0]), PF(ioBig[1]), 2, iw, ih, nb, fs, s);
-  STEP(3);
-  // steps 4-7 : blurred plab, unit gradient, edge magnitude, NMS thinning (thinned strength stays in buf1)
-  RD_LAUNCH(k_pack_plab_r, rd_gy(g1, nb), 256, 0, s, PU(buf[1]), PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), n, fs);
-  STEP(4);
+  // steps 1-4 : BGR -> packed Lab (kept in buf0); recursive Gaussian r=2 on L, a, b straight from the packed plane
+  // (blurred channels in tmp1..3, blurred packed Lab in buf1).  Scratch: three planes of each ioBig.
+  rd_bgr2plab_run(PU(buf[0]), din, din_fs, iw, ih, ws, nb, fs, s);
+  STEP(1);
+  rd_iirblur3_run(PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), PU(buf[1]), PU(buf[0]), PF(ioBig[1]), PF(ioBig[0]), o->P / 4, 2, iw, ih, nb, fs, s);
+  STEP(3); STEP(4);
   RD_LAUNCH(k_edgevec_r, rd_gz(G2, nb), RB, 0, s, (float2 *)ioBig[0]->dptr, PF(tmp[1]), iw, ih, fs);
   STEP(5);
   RD_LAUNCH(k_edge_plab_r, rd_gz(G2, nb), RB, 0, s, PF(tmp[0]), PU(buf[1]), iw, ih, fs);
@@ -408,13 +408,8 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   // step 12 : int and i8 edge masks
   RD_LAUNCH(kr_threshold_cast_c, rd_gy(g1, nb), 256, 0, s, PI(tmp[0]), (int8_t *)tmp[1]->dptr, PI(buf[2]), n, fs);
   STEP(12);
-  // step 13 : 10 x (blblur0, blblur1)
-  RD_LAUNCH(kr_blblur<0>, rd_gz(G2, nb), RB, 0, s, PU(tmp[0]), (const int8_t *)tmp[1]->dptr, PU(buf[0]), iw, ih, fs);
-  RD_LAUNCH(kr_blblur<1>, rd_gz(G2, nb), RB, 0, s, PU(buf[4]), (const int8_t *)tmp[1]->dptr, PU(tmp[0]), iw, ih, fs);
-  for (int i = 0; i < 9; i++) {
-    RD_LAUNCH(kr_blblur<0>, rd_gz(G2, nb), RB, 0, s, PU(tmp[0]), (const int8_t *)tmp[1]->dptr, PU(buf[4]), iw, ih, fs);
-    RD_LAUNCH(kr_blblur<1>, rd_gz(G2, nb), RB, 0, s, PU(buf[4]), (const int8_t *)tmp[1]->dptr, PU(tmp[0]), iw, ih, fs);
-  }
+  // step 13 : 10 x (blblur0, blblur1); walk extents live behind the i8 mask in tmp1
+  rd_blblur_run(PU(buf[4]), PU(tmp[0]), PU(buf[0]), (const int8_t *)tmp[1]->dptr, (uint8_t *)tmp[1]->dptr + (size_t)n, 10, iw, ih, nb, fs, s);
   STEP(13);
   // step 14 : quantize 24^3, despeckle
   RD_LAUNCH(kr_quantize, rd_gy(g1, nb), 256, 0, s, PU(tmp[0]), PU(buf[4]), 24, 24, 24, n, fs);
@@ -434,7 +429,7 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   rd_labelMerge(PI(buf[5]), PI(tmp[4]), PU(buf[4]), PI(tmp[1]), PI(buf[2]), tmp[5]->dptr, iw, ih, nb, fs, s);
   STEP(17);
   // step 18 : region sizes on top of the junction map (Q2), small regions absorbed (Jacobi: snapshot in tmp4)
-  RD_LAUNCH(kr_calcSize, rd_gy(g1, nb), 256, 0, s, PI(tmp[0]), PI(buf[5]), n, fs);
+  rd_calcSize_run(PI(tmp[0]), PI(buf[5]), iw, ih, nb, fs, s);
   rd_k_copy(PI(tmp[4]), PI(buf[5]), n, nb, fs, s);
   RD_LAUNCH(kr_despeckle2, rd_gz(G2, nb), RB, 0, s, PI(buf[5]), PI(tmp[4]), PI(tmp[0]), 16, iw, ih, fs);
   STEP(18);
@@ -530,6 +525,7 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   const int cap = (int)((size_t)iw * ih * 16 / sizeof(LS_t)) - 1;
   if (o->maxLS > cap) o->maxLS = cap;
   o->fs = 22 * P + bb;
+  o->P = P;
   RD_CUDA(cudaMalloc((void **)&o->dbase, o->fs * nb));
   // CANONICAL (Q1): memory the reference never initialises reads as zero on the first frame
   RD_CUDA(cudaMemset(o->dbase, 0, o->fs * nb));

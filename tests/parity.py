@@ -18,7 +18,7 @@ import oracle_lib as ol  # noqa: E402
 # step -> [(buffer name, dtype, how many elements are meaningful: 'n', '2n', 'bytes_n', 'ls', '4n')]
 STEP_BUFFERS = {
     1: [("buf0", np.uint32, "n")],
-    2: [("tmp0", np.float32, "n"), ("tmp1", np.float32, "n"), ("tmp2", np.float32, "n")],
+    # step 2 (unpack to three float planes) has no counterpart: the blur reads the packed plane directly
     3: [("tmp1", np.float32, "n"), ("tmp2", np.float32, "n"), ("tmp3", np.float32, "n")],
     4: [("buf1", np.uint32, "n")],
     5: [("ioBig0", np.float32, "2n")],

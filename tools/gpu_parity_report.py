@@ -13,7 +13,7 @@ import oracle_lib as ol  # noqa: E402
 import rectdetect_b200 as rd  # noqa: E402
 
 iw, ih, seed = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (640, 480, 1)
-steps = [int(a) for a in sys.argv[4:]] or list(range(1, 22))
+steps = [int(a) for a in sys.argv[4:]] or sorted(parity.STEP_BUFFERS)
 print("devices:", rd.device_count(), rd.lib().rd_version())
 dev = rd.Device(0)
 t0 = time.time()
