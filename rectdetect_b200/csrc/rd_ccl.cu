@@ -27,11 +27,12 @@
 // ---- link functors.  load(x, y) reads what the predicate needs to know about ONE pixel (each pixel of the tile and
 // of its one-pixel apron above / beside is loaded once into shared memory); link(...) then decides, from the staged
 // values of a pixel (c) and of its W, NW, N, NE neighbours, which of the four belong to the same component. ----
-struct Link8x {                       // label8xMain_int_int: equal value, value != bgc (oclimgutil.cl:511-538)
+template <class PIX>
+struct Link8x {                       // label8xMain_int_int: equal value, value != bgc (oclimgutil.cl:511-538); PIX = int or uint8_t plane
   typedef int V;
-  const int *pix; int bgc, iw, ih;
+  const PIX *pix; int bgc, iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix); }
-  __device__ __forceinline__ V load(int x, int y) const { return pix[(size_t)y * iw + x]; }
+  __device__ __forceinline__ V load(int x, int y) const { return (int)pix[(size_t)y * iw + x]; }
   __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
     if (c == bgc) return L_BG;
     unsigned m = 0;
@@ -62,9 +63,10 @@ struct LinkPl {                       // labelpl_main: numbers (+1) both non-zer
     return m;
   }
 };
+template <class MASK>
 struct LinkMerge {                    // labelxPreprocess + labelMergeMain, canonical symmetric form (see rd_rect.cu / DESIGN.md)
   struct V { uint32_t pix; uint32_t fl; };        // fl bit 0: mask != 0, bit 1: edge <= 0
-  const uint32_t *pix; const int *mask; const int *edge; int iw, ih;
+  const uint32_t *pix; const MASK *mask; const int *edge; int iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix, mask, edge); }
   __device__ __forceinline__ V load(int x, int y) const {
     const size_t p = (size_t)y * iw + x;
@@ -237,7 +239,13 @@ static void ccl_core(int *label, uint8_t *links, LinkFn f, int iw, int ih, int n
 
 // scratch: iw*ih bytes
 void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  Link8x f = {pix, bgc, iw, ih};
+  Link8x<int> f = {pix, bgc, iw, ih};
+  ccl_core(label, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  RD_LAUNCH(k_ccl_flatten, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, label, (const uint8_t *)scratch, -1, iw * ih, fs);
+}
+// same on a byte plane (the fused string clean-up kernels emit bytes)
+void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  Link8x<uint8_t> f = {pix, bgc, iw, ih};
   ccl_core(label, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
   RD_LAUNCH(k_ccl_flatten, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, label, (const uint8_t *)scratch, -1, iw * ih, fs);
 }
@@ -249,7 +257,14 @@ void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, int n
 }
 // labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331), converged.  work: iw*ih ints, scratch: iw*ih bytes; out may not alias work
 void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  LinkMerge f = {pix, mask, edge, iw, ih};
+  LinkMerge<int> f = {pix, mask, edge, iw, ih};
+  ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  const dim3 b(32, 8);
+  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, pix, iw, ih, fs);
+}
+// same with the merge mask as a byte plane
+void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  LinkMerge<uint8_t> f = {pix, mask, edge, iw, ih};
   ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
   const dim3 b(32, 8);
   RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, pix, iw, ih, fs);

@@ -406,3 +406,365 @@ void rd_iirblur3_run(float *outL, float *outA, float *outB, uint32_t *outPlab, c
   RD_LAUNCH(kf_iir_v3, dim3(rd_cdiv(iw, 128), 6, nb), 128, 0, s, sf, sf + pp, sf + 2 * pp, sb, sb + pp, sb + 2 * pp, outL, outA, outB, r, iw, ih, fs);
   RD_LAUNCH(kf_iir_fin3, dim3(rd_cdiv(n, 256), nb), 256, 0, s, outL, outA, outB, outPlab, sf, sf + pp, sf + 2 * pp, sb, sb + pp, sb + 2 * pp, outL, outA, outB, r, n, fs);
 }
+
+// =============================================================================================== Stage A, second half
+// edgevec_f + edge_plab + thinthres_f_f_f2 (oclimgutil.cl:395-471, oclrect.c:253-258) in one kernel.  A CTA produces a
+// 32x32 tile of thinned edge strength.  It stages the blurred packed-Lab tile (apron 5) and the blurred L tile (apron 2)
+// in shared memory, computes the edge-magnitude tile (apron 4: the bicubic taps of the four NMS samples reach 3 pixels
+// back and 4 forward) and the unit gradient of every output pixel, and takes the NMS samples from shared memory.  The
+// reference's mirror border rule is applied by indexing the tiles with mirrored image coordinates.
+#define ET_T 32
+#define ET_PA 5                      // packed Lab apron
+#define ET_MA 4                      // magnitude apron
+#define ET_LA 2                      // L apron
+#define ET_PW (ET_T + 2 * ET_PA)
+#define ET_MW (ET_T + 2 * ET_MA)
+#define ET_LW (ET_T + 2 * ET_LA)
+struct TileMag {                     // Plane interface of rd_bicubic: at(x, y) = magnitude at the mirrored position
+  const float *m; int x0, y0, iw, ih;
+  __device__ __forceinline__ float at(int x, int y) const { return m[(rd_mirror1(y, ih) - y0) * ET_MW + (rd_mirror1(x, iw) - x0)]; }
+};
+__global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, thin, blurL, blurP);
+  __shared__ uint32_t sp[ET_PW * ET_PW];
+  __shared__ float sm[ET_MW * ET_MW];
+  __shared__ float sl[ET_LW * ET_LW];
+  const int bx = blockIdx.x * ET_T, by = blockIdx.y * ET_T;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  // stage: in-image positions only (everything below indexes with mirrored, hence in-image, coordinates)
+  for (int i = tid; i < ET_PW * ET_PW; i += 256) {
+    const int gx = bx - ET_PA + i % ET_PW, gy = by - ET_PA + i / ET_PW;
+    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) sp[i] = blurP[(size_t)gy * iw + gx];
+  }
+  for (int i = tid; i < ET_LW * ET_LW; i += 256) {
+    const int gx = bx - ET_LA + i % ET_LW, gy = by - ET_LA + i / ET_LW;
+    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) sl[i] = blurL[(size_t)gy * iw + gx];
+  }
+  __syncthreads();
+  // edge magnitude on the apron-4 tile, at in-image positions
+  const int px0 = bx - ET_PA, py0 = by - ET_PA;
+  for (int i = tid; i < ET_MW * ET_MW; i += 256) {
+    const int gx = bx - ET_MA + i % ET_MW, gy = by - ET_MA + i / ET_MW;
+    if (gx < 0 || gx >= iw || gy < 0 || gy >= ih) continue;
+    const int xm = rd_mirror1(gx - 1, iw) - px0, xc = gx - px0, xp = rd_mirror1(gx + 1, iw) - px0;
+    const int ym = (rd_mirror1(gy - 1, ih) - py0) * ET_PW, yc = (gy - py0) * ET_PW, yp = (rd_mirror1(gy + 1, ih) - py0) * ET_PW;
+    sm[i] = rd_edge_plab_at(sp[ym + xc], sp[yc + xm], sp[yp + xc], sp[yc + xp], sp[ym + xm], sp[yp + xp], sp[ym + xp], sp[yp + xm]);
+  }
+  __syncthreads();
+  const TileMag mag = {sm, bx - ET_MA, by - ET_MA, iw, ih};
+  const int lx0 = bx - ET_LA, ly0 = by - ET_LA;
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    const int x = bx + threadIdx.x, y = by + threadIdx.y + k * 8;
+    if (x >= iw || y >= ih) continue;
+    float vx = 0, vy = 0;
+#pragma unroll
+    for (int yy = -2; yy <= 2; yy++) {
+      const int ry = (rd_mirror1(y + yy, ih) - ly0) * ET_LW;
+#pragma unroll
+      for (int xx = -2; xx <= 2; xx++) {
+        const float s = sl[ry + rd_mirror1(x + xx, iw) - lx0];
+        vx = __fadd_rn(vx, __fmul_rn(RD_V5C[(xx + 2) + (yy + 2) * 5], s));
+        vy = __fadd_rn(vy, __fmul_rn(RD_V5C[(yy + 2) + (xx + 2) * 5], s));
+      }
+    }
+    const float2 v = rd_edgevec_normalise(vx, vy);
+    // thinthres: the outer samples only matter where the pixel is a local maximum along the gradient
+    const float fx = (float)x, fy = (float)y;
+    const float a0 = mag.at(x, y);
+    const float am1 = rd_bicubic(mag, __fsub_rn(fx, v.x), __fsub_rn(fy, v.y));
+    const float ap1 = rd_bicubic(mag, __fadd_rn(fx, v.x), __fadd_rn(fy, v.y));
+    float r = 0.0f;
+    if (am1 <= a0 && a0 >= ap1) {
+      const float vx2 = __fmul_rn(2.0f, v.x), vy2 = __fmul_rn(2.0f, v.y);
+      const float am2 = rd_bicubic(mag, __fsub_rn(fx, vx2), __fsub_rn(fy, vy2));
+      const float ap2 = rd_bicubic(mag, __fadd_rn(fx, vx2), __fadd_rn(fy, vy2));
+      r = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(am2, am1), a0), ap1), ap2);
+    }
+    thin[(size_t)y * iw + x] = r;
+  }
+}
+void rd_edge_thin_run(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(kf_edge_thin, dim3(rd_cdiv(iw, ET_T), rd_cdiv(ih, ET_T), nb), dim3(32, 8), 0, s, thin, blurL, blurP, iw, ih, fs);
+}
+
+// =============================================================================================== Stage B, string clean-up
+// threshold_f_f / cast_i_f (oclrect.c:262-263) + simpleJunction + simpleConnect + stringify 0 + stringify 1
+// (oclrect.cl:74-135, oclrect.c:265-272) in one kernel on byte tiles in shared memory.  Output: the cleaned 0/1 string
+// image as a byte plane.  Each stage shrinks the valid region by its stencil radius: 40x40 edge tile -> 38 -> 36 -> 34 -> 32.
+#define ST_T 32
+#define ST_A 4
+#define ST_W (ST_T + 2 * ST_A)
+__device__ __forceinline__ bool st_inside(int gx, int gy, int iw, int ih, int border) { return gx >= border && gy >= border && gx < iw - border && gy < ih - border; }
+__global__ void __launch_bounds__(256) kf_strings1(uint8_t *out, const float *thin, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, thin);
+  __shared__ uint8_t a[ST_W * ST_W], b[ST_W * ST_W];
+  const int bx = blockIdx.x * ST_T - ST_A, by = blockIdx.y * ST_T - ST_A;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  // edge bitmap #1 : thin > 0 (0 outside the image)
+  for (int i = tid; i < ST_W * ST_W; i += 256) {
+    const int gx = bx + i % ST_W, gy = by + i / ST_W;
+    a[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih && thin[(size_t)gy * iw + gx] > 0.0f) ? 1 : 0;
+  }
+  __syncthreads();
+  // simpleJunction (oclrect.cl:74): 1 + number of set neighbours, isolated pixels and the 1-px frame -> 0
+  for (int i = tid; i < ST_W * ST_W; i += 256) {
+    const int tx = i % ST_W, ty = i / ST_W;
+    uint8_t r = 0;
+    if (tx >= 1 && ty >= 1 && tx < ST_W - 1 && ty < ST_W - 1 && st_inside(bx + tx, by + ty, iw, ih, 1) && a[i]) {
+      const int c = 1 + a[i - 1] + a[i + 1] + a[i - ST_W] + a[i + ST_W] + a[i - ST_W - 1] + a[i - ST_W + 1] + a[i + ST_W - 1] + a[i + ST_W + 1];
+      r = c == 1 ? 0 : c;
+    }
+    b[i] = r;
+  }
+  __syncthreads();
+  // simpleConnect (oclrect.cl:97): fill one-pixel gaps next to end pixels (value 2); 2-px frame -> 0
+  for (int i = tid; i < ST_W * ST_W; i += 256) {
+    const int tx = i % ST_W, ty = i / ST_W;
+    uint8_t r = 0;
+    if (tx >= 2 && ty >= 2 && tx < ST_W - 2 && ty < ST_W - 2 && st_inside(bx + tx, by + ty, iw, ih, 2)) {
+      r = b[i] != 0;
+      if (!r) {
+        const int w = b[i - 1], e = b[i + 1], n = b[i - ST_W], s = b[i + ST_W];
+        const int nw = b[i - ST_W - 1], ne = b[i - ST_W + 1], sw = b[i + ST_W - 1], se = b[i + ST_W + 1];
+        r = (w == 2 && e != 0) || (w != 0 && e == 2) || (n == 2 && s != 0) || (n != 0 && s == 2) || (nw == 2 && se == 2) || (ne == 2 && sw == 2) ||
+            (e == 2 && sw == 2) || (w == 2 && se == 2) || (ne == 2 && s == 2) || (nw == 2 && s == 2);
+      }
+    }
+    a[i] = r;
+  }
+  __syncthreads();
+  // stringify mod2 = 0 then 1 (oclrect.cl:123): checkerboard removal of L-corner pixels, 1-px frame copied
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const uint8_t *src = pass == 0 ? a : b;
+    uint8_t *dst = pass == 0 ? b : a;
+    for (int i = tid; i < ST_W * ST_W; i += 256) {
+      const int tx = i % ST_W, ty = i / ST_W;
+      const int lo = 3 + pass, hi = ST_W - 3 - pass;
+      if (tx < lo || ty < lo || tx >= hi || ty >= hi) continue;
+      const int gx = bx + tx, gy = by + ty;
+      uint8_t r = src[i];
+      if (st_inside(gx, gy, iw, ih, 1) && ((gx + gy) & 1) == pass) {
+        const bool n = src[i - ST_W] != 0, s = src[i + ST_W] != 0, w = src[i - 1] != 0, e = src[i + 1] != 0;
+        if ((n || s) && (w || e)) r = 0;
+      }
+      dst[i] = r;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int tx = ST_A + threadIdx.x, ty = ST_A + threadIdx.y + k * 8;
+    const int gx = bx + tx, gy = by + ty;
+    if (gx < iw && gy < ih) out[(size_t)gy * iw + gx] = a[ty * ST_W + tx];
+  }
+}
+void rd_strings1_run(uint8_t *out, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(kf_strings1, dim3(rd_cdiv(iw, ST_T), rd_cdiv(ih, ST_T), nb), dim3(32, 8), 0, s, out, thin, iw, ih, fs);
+}
+
+// filterStrength(500) + threshold_i_i + cast_c_i (oclrect.c:277-284) and filterStrength(2500) + threshold_i_i
+// (oclrect.c:307-312) from one read of the labels: weak mask (i8, stops the edge-preserving blur) and strong-edge bitmap
+// (0/1 ints, the polyline input).  filterStrength leaves the 1-px frame alone, so there the label itself decides.
+__global__ void kf_filter_masks(int8_t *weak, int *strong, const int *label, const int *str, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, weak, strong, label, str);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const int p = y * iw + x, l = label[p];
+  int wk = l > 0, sg = l > 0;
+  if (l > 0 && x > 0 && y > 0 && x < iw - 1 && y < ih - 1) {
+    const int v = str[l];
+    wk = v >= 500;
+    sg = v >= 500 && v >= 2500;
+  }
+  weak[p] = (int8_t)wk;
+  strong[p] = sg;
+}
+void rd_filter_masks_run(int8_t *weak, int *strong, const int *label, const int *str, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  const dim3 b(32, 8);
+  RD_LAUNCH(kf_filter_masks, dim3(rd_cdiv(iw, 32), rd_cdiv(ih, 8), nb), b, 0, s, weak, strong, label, str, iw, ih, fs);
+}
+
+// quantize(24,24,24) + despeckle (oclrect.cl:207-244, oclrect.c:300-303): the 34x34 quantised tile lives in shared memory
+#define QD_T 32
+#define QD_W (QD_T + 2)
+__device__ __forceinline__ uint32_t quant24(uint32_t v) {
+  float l, a, b;
+  rd_unpacklab(v, l, a, b);
+  return rd_packlab(__fdiv_rn(roundf(__fmul_rn(l, 24.0f)), 24.0f), __fdiv_rn(roundf(__fmul_rn(a, 24.0f)), 24.0f), __fdiv_rn(roundf(__fmul_rn(b, 24.0f)), 24.0f));
+}
+__global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in, thin);
+  __shared__ uint32_t q[QD_W * QD_W];
+  __shared__ uint8_t e[QD_W * QD_W];                          // 1: edge pixel (thinned strength >= 1e-6), 2: outside the image
+  const int bx = blockIdx.x * QD_T - 1, by = blockIdx.y * QD_T - 1;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < QD_W * QD_W; i += 256) {
+    const int gx = bx + i % QD_W, gy = by + i / QD_W;
+    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) {
+      const size_t p = (size_t)gy * iw + gx;
+      q[i] = quant24(in[p]);
+      e[i] = thin[p] >= 1e-6f ? 1 : 0;
+    } else { q[i] = 0; e[i] = 2; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int tx = 1 + threadIdx.x, ty = 1 + threadIdx.y + k * 8;
+    const int gx = bx + tx, gy = by + ty;
+    if (gx >= iw || gy >= ih) continue;
+    const int i = ty * QD_W + tx;
+    uint32_t r = q[i];
+    if (e[i] == 1) {
+      float dist = 1e+10f, l0, a0, b0;
+      rd_unpacklab(r, l0, a0, b0);
+#pragma unroll
+      for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+        for (int xx = -1; xx <= 1; xx++) {
+          const int j = i + yy * QD_W + xx;
+          if (e[j] != 0) continue;                            // edge pixels and positions outside the image do not donate
+          float l1, a1, b1;
+          const uint32_t v = q[j];
+          rd_unpacklab(v, l1, a1, b1);
+          const float d = rd_distance3(__fsub_rn(l1, l0), __fsub_rn(a1, a0), __fsub_rn(b1, b0));
+          if (d < dist) { r = v; dist = d; }
+        }
+    }
+    out[(size_t)gy * iw + gx] = r;
+  }
+}
+void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(kf_quant_despeckle, dim3(rd_cdiv(iw, QD_T), rd_cdiv(ih, QD_T), nb), dim3(32, 8), 0, s, out, in, thin, iw, ih, fs);
+}
+
+// simpleJunction of the strong edges + clear + mkMergeMask0 + mkMergeMask1 (oclrect.cl:74, 246-287, oclrect.c:314-321).
+// The reference scatters constants around every junction-map pixel; here a CTA computes the junction map on its 32x32
+// tile plus an apron of 8 (the largest radius), scatters into a shared-memory mask and writes the centre.  Also writes
+// the junction values themselves into `junc`, which the region-size histogram then accumulates on top of.
+#define JM_T 32
+#define JM_A 8
+#define JM_W (JM_T + 2 * JM_A)
+__global__ void __launch_bounds__(256) kf_junction_mask(uint8_t *mask, int *junc, const int *strong, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, mask, junc, strong);
+  __shared__ uint8_t sg[(JM_W + 2) * (JM_W + 2)];             // strong bitmap, one more pixel of apron for the 3x3 count
+  __shared__ uint8_t jn[JM_W * JM_W];
+  __shared__ uint8_t mk[JM_W * JM_W];
+  const int bx = blockIdx.x * JM_T - JM_A, by = blockIdx.y * JM_T - JM_A;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int SW = JM_W + 2;
+  for (int i = tid; i < SW * SW; i += 256) {
+    const int gx = bx - 1 + i % SW, gy = by - 1 + i / SW;
+    sg[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih && strong[(size_t)gy * iw + gx] > 0) ? 1 : 0;
+  }
+  for (int i = tid; i < JM_W * JM_W; i += 256) mk[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < JM_W * JM_W; i += 256) {
+    const int tx = i % JM_W, ty = i / JM_W;
+    const int gx = bx + tx, gy = by + ty;
+    const int c = (ty + 1) * SW + tx + 1;
+    uint8_t r = 0;
+    if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && sg[c]) {
+      const int n = 1 + sg[c - 1] + sg[c + 1] + sg[c - SW] + sg[c + SW] + sg[c - SW - 1] + sg[c - SW + 1] + sg[c + SW - 1] + sg[c + SW + 1];
+      r = n == 1 ? 0 : n;
+    }
+    jn[i] = r;
+  }
+  __syncthreads();
+  // mkMergeMask0: ring 16 <= d^2 < 36 := 1
+  for (int i = tid; i < JM_W * JM_W; i += 256) {
+    if (jn[i] == 0) continue;
+    const int tx = i % JM_W, ty = i / JM_W;
+    for (int yy = max(ty - 6, 0); yy <= min(ty + 6, JM_W - 1); yy++)
+      for (int xx = max(tx - 6, 0); xx <= min(tx + 6, JM_W - 1); xx++) {
+        const int d = (yy - ty) * (yy - ty) + (xx - tx) * (xx - tx);
+        if (16 <= d && d < 36) mk[yy * JM_W + xx] = 1;
+      }
+  }
+  __syncthreads();
+  // mkMergeMask1: disc d^2 < 64 around end pixels (2), d^2 < 16 around the others := 0
+  for (int i = tid; i < JM_W * JM_W; i += 256) {
+    const int j = jn[i];
+    if (j == 0) continue;
+    const int tx = i % JM_W, ty = i / JM_W;
+    const int r = j == 2 ? 8 : 4, lim = j == 2 ? 64 : 16;
+    for (int yy = max(ty - r, 0); yy <= min(ty + r, JM_W - 1); yy++)
+      for (int xx = max(tx - r, 0); xx <= min(tx + r, JM_W - 1); xx++) {
+        const int d = (yy - ty) * (yy - ty) + (xx - tx) * (xx - tx);
+        if (d < lim) mk[yy * JM_W + xx] = 0;
+      }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int tx = JM_A + threadIdx.x, ty = JM_A + threadIdx.y + k * 8;
+    const int gx = bx + tx, gy = by + ty;
+    if (gx < iw && gy < ih) {
+      mask[(size_t)gy * iw + gx] = mk[ty * JM_W + tx];
+      junc[(size_t)gy * iw + gx] = jn[ty * JM_W + tx];
+    }
+  }
+}
+void rd_junction_mask_run(uint8_t *mask, int *junc, const int *strong, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(kf_junction_mask, dim3(rd_cdiv(iw, JM_T), rd_cdiv(ih, JM_T), nb), dim3(32, 8), 0, s, mask, junc, strong, iw, ih, fs);
+}
+
+// despeckle2(16) in its Jacobi form + markBoundary (oclrect.cl:348-390, oclrect.c:336-340): region labels with an apron
+// of 3 and their sizes are staged; the absorbed labels are formed on the apron-2 tile, the boundary test on the centre.
+#define DB_T 32
+#define DB_A 3
+#define DB_W (DB_T + 2 * DB_A)
+__global__ void __launch_bounds__(256) kf_despeckle2_boundary(int *out, const int *label, const int *size, int thre, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, label, size);
+  __shared__ int sl[DB_W * DB_W];
+  __shared__ int ss[DB_W * DB_W];
+  __shared__ int sd[DB_W * DB_W];
+  const int bx = blockIdx.x * DB_T - DB_A, by = blockIdx.y * DB_T - DB_A;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < DB_W * DB_W; i += 256) {
+    const int gx = bx + i % DB_W, gy = by + i / DB_W;
+    int l = -1, sz = 0;
+    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) { l = label[(size_t)gy * iw + gx]; sz = size[l]; }
+    sl[i] = l; ss[i] = sz;
+  }
+  __syncthreads();
+  for (int i = tid; i < DB_W * DB_W; i += 256) {
+    const int tx = i % DB_W, ty = i / DB_W;
+    const int gx = bx + tx, gy = by + ty;
+    int res = sl[i];
+    if (tx >= 1 && ty >= 1 && tx < DB_W - 1 && ty < DB_W - 1 && gx >= 0 && gx < iw && gy >= 0 && gy < ih && !(ss[i] > thre)) {
+      int maxSize = 0;
+#pragma unroll
+      for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+        for (int xx = -1; xx <= 1; xx++) {
+          if (gx + xx < 0 || gx + xx >= iw || gy + yy < 0 || gy + yy >= ih) continue;
+          const int j = i + yy * DB_W + xx;
+          if (ss[j] > maxSize) { maxSize = ss[j]; res = sl[j]; }
+        }
+    }
+    sd[i] = res;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int tx = DB_A + threadIdx.x, ty = DB_A + threadIdx.y + k * 8;
+    const int gx = bx + tx, gy = by + ty;
+    if (gx >= iw || gy >= ih) continue;
+    int r = -1;
+    if (!(gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2)) {
+      const int i = ty * DB_W + tx, c0 = sd[i];
+      bool nearEdge = false;
+#pragma unroll
+      for (int yy = -2; yy <= 2; yy++)
+#pragma unroll
+        for (int xx = -2; xx <= 2; xx++) nearEdge |= sd[i + yy * DB_W + xx] != c0;
+      if (nearEdge) r = c0;
+    }
+    out[(size_t)gy * iw + gx] = r;
+  }
+}
+void rd_despeckle2_boundary_run(int *out, const int *label, const int *size, int thre, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(kf_despeckle2_boundary, dim3(rd_cdiv(iw, DB_T), rd_cdiv(ih, DB_T), nb), dim3(32, 8), 0, s, out, label, size, thre, iw, ih, fs);
+}

@@ -29,6 +29,14 @@ void rd_iirblur3_run(float *outL, float *outA, float *outB, uint32_t *outPlab, c
                      int nb, size_t fs, cudaStream_t s);
 void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int8_t *edge, uint8_t *ext, int iters, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_calcSize_run(int *out, const int *label, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_edge_thin_run(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_strings1_run(uint8_t *out, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_filter_masks_run(int8_t *weak, int *strong, const int *label, const int *str, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_junction_mask_run(uint8_t *mask, int *junc, const int *strong, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_despeckle2_boundary_run(int *out, const int *label, const int *size, int thre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_tail_gather_host(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, rd_tail_sample *out);
 
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
@@ -452,6 +460,45 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
 #undef STEP
 }
 
+// The production schedule: same results as gpu_task (the step-by-step replay above, kept for the intermediate-parity
+// tests), but with the fused kernels of rd_fast.cu and a buffer plan of its own.  Plane roles:
+//   buf0 packed Lab -> (later) segment-id map     buf1 blurred packed Lab -> string labels      buf2 thinned strength
+//   buf3 strength accumulator / strong-edge bitmap (carried to the next frame)      buf4 smoothed colours -> region labels
+//   tmp1..3 blurred L, a, b -> weak mask + walk extents (tmp1), flat colours (tmp2), blur ping-pong / merge mask (tmp3)
+//   tmp0 string bytes -> junction map + region sizes   tmp4 CCL link bytes   tmp5 strong-edge bitmap of this frame
+//   iobuf1 region-boundary (segid) map   ioBig0 blur scratch -> segment list   ioBig1 blur scratch -> polyline scratch -> vote table
+static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int nb, cudaStream_t s) {
+  const int iw = o->iw, ih = o->ih, n = iw * ih;
+  const size_t fs = o->fs;
+  cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
+  // Stage A (oclrect.c:245-263)
+  rd_bgr2plab_run(PU(buf[0]), din, din_fs, iw, ih, ws, nb, fs, s);
+  rd_iirblur3_run(PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), PU(buf[1]), PU(buf[0]), PF(ioBig[1]), PF(ioBig[0]), o->P / 4, 2, iw, ih, nb, fs, s);
+  rd_edge_thin_run(PF(buf[2]), PF(tmp[1]), PU(buf[1]), iw, ih, nb, fs, s);
+  // Stage B (oclrect.c:265-342)
+  rd_strings1_run((uint8_t *)tmp[0]->dptr, PF(buf[2]), iw, ih, nb, fs, s);
+  rd_label8x_u8(PI(buf[1]), (const uint8_t *)tmp[0]->dptr, tmp[4]->dptr, -1, iw, ih, nb, fs, s);
+  RD_LAUNCH(kr_calcStrength, rd_gz(G2, nb), RB, 0, s, PI(buf[3]), PF(buf[2]), PI(buf[1]), iw, ih, fs);
+  rd_filter_masks_run((int8_t *)tmp[1]->dptr, PI(tmp[5]), PI(buf[1]), PI(buf[3]), iw, ih, nb, fs, s);
+  rd_blblur_run(PU(buf[4]), PU(tmp[3]), PU(buf[0]), (const int8_t *)tmp[1]->dptr, (uint8_t *)tmp[1]->dptr + (size_t)n, 10, iw, ih, nb, fs, s);
+  rd_quant_despeckle_run(PU(tmp[2]), PU(buf[4]), PF(buf[2]), iw, ih, nb, fs, s);
+  rd_junction_mask_run((uint8_t *)tmp[3]->dptr, PI(tmp[0]), PI(tmp[5]), iw, ih, nb, fs, s);
+  rd_labelMerge_u8(PI(buf[4]), PI(buf[5]), PU(tmp[2]), (const uint8_t *)tmp[3]->dptr, PI(tmp[5]), tmp[4]->dptr, iw, ih, nb, fs, s);
+  rd_calcSize_run(PI(tmp[0]), PI(buf[4]), iw, ih, nb, fs, s);
+  rd_despeckle2_boundary_run(PI(tmp[1]), PI(buf[4]), PI(tmp[0]), 16, iw, ih, nb, fs, s);
+  rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[4]->dptr, -1, iw, ih, nb, fs, s);
+  rd_k_copy(PI(buf[3]), PI(tmp[5]), n, nb, fs, s);                 // the bitmap the next frame's strengths accumulate on
+  // Stage C (oclrect.c:361); tmp2 still holds the flat colours, i.e. the non-zero frame simpleConnect leaves behind
+  rd_polyline_run((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(tmp[5]), PI(ioBig[1]), PI(tmp[0]), PI(tmp[1]), PI(tmp[2]), PI(tmp[3]), PI(tmp[4]),
+                  PI(buf[5]), 4.0f, 20, iw, ih, nb, fs, s);
+  // Stage D (oclrect.c:365-367) and the compact read-back record
+  const int nentry = n * 4 / 5;
+  rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
+  RD_LAUNCH(kr_reduceLS<0>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS<1>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
+  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
+}
+
 // ---- fused / specialised Stage A kernels of the rect pipeline ----
 #define RD_TABLE_QUAL static __device__ const
 #include "rd_tables.inc"
@@ -569,7 +616,7 @@ static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, 
     din_fs = frame_stride;
   }
   if (fresh) RD_CUDA(cudaMemset2DAsync(o->buf[3]->dptr, o->fs, 0, (size_t)iw * ih * 4, count, s));
-  gpu_task(o, din, din_fs, ws, 0, count, s);
+  gpu_task_fast(o, din, din_fs, ws, count, s);
   const size_t chunk = o->blobBytes < FIRST_CHUNK ? o->blobBytes : FIRST_CHUNK;
   RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], o->blobBytes, o->dblob, o->fs, chunk, count, cudaMemcpyDeviceToHost, s));
   RD_CUDA(cudaEventRecord(o->events[page], s));
@@ -673,7 +720,8 @@ void rd_oclrect_run_device(struct oclrect_t *o, const uint8_t *imgData, int ws, 
   chk(o);
   cudaStream_t s = rd_stream(o->queue);
   RD_CUDA(cudaMemcpyAsync(o->iobuf[0]->dptr, imgData, (size_t)ws * o->ih, cudaMemcpyHostToDevice, s));
-  if (stop_step != -1) gpu_task(o, (const uint8_t *)o->iobuf[0]->dptr, o->fs, ws, stop_step, 1, s);
+  if (stop_step > 0) gpu_task(o, (const uint8_t *)o->iobuf[0]->dptr, o->fs, ws, stop_step, 1, s);
+  else if (stop_step == 0) gpu_task_fast(o, (const uint8_t *)o->iobuf[0]->dptr, o->fs, ws, 1, s);
   RD_CUDA(cudaStreamSynchronize(s));
 }
 
