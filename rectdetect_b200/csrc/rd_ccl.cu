@@ -91,9 +91,17 @@ struct LinkMerge {                    // labelxPreprocess + labelMergeMain, cano
   }
 };
 
+// find with path halving: every second node on the way is re-pointed at its grandparent.  A stale write can only
+// replace a parent by one of its ancestors (parents only ever move towards the root), so concurrent walks stay valid.
 __device__ __forceinline__ int sm_find(volatile int *L, int x) {
   int p = L[x];
-  while (p != x) { x = p; p = L[x]; }
+  while (p != x) {
+    const int g = L[p];
+    if (g == p) return p;
+    L[x] = g;
+    x = g;
+    p = L[x];
+  }
   return x;
 }
 __device__ __forceinline__ void sm_unite(int *L, int a, int b) {

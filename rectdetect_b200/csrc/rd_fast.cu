@@ -77,66 +77,119 @@ __global__ void __launch_bounds__(256) kf_blb_extents(uint8_t *extH, uint8_t *ex
 // floor(c / w) for 0 <= c < 2^16, 1 <= w <= 10 : one multiply-high by ceil(2^32 / w)
 __constant__ const unsigned BLB_RCP[11] = {0u, 0u, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u, 0x1c71c71du, 0x1999999au};
 __device__ __forceinline__ unsigned blb_div(unsigned c, unsigned w) { return w == 1 ? c : __umulhi(c, BLB_RCP[w]); }
+__device__ __forceinline__ unsigned blb_div_r(unsigned c, unsigned rcp) { return rcp == 0 ? c : __umulhi(c, rcp); }
 __device__ __forceinline__ uint32_t blb_mean(unsigned c0, unsigned c1, unsigned c2, unsigned w) {
   // packlabbl(csum / wsum): the quotients cannot leave their fields (means of in-range values), so no clamp is needed
   return (blb_div(c2, w) << 22) | (blb_div(c1, w) << 12) | blb_div(c0, w);
 }
 
-#define IT_TX 64
-#define IT_TY 32
-#define IT_PW (IT_TX + 2 * BLB)        // input tile pitch
 // Shared-memory tiles hold the three channels spread out in one 64-bit word (L at bit 0, a at bit 20, b at bit 40), so
 // a walk is a chain of plain 64-bit adds (at most 10 terms of at most 12 bits each: no field can overflow into the next).
 typedef unsigned long long blb_w;
 __device__ __forceinline__ blb_w blb_spread(uint32_t v) { return (blb_w)(v & 4095u) | ((blb_w)((v >> 12) & 1023u) << 20) | ((blb_w)(v >> 22) << 40); }
 __device__ __forceinline__ uint32_t blb_pack(blb_w w) { return (uint32_t)(w & 4095u) | ((uint32_t)((w >> 20) & 1023u) << 12) | ((uint32_t)(w >> 40) << 22); }
-// sum of c[-(nb_-1)..0] and c[0..nf_-1] (the centre counts once per walk that reaches it), then the packed mean
-__device__ __forceinline__ uint32_t blb_walk(const blb_w *c, int stride, int nb_, int nf_) {
-  blb_w acc = 0;
-#pragma unroll
-  for (int d = 0; d <= BLB; d++) {
-    if (d < nb_) acc += c[-d * stride];
-    if (d < nf_) acc += c[d * stride];
-  }
-  const unsigned w = nb_ + nf_;
-  if (w == 0) return blb_pack(c[0]);
+__device__ __forceinline__ uint32_t blb_finish(blb_w acc, blb_w centre, unsigned w) {
+  if (w == 0) return blb_pack(centre);
   return blb_mean((unsigned)(acc & 0xfffffu), (unsigned)((acc >> 20) & 0xfffffu), (unsigned)(acc >> 40), w);
 }
-// one iteration = blblur0 then blblur1.  Input tile (TY+8) x (TX+8) -> x pass on (TY+8) x TX -> y pass on TY x TX.
-// CTA = 64 x 4 threads; everything the two passes need (pixels and walk extents) is staged in shared memory first.
-__global__ void __launch_bounds__(256) kf_blb_iter(uint32_t *out, const uint32_t *in, const uint8_t *extH, const uint8_t *extV, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, out, in, extH, extV);
-  __shared__ blb_w tin[(IT_TY + 2 * BLB) * IT_PW];
-  __shared__ blb_w th[(IT_TY + 2 * BLB) * IT_TX];
-  __shared__ uint8_t eh[(IT_TY + 2 * BLB) * IT_TX];
-  __shared__ uint8_t ev[IT_TY * IT_TX];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int bx = blockIdx.x * IT_TX, by = blockIdx.y * IT_TY;
-  const int gx = bx + tx;
+
+// ---- the iteration kernel -------------------------------------------------------------------------------------------
+// (Two CTA-tiled variants were measured first - a 64x32 tile staged by plain loads, and a persistent one staged by
+// cp.async.bulk into a double buffer - and both sat at ~15 us per frame-iteration on CTA barriers and apron recomputation;
+// see DESIGN.md.)
+// One WARP owns a 32-pixel-wide strip of up to SB_CH rows and streams down it, so nothing ever waits on a CTA barrier:
+//  - per row it loads 40 pixels (apron 4 each side) and the row's x-extents, forms the running sums of the row with a
+//    shuffle scan, and every lane takes its x-pass mean from four entries of that row of sums;
+//  - each lane keeps the running sum of ITS column of x-pass results in a 16-row ring in shared memory, and as soon as
+//    row y+4 is in, the y-pass mean of row y is four ring entries away.  No row is loaded or x-filtered twice within a strip
+//    (the tiled kernels above redo the 8 apron rows of every 32-row tile).
+// Field widths: a strip adds at most SB_CH_MAX + 8 values of at most 12 bits per field, inside the 20-bit fields.
+#define SB_CH_MIN 32                 // strip heights are chosen per launch (see rd_blblur_run) within [SB_CH_MIN, SB_CH_MAX]
+#define SB_CH_MAX 240                // (240 + 8) rows x 4095 still fits the 20-bit fields of the running sums
+#define SB_RING 16
+#define SB_WARPS 8
+__device__ __forceinline__ blb_w blb_scan_up(blb_w v, int lane, int steps) {
 #pragma unroll
-  for (int r = ty; r < IT_TY + 2 * BLB; r += 4) {
-    const int gy = by - BLB + r;
-    const bool rowok = gy >= 0 && gy < ih;
-    const size_t rb = (size_t)gy * iw;
-    const int gl = bx - BLB + tx;                                   // tile column tx
-    tin[r * IT_PW + tx] = blb_spread((rowok && gl >= 0 && gl < iw) ? in[rb + gl] : 0u);
-    if (tx < 2 * BLB) { const int g2 = gl + IT_TX; tin[r * IT_PW + IT_TX + tx] = blb_spread((rowok && g2 < iw) ? in[rb + g2] : 0u); }
-    eh[r * IT_TX + tx] = (rowok && gx < iw) ? extH[rb + gx] : (uint8_t)0;
-    if (r < IT_TY) { const int g3 = by + r; ev[r * IT_TX + tx] = (g3 < ih && gx < iw) ? extV[(size_t)g3 * iw + gx] : (uint8_t)0; }
+  for (int k = 0; k < 5; k++) {
+    if (k < steps) { const blb_w t = __shfl_up_sync(0xffffffffu, v, 1 << k); if (lane >= (1 << k)) v += t; }
   }
-  __syncthreads();
-#pragma unroll
-  for (int r = ty; r < IT_TY + 2 * BLB; r += 4) {
-    const unsigned e = eh[r * IT_TX + tx];
-    th[r * IT_TX + tx] = blb_spread(blb_walk(tin + r * IT_PW + tx + BLB, 1, e & 15, e >> 4));
+  return v;
+}
+__global__ void __launch_bounds__(SB_WARPS * 32) kf_blb_stream(uint32_t *out, const uint32_t *in, const uint8_t *extH, const uint8_t *extV, int iw, int ih, int nb,
+                                                               int strips, int chunks, int ch, size_t fs) {
+  __shared__ blb_w rowP[SB_WARPS][48];
+  __shared__ blb_w ring[SB_WARPS][SB_RING][32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int wid = blockIdx.x * SB_WARPS + wp;
+  if (wid >= strips * chunks * nb) return;
+  const int sx = wid % strips, cy = (wid / strips) % chunks, z = wid / (strips * chunks);
+  rd_batch_off((size_t)z * fs, out, in, extH, extV);
+  const int x = sx * 32 + lane, xa = x - BLB, xb = x + 32 - BLB;
+  const bool oka = xa >= 0 && xa < iw, okb = lane < 2 * BLB && xb < iw, okx = x < iw;
+  const int y0 = cy * ch, y1 = min(y0 + ch, ih);
+  const int first = max(y0 - BLB, 0), last = min(y1 + BLB, ih);
+  blb_w *P = rowP[wp];
+  blb_w (*R)[32] = ring[wp];
+  blb_w Q = 0;
+  R[first & (SB_RING - 1)][lane] = 0;
+  // two rows of look-ahead in registers
+  uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+  unsigned e0 = 0, e1 = 0;
+  {
+    const size_t r0 = (size_t)first * iw, r1 = (size_t)(first + 1) * iw;
+    if (oka) a0 = in[r0 + xa];
+    if (okb) b0 = in[r0 + xb];
+    if (okx) e0 = extH[r0 + x];
+    if (first + 1 < last) { if (oka) a1 = in[r1 + xa]; if (okb) b1 = in[r1 + xb]; if (okx) e1 = extH[r1 + x]; }
   }
-  __syncthreads();
-#pragma unroll
-  for (int r = ty; r < IT_TY; r += 4) {
-    const int gy = by + r;
-    const unsigned e = ev[r * IT_TX + tx];
-    const uint32_t v = blb_walk(th + (r + BLB) * IT_TX + tx, IT_TX, e & 15, e >> 4);
-    if (gx < iw && gy < ih) out[(size_t)gy * iw + gx] = v;
+  for (int y = first; y < last; y++) {
+    const uint32_t a = a0, b = b0;
+    const unsigned e = e0;
+    a0 = a1; b0 = b1; e0 = e1;
+    a1 = 0; b1 = 0; e1 = 0;
+    if (y + 2 < last) {
+      const size_t r2 = (size_t)(y + 2) * iw;
+      if (oka) a1 = in[r2 + xa];
+      if (okb) b1 = in[r2 + xb];
+      if (okx) e1 = extH[r2 + x];
+    }
+    const int yv = y - BLB;
+    unsigned ev = 0;
+    const bool doV = yv >= y0 && okx;
+    if (doV) ev = extV[(size_t)yv * iw + x];
+    // x pass: running sums of the 40-pixel row
+    const blb_w wa = blb_spread(a), wb = blb_spread(b);
+    const blb_w ia = blb_scan_up(wa, lane, 5);
+    const blb_w ta = __shfl_sync(0xffffffffu, ia, 31);
+    const blb_w ib = blb_scan_up(wb, lane, 3);
+    P[lane] = ia - wa;
+    if (lane < 2 * BLB) P[32 + lane] = ta + ib - wb;
+    if (lane == 2 * BLB - 1) P[32 + 2 * BLB] = ta + ib;
+    __syncwarp();
+    const int c = lane + BLB, nl = e & 15, nr = e >> 4;
+    const blb_w pc = P[c], pc1 = P[c + 1];
+    const blb_w hs = (pc1 - P[c + 1 - nl]) + (P[c + nr] - pc);
+    const blb_w h = (nl + nr) == 0 ? (pc1 - pc) : blb_spread(blb_finish(hs, 0, nl + nr));
+    __syncwarp();
+    // y pass: column running sums in the ring; row yv = y - 4 is complete once Q[y + 1] is known
+    Q += h;
+    R[(y + 1) & (SB_RING - 1)][lane] = Q;
+    if (doV) {
+      const int nu = ev & 15, nd = ev >> 4;
+      const blb_w qa = R[(yv + 1) & (SB_RING - 1)][lane], qd = R[yv & (SB_RING - 1)][lane];
+      const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][lane]) + (R[(yv + nd) & (SB_RING - 1)][lane] - qd);
+      out[(size_t)yv * iw + x] = blb_finish(vs, qa - qd, nu + nd);
+    }
+  }
+  // rows whose downward walk is cut by the bottom of the image rather than by the strip
+  if (okx) {
+    for (int yv = max(y0, last - BLB); yv < y1; yv++) {
+      const unsigned ev = extV[(size_t)yv * iw + x];
+      const int nu = ev & 15, nd = ev >> 4;
+      const blb_w qa = R[(yv + 1) & (SB_RING - 1)][lane], qd = R[yv & (SB_RING - 1)][lane];
+      const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][lane]) + (R[(yv + nd) & (SB_RING - 1)][lane] - qd);
+      out[(size_t)yv * iw + x] = blb_finish(vs, qa - qd, nu + nd);
+    }
   }
 }
 
@@ -144,11 +197,22 @@ __global__ void __launch_bounds__(256) kf_blb_iter(uint32_t *out, const uint32_t
 void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int8_t *edge, uint8_t *ext, int iters, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   uint8_t *extH = ext, *extV = ext + (size_t)iw * ih;
   RD_LAUNCH(kf_blb_extents, dim3(rd_cdiv(iw, EX_TX), rd_cdiv(ih, EX_TY), nb), 256, 0, s, extH, extV, edge, iw, ih, fs);
-  const dim3 g(rd_cdiv(iw, IT_TX), rd_cdiv(ih, IT_TY), nb);
+  // strip height: as many strips as fit the machine in one wave (4 CTAs of 8 warps per SM at 58 registers), so that no SM
+  // idles behind a straggler; clamped so that the running sums stay inside their fields and strips stay worth their apron
+  static int sms = 0;
+  if (!sms) { int dev = 0; RD_CUDA(cudaGetDevice(&dev)); RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+  const int strips = rd_cdiv(iw, 32);
+  int chunks = (sms * 4 * SB_WARPS) / (strips * nb);
+  if (chunks < 1) chunks = 1;
+  int ch = rd_cdiv(ih, chunks);
+  if (ch < SB_CH_MIN) ch = SB_CH_MIN;
+  if (ch > SB_CH_MAX) ch = SB_CH_MAX;
+  chunks = rd_cdiv(ih, ch);
+  const int blocks = rd_cdiv(strips * chunks * nb, SB_WARPS);
   const uint32_t *cur = src;
   for (int i = 0; i < iters; i++) {
     uint32_t *o = ((iters - i) & 1) ? dst : pong;       // the last iteration lands in dst
-    RD_LAUNCH(kf_blb_iter, g, dim3(IT_TX, 4), 0, s, o, cur, extH, extV, iw, ih, fs);
+    RD_LAUNCH(kf_blb_stream, blocks, SB_WARPS * 32, 0, s, o, cur, extH, extV, iw, ih, nb, strips, chunks, ch, fs);
     cur = o;
   }
 }
@@ -420,54 +484,64 @@ void rd_iirblur3_run(float *outL, float *outA, float *outB, uint32_t *outPlab, c
 #define ET_PW (ET_T + 2 * ET_PA)
 #define ET_MW (ET_T + 2 * ET_MA)
 #define ET_LW (ET_T + 2 * ET_LA)
-struct TileMag {                     // Plane interface of rd_bicubic: at(x, y) = magnitude at the mirrored position
-  const float *m; int x0, y0, iw, ih;
-  __device__ __forceinline__ float at(int x, int y) const { return m[(rd_mirror1(y, ih) - y0) * ET_MW + (rd_mirror1(x, iw) - x0)]; }
+// mirror for tile staging: positions far outside the image (never consulted) are clamped so that the load stays in bounds
+__device__ __forceinline__ int mirror_safe(int x, int n) { return min(max(rd_mirror1(x, n), 0), n - 1); }
+struct TileMag {                     // Plane interface of rd_bicubic: the tile already holds the mirror-extended magnitude
+  const float *m; int x0, y0;
+  __device__ __forceinline__ float at(int x, int y) const { return m[(y - y0) * ET_MW + (x - x0)]; }
 };
+// Every tile is filled for ALL its positions with the value of the mirrored image position (the reference's border rule,
+// oclimgutil.cl:41-45), so the inner loops index with plain offsets and no coordinate is mirrored more than once.
 __global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, size_t fs) {
   rd_batch_z(fs, thin, blurL, blurP);
   __shared__ uint32_t sp[ET_PW * ET_PW];
   __shared__ float sm[ET_MW * ET_MW];
   __shared__ float sl[ET_LW * ET_LW];
   const int bx = blockIdx.x * ET_T, by = blockIdx.y * ET_T;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  // stage: in-image positions only (everything below indexes with mirrored, hence in-image, coordinates)
-  for (int i = tid; i < ET_PW * ET_PW; i += 256) {
-    const int gx = bx - ET_PA + i % ET_PW, gy = by - ET_PA + i / ET_PW;
-    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) sp[i] = blurP[(size_t)gy * iw + gx];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  // stage the packed-Lab tile (apron 5) and the L tile (apron 2) at mirrored coordinates
+  for (int r = ty; r < ET_PW; r += 8) {
+    const size_t rb = (size_t)mirror_safe(by - ET_PA + r, ih) * iw;
+    sp[r * ET_PW + tx] = blurP[rb + mirror_safe(bx - ET_PA + tx, iw)];
+    if (tx < ET_PW - 32) sp[r * ET_PW + 32 + tx] = blurP[rb + mirror_safe(bx - ET_PA + 32 + tx, iw)];
   }
-  for (int i = tid; i < ET_LW * ET_LW; i += 256) {
-    const int gx = bx - ET_LA + i % ET_LW, gy = by - ET_LA + i / ET_LW;
-    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) sl[i] = blurL[(size_t)gy * iw + gx];
-  }
-  __syncthreads();
-  // edge magnitude on the apron-4 tile, at in-image positions
-  const int px0 = bx - ET_PA, py0 = by - ET_PA;
-  for (int i = tid; i < ET_MW * ET_MW; i += 256) {
-    const int gx = bx - ET_MA + i % ET_MW, gy = by - ET_MA + i / ET_MW;
-    if (gx < 0 || gx >= iw || gy < 0 || gy >= ih) continue;
-    const int xm = rd_mirror1(gx - 1, iw) - px0, xc = gx - px0, xp = rd_mirror1(gx + 1, iw) - px0;
-    const int ym = (rd_mirror1(gy - 1, ih) - py0) * ET_PW, yc = (gy - py0) * ET_PW, yp = (rd_mirror1(gy + 1, ih) - py0) * ET_PW;
-    sm[i] = rd_edge_plab_at(sp[ym + xc], sp[yc + xm], sp[yp + xc], sp[yc + xp], sp[ym + xm], sp[yp + xp], sp[ym + xp], sp[yp + xm]);
+  for (int r = ty; r < ET_LW; r += 8) {
+    const size_t rb = (size_t)mirror_safe(by - ET_LA + r, ih) * iw;
+    sl[r * ET_LW + tx] = blurL[rb + mirror_safe(bx - ET_LA + tx, iw)];
+    if (tx < ET_LW - 32) sl[r * ET_LW + 32 + tx] = blurL[rb + mirror_safe(bx - ET_LA + 32 + tx, iw)];
   }
   __syncthreads();
-  const TileMag mag = {sm, bx - ET_MA, by - ET_MA, iw, ih};
-  const int lx0 = bx - ET_LA, ly0 = by - ET_LA;
+  // edge magnitude on the apron-4 tile.  Position (gx, gy) of the tile stands for the image position (mirror(gx), mirror(gy));
+  // its 3x3 neighbourhood is taken around THAT position (the packed tile is indexed through the mirrored centre).
+  for (int r = ty; r < ET_MW; r += 8) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int c = tx + h * 32;
+      if (c >= ET_MW) continue;
+      const int gx = bx - ET_MA + c, gy = by - ET_MA + r;
+      if (gx > iw + ET_MA - 1 || gy > ih + ET_MA - 1) continue;           // beyond the apron of the last in-image pixel: never read
+      const int mx = rd_mirror1(gx, iw), my = rd_mirror1(gy, ih);
+      // tile coordinates of the mirrored centre: the tile spans [bx-5, bx+36], and mirroring keeps a position within 5 of where it was
+      const uint32_t *q = sp + (my - (by - ET_PA)) * ET_PW + (mx - (bx - ET_PA));
+      sm[r * ET_MW + c] = rd_edge_plab_at(q[-ET_PW], q[-1], q[ET_PW], q[1], q[-ET_PW - 1], q[ET_PW + 1], q[-ET_PW + 1], q[ET_PW - 1]);
+    }
+  }
+  __syncthreads();
+  const TileMag mag = {sm, bx - ET_MA, by - ET_MA};
 #pragma unroll 1
   for (int k = 0; k < 4; k++) {
-    const int x = bx + threadIdx.x, y = by + threadIdx.y + k * 8;
+    const int x = bx + tx, y = by + ty + k * 8;
     if (x >= iw || y >= ih) continue;
     float vx = 0, vy = 0;
+    const float *lc = sl + (y - (by - ET_LA)) * ET_LW + (x - (bx - ET_LA));
 #pragma unroll
-    for (int yy = -2; yy <= 2; yy++) {
-      const int ry = (rd_mirror1(y + yy, ih) - ly0) * ET_LW;
+    for (int yy = -2; yy <= 2; yy++)
 #pragma unroll
       for (int xx = -2; xx <= 2; xx++) {
-        const float s = sl[ry + rd_mirror1(x + xx, iw) - lx0];
+        const float s = lc[yy * ET_LW + xx];
         vx = __fadd_rn(vx, __fmul_rn(RD_V5C[(xx + 2) + (yy + 2) * 5], s));
         vy = __fadd_rn(vy, __fmul_rn(RD_V5C[(yy + 2) + (xx + 2) * 5], s));
       }
-    }
     const float2 v = rd_edgevec_normalise(vx, vy);
     // thinthres: the outer samples only matter where the pixel is a local maximum along the gradient
     const float fx = (float)x, fy = (float)y;
@@ -646,63 +720,71 @@ void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin
 #define JM_T 32
 #define JM_A 8
 #define JM_W (JM_T + 2 * JM_A)
+// half-widths of the discs d^2 < 64 and d^2 < 16, and the |dx| range of the ring 16 <= d^2 < 36, per row offset |dy|
+__constant__ const int JM_D8[8] = {7, 7, 7, 7, 6, 6, 5, 3};
+__constant__ const int JM_D4[4] = {3, 3, 3, 2};
+__constant__ const int JM_RLO[6] = {4, 4, 4, 3, 0, 0};
+__constant__ const int JM_RHI[6] = {5, 5, 5, 5, 4, 3};
+__device__ __forceinline__ unsigned long long jm_span(int lo, int hi) { return ((1ull << (hi - lo + 1)) - 1ull) << lo; }   // bits lo..hi
 __global__ void __launch_bounds__(256) kf_junction_mask(uint8_t *mask, int *junc, const int *strong, int iw, int ih, size_t fs) {
   rd_batch_z(fs, mask, junc, strong);
   __shared__ uint8_t sg[(JM_W + 2) * (JM_W + 2)];             // strong bitmap, one more pixel of apron for the 3x3 count
   __shared__ uint8_t jn[JM_W * JM_W];
-  __shared__ uint8_t mk[JM_W * JM_W];
+  __shared__ unsigned long long rowA[JM_W], rowE[JM_W];       // per tile row: bit x set where the junction map is non-zero / equals 2
+  __shared__ int any;
   const int bx = blockIdx.x * JM_T - JM_A, by = blockIdx.y * JM_T - JM_A;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int lane = threadIdx.x, wy = threadIdx.y, tid = wy * 32 + lane;
   const int SW = JM_W + 2;
+  if (tid == 0) any = 0;
   for (int i = tid; i < SW * SW; i += 256) {
     const int gx = bx - 1 + i % SW, gy = by - 1 + i / SW;
     sg[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih && strong[(size_t)gy * iw + gx] > 0) ? 1 : 0;
   }
-  for (int i = tid; i < JM_W * JM_W; i += 256) mk[i] = 0;
   __syncthreads();
-  for (int i = tid; i < JM_W * JM_W; i += 256) {
-    const int tx = i % JM_W, ty = i / JM_W;
-    const int gx = bx + tx, gy = by + ty;
-    const int c = (ty + 1) * SW + tx + 1;
-    uint8_t r = 0;
-    if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && sg[c]) {
-      const int n = 1 + sg[c - 1] + sg[c + 1] + sg[c - SW] + sg[c + SW] + sg[c - SW - 1] + sg[c - SW + 1] + sg[c + SW - 1] + sg[c + SW + 1];
-      r = n == 1 ? 0 : n;
+  // junction map of the apron-8 tile, one warp per row, and its two bit rows
+  for (int ty = wy; ty < JM_W; ty += 8) {
+    unsigned long long a = 0, e = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int tx = lane + half * 32;
+      int r = 0;
+      if (tx < JM_W) {
+        const int gx = bx + tx, gy = by + ty, c = (ty + 1) * SW + tx + 1;
+        if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && sg[c]) {
+          const int n = 1 + sg[c - 1] + sg[c + 1] + sg[c - SW] + sg[c + SW] + sg[c - SW - 1] + sg[c - SW + 1] + sg[c + SW - 1] + sg[c + SW + 1];
+          r = n == 1 ? 0 : n;
+        }
+        jn[ty * JM_W + tx] = (uint8_t)r;
+      }
+      a |= (unsigned long long)__ballot_sync(0xffffffffu, r != 0) << (half * 32);
+      e |= (unsigned long long)__ballot_sync(0xffffffffu, r == 2) << (half * 32);
     }
-    jn[i] = r;
+    if (lane == 0) { rowA[ty] = a; rowE[ty] = e; if (a) any = 1; }
   }
   __syncthreads();
-  // mkMergeMask0: ring 16 <= d^2 < 36 := 1
-  for (int i = tid; i < JM_W * JM_W; i += 256) {
-    if (jn[i] == 0) continue;
-    const int tx = i % JM_W, ty = i / JM_W;
-    for (int yy = max(ty - 6, 0); yy <= min(ty + 6, JM_W - 1); yy++)
-      for (int xx = max(tx - 6, 0); xx <= min(tx + 6, JM_W - 1); xx++) {
-        const int d = (yy - ty) * (yy - ty) + (xx - tx) * (xx - tx);
-        if (16 <= d && d < 36) mk[yy * JM_W + xx] = 1;
-      }
-  }
-  __syncthreads();
-  // mkMergeMask1: disc d^2 < 64 around end pixels (2), d^2 < 16 around the others := 0
-  for (int i = tid; i < JM_W * JM_W; i += 256) {
-    const int j = jn[i];
-    if (j == 0) continue;
-    const int tx = i % JM_W, ty = i / JM_W;
-    const int r = j == 2 ? 8 : 4, lim = j == 2 ? 64 : 16;
-    for (int yy = max(ty - r, 0); yy <= min(ty + r, JM_W - 1); yy++)
-      for (int xx = max(tx - r, 0); xx <= min(tx + r, JM_W - 1); xx++) {
-        const int d = (yy - ty) * (yy - ty) + (xx - tx) * (xx - tx);
-        if (d < lim) mk[yy * JM_W + xx] = 0;
-      }
-  }
-  __syncthreads();
+  const bool some = any != 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int tx = JM_A + threadIdx.x, ty = JM_A + threadIdx.y + k * 8;
+    const int tx = JM_A + lane, ty = JM_A + wy + k * 8;
     const int gx = bx + tx, gy = by + ty;
+    int m = 0;
+    if (some) {
+      bool zero = false, one = false;
+#pragma unroll
+      for (int dy = -7; dy <= 7; dy++) { const int w = JM_D8[dy < 0 ? -dy : dy]; zero |= (rowE[ty + dy] & jm_span(tx - w, tx + w)) != 0; }
+#pragma unroll
+      for (int dy = -3; dy <= 3; dy++) { const int w = JM_D4[dy < 0 ? -dy : dy]; zero |= (rowA[ty + dy] & jm_span(tx - w, tx + w)) != 0; }
+#pragma unroll
+      for (int dy = -5; dy <= 5; dy++) {
+        const int ad = dy < 0 ? -dy : dy, lo = JM_RLO[ad], hi = JM_RHI[ad];
+        const unsigned long long sel = lo == 0 ? jm_span(tx - hi, tx + hi) : (jm_span(tx - hi, tx - lo) | jm_span(tx + lo, tx + hi));
+        one |= (rowA[ty + dy] & sel) != 0;
+      }
+      m = zero ? 0 : (one ? 1 : 0);
+    }
     if (gx < iw && gy < ih) {
-      mask[(size_t)gy * iw + gx] = mk[ty * JM_W + tx];
-      junc[(size_t)gy * iw + gx] = jn[ty * JM_W + tx];
+      mask[(size_t)gy * iw + gx] = (uint8_t)m;
+      junc[(size_t)gy * iw + gx] = some ? jn[ty * JM_W + tx] : 0;
     }
   }
 }

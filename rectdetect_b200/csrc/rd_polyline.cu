@@ -30,7 +30,7 @@ static_assert(sizeof(LS_t) == 56 && sizeof(LSX_t) == 56, "list entries are 56 by
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
 #define IS_BORDER1 (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1)
 // kernels over the compact list of labelled pixels: grid-stride loop, `continue` instead of `return`
-#define PLIST_LOOP const int pcount_ = plist[0]; for (int k_ = blockIdx.x * blockDim.x + threadIdx.x; k_ < pcount_; k_ += gridDim.x * blockDim.x)
+#define PLIST_LOOP const int pcount_ = plist[0]; for (int k_ = threadIdx.x; k_ < pcount_; k_ += blockDim.x)
 #define PLIST_XY const int p0 = plist[k_ + 1]; const int x = p0 % iw, y = p0 / iw; (void)x; (void)y
 #define LIST_BLOCKS 32
 
@@ -328,11 +328,10 @@ __device__ __forceinline__ void closestPoint(float vx, float vy, float wx, float
 
 // init: zero the list entries of the K initial strings (K = table[0], oclpolyline.c:192 clears the whole list), reset
 // the per-string start / end pixel slots and the arg-max slots, and arm the iteration flags (oclpolyline.cl:442-444)
-__global__ void kp_mkpl_init(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const int *table, int *flags, int maxIter, size_t fs) {
-  rd_batch_y(fs, gp, aux, winner, table, flags);
+__device__ __forceinline__ void d_mkpl_init(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const int *table, int *flags, int maxIter) {
   const int cap2 = min(cap, lsListSize / (int)sizeof(LS_t));
   const int K = min(table[0], cap2 - 1);
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int t = (int)threadIdx.x, nt = (int)blockDim.x;
   if (t < maxIter + 1) flags[t] = t == 0 ? 1 : 0;
   int *raw = (int *)gp;
   for (int i = t; i < (K + 1) * 14; i += nt) raw[i] = 0;
@@ -340,8 +339,7 @@ __global__ void kp_mkpl_init(LS_t *gp, int lsListSize, int *aux, int *winner, in
 }
 // pass0a: per-string start pixel (the LAST pixel in raster order whose number is 1, as a sequential sweep leaves it),
 // pixel count, largest number, and the list header (largest id).  aux[g] / aux[cap+g] : start / end pixel index.
-__global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, const int *plist, int iw, size_t fs) {
-  rd_batch_y(fs, gp, aux, numberin, labelin, plist);
+__device__ __forceinline__ void d_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, const int *plist, int iw) {
   PLIST_LOOP {
     PLIST_XY;
     const int g = labelin[p0], n = numberin[p0];
@@ -352,8 +350,7 @@ __global__ void kp_mkpl_pass0a(LS_t *gp, int lsListSize, int *aux, int cap, cons
     atomicMax((int *)gp, g);
   }
 }
-__global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, const int *plist, int iw, size_t fs) {
-  rd_batch_y(fs, gp, aux, numberin, labelin, plist);
+__device__ __forceinline__ void d_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, const int *numberin, const int *labelin, const int *plist, int iw) {
   PLIST_LOOP {
     PLIST_XY;
     const int g = labelin[p0], n = numberin[p0];
@@ -365,10 +362,9 @@ __global__ void kp_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux, int cap, cons
   }
 }
 // one thread per list entry: turn the start / end pixel indices into coordinates
-__global__ void kp_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw, size_t fs) {
-  rd_batch_y(fs, gp, aux);
+__device__ __forceinline__ void d_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw) {
   const int count = min(*(const int *)gp, cap - 1);
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count; g += gridDim.x * blockDim.x) {
+  for (int g = (int)threadIdx.x + 1; g <= count; g += (int)blockDim.x) {
     const int sp = aux[g] - 1, ep = aux[cap + g];
     if (sp >= 0) { gp[g].x0 = (float)(sp % iw); gp[g].y0 = (float)(sp / iw); gp[g].level = 0; }
     if (ep >= 0 && ep != 0x7fffffff) { gp[g].x1 = (float)(ep % iw); gp[g].y1 = (float)(ep / iw); gp[g].polyid = g; }
@@ -377,16 +373,14 @@ __global__ void kp_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw, size_t
 }
 __global__ void kp_fill(int *out, int v, int n, size_t fs) {
   rd_batch_y(fs, out);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)threadIdx.x;
   if (i < n) out[i] = v;
 }
 
 // pass1 (oclpolyline.cl:509): distance of every labelled pixel to the chord of its segment, xor-ed with 13 bits of the
 // per-pixel hash (oclpolyline.cl:883, seed 0, evaluated in place instead of being read from a plane), kept per list
 // slot, and the per-segment maximum.
-__global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *dist, const int *labelin, const int *plist, const int *flags, int nIter, int iw, size_t fs) {
-  rd_batch_y(fs, gp, dist, labelin, plist, flags);
-  if (flags[nIter - 1] == 0) return;
+__device__ __forceinline__ void d_mkpl_pass1(LS_t *gp, int lsListSize, int *dist, const int *labelin, const int *plist, const int *flags, int nIter, int iw) {
   PLIST_LOOP {
     PLIST_XY;
     const int g = labelin[p0];
@@ -402,9 +396,7 @@ __global__ void kp_mkpl_pass1(LS_t *gp, int lsListSize, int *dist, const int *la
   }
 }
 // pass2a: winner[g] = smallest pixel index attaining maxDist
-__global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, const int *dist, const int *labelin, const int *plist, const int *flags, int nIter, int iw, size_t fs) {
-  rd_batch_y(fs, gp, winner, dist, labelin, plist, flags);
-  if (flags[nIter - 1] == 0) return;
+__device__ __forceinline__ void d_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, const int *dist, const int *labelin, const int *plist, const int *flags, int nIter, int iw) {
   PLIST_LOOP {
     PLIST_XY;
     const int g = labelin[p0];
@@ -417,9 +409,7 @@ __global__ void kp_mkpl_pass2a(const LS_t *gp, int lsListSize, int *winner, cons
 }
 // pass2b: single CTA; decides the splits of this iteration, numbers the new entries by a prefix sum over the
 // parent id and rewrites the list.  Also resets winner[] for the next iteration.
-__global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize, int *winner, const int *numberin, const int *flags, int nIter, float minerror, int iw, size_t fs) {
-  rd_batch_x(fs, gp, winner, numberin, flags);
-  if (flags[nIter - 1] == 0) return;
+__device__ __forceinline__ void d_mkpl_pass2b(LS_t *gp, int lsListSize, int *winner, const int *numberin, const int *flags, int nIter, float minerror, int iw) {
   __shared__ int wsum[32];
   __shared__ int carry, total;
   const int count = *(const int *)gp;
@@ -482,9 +472,7 @@ __global__ void __launch_bounds__(1024) kp_mkpl_pass2b(LS_t *gp, int lsListSize,
   }
   if (threadIdx.x == 0) *(int *)gp = carry;
 }
-__global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, const int *plist, int *flags, int nIter, int iw, size_t fs) {
-  rd_batch_y(fs, gp, numberin, labelinout, plist, flags);
-  if (flags[nIter - 1] == 0) return;
+__device__ __forceinline__ void d_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, const int *plist, int *flags, int nIter, int iw) {
   PLIST_LOOP {
     PLIST_XY;
     const int g = labelinout[p0];
@@ -495,10 +483,9 @@ __global__ void kp_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberi
 }
 
 // ---------------------------------------------------------------------------- refine (oclpolyline.cl:680-809)
-__global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls, size_t fs) {
-  rd_batch_y(fs, lsx, ls);
+__device__ __forceinline__ void d_refine_pass0(LSX_t *lsx, const LS_t *ls) {
   const int count_ = *(const int *)ls;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
+  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
   if (ls[g].polyid == 0) continue;
   LSX_t v;
   v.dirSEx = (short)(int)__fsub_rn(ls[g].x1, ls[g].x0);          // convert_short2: truncation (Q18)
@@ -511,8 +498,7 @@ __global__ void kp_refine_pass0(LSX_t *lsx, const LS_t *ls, size_t fs) {
   lsx[g] = v;
   }
 }
-__global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, const int *plist, int iw, size_t fs) {
-  rd_batch_y(fs, lsx, ls, lsIdIn, plist);
+__device__ __forceinline__ void d_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, const int *plist, int iw) {
   PLIST_LOOP {
     PLIST_XY;
     const int g = lsIdIn[p0];
@@ -530,10 +516,9 @@ __global__ void kp_refine_pass1(LSX_t *lsx, const LS_t *ls, const int *lsIdIn, c
     atomicAdd((ull *)&lsx[g].my1, (ull)__float2ll_rn(__fmul_rn((float)ax1, (float)ay)));
   }
 }
-__global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls, size_t fs) {
-  rd_batch_y(fs, lsx, ls);
+__device__ __forceinline__ void d_refine_pass2(const LSX_t *lsx, LS_t *ls) {
   const int count_ = *(const int *)ls;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
+  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
   if (ls[g].polyid == 0) continue;
   const float mx00 = (float)lsx[g].mx00, mx01 = (float)lsx[g].mx01, mx11 = (float)lsx[g].mx11, my0 = (float)lsx[g].my0, my1 = (float)lsx[g].my1;
   float rdet = __fsub_rn(__fmul_rn(mx00, mx11), __fmul_rn(mx01, mx01));
@@ -549,10 +534,9 @@ __global__ void kp_refine_pass2(const LSX_t *lsx, LS_t *ls, size_t fs) {
   }
 }
 // pass3a computes the vertex g shares with its right neighbour from the unmodified list; pass3b writes it to both
-__global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls, size_t fs) {
-  rd_batch_y(fs, vtx, ls);
+__device__ __forceinline__ void d_refine_pass3a(float2 *vtx, const LS_t *ls) {
   const int count_ = *(const int *)ls;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
+  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
   float2 r = make_float2(__int_as_float(0x7fc00000), 0.0f);     // NaN = nothing to write
   if (ls[g].polyid != 0 && ls[g].rightPtr != 0) {
     const int h = ls[g].rightPtr;
@@ -572,10 +556,9 @@ __global__ void kp_refine_pass3a(float2 *vtx, const LS_t *ls, size_t fs) {
   vtx[g] = r;
   }
 }
-__global__ void kp_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot, size_t fs) {
-  rd_batch_y(fs, vtx, ls, rightPtrSnapshot);
+__device__ __forceinline__ void d_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot) {
   const int count_ = *(const int *)ls;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x + 1; g <= count_; g += gridDim.x * blockDim.x) {
+  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
   (void)rightPtrSnapshot;
   const float2 r = vtx[g];
   if (r.x != r.x) {
@@ -586,6 +569,41 @@ __global__ void kp_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPt
   ls[g].x1 = r.x; ls[g].y1 = r.y;
   ls[h].x0 = r.x; ls[h].y0 = r.y;
   }
+}
+
+// mkpl (oclpolyline.c:186-216) + refine (oclpolyline.c:299-306) for one frame per CTA.
+__global__ void __launch_bounds__(1024) kp_polyline_list(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const int *table, int *flags, int *dist,
+                                                         const int *numberin, int *labelinout, const int *plist, LSX_t *lsx, float2 *vtx, float minerror, int iw, size_t fs) {
+  rd_batch_x(fs, gp, aux, winner, table, flags, dist, numberin, labelinout, plist, lsx, vtx);
+  const int N = 16;
+  d_mkpl_init(gp, lsListSize, aux, winner, cap, table, flags, N);
+  __syncthreads();
+  d_mkpl_pass0a(gp, lsListSize, aux, cap, numberin, labelinout, plist, iw);
+  __syncthreads();
+  d_mkpl_pass0b(gp, lsListSize, aux, cap, numberin, labelinout, plist, iw);
+  __syncthreads();
+  d_mkpl_pass0c(gp, aux, cap, iw);
+  __syncthreads();
+  for (int it = 1; it < N; it++) {
+    if (flags[it - 1] == 0) break;                 // nothing moved in the previous round: every later round is a no-op too
+    d_mkpl_pass1(gp, lsListSize, dist, labelinout, plist, flags, it, iw);
+    __syncthreads();
+    d_mkpl_pass2a(gp, lsListSize, winner, dist, labelinout, plist, flags, it, iw);
+    __syncthreads();
+    d_mkpl_pass2b(gp, lsListSize, winner, numberin, flags, it, minerror, iw);
+    __syncthreads();
+    d_mkpl_pass3(gp, lsListSize, numberin, labelinout, plist, flags, it, iw);
+    __syncthreads();
+  }
+  d_refine_pass0(lsx, gp);
+  __syncthreads();
+  d_refine_pass1(lsx, gp, labelinout, plist, iw);
+  __syncthreads();
+  d_refine_pass2(lsx, gp);
+  __syncthreads();
+  d_refine_pass3a(vtx, gp);
+  __syncthreads();
+  d_refine_pass3b(vtx, gp, (const int *)NULL);
 }
 
 // ---------------------------------------------------------------------------- the schedule (oclpolyline.c:218-309)
@@ -639,33 +657,15 @@ void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, 
     RD_LAUNCH(kp_relabel_rank, rd_gy(nblk, nb), RL_BLOCK, 0, s, table, blockCount, lsIdOut, iw, ih, fs);
     RD_LAUNCH(kp_relabel_pass1, rd_gz(G2, nb), PB, 0, s, lsIdOut, table, plist, iw, ih, fs);
   }
-  const int cap = lsListSize / (int)sizeof(LS_t);
-  const dim3 lg(LIST_BLOCKS, nb), sg(4, nb);
-  // step 11 : mkpl.  aux (start / end pixel per string) and winner (arg-max pixel per segment) sit behind the table
+  // steps 11-12 : mkpl and refine in ONE launch (kp_polyline_list: one CTA per frame walks the compact pixel list and
+  // the segment list; the 60-odd launches of the reference's split loop are __syncthreads here).
+  // aux (start / end pixel per string) and winner (arg-max pixel per segment) sit behind the table; the LSX mirror of
+  // the list is at the start of tmpBig (the table is dead by then), shared vertices in tmp3 (the distance slots are dead by then).
   {
+    const int cap = lsListSize / (int)sizeof(LS_t);
     int *aux = tmpBig + n + 8, *winner = aux + 2 * (size_t)cap;
-    int *flags = tmp4, *dist = tmp3;
-    const int N = 16;
-    RD_LAUNCH(kp_mkpl_init, rd_gy(8, nb), 256, 0, s, lsList, lsListSize, aux, winner, cap, table, flags, N, fs);
-    RD_LAUNCH(kp_mkpl_pass0a, lg, 256, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, plist, iw, fs);
-    RD_LAUNCH(kp_mkpl_pass0b, lg, 256, 0, s, lsList, lsListSize, aux, cap, tmp2, lsIdOut, plist, iw, fs);
-    RD_LAUNCH(kp_mkpl_pass0c, sg, 256, 0, s, lsList, aux, cap, iw, fs);
-    for (int i = 0; i < N - 1; i++) {
-      RD_LAUNCH(kp_mkpl_pass1, lg, 256, 0, s, lsList, lsListSize, dist, lsIdOut, plist, flags, i + 1, iw, fs);
-      RD_LAUNCH(kp_mkpl_pass2a, lg, 256, 0, s, lsList, lsListSize, winner, dist, lsIdOut, plist, flags, i + 1, iw, fs);
-      RD_LAUNCH(kp_mkpl_pass2b, dim3(nb), 1024, 0, s, lsList, lsListSize, winner, tmp2, flags, i + 1, minerror, iw, fs);
-      RD_LAUNCH(kp_mkpl_pass3, lg, 256, 0, s, lsList, lsListSize, tmp2, lsIdOut, plist, flags, i + 1, iw, fs);
-    }
-  }
-  // step 12 : sub-pixel refinement.  LSX mirror of the list in tmpBig, shared vertices in tmp3
-  {
-    LSX_t *lsx = (LSX_t *)tmpBig;
-    float2 *vtx = (float2 *)tmp3;                                 // the distance slots are dead after mkpl; 8 B x (count+1) <= P
-    RD_LAUNCH(kp_refine_pass0, sg, 256, 0, s, lsx, lsList, fs);
-    RD_LAUNCH(kp_refine_pass1, lg, 256, 0, s, lsx, lsList, lsIdOut, plist, iw, fs);
-    RD_LAUNCH(kp_refine_pass2, sg, 256, 0, s, lsx, lsList, fs);
-    RD_LAUNCH(kp_refine_pass3a, sg, 256, 0, s, vtx, lsList, fs);
-    RD_LAUNCH(kp_refine_pass3b, sg, 256, 0, s, vtx, lsList, (const int *)NULL, fs);
+    RD_LAUNCH(kp_polyline_list, dim3(nb), 1024, 0, s, lsList, lsListSize, aux, winner, cap, table, tmp4, tmp3, tmp2, lsIdOut, plist, (LSX_t *)tmpBig,
+              (float2 *)tmp3, minerror, iw, fs);
   }
   (void)tmp5;
 }
