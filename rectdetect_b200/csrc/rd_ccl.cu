@@ -225,6 +225,23 @@ __global__ void k_ccl_flatten(int *label, const uint8_t *links, int bgval, int n
 // The flatten above rewrites label[] while other threads still walk it; every intermediate value is an ancestor of
 // the pixel (parents only ever move towards the root), so concurrent walks stay correct.
 
+// flatten + compaction: foreground pixels are also appended to `list` (list[0] = count, entries from 1, any order)
+__global__ void k_ccl_flatten_list(int *label, const uint8_t *links, int *list, int bgval, int n, size_t fs) {
+  rd_batch_y(fs, label, links, list);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool fg = false;
+  if (p < n) {
+    if (links[p] & L_BG) label[p] = bgval;
+    else { label[p] = rd_uf_find(label, p); fg = true; }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, fg);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(list, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (fg) list[1 + base + __popc(m & ((1u << lane) - 1))] = p;
+}
 // labelMerge: interior pixels get the root, image-border pixels keep their labelxPreprocess value (oclrect.cl:289-298)
 __global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *pix, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, label, pix);
@@ -250,6 +267,12 @@ void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int 
   Link8x<int> f = {pix, bgc, iw, ih};
   ccl_core(label, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
   RD_LAUNCH(k_ccl_flatten, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, label, (const uint8_t *)scratch, -1, iw * ih, fs);
+}
+// byte plane in, labels out, and the foreground pixels gathered into `list` (list[0] must be zero on entry)
+void rd_label8x_u8_list(int *label, const uint8_t *pix, void *scratch, int *list, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  Link8x<uint8_t> f = {pix, bgc, iw, ih};
+  ccl_core(label, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  RD_LAUNCH(k_ccl_flatten_list, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, label, (const uint8_t *)scratch, list, -1, iw * ih, fs);
 }
 // same on a byte plane (the fused string clean-up kernels emit bytes)
 void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s) {

@@ -704,3 +704,284 @@ cl_event oclpolyline_execute(oclpolyline_t *thiz, cl_mem lsList, int lsListSize,
 }
 
 }  // extern "C"
+
+// =============================================================================================== the rect pipeline's polyline stage
+// rd_polyline_fast computes what rd_polyline_run computes (same lsIdOut map, same list) for the device schedule of
+// rd_rect.cu, where the stale frame simpleConnect leaves behind (oclpolyline.cl:91) is known to be non-zero:
+//   - the five string clean-up kernels of step 1 are one shared-memory kernel on byte tiles;
+//   - the foreground of the string labelling is gathered into a compact pixel list, and end finding, numbering, the
+//     loop breaker, size filter and relabelling only touch listed pixels (a few % of the frame) instead of sweeping planes;
+//   - ids are handed out in raster order of the root pixels by ranking the (few hundred) roots against each other.
+#define S2_T 32
+#define S2_A 6
+#define S2_W (S2_T + 2 * S2_A)
+__global__ void __launch_bounds__(256) kf_strings2(uint8_t *out, int *copyOut, int *list, const int *strong, int ring, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, copyOut, list, strong);
+  __shared__ uint8_t a[S2_W * S2_W], b[S2_W * S2_W];
+  const int bx = blockIdx.x * S2_T - S2_A, by = blockIdx.y * S2_T - S2_A;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) list[0] = 0;
+  for (int i = tid; i < S2_W * S2_W; i += 256) {
+    const int gx = bx + i % S2_W, gy = by + i / S2_W;
+    a[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih && strong[(size_t)gy * iw + gx] != 0) ? 1 : 0;
+  }
+  __syncthreads();
+  // simpleJunction (oclpolyline.cl:66)
+  for (int i = tid; i < S2_W * S2_W; i += 256) {
+    const int tx = i % S2_W, ty = i / S2_W;
+    const int gx = bx + tx, gy = by + ty;
+    uint8_t r = 0;
+    if (tx >= 1 && ty >= 1 && tx < S2_W - 1 && ty < S2_W - 1 && gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && a[i]) {
+      const int c = 1 + a[i - 1] + a[i + 1] + a[i - S2_W] + a[i + S2_W] + a[i - S2_W - 1] + a[i - S2_W + 1] + a[i + S2_W - 1] + a[i + S2_W + 1];
+      r = c == 1 ? 0 : c;
+    }
+    b[i] = r;
+  }
+  __syncthreads();
+  // simpleConnect (oclpolyline.cl:89): bridges one-pixel gaps between two end pixels; the 2-px frame keeps what was there (`ring`)
+  for (int i = tid; i < S2_W * S2_W; i += 256) {
+    const int tx = i % S2_W, ty = i / S2_W;
+    const int gx = bx + tx, gy = by + ty;
+    uint8_t r = 0;
+    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) {
+      if (gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2) r = (uint8_t)ring;
+      else if (tx >= 3 && ty >= 3 && tx < S2_W - 3 && ty < S2_W - 3) {
+        r = b[i] != 0;
+        if (!r) {
+          const int W1 = S2_W, W2 = 2 * S2_W;
+          r = (b[i - 2] != 0 && b[i - 1] == 2 && b[i + 1] == 2 && b[i + 2] != 0) ||
+              (b[i - W2] != 0 && b[i - W1] == 2 && b[i + W1] == 2 && b[i + W2] != 0) ||
+              (b[i - W2 - 2] != 0 && b[i - W1 - 1] == 2 && b[i + W1 + 1] == 2 && b[i + W2 + 2] != 0) ||
+              (b[i - W2 + 2] != 0 && b[i - W1 + 1] == 2 && b[i + W1 - 1] == 2 && b[i + W2 - 2] != 0) ||
+              (b[i + 2] != 0 && b[i + 1] == 2 && b[i + W1 - 1] == 2 && b[i + W1 - 2] != 0) ||
+              (b[i - 2] != 0 && b[i - 1] == 2 && b[i + W1 + 1] == 2 && b[i + W1 + 2] != 0) ||
+              (b[i - W2 + 1] != 0 && b[i - W1 + 1] == 2 && b[i + W1] == 2 && b[i + W2] != 0) ||
+              (b[i - W2 - 1] != 0 && b[i - W1 - 1] == 2 && b[i + W1] == 2 && b[i + W2] != 0);
+        }
+      }
+    }
+    a[i] = r;
+  }
+  __syncthreads();
+  // stringify 0, 1 (oclpolyline.cl:112)
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const uint8_t *src = pass == 0 ? a : b;
+    uint8_t *dst = pass == 0 ? b : a;
+    for (int i = tid; i < S2_W * S2_W; i += 256) {
+      const int tx = i % S2_W, ty = i / S2_W;
+      const int lo = 4 + pass, hi = S2_W - 4 - pass;
+      if (tx < lo || ty < lo || tx >= hi || ty >= hi) continue;
+      const int gx = bx + tx, gy = by + ty;
+      uint8_t r = src[i];
+      if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && ((gx + gy) & 1) == pass) {
+        const bool n = src[i - S2_W] != 0, s = src[i + S2_W] != 0, w = src[i - 1] != 0, e = src[i + 1] != 0;
+        if ((n || s) && (w || e)) r = 0;
+      }
+      dst[i] = r;
+    }
+    __syncthreads();
+  }
+  // removeBranch (oclpolyline.cl:126): only pixels with at most two neighbours stay
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int tx = S2_A + threadIdx.x, ty = S2_A + threadIdx.y + k * 8;
+    const int gx = bx + tx, gy = by + ty;
+    if (gx >= iw || gy >= ih) continue;
+    const int i = ty * S2_W + tx;
+    uint8_t r = 0;
+    if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && a[i]) {
+      const int c = (a[i - 1] != 0) + (a[i + 1] != 0) + (a[i - S2_W] != 0) + (a[i + S2_W] != 0) + (a[i - S2_W - 1] != 0) + (a[i - S2_W + 1] != 0) +
+                    (a[i + S2_W - 1] != 0) + (a[i + S2_W + 1] != 0);
+      r = c <= 2 ? 1 : 0;
+    }
+    const size_t p = (size_t)gy * iw + gx;
+    out[p] = r;
+    if (copyOut) copyOut[p] = strong[p];
+  }
+}
+
+// ---- list kernels: grid-stride over the compact list of string pixels (frame = blockIdx.y) ----
+#define SL_LOOP const int scount_ = list[0]; for (int k_ = blockIdx.x * blockDim.x + threadIdx.x; k_ < scount_; k_ += gridDim.x * blockDim.x)
+#define SL_P const int p0 = list[k_ + 1]; const int x = p0 % iw, y = p0 / iw; (void)x; (void)y
+
+// loop breaker, part 1 of 3 (oclpolyline.cl:149-167): roots start out with "no end seen"
+__global__ void kl_ends_reset(int *nEnds, const int *label, const int *list, int iw, size_t fs) {
+  rd_batch_y(fs, nEnds, label, list);
+  SL_LOOP { SL_P; if (label[p0] == p0) nEnds[p0] = 0; }
+}
+// part 2: a string pixel with exactly one neighbour (simpleJunction value 2) marks its string as open
+__global__ void kl_ends_mark(int *nEnds, const uint8_t *str, const int *label, const int *list, int iw, size_t fs) {
+  rd_batch_y(fs, nEnds, str, label, list);
+  SL_LOOP {
+    SL_P;
+    int c = 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c += str[p0 + RD_RX[i] + RD_RY[i] * iw] != 0;
+    if (c == 2) nEnds[label[p0]] = 1;
+  }
+}
+// part 3: closed loops lose their root pixel
+__global__ void kl_break_loops(uint8_t *str, int *label, const int *nEnds, const int *list, int iw, size_t fs) {
+  rd_batch_y(fs, str, label, nEnds, list);
+  SL_LOOP { SL_P; if (label[p0] == p0 && nEnds[p0] == 0) { str[p0] = 0; label[p0] = -1; } }
+}
+__global__ void kl_findEnds0(int *nextout, int *prevout, int *flagout, const int *labelin, const int *list, int iw, size_t fs) {
+  rd_batch_y(fs, nextout, prevout, flagout, labelin, list);
+  SL_LOOP {
+    SL_P;
+    if (labelin[p0] == -1) continue;
+    int npx, npy, a, b, flag = 0;
+    getnp(labelin, p0, iw, npx, npy);
+    if (npx != p0) { getnp(labelin, npx, iw, a, b); if (a == p0) flag |= 1; }
+    if (npy != p0) { getnp(labelin, npy, iw, a, b); if (b == p0) flag |= 2; }
+    nextout[p0] = npx; prevout[p0] = npy; flagout[p0] = flag;
+  }
+}
+__global__ void kl_findEnds1(int *nextout, int *prevout, int *flaginout, const int *nextin, const int *previn, const int *labelin, const int *list, int page, int iw, size_t fs) {
+  rd_batch_y(fs, nextout, prevout, flaginout, nextin, previn, labelin, list);
+  SL_LOOP {
+    SL_P;
+    if (labelin[p0] == -1) continue;
+    const volatile int *fl = flaginout;
+    const int f0 = fl[p0];
+    bool revn = page == 0 ? ((f0 & 1) != 0) : ((f0 & 4) != 0);
+    bool revp = page == 0 ? ((f0 & 2) != 0) : ((f0 & 8) != 0);
+    int nn = nextin[p0], pp = previn[p0];
+    for (int i = 0; i < 8; i++) {
+      const int nn2 = revn ? previn[nn] : nextin[nn];
+      const int pp2 = revp ? nextin[pp] : previn[pp];
+      int nflag = fl[nn], pflag = fl[pp];
+      if (page != 0) { nflag >>= 2; pflag >>= 2; }
+      revn = revn ? ((nflag & 2) == 0) : ((nflag & 1) != 0);
+      revp = revp ? ((pflag & 1) == 0) : ((pflag & 2) != 0);
+      nn = nn2; pp = pp2;
+    }
+    int f = f0;
+    if (page == 0) { f &= 3; f |= revn ? 4 : 0; f |= revp ? 8 : 0; }
+    else { f &= (3 << 2); f |= revn ? 1 : 0; f |= revp ? 2 : 0; }
+    flaginout[p0] = f;
+    nextout[p0] = nn; prevout[p0] = pp;
+  }
+}
+__global__ void kl_findEnds2(int *numout, int *linkout, const int *nextin, const int *previn, const int *labelin, const int *list, int iw, size_t fs) {
+  rd_batch_y(fs, numout, linkout, nextin, previn, labelin, list);
+  SL_LOOP {
+    SL_P;
+    int num = 0, link = -1;
+    if (labelin[p0] != -1) {
+      int npx, npy;
+      getnp(labelin, p0, iw, npx, npy);
+      link = nextin[p0] < previn[p0] ? npx : npy;
+      num = link == p0 ? 0 : 1;
+    }
+    numout[p0] = num; linkout[p0] = link;
+  }
+}
+// pl1 (optional): number + 1 where the number is non-zero, for the labelpl step (plane cleared by the caller)
+__global__ void kl_number(int *numout, int *linkout, int *pl1, const int *numin, const int *linkin, const int *list, int iw, int npix, size_t fs) {
+  rd_batch_y(fs, numout, linkout, pl1, numin, linkin, list);
+  SL_LOOP {
+    SL_P;
+    int no = 0, lo = -1;
+    const int l0 = linkin[p0];
+    if (l0 == -1) { no = numin[p0]; lo = -1; }
+    else {
+      int n = numin[p0], l = l0;
+      bool bail = false;
+      for (int i = 0; i < 32; i++) {
+        if (!(0 < l && l < npix)) { bail = true; break; }
+        n += numin[l];
+        l = linkin[l];
+      }
+      if (!bail) { no = n; lo = l; }
+    }
+    numout[p0] = no; linkout[p0] = lo;
+    if (pl1 && no != 0) pl1[p0] = no + 1;
+  }
+}
+// calcSize / filterSize (oclpolyline.cl:357-378) on the list; roots are also gathered (roots[0] = count) for the ranking
+__global__ void kl_size_reset(int *size, int *roots, const int *lab, const int *list, int iw, size_t fs) {
+  rd_batch_y(fs, size, roots, lab, list);
+  if (blockIdx.x == 0 && threadIdx.x == 0) roots[0] = 0;
+  SL_LOOP { SL_P; if (lab[p0] == p0) size[p0] = 0; }
+}
+__global__ void kl_size_count(int *size, const int *lab, const int *list, int iw, size_t fs) {
+  rd_batch_y(fs, size, lab, list);
+  SL_LOOP { SL_P; const int b = lab[p0]; if (b != 0) atomicAdd(size + b, 1); }
+}
+__global__ void kl_roots(int *roots, const int *size, const int *lab, const int *list, int sizeThre, int iw, size_t fs) {
+  rd_batch_y(fs, roots, size, lab, list);
+  SL_LOOP { SL_P; if (lab[p0] == p0 && size[p0] > sizeThre) roots[1 + atomicAdd(roots, 1)] = p0; }
+}
+// ids 1..K in raster order of the surviving roots (relabel_pass0, oclpolyline.cl:380, canonical order Q4); table[0] = K
+__global__ void kl_rank(int *table, const int *roots, size_t fs) {
+  rd_batch_y(fs, table, roots);
+  const int K = roots[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) table[0] = K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+    const int r = roots[1 + i];
+    int rank = 1;
+    for (int j = 0; j < K; j++) rank += roots[1 + j] < r;
+    table[r + 1] = rank;
+  }
+}
+// filterSize + relabel_pass1 (oclpolyline.cl:367, 400): lsIdOut was cleared by the caller
+__global__ void kl_relabel(int *lsIdOut, const int *table, const int *size, const int *lab, const int *list, int sizeThre, int iw, size_t fs) {
+  rd_batch_y(fs, lsIdOut, table, size, lab, list);
+  SL_LOOP { SL_P; const int b = lab[p0]; if (b != 0 && size[b] > sizeThre) lsIdOut[p0] = table[b + 1]; }
+}
+
+void rd_label8x_u8_list(int *label, const uint8_t *pix, void *scratch, int *list, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+
+// in: strong-edge bitmap; copyOut (optional): receives a copy of `in`; t0..t5: scratch planes; tmpBig: 4 planes
+void rd_polyline_fast(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *copyOut, int *tmpBig, int *t0, int *t1, int *t2, int *t3, int *t4, int *t5,
+                      float minerror, int sizeThre, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  const int n = iw * ih;
+  uint8_t *str = (uint8_t *)t0;
+  int *roots = t0 + (n + 3) / 4 + 4;                       // behind the string bytes
+  int *list = t2;
+  int *nextA = t3, *prevA = t4, *nextB = tmpBig, *prevB = tmpBig + n, *flags1 = tmpBig + 2 * (size_t)n;
+  const dim3 lg(LIST_BLOCKS, nb);
+  // step 1 : string clean-up, one kernel (also zeroes the list counter and copies the bitmap for the next frame)
+  RD_LAUNCH(kf_strings2, dim3(rd_cdiv(iw, S2_T), rd_cdiv(ih, S2_T), nb), dim3(32, 8), 0, s, str, copyOut, list, in, 1, iw, ih, fs);
+  // step 2 : string id = smallest pixel index; foreground gathered into `list`
+  rd_label8x_u8_list(lsIdOut, str, t1, list, 0, iw, ih, nb, fs, s);
+  // step 3 : closed loops lose their root pixel
+  RD_LAUNCH(kl_ends_reset, lg, 256, 0, s, t5, lsIdOut, list, iw, fs);
+  RD_LAUNCH(kl_ends_mark, lg, 256, 0, s, t5, str, lsIdOut, list, iw, fs);
+  RD_LAUNCH(kl_break_loops, lg, 256, 0, s, str, lsIdOut, t5, list, iw, fs);
+  // steps 4-6 : string ends
+  RD_LAUNCH(kl_findEnds0, lg, 256, 0, s, nextA, prevA, flags1, lsIdOut, list, iw, fs);
+  RD_LAUNCH(kl_findEnds1, lg, 256, 0, s, nextB, prevB, flags1, nextA, prevA, lsIdOut, list, 0, iw, fs);
+  RD_LAUNCH(kl_findEnds1, lg, 256, 0, s, nextA, prevA, flags1, nextB, prevB, lsIdOut, list, 1, iw, fs);
+  RD_LAUNCH(kl_findEnds1, lg, 256, 0, s, nextB, prevB, flags1, nextA, prevA, lsIdOut, list, 0, iw, fs);
+  RD_LAUNCH(kl_findEnds1, lg, 256, 0, s, nextA, prevA, flags1, nextB, prevB, lsIdOut, list, 1, iw, fs);
+  int *numA = tmpBig, *linkA = tmpBig + n;                 // (nextB / prevB are dead)
+  RD_LAUNCH(kl_findEnds2, lg, 256, 0, s, numA, linkA, nextA, prevA, lsIdOut, list, iw, fs);
+  // step 7 : distance from the start; the last round also writes number + 1 into the cleared plane the next labelling reads
+  int *numB = t3, *linkB = t4, *pl1 = t5;
+  RD_LAUNCH(kl_number, lg, 256, 0, s, numB, linkB, (int *)NULL, numA, linkA, list, iw, n, fs);
+  RD_LAUNCH(kl_number, lg, 256, 0, s, numA, linkA, (int *)NULL, numB, linkB, list, iw, n, fs);
+  rd_k_clear(pl1, n, nb, fs, s);
+  RD_LAUNCH(kl_number, lg, 256, 0, s, numB, linkB, pl1, numA, linkA, list, iw, n, fs);
+  int *number = numB;                                      // t3, survives to the end
+  // step 8 : split touching strings
+  int *lab3 = tmpBig + 3 * (size_t)n;
+  rd_labelpl(lab3, pl1, t1, iw, ih, nb, fs, s);
+  // steps 9-10 : drop short strings, ids 1..K in raster order of the roots
+  int *size = t4, *table = tmpBig;
+  RD_LAUNCH(kl_size_reset, lg, 256, 0, s, size, roots, lab3, list, iw, fs);
+  RD_LAUNCH(kl_size_count, lg, 256, 0, s, size, lab3, list, iw, fs);
+  RD_LAUNCH(kl_roots, lg, 256, 0, s, roots, size, lab3, list, sizeThre, iw, fs);
+  RD_LAUNCH(kl_rank, dim3(4, nb), 256, 0, s, table, roots, fs);
+  rd_k_clear(lsIdOut, n, nb, fs, s);
+  RD_LAUNCH(kl_relabel, lg, 256, 0, s, lsIdOut, table, size, lab3, list, sizeThre, iw, fs);
+  // steps 11-12 : mkpl + refine on the same list (pixels without an id are skipped there)
+  {
+    const int cap = lsListSize / (int)sizeof(LS_t);
+    int *aux = tmpBig + n + 8, *winner = aux + 2 * (size_t)cap;
+    RD_LAUNCH(kp_polyline_list, dim3(nb), 1024, 0, s, lsList, lsListSize, aux, winner, cap, table, t5, t4, number, lsIdOut, list, (LSX_t *)tmpBig, (float2 *)t4,
+              minerror, iw, fs);
+  }
+}

@@ -37,6 +37,8 @@ void rd_junction_mask_run(uint8_t *mask, int *junc, const int *strong, int iw, i
 void rd_despeckle2_boundary_run(int *out, const int *label, const int *size, int thre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_polyline_fast(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *copyOut, int *tmpBig, int *t0, int *t1, int *t2, int *t3, int *t4, int *t5,
+                      float minerror, int sizeThre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_tail_gather_host(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, rd_tail_sample *out);
 
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
@@ -487,10 +489,9 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   rd_calcSize_run(PI(tmp[0]), PI(buf[4]), iw, ih, nb, fs, s);
   rd_despeckle2_boundary_run(PI(tmp[1]), PI(buf[4]), PI(tmp[0]), 16, iw, ih, nb, fs, s);
   rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[4]->dptr, -1, iw, ih, nb, fs, s);
-  rd_k_copy(PI(buf[3]), PI(tmp[5]), n, nb, fs, s);                 // the bitmap the next frame's strengths accumulate on
-  // Stage C (oclrect.c:361); tmp2 still holds the flat colours, i.e. the non-zero frame simpleConnect leaves behind
-  rd_polyline_run((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(tmp[5]), PI(ioBig[1]), PI(tmp[0]), PI(tmp[1]), PI(tmp[2]), PI(tmp[3]), PI(tmp[4]),
-                  PI(buf[5]), 4.0f, 20, iw, ih, nb, fs, s);
+  // Stage C (oclrect.c:361).  The clean-up kernel also copies the bitmap into buf3, where the next frame's strengths accumulate.
+  rd_polyline_fast((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(tmp[5]), PI(buf[3]), PI(ioBig[1]), PI(tmp[0]), PI(tmp[1]), PI(tmp[2]), PI(tmp[3]), PI(tmp[4]),
+                   PI(buf[5]), 4.0f, 20, iw, ih, nb, fs, s);
   // Stage D (oclrect.c:365-367) and the compact read-back record
   const int nentry = n * 4 / 5;
   rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
