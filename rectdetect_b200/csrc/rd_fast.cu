@@ -362,17 +362,34 @@ __global__ void __launch_bounds__(192) kf_iir_h3(float *f0, float *f1, float *f2
     default: iir_h_chain<2, 1>(b2 + ro, row, c, warm, iw); break;
   }
 }
-// pass1 (oclimgutil.cl:580) for the three channels: h = bwd + fwd - in*coef0, in place of the forward planes
+// pass1 (oclimgutil.cl:580) for the three channels: h = bwd + fwd - in*coef0, in place of the forward planes; 4 pixels per thread
+__device__ __forceinline__ float iir_comb(float b, float f, float in, float c0) { return __fsub_rn(__fadd_rn(b, f), __fmul_rn(in, c0)); }
 __global__ void kf_iir_mid3(float *f0, float *f1, float *f2, const float *b0, const float *b1, const float *b2, const uint32_t *plab, int r, int n, size_t fs) {
   rd_batch_y(fs, f0, f1, f2, b0, b1, b2, plab);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const float c0 = RD_IIRCOEF[r][0];
-  float l, a, b;
-  rd_unpacklab(plab[i], l, a, b);
-  f0[i] = __fsub_rn(__fadd_rn(b0[i], f0[i]), __fmul_rn(l, c0));
-  f1[i] = __fsub_rn(__fadd_rn(b1[i], f1[i]), __fmul_rn(a, c0));
-  f2[i] = __fsub_rn(__fadd_rn(b2[i], f2[i]), __fmul_rn(b, c0));
+  if (i + 3 < n) {
+    const uint4 p = *(const uint4 *)(plab + i);
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+    float4 F0 = *(float4 *)(f0 + i), F1 = *(float4 *)(f1 + i), F2 = *(float4 *)(f2 + i);
+    const float4 B0 = *(const float4 *)(b0 + i), B1 = *(const float4 *)(b1 + i), B2 = *(const float4 *)(b2 + i);
+    float *pf0 = (float *)&F0, *pf1 = (float *)&F1, *pf2 = (float *)&F2;
+    const float *pb0 = (const float *)&B0, *pb1 = (const float *)&B1, *pb2 = (const float *)&B2;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float l, a, b;
+      rd_unpacklab(pw[k], l, a, b);
+      pf0[k] = iir_comb(pb0[k], pf0[k], l, c0); pf1[k] = iir_comb(pb1[k], pf1[k], a, c0); pf2[k] = iir_comb(pb2[k], pf2[k], b, c0);
+    }
+    *(float4 *)(f0 + i) = F0; *(float4 *)(f1 + i) = F1; *(float4 *)(f2 + i) = F2;
+  } else {
+    for (int k = i; k < n; k++) {
+      float l, a, b;
+      rd_unpacklab(plab[k], l, a, b);
+      f0[k] = iir_comb(b0[k], f0[k], l, c0); f1[k] = iir_comb(b1[k], f1[k], a, c0); f2[k] = iir_comb(b2[k], f2[k], b, c0);
+    }
+  }
 }
 // Vertical: one thread per (column, channel, direction), coalesced across the warp; the rows of the next eight steps are
 // loaded while the current eight are computed.
@@ -414,18 +431,36 @@ __global__ void __launch_bounds__(128) kf_iir_v3(float *vf0, float *vf1, float *
     o[(size_t)(y0 + k * sgn) * iw] = st.step1(v, c);
   }
 }
-// pass3 (oclimgutil.cl:629) for the three channels + pack_plab (oclimgutil.cl:325): blurred L plane and blurred packed Lab
+// pass3 (oclimgutil.cl:629) for the three channels + pack_plab (oclimgutil.cl:325): blurred L plane and blurred packed Lab;
+// outL / outA / outB alias h0 / h1 / h2 (each thread reads its own four elements before writing them)
 __global__ void kf_iir_fin3(float *outL, float *outA, float *outB, uint32_t *outPlab, const float *vf0, const float *vf1, const float *vf2, const float *vb0,
-                            const float *vb1, const float *vb2, const float *h0, const float *h1, const float *h2, int r, int n, size_t fs) {
-  rd_batch_y(fs, outL, outA, outB, outPlab, vf0, vf1, vf2, vb0, vb1, vb2, h0, h1, h2);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                            const float *vb1, const float *vb2, int r, int n, size_t fs) {
+  rd_batch_y(fs, outL, outA, outB, outPlab, vf0, vf1, vf2, vb0, vb1, vb2);
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const float c0 = RD_IIRCOEF[r][0];
-  const float l = __fsub_rn(__fadd_rn(vb0[i], vf0[i]), __fmul_rn(h0[i], c0));
-  const float a = __fsub_rn(__fadd_rn(vb1[i], vf1[i]), __fmul_rn(h1[i], c0));
-  const float b = __fsub_rn(__fadd_rn(vb2[i], vf2[i]), __fmul_rn(h2[i], c0));
-  outL[i] = l; outA[i] = a; outB[i] = b;
-  outPlab[i] = rd_packlab(l, a, b);
+  if (i + 3 < n) {
+    float4 H0 = *(float4 *)(outL + i), H1 = *(float4 *)(outA + i), H2 = *(float4 *)(outB + i);
+    const float4 F0 = *(const float4 *)(vf0 + i), F1 = *(const float4 *)(vf1 + i), F2 = *(const float4 *)(vf2 + i);
+    const float4 B0 = *(const float4 *)(vb0 + i), B1 = *(const float4 *)(vb1 + i), B2 = *(const float4 *)(vb2 + i);
+    float *h0 = (float *)&H0, *h1 = (float *)&H1, *h2 = (float *)&H2;
+    const float *pf0 = (const float *)&F0, *pf1 = (const float *)&F1, *pf2 = (const float *)&F2, *pb0 = (const float *)&B0, *pb1 = (const float *)&B1, *pb2 = (const float *)&B2;
+    uint4 P;
+    uint32_t *pp = (uint32_t *)&P;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      h0[k] = iir_comb(pb0[k], pf0[k], h0[k], c0); h1[k] = iir_comb(pb1[k], pf1[k], h1[k], c0); h2[k] = iir_comb(pb2[k], pf2[k], h2[k], c0);
+      pp[k] = rd_packlab(h0[k], h1[k], h2[k]);
+    }
+    *(float4 *)(outL + i) = H0; *(float4 *)(outA + i) = H1; *(float4 *)(outB + i) = H2;
+    *(uint4 *)(outPlab + i) = P;
+  } else {
+    for (int k = i; k < n; k++) {
+      const float l = iir_comb(vb0[k], vf0[k], outL[k], c0), a = iir_comb(vb1[k], vf1[k], outA[k], c0), b = iir_comb(vb2[k], vf2[k], outB[k], c0);
+      outL[k] = l; outA[k] = a; outB[k] = b;
+      outPlab[k] = rd_packlab(l, a, b);
+    }
+  }
 }
 
 // =============================================================================================== BGR8 -> packed Lab
@@ -466,9 +501,9 @@ void rd_iirblur3_run(float *outL, float *outA, float *outB, uint32_t *outPlab, c
                      int nb, size_t fs, cudaStream_t s) {
   const int n = iw * ih;
   RD_LAUNCH(kf_iir_h3, dim3(rd_cdiv(ih, 32), nb), 192, 0, s, outL, outA, outB, sb, sb + pp, sb + 2 * pp, plab, r, iw, ih, fs);
-  RD_LAUNCH(kf_iir_mid3, dim3(rd_cdiv(n, 256), nb), 256, 0, s, outL, outA, outB, sb, sb + pp, sb + 2 * pp, plab, r, n, fs);
+  RD_LAUNCH(kf_iir_mid3, dim3(rd_cdiv(rd_cdiv(n, 4), 256), nb), 256, 0, s, outL, outA, outB, sb, sb + pp, sb + 2 * pp, plab, r, n, fs);
   RD_LAUNCH(kf_iir_v3, dim3(rd_cdiv(iw, 128), 6, nb), 128, 0, s, sf, sf + pp, sf + 2 * pp, sb, sb + pp, sb + 2 * pp, outL, outA, outB, r, iw, ih, fs);
-  RD_LAUNCH(kf_iir_fin3, dim3(rd_cdiv(n, 256), nb), 256, 0, s, outL, outA, outB, outPlab, sf, sf + pp, sf + 2 * pp, sb, sb + pp, sb + 2 * pp, outL, outA, outB, r, n, fs);
+  RD_LAUNCH(kf_iir_fin3, dim3(rd_cdiv(rd_cdiv(n, 4), 256), nb), 256, 0, s, outL, outA, outB, outPlab, sf, sf + pp, sf + 2 * pp, sb, sb + pp, sb + 2 * pp, r, n, fs);
 }
 
 // =============================================================================================== Stage A, second half
@@ -692,6 +727,7 @@ __global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const u
     uint32_t r = q[i];
     if (e[i] == 1) {
       float dist = 1e+10f, l0, a0, b0;
+      double bestsq = 1e+300;
       rd_unpacklab(r, l0, a0, b0);
 #pragma unroll
       for (int yy = -1; yy <= 1; yy++)
@@ -702,8 +738,13 @@ __global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const u
           float l1, a1, b1;
           const uint32_t v = q[j];
           rd_unpacklab(v, l1, a1, b1);
-          const float d = rd_distance3(__fsub_rn(l1, l0), __fsub_rn(a1, a0), __fsub_rn(b1, b0));
-          if (d < dist) { r = v; dist = d; }
+          // distance() = (float)sqrt(exact double sum) (canonical form).  The rounded root is monotone in the sum,
+          // so a sum that is not smaller than the best one so far cannot give a smaller distance: skip its square root.
+          const double dl = (double)__fsub_rn(l1, l0), da = (double)__fsub_rn(a1, a0), db = (double)__fsub_rn(b1, b0);
+          const double sq = __dadd_rn(__dadd_rn(__dmul_rn(dl, dl), __dmul_rn(da, da)), __dmul_rn(db, db));
+          if (!(sq < bestsq)) continue;
+          const float d = (float)__dsqrt_rn(sq);
+          if (d < dist) { r = v; dist = d; bestsq = sq; }
         }
     }
     out[(size_t)gy * iw + gx] = r;

@@ -308,6 +308,46 @@ __global__ void kr_reduceLS(int *out, const int *boundaryin, const int *lsidin, 
   }
 }
 
+// The same two phases over the compact list of string pixels the polyline stage leaves behind (list[0] = count): only
+// pixels that carry a segment id vote, and they are a few percent of the frame.
+template <int PHASE>
+__global__ void kr_reduceLS_list(int *out, const int *boundaryin, const int *lsidin, const int *list, int iw, int ih, int nentry, size_t fs) {
+  rd_batch_y(fs, out, boundaryin, lsidin, list);
+  const int count = list[0];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const int p0 = list[k + 1], x = p0 % iw, y = p0 / iw;
+    if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) continue;
+    const int lsid = lsidin[p0];
+    if (lsid <= 0) continue;
+    int lastbid = 0;
+    for (int yy = -3; yy <= 3; yy++) {
+      if (y + yy < 0 || ih <= y + yy) continue;
+      for (int xx = -3; xx <= 3; xx++) {
+        if (x + xx < 0 || iw <= x + xx) continue;
+        const int bid = boundaryin[(y + yy) * iw + x + xx];
+        if (bid <= 0 || bid == lastbid) continue;
+        lastbid = bid;
+        const int hash = (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry);
+        int *e = out + (size_t)hash * 5;
+        if (PHASE == 0) {
+          int cur = *(volatile int *)e;
+          while (cur == 0 || lsid < cur) {
+            const int prev = atomicCAS(e, cur, lsid);
+            if (prev == cur) break;
+            cur = prev;
+          }
+        } else {
+          if (e[0] != lsid) continue;
+          atomicMax(e + 1, iw - x);
+          atomicMax(e + 2, x);
+          atomicMax(e + 3, ih - y);
+          atomicMax(e + 4, y);
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- read-back record for the host tail
 // Blob layout: [0] int n, [1] int n_gathered, ... 64-byte header; LS_t[n_g+1] at byte 64; rd_tail_sample[(n_g+1)*15] behind it
 // (8-byte aligned).  n_g = min(n, maxLS).  Double arithmetic exactly as oclrect.c:1069-1084 (no FMA, IEEE sqrt/div).
@@ -495,8 +535,8 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   // Stage D (oclrect.c:365-367) and the compact read-back record
   const int nentry = n * 4 / 5;
   rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
-  RD_LAUNCH(kr_reduceLS<0>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
-  RD_LAUNCH(kr_reduceLS<1>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS_list<0>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);   // tmp2: the polyline stage's pixel list
+  RD_LAUNCH(kr_reduceLS_list<1>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
   RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
 }
 
