@@ -34,17 +34,11 @@ TAN_AOV = math.tan(math.radians(36.0))
 # algorithmic (compulsory) bytes per pixel of each kernel: planes it must read + planes it must write, 4 B each unless
 # noted (DESIGN.md "Kernels").  Used for roofline.achieved of whichever kernel dominates the step.
 KERNEL_BYTES_PER_PX = {
-    "k_bgr2plab_unpack": 3 + 16, "k_iir_h": 12, "k_iir_v": 12, "k_iir_pass1": 16, "k_iir_pass3": 16, "k_pack_plab_r": 16,
-    "k_edgevec_r": 12, "k_edge_plab_r": 8, "k_thinthres_r": 16, "kr_threshold_cast": 12, "kr_simpleJunction": 8,
-    "kr_simpleConnect": 8, "kr_stringify": 8, "k_ccl_tile<LinkFn>": 9, "k_ccl_seams": 1, "k_ccl_flatten": 9,
-    "k_ccl_flatten_merge": 12, "kr_calcStrength": 8, "kr_filterStrength": 8, "kr_threshold_cast_c": 9, "kr_blblur<0>": 9,
-    "kr_blblur<1>": 9, "kr_quantize": 8, "kr_despeckle": 12, "kr_threshold_i_i": 8, "k_clear": 4, "k_copy": 8,
-    "kr_mkMergeMask0": 4, "kr_mkMergeMask1": 4, "kr_calcSize": 4, "kr_despeckle2": 8, "kr_markBoundary": 8,
-    "kp_simpleJunction": 8, "kp_simpleConnect": 8, "kp_stringify": 8, "kp_removeBranch": 8, "kp_countEnds": 8, "kp_breakLoops": 4,
-    "kp_findEnds0": 16, "kp_findEnds1": 24, "kp_findEnds2": 20, "kp_number": 16, "kp_plus1": 8, "kp_calcSize": 4,
-    "kp_filterSize": 12, "kp_relabel_count": 4, "kp_relabel_rank": 4, "kp_relabel_pass1": 8, "kp_mkpl_pass0a": 8,
-    "kp_mkpl_pass0b": 8, "kp_mkpl_pass1": 12, "kp_mkpl_pass2a": 8, "kp_mkpl_pass3": 8, "kp_refine_pass1": 4, "k_rand": 4,
-    "kr_reduceLS<0>": 8, "kr_reduceLS<1>": 8,
+    # production schedule
+    "kf_bgr2plab4": 7, "kf_bgr2plab1": 7, "kf_iir_h3": 28, "kf_iir_mid3": 40, "kf_iir_v3": 36, "kf_iir_fin3": 52, "kf_edge_thin": 12,
+    "kf_strings1": 5, "k_ccl_tile<LinkFn>": 9, "k_ccl_seams": 1, "k_ccl_flatten": 9, "k_ccl_flatten_list": 9, "k_ccl_flatten_merge": 12,
+    "kr_calcStrength": 8, "kf_filter_masks": 9, "kf_blb_extents": 3, "kf_blb_stream": 10, "kf_quant_despeckle": 12, "kf_junction_mask": 9,
+    "kf_calcSize": 4, "kf_despeckle2_boundary": 8, "kf_strings2": 9, "k_clear4": 4, "k_clear": 4, "k_copy4": 8,
 }
 
 
@@ -149,8 +143,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--w", type=int, default=1280)
     ap.add_argument("--h", type=int, default=720)
-    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--nctx", type=int, default=4, help="pipeline objects (streams) per GPU")
+    ap.add_argument("--frames", type=int, default=192, help="frames per GPU per step")
+    ap.add_argument("--nctx", type=int, default=6, help="pipeline objects (streams) per GPU")
     ap.add_argument("--fpl", type=int, default=8, help="frames per kernel launch")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample")
