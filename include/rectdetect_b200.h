@@ -184,7 +184,8 @@ void rd_rect_reduceLS(cl_mem out, cl_mem boundary, cl_mem lsid, int iw, int ih, 
 /* L3 introspection: device buffers of an oclrect_t by the reference's names ("buf0".."buf5", "tmp0".."tmp5",
  * "iobuf0", "iobuf1", "ioBig0", "ioBig1"; oclrect.c:51-53), and the host tail on caller-provided arrays. */
 cl_mem rd_oclrect_buffer(struct oclrect_t *thiz, const char *name);
-/* run genGPUTask's device schedule only (no read-back, no host tail); stop_step as in SURVEY.md 10.1, 0 = all */
+/* run genGPUTask's device schedule only (no read-back, no host tail); stop_step > 0: the operator-level replay stopped at
+ * that step of SURVEY.md 10.1; 0: the production schedule; < 0: the production schedule stopped after stage -stop_step */
 void   rd_oclrect_run_device(struct oclrect_t *thiz, const uint8_t *imgData, int ws, int stop_step);
 /* executeCPUTask (oclrect.c:1049) on host arrays: ls = list incl. header, segid = plane, votes = int[nentry][5] */
 rect_t *rd_rect_tail(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, double tanAOV);

@@ -193,23 +193,259 @@ __global__ void __launch_bounds__(SB_WARPS * 32) kf_blb_stream(uint32_t *out, co
   }
 }
 
+// ---- walk extents, bit-parallel ------------------------------------------------------------------------------------
+// The stop rules of blb_extent() only combine the edge bit of a position with those of the previous / next position of
+// the walk and of the perpendicular neighbour, so they can be evaluated for 32 positions at once on bit rows:
+//   stopBack(q) = E(q) & ~E(q-1)  |  hasSide & ~E(q) & E(q-1) & Side(q)        (never at q == 0; q < 0 always stops)
+//   stopFwd(q)  = ~E(q) & E(q+1)  |  oe & ~E(q)                                 (q beyond the last position always stops)
+// and an extent is the number of clear bits in front of the first stop (at most 5).  One warp streams down a strip
+// of 32 columns: the rows arrive as ballot words (x walk), every lane keeps the history of its own column and of the
+// column to its right in two registers (y walk: row y - b is bit b).
+#define EXS_WARPS 8
+__device__ __forceinline__ unsigned exs_stop_back(unsigned e, unsigned eprev, unsigned side) { return (e & ~eprev) | (~e & eprev & side); }
+__global__ void __launch_bounds__(EXS_WARPS * 32) kf_blb_extents_s(uint8_t *extH, uint8_t *extV, const int8_t *edge, int iw, int ih, int nb, int strips, int chunks,
+                                                                   int ch, size_t fs) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * EXS_WARPS + (threadIdx.x >> 5);
+  if (wid >= strips * chunks * nb) return;
+  const int sx = wid % strips, cy = (wid / strips) % chunks, z = wid / (strips * chunks);
+  rd_batch_off((size_t)z * fs, extH, extV, edge);
+  const int x0 = sx * 32, x = x0 + lane;
+  const int y0 = cy * ch, y1 = min(y0 + ch, ih);
+  const int first = max(y0 - 5, 0);
+  const bool okl = x - 32 >= 0, okc = x < iw, okr = x + 32 < iw;
+  // positions of the x walk that do not exist: left of column 0 (all of the left word when x0 == 0), right of column iw - 1
+  const unsigned negL = x0 == 0 ? 0xffffffffu : 0u;
+  const unsigned invC = x0 + 32 <= iw ? 0u : (0xffffffffu << (iw - x0));
+  const unsigned invR = x0 + 64 <= iw ? 0u : (x0 + 32 >= iw ? 0xffffffffu : (0xffffffffu << (iw - x0 - 32)));
+  unsigned pl = 0, pc = 0, pr = 0;                      // previous row as bit words: columns x0-32.., x0.., x0+32..
+  unsigned col = 0, colS = 0;                           // column histories: bit b = row (y - b) of column x / x + 1
+  for (int y = first; y < y1 + 5; y++) {
+    bool el = false, ec = false, er = false;
+    if (y < ih) {
+      const int8_t *row = edge + (size_t)y * iw + x;
+      if (okl) el = row[-32] != 0;
+      if (okc) ec = row[0] != 0;
+      if (okr) er = row[32] != 0;
+    }
+    const unsigned cl = __ballot_sync(0xffffffffu, el), cc = __ballot_sync(0xffffffffu, ec), cr = __ballot_sync(0xffffffffu, er);
+    // ---- x walk of row y - 1 (its perpendicular neighbour is row y; past the last row cc == 0 and the side rule is void)
+    const int yh = y - 1;
+    if (yh >= y0 && yh < y1) {
+      const unsigned prevC = (pc << 1) | (pl >> 31), prevL = pl << 1;          // bit 0 of prevL belongs to a word never consulted
+      unsigned sbC = exs_stop_back(pc, prevC, cc), sbL = exs_stop_back(pl, prevL, cl) | negL;
+      if (x0 == 0) sbC &= ~1u;                                                   // no rule applies at position 0
+      const unsigned nextC = (pc >> 1) | (pr << 31), nextR = pr >> 1;          // bit 31 of nextR likewise
+      const unsigned faC = (~pc & nextC) | invC, faR = (~pr & nextR) | invR;    // forward stops when the origin is not an edge pixel
+      const unsigned fbC = ~pc | invC, fbR = ~pr | invR;                        // ... and when it is
+      const unsigned long long back = (((unsigned long long)sbC << 32) | sbL) >> (lane + 28);
+      const bool oe = (pc >> lane) & 1u;
+      const unsigned long long fwd = (((unsigned long long)(oe ? fbR : faR) << 32) | (oe ? fbC : faC)) >> lane;
+      const unsigned tb = (unsigned)back & 31u, tf = (unsigned)fwd & 31u;
+      const unsigned nl = __clz(tb) - 27, nr = tf ? __ffs(tf) - 1 : 5;
+      if (okc) extH[(size_t)yh * iw + x] = (uint8_t)(nl | (nr << 4));
+    }
+    pl = cl; pc = cc; pr = cr;
+    // ---- y walk of row y - 5: rows y - 10 .. y are bits 10 .. 0
+    const unsigned long long both = ((unsigned long long)cr << 32) | cc;
+    col = (col << 1) | (unsigned)ec;
+    colS = (colS << 1) | ((unsigned)(both >> (lane + 1)) & 1u);
+    const int yv = y - 5;
+    if (yv >= y0 && yv < y1) {
+      const bool hasSide = x < iw - 1;
+      unsigned sb = exs_stop_back(col, col >> 1, hasSide ? colS : 0u);
+      if (y < 31) sb |= 0xffffffffu << (y + 1);                                  // rows above the image
+      if (y < 32) sb &= ~(1u << y);                                              // row 0
+      const bool oe = (col >> 5) & 1u;
+      unsigned fw = oe ? ~col : (~col & (col << 1));
+      if (y >= ih) fw |= (2u << (y - ih)) - 1u;                                  // rows below the image
+      const unsigned tb = (sb >> 5) & 31u, tf = (fw >> 1) & 31u;
+      const unsigned nu = tb ? __ffs(tb) - 1 : 5, nd = __clz(tf) - 27;
+      if (okc) extV[(size_t)yv * iw + x] = (uint8_t)(nu | (nd << 4));
+    }
+  }
+}
+
+// ---- the iteration kernel, four pixels per lane --------------------------------------------------------------------
+// Same streaming scheme as kf_blb_stream on strips of 128 columns: a lane owns four consecutive pixels (one 128-bit
+// load / store per row), so the shuffle scan of the row sums is paid once per four pixels and the apron of the x pass
+// (four pixels each side, one 128-bit load by lane 0 and one by lane 1) shrinks from 25 % to 6 %.  The running sums of a
+// row go to shared memory as P[i & 3][i >> 2] (i = position in the 136-pixel row), which keeps the lanes of a warp on
+// different banks whatever their extents; the column sums live in a 16-row ring with one column per (lane, pixel).
+// All sums are kept modulo 2^64; a window sum is a difference of two of them and always fits its 20-bit field.
+#define S4_WARPS 4
+#define S4_PP 36
+struct S4Smem { blb_w P[2][4][S4_PP]; blb_w R[SB_RING][4][32]; };
+// floor(c / w) = umulhi(2c, ceil(2^31 / w)) for c < 2^16, 1 <= w <= 10
+__constant__ const unsigned S4_M31[16] = {0u, 0x80000000u, 0x40000000u, 0x2aaaaaabu, 0x20000000u, 0x1999999au, 0x15555556u, 0x12492493u, 0x10000000u, 0x0e38e38fu, 0x0ccccccdu, 0u, 0u, 0u, 0u, 0u};
+__device__ __forceinline__ void s4_fields2(blb_w s, unsigned &f0, unsigned &f1, unsigned &f2) {      // the three fields, doubled
+  const unsigned lo = (unsigned)s, hi = (unsigned)(s >> 32);
+  f0 = (lo << 1) & 0x1ffffeu; f1 = __funnelshift_r(lo, hi, 19) & 0x1ffffeu; f2 = (hi >> 7) & 0x1ffffeu;
+}
+__device__ __forceinline__ blb_w s4_mean_spread(blb_w s, unsigned m) {
+  unsigned f0, f1, f2;
+  s4_fields2(s, f0, f1, f2);
+  const unsigned q0 = __umulhi(f0, m), q1 = __umulhi(f1, m), q2 = __umulhi(f2, m);
+  return ((blb_w)(q2 << 8) << 32) | (blb_w)(q0 | (q1 << 20));
+}
+__device__ __forceinline__ uint32_t s4_mean_packed(blb_w s, unsigned m) {
+  unsigned f0, f1, f2;
+  s4_fields2(s, f0, f1, f2);
+  return (__umulhi(f2, m) << 22) | (__umulhi(f1, m) << 12) | __umulhi(f0, m);
+}
+__global__ void __launch_bounds__(S4_WARPS * 32) kf_blb_stream4(uint32_t *out, const uint32_t *in, const uint8_t *extH, const uint8_t *extV, int iw, int ih, int nb,
+                                                                int strips, int chunks, int ch, size_t fs) {
+  extern __shared__ __align__(16) unsigned char s4_raw[];
+  __shared__ unsigned rcp[16];
+  if (threadIdx.x < 16) rcp[threadIdx.x] = S4_M31[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int wid = blockIdx.x * S4_WARPS + wp;
+  if (wid >= strips * chunks * nb) return;
+  S4Smem &sm = ((S4Smem *)s4_raw)[wp];
+  const int sx = wid % strips, cy = (wid / strips) % chunks, z = wid / (strips * chunks);
+  rd_batch_off((size_t)z * fs, out, in, extH, extV);
+  const int x0 = sx * 128, x = x0 + 4 * lane;
+  const bool okx = x < iw;
+  const bool okap = (lane == 0 && sx > 0) || (lane == 1 && x0 + 128 < iw);
+  const int q4 = iw >> 2, cx = x >> 2, cap = (lane == 0 ? x0 - 4 : x0 + 128) >> 2;
+  const int y0 = cy * ch, y1 = min(y0 + ch, ih);
+  const int first = max(y0 - BLB, 0), last = min(y1 + BLB, ih);
+  const uint4 *in4 = (const uint4 *)in;
+  const uint32_t *eh4 = (const uint32_t *)extH, *ev4 = (const uint32_t *)extV;
+  uint4 *out4 = (uint4 *)out;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  blb_w Q[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 4; k++) sm.R[first & (SB_RING - 1)][k][lane] = 0;
+  // two rows of look-ahead in registers
+  uint4 v0 = zero4, v1 = zero4, a0 = zero4, a1 = zero4;
+  unsigned e0 = 0, e1 = 0;
+  {
+    const size_t r0 = (size_t)first * q4, r1 = r0 + q4;
+    if (okx) { v0 = in4[r0 + cx]; e0 = eh4[r0 + cx]; }
+    if (okap) a0 = in4[r0 + cap];
+    if (first + 1 < last) {
+      if (okx) { v1 = in4[r1 + cx]; e1 = eh4[r1 + cx]; }
+      if (okap) a1 = in4[r1 + cap];
+    }
+  }
+  for (int y = first; y < last; y++) {
+    const uint4 v = v0, ap = a0;
+    const unsigned e = e0;
+    v0 = v1; a0 = a1; e0 = e1;
+    v1 = zero4; a1 = zero4; e1 = 0;
+    if (y + 2 < last) {
+      const size_t r2 = (size_t)(y + 2) * q4;
+      if (okx) { v1 = in4[r2 + cx]; e1 = eh4[r2 + cx]; }
+      if (okap) a1 = in4[r2 + cap];
+    }
+    const int yv = y - BLB;
+    const bool doV = yv >= y0 && okx;
+    unsigned ev = 0;
+    if (doV) ev = ev4[(size_t)yv * q4 + cx];
+    // ---- x pass: running sums of the 136-pixel row
+    blb_w w[4] = {blb_spread(v.x), blb_spread(v.y), blb_spread(v.z), blb_spread(v.w)};
+    const blb_w aw0 = blb_spread(ap.x), aw1 = blb_spread(ap.y), aw2 = blb_spread(ap.z), aw3 = blb_spread(ap.w);
+    const blb_w s1 = w[0] + w[1], s2 = s1 + w[2], s3 = s2 + w[3];
+    const blb_w as1 = aw0 + aw1, as2 = as1 + aw2, as3 = as2 + aw3;
+    const blb_w S = blb_scan_up(s3, lane, 5);
+    const blb_w T = __shfl_sync(0xffffffffu, S, 31), LA = __shfl_sync(0xffffffffu, as3, 0);
+    blb_w pc[5];                                                    // running sums in front of the lane's pixels 0..3 and behind pixel 3
+    pc[0] = LA + S - s3; pc[1] = pc[0] + w[0]; pc[2] = pc[0] + s1; pc[3] = pc[0] + s2; pc[4] = pc[0] + s3;
+    blb_w (*P)[S4_PP] = sm.P[y & 1];
+#pragma unroll
+    for (int k = 0; k < 4; k++) P[k][lane + 1] = pc[k];
+    if (lane == 0) { P[0][0] = 0; P[1][0] = aw0; P[2][0] = as1; P[3][0] = as2; }
+    if (lane == 1) { const blb_w b = LA + T; P[0][33] = b; P[1][33] = b + aw0; P[2][33] = b + as1; P[3][33] = b + as2; P[0][34] = b + as3; }
+    __syncwarp();
+    blb_w h[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned ek = (e >> (8 * k)) & 255u, nl = ek & 15u, nr = ek >> 4;
+      const unsigned j1 = k + 5 - nl, j2 = k + 4 + nr;            // positions relative to the lane's column block
+      const blb_w hs = (pc[k + 1] - P[j1 & 3][lane + (j1 >> 2)]) + (P[j2 & 3][lane + (j2 >> 2)] - pc[k]);
+      const unsigned ws = nl + nr;
+      h[k] = ws == 0 ? w[k] : s4_mean_spread(hs, rcp[ws]);
+    }
+    // ---- y pass: column running sums in the ring; row yv = y - 4 is complete once the sums behind row y are known
+    blb_w (*R)[4][32] = sm.R;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { Q[k] += h[k]; R[(y + 1) & (SB_RING - 1)][k][lane] = Q[k]; }
+    if (doV) {
+      uint32_t res[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned ek = (ev >> (8 * k)) & 255u, nu = ek & 15u, nd = ek >> 4;
+        const blb_w qa = R[(yv + 1) & (SB_RING - 1)][k][lane], qd = R[yv & (SB_RING - 1)][k][lane];
+        const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][k][lane]) + (R[(yv + nd) & (SB_RING - 1)][k][lane] - qd);
+        const unsigned ws = nu + nd;
+        res[k] = ws == 0 ? blb_pack(qa - qd) : s4_mean_packed(vs, rcp[ws]);
+      }
+      out4[(size_t)yv * q4 + cx] = make_uint4(res[0], res[1], res[2], res[3]);
+    }
+  }
+  // rows whose downward walk is cut by the bottom of the image rather than by the strip
+  if (okx) {
+    blb_w (*R)[4][32] = sm.R;
+    for (int yv = max(y0, last - BLB); yv < y1; yv++) {
+      const unsigned ev = ev4[(size_t)yv * q4 + cx];
+      uint32_t res[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned ek = (ev >> (8 * k)) & 255u, nu = ek & 15u, nd = ek >> 4;
+        const blb_w qa = R[(yv + 1) & (SB_RING - 1)][k][lane], qd = R[yv & (SB_RING - 1)][k][lane];
+        const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][k][lane]) + (R[(yv + nd) & (SB_RING - 1)][k][lane] - qd);
+        const unsigned ws = nu + nd;
+        res[k] = ws == 0 ? blb_pack(qa - qd) : s4_mean_packed(vs, rcp[ws]);
+      }
+      out4[(size_t)yv * q4 + cx] = make_uint4(res[0], res[1], res[2], res[3]);
+    }
+  }
+}
+
+static int rd_sm_count() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; RD_CUDA(cudaGetDevice(&dev)); RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+  return sms;
+}
+// strip height for a streaming kernel: enough strips to fill `warps_per_sm` warp slots of every SM in one wave, but not
+// shorter than `min_ch` rows (each strip re-reads its apron rows) nor longer than `max_ch`
+static int rd_strip_height(int strips, int nb, int ih, int warps_per_sm, int min_ch, int max_ch) {
+  int chunks = (rd_sm_count() * warps_per_sm) / (strips * nb);
+  if (chunks < 1) chunks = 1;
+  int ch = rd_cdiv(ih, chunks);
+  if (ch < min_ch) ch = min_ch;
+  if (ch > max_ch) ch = max_ch;
+  return ch;
+}
+
 // steps 13 of genGPUTask: src -> 10 iterations -> dst, ping-ponging through `pong`; ext: 2*iw*ih bytes of scratch
 void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int8_t *edge, uint8_t *ext, int iters, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   uint8_t *extH = ext, *extV = ext + (size_t)iw * ih;
-  RD_LAUNCH(kf_blb_extents, dim3(rd_cdiv(iw, EX_TX), rd_cdiv(ih, EX_TY), nb), 256, 0, s, extH, extV, edge, iw, ih, fs);
-  // strip height: as many strips as fit the machine in one wave (4 CTAs of 8 warps per SM at 58 registers), so that no SM
-  // idles behind a straggler; clamped so that the running sums stay inside their fields and strips stay worth their apron
-  static int sms = 0;
-  if (!sms) { int dev = 0; RD_CUDA(cudaGetDevice(&dev)); RD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
-  const int strips = rd_cdiv(iw, 32);
-  int chunks = (sms * 4 * SB_WARPS) / (strips * nb);
-  if (chunks < 1) chunks = 1;
-  int ch = rd_cdiv(ih, chunks);
-  if (ch < SB_CH_MIN) ch = SB_CH_MIN;
-  if (ch > SB_CH_MAX) ch = SB_CH_MAX;
-  chunks = rd_cdiv(ih, ch);
-  const int blocks = rd_cdiv(strips * chunks * nb, SB_WARPS);
+  {
+    const int strips = rd_cdiv(iw, 32), ch = rd_strip_height(strips, nb, ih, 32, 40, 1 << 20), chunks = rd_cdiv(ih, ch);
+    RD_LAUNCH(kf_blb_extents_s, rd_cdiv(strips * chunks * nb, EXS_WARPS), EXS_WARPS * 32, 0, s, extH, extV, edge, iw, ih, nb, strips, chunks, ch, fs);
+  }
   const uint32_t *cur = src;
+  if ((iw & 3) == 0) {
+    static bool attr = false;
+    const size_t smem = S4_WARPS * sizeof(S4Smem);
+    if (!attr) { RD_CUDA(cudaFuncSetAttribute(kf_blb_stream4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    // 12 warps per SM fit (18.25 KB of shared memory each)
+    const int strips = rd_cdiv(iw, 128), ch = rd_strip_height(strips, nb, ih, 12, 48, 1 << 20), chunks = rd_cdiv(ih, ch);
+    const int blocks = rd_cdiv(strips * chunks * nb, S4_WARPS);
+    for (int i = 0; i < iters; i++) {
+      uint32_t *o = ((iters - i) & 1) ? dst : pong;     // the last iteration lands in dst
+      RD_LAUNCH(kf_blb_stream4, blocks, S4_WARPS * 32, smem, s, o, cur, extH, extV, iw, ih, nb, strips, chunks, ch, fs);
+      cur = o;
+    }
+    return;
+  }
+  // widths that are not a multiple of four: one pixel per lane.  Strip height: as many strips as fit the machine in one wave
+  // (4 CTAs of 8 warps per SM at 58 registers); clamped so that strips stay worth their apron
+  const int strips = rd_cdiv(iw, 32), ch = rd_strip_height(strips, nb, ih, 4 * SB_WARPS, SB_CH_MIN, SB_CH_MAX), chunks = rd_cdiv(ih, ch);
+  const int blocks = rd_cdiv(strips * chunks * nb, SB_WARPS);
   for (int i = 0; i < iters; i++) {
     uint32_t *o = ((iters - i) & 1) ? dst : pong;       // the last iteration lands in dst
     RD_LAUNCH(kf_blb_stream, blocks, SB_WARPS * 32, 0, s, o, cur, extH, extV, iw, ih, nb, strips, chunks, ch, fs);

@@ -509,29 +509,45 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
 //   tmp1..3 blurred L, a, b -> weak mask + walk extents (tmp1), flat colours (tmp2), blur ping-pong / merge mask (tmp3)
 //   tmp0 string bytes -> junction map + region sizes   tmp4 CCL link bytes   tmp5 strong-edge bitmap of this frame
 //   iobuf1 region-boundary (segid) map   ioBig0 blur scratch -> segment list   ioBig1 blur scratch -> polyline scratch -> vote table
-static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int nb, cudaStream_t s) {
+// stop_stage > 0 ends the schedule after that stage (tests compare the planes of the production schedule stage by stage,
+// tests/parity.py FAST_STAGES); 0 runs everything.
+static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int nb, cudaStream_t s, int stop_stage = 0) {
+#define STAGE(k) do { if (stop_stage == (k)) return; } while (0)
   const int iw = o->iw, ih = o->ih, n = iw * ih;
   const size_t fs = o->fs;
   cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
   // Stage A (oclrect.c:245-263)
   rd_bgr2plab_run(PU(buf[0]), din, din_fs, iw, ih, ws, nb, fs, s);
+  STAGE(1);
   rd_iirblur3_run(PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), PU(buf[1]), PU(buf[0]), PF(ioBig[1]), PF(ioBig[0]), o->P / 4, 2, iw, ih, nb, fs, s);
+  STAGE(2);
   rd_edge_thin_run(PF(buf[2]), PF(tmp[1]), PU(buf[1]), iw, ih, nb, fs, s);
+  STAGE(3);
   // Stage B (oclrect.c:265-342)
   rd_strings1_run((uint8_t *)tmp[0]->dptr, PF(buf[2]), iw, ih, nb, fs, s);
+  STAGE(4);
   rd_label8x_u8(PI(buf[1]), (const uint8_t *)tmp[0]->dptr, tmp[4]->dptr, -1, iw, ih, nb, fs, s);
+  STAGE(5);
   RD_LAUNCH(kr_calcStrength, rd_gz(G2, nb), RB, 0, s, PI(buf[3]), PF(buf[2]), PI(buf[1]), iw, ih, fs);
   rd_filter_masks_run((int8_t *)tmp[1]->dptr, PI(tmp[5]), PI(buf[1]), PI(buf[3]), iw, ih, nb, fs, s);
+  STAGE(6);
   rd_blblur_run(PU(buf[4]), PU(tmp[3]), PU(buf[0]), (const int8_t *)tmp[1]->dptr, (uint8_t *)tmp[1]->dptr + (size_t)n, 10, iw, ih, nb, fs, s);
+  STAGE(7);
   rd_quant_despeckle_run(PU(tmp[2]), PU(buf[4]), PF(buf[2]), iw, ih, nb, fs, s);
+  STAGE(8);
   rd_junction_mask_run((uint8_t *)tmp[3]->dptr, PI(tmp[0]), PI(tmp[5]), iw, ih, nb, fs, s);
+  STAGE(9);
   rd_labelMerge_u8(PI(buf[4]), PI(buf[5]), PU(tmp[2]), (const uint8_t *)tmp[3]->dptr, PI(tmp[5]), tmp[4]->dptr, iw, ih, nb, fs, s);
+  STAGE(10);
   rd_calcSize_run(PI(tmp[0]), PI(buf[4]), iw, ih, nb, fs, s);
   rd_despeckle2_boundary_run(PI(tmp[1]), PI(buf[4]), PI(tmp[0]), 16, iw, ih, nb, fs, s);
+  STAGE(11);
   rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[4]->dptr, -1, iw, ih, nb, fs, s);
+  STAGE(12);
   // Stage C (oclrect.c:361).  The clean-up kernel also copies the bitmap into buf3, where the next frame's strengths accumulate.
   rd_polyline_fast((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(tmp[5]), PI(buf[3]), PI(ioBig[1]), PI(tmp[0]), PI(tmp[1]), PI(tmp[2]), PI(tmp[3]), PI(tmp[4]),
                    PI(buf[5]), 4.0f, 20, iw, ih, nb, fs, s);
+  STAGE(13);
   // Stage D (oclrect.c:365-367) and the compact read-back record
   const int nentry = n * 4 / 5;
   rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
@@ -762,7 +778,7 @@ void rd_oclrect_run_device(struct oclrect_t *o, const uint8_t *imgData, int ws, 
   cudaStream_t s = rd_stream(o->queue);
   RD_CUDA(cudaMemcpyAsync(o->iobuf[0]->dptr, imgData, (size_t)ws * o->ih, cudaMemcpyHostToDevice, s));
   if (stop_step > 0) gpu_task(o, (const uint8_t *)o->iobuf[0]->dptr, o->fs, ws, stop_step, 1, s);
-  else if (stop_step == 0) gpu_task_fast(o, (const uint8_t *)o->iobuf[0]->dptr, o->fs, ws, 1, s);
+  else gpu_task_fast(o, (const uint8_t *)o->iobuf[0]->dptr, o->fs, ws, 1, s, -stop_step);      // stop_step < 0: stage -stop_step of the production schedule
   RD_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -92,6 +92,68 @@ def compare_steps(iw, ih, seed, steps, rd, dev, ws=None, frames_before=0):
     return out
 
 
+# ---- the production schedule (rd_rect.cu : gpu_task_fast) stage by stage.  Its planes live in other buffers and narrower
+# types than the reference's; every entry maps one plane to the oracle step / buffer that holds the same values.
+# stage -> [(cuda buffer, dtype, kind, oracle step, oracle buffer, oracle dtype, oracle kind)]
+FAST_STAGES = {
+    1: [("buf0", np.uint32, "n", 1, "buf0", np.uint32, "n")],
+    2: [("tmp1", np.float32, "n", 3, "tmp1", np.float32, "n"), ("tmp2", np.float32, "n", 3, "tmp2", np.float32, "n"),
+        ("tmp3", np.float32, "n", 3, "tmp3", np.float32, "n"), ("buf1", np.uint32, "n", 4, "buf1", np.uint32, "n")],
+    3: [("buf2", np.float32, "n", 7, "buf1", np.float32, "n")],                       # thinned edge strength
+    4: [("tmp0", np.uint8, "bytes_n", 9, "tmp1", np.int32, "n")],                     # cleaned string image
+    5: [("buf1", np.int32, "n", 10, "buf2", np.int32, "n")],                          # string components
+    6: [("buf3", np.int32, "n", 11, "buf3", np.int32, "n"), ("tmp1", np.int8, "bytes_n", 12, "tmp1", np.int8, "bytes_n"),
+        ("tmp5", np.int32, "n", 15, "buf3", np.int32, "n")],                          # strengths, weak mask, strong-edge bitmap
+    7: [("buf4", np.uint32, "n", 13, "buf4", np.uint32, "n")],                        # edge-preserving blur
+    8: [("tmp2", np.uint32, "n", 14, "buf4", np.uint32, "n")],                        # quantised + despeckled colours
+    9: [("tmp3", np.uint8, "bytes_n", 16, "tmp1", np.int32, "n"), ("tmp0", np.int32, "n", 16, "tmp0", np.int32, "n")],
+    10: [("buf4", np.int32, "n", 17, "buf5", np.int32, "n")],                         # colour regions
+    11: [("tmp0", np.int32, "n", 18, "tmp0", np.int32, "n"), ("tmp1", np.int32, "n", 19, "tmp1", np.int32, "n")],
+    12: [("iobuf1", np.int32, "n", 19, "iobuf1", np.int32, "n")],                     # segid map
+    13: [("buf0", np.int32, "n", 20, "buf0", np.int32, "n"), ("ioBig0", np.int32, "ls", 20, "ioBig0", np.int32, "ls"),
+         ("buf3", np.int32, "n", 15, "buf3", np.int32, "n")],
+    0: [("ioBig1", np.int32, "4n", 21, "ioBig1", np.int32, "4n")],                    # vote table
+}
+
+
+def compare_fast_stages(iw, ih, seed, stages, rd, dev, ws=None):
+    """production schedule stopped after each of `stages` (0 = run to the end) against the oracle's planes;
+    returns list of (stage, buffer, mismatches, total, detail)"""
+    img = ol.synth_frame(iw, ih, seed, ws=ws)
+    n = iw * ih
+    out = []
+    ora = {}
+
+    def oracle_plane(step, name, dtype, kind):
+        if (step, name) not in ora:
+            o = ol.OracleRect(iw, ih)
+            o.gpu_task(img, ws=img.shape[-1], stop_step=step)
+            for nm in ("buf0", "buf1", "buf2", "buf3", "buf4", "buf5", "tmp0", "tmp1", "tmp2", "tmp3", "iobuf1", "ioBig0", "ioBig1"):
+                ora[(step, nm)] = o.buffer(nm).copy()
+            o.close()
+        return _view(ora[(step, name)], dtype, kind, n)
+
+    for k in stages:
+        g = rd.OclRect(dev, iw, ih)
+        g.run_device(img, stop_step=-k)
+        for name, dtype, kind, ostep, oname, odtype, okind in FAST_STAGES[k]:
+            a = oracle_plane(ostep, oname, odtype, okind)
+            b = _view(g.buffer(name), dtype, kind, n)
+            if a.shape != b.shape:
+                out.append((k, name, -1, a.size, "shape %s vs %s" % (a.shape, b.shape)))
+                continue
+            if a.dtype != b.dtype:
+                a, b = a.astype(np.int64), b.astype(np.int64)
+            bad = np.flatnonzero(_bits(a) != _bits(b))
+            detail = ""
+            if bad.size:
+                i = int(bad[0])
+                detail = "first at %d (x=%d,y=%d): oracle %r cuda %r" % (i, i % iw, (i // iw) % ih, a[i], b[i])
+            out.append((k, name, int(bad.size), int(a.size), detail))
+        g.close()
+    return out
+
+
 def canon_rects(r):
     """sort a rect list into a canonical order (the reference's order is a hash-map iteration order)"""
     if len(r) == 0:

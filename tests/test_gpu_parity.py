@@ -48,6 +48,13 @@ def test_key_steps_bit_exact_720p(rd, gpu_dev):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("iw,ih,seed", [(640, 480, 1), (333, 217, 7), (1280, 720, 2)])
+def test_production_schedule_stage_planes_bit_exact(rd, gpu_dev, iw, ih, seed):
+    # the fused / list-based kernels of gpu_task_fast, stopped after every stage: each plane equals the oracle's
+    bad = [r for r in parity.compare_fast_stages(iw, ih, seed, sorted(parity.FAST_STAGES), rd, gpu_dev) if r[2] != 0]
+    assert not bad, bad
+
+
 def test_row_stride_wider_than_the_image(rd, gpu_dev):
     iw, ih = 300, 200
     bad = [r for r in parity.compare_steps(iw, ih, 11, [1, 8, 21], rd, gpu_dev, ws=4 * iw - 3) if r[2] != 0]

@@ -20,6 +20,8 @@ t0 = time.time()
 for k, name, bad, total, detail in parity.compare_steps(iw, ih, seed, steps, rd, dev):
     print("step %2d %-7s %s %d/%d %s" % (k, name, "OK  " if bad == 0 else "FAIL", bad, total, detail), flush=True)
 print("steps took %.1f s" % (time.time() - t0))
+for k, name, bad, total, detail in parity.compare_fast_stages(iw, ih, seed, sorted(parity.FAST_STAGES), rd, dev):
+    print("fast stage %2d %-7s %s %d/%d %s" % (k, name, "OK  " if bad == 0 else "FAIL", bad, total, detail), flush=True)
 # whole pipeline through the public entry point
 img = ol.synth_frame(iw, ih, seed)
 o = ol.OracleRect(iw, ih)

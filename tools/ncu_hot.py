@@ -35,5 +35,5 @@ n = sum(v for v, _, _ in lines) or 1
 print(rows[0][1][:100], "| samples", int(n), "| sass lines", len(lines))
 print("stalls:", ", ".join("%s %.0f%%" % (k[6:], 100 * v / n) for k, v in tot.most_common(7)))
 print("by opcode (samples%, executed):", ", ".join("%s %.0f%% %d" % (k, 100 * v / n, execs[k]) for k, v in byop.most_common(10)))
-for v, sx, e in sorted(lines, reverse=True)[:10]:
+for v, sx, e in sorted(lines, reverse=True)[:int(sys.argv[4]) if len(sys.argv) > 4 else 10]:
     print("  %5.1f%%  exec=%-9s %s" % (100 * v / n, e, sx))
