@@ -116,9 +116,26 @@ __device__ __forceinline__ void sm_unite(int *L, int a, int b) {
   }
 }
 
-// One CTA per 32x32 tile, one warp per tile row at a time (8 warps x 4 rows).  Horizontal runs are resolved with a
-// warp ballot: every pixel starts out pointing at the first pixel of its run (depth 1), so the union-find only has
-// to stitch runs of adjacent rows together.
+// neighbour exchange inside a warp for the staged values (int, or the two words of LinkMerge::V)
+__device__ __forceinline__ int ccl_up1(int v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ int ccl_down1(int v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+template <class V> __device__ __forceinline__ V ccl_up1(V v) { V r; r.pix = __shfl_up_sync(0xffffffffu, v.pix, 1); r.fl = __shfl_up_sync(0xffffffffu, v.fl, 1); return r; }
+template <class V> __device__ __forceinline__ V ccl_down1(V v) { V r; r.pix = __shfl_down_sync(0xffffffffu, v.pix, 1); r.fl = __shfl_down_sync(0xffffffffu, v.fl, 1); return r; }
+
+// One CTA per 32x32 tile; warp w owns the four consecutive tile rows 4w .. 4w+3, lane = column.
+//  1. The predicate inputs are loaded once per pixel (coalesced) and handed to the neighbours by shuffles: a warp keeps the
+//     row above in registers, lanes 0 / 31 fetch the columns beside the tile.  The link masks go to the byte plane and to
+//     shared memory; horizontal runs are resolved with a ballot (every pixel starts out pointing at the first pixel of its
+//     run), so the union-find only has to stitch runs of adjacent rows together.
+//  2. The unions that are still needed are appended to a list in shared memory, skipping every link that another link
+//     implies: the link to N is implied when the W neighbour has it too and both pairs are W-linked; the links to NW / NE
+//     are implied by the link to N when N is W-linked to them.  (Each skipped union follows from links that are themselves
+//     processed, so the components are unchanged - also for predicates that are not transitive.)  A uniform tile needs 31
+//     unions instead of ~3000.
+//  3. The list is processed densely, one union per thread (the unions of a row are few and scattered, and walking them in
+//     place left most lanes of a warp idle), then the run starts - also gathered in a list - look up their roots, and every
+//     pixel reads its root through its run start (two hops).
+#define CCL_MAXPAIRS (3 * TW * TH)
 template <class LinkFn>
 __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *links, LinkFn f, int iw, int ih, size_t fs) {
   rd_batch_z(fs, label, links);
@@ -126,23 +143,39 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
   typedef typename LinkFn::V V;
   __shared__ int L[TW * TH];
   __shared__ uint8_t M[TW * TH];
-  __shared__ V T[(TH + 1) * (TW + 2)];                            // tile + the row above + a column on each side
+  __shared__ unsigned pairs[CCL_MAXPAIRS];
+  __shared__ unsigned short starts_list[TW * TH];
+  __shared__ int npairs, nstarts;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;        // 8 warps, each warp owns rows wy, wy+8, wy+16, wy+24
+  const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int x = x0 + lx;
-  for (int i = threadIdx.x; i < (TH + 1) * (TW + 2); i += CCL_THREADS) {
-    const int tx = i % (TW + 2), ty = i / (TW + 2);
-    const int gx = x0 - 1 + tx, gy = y0 - 1 + ty;
-    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) T[i] = f.load(gx, gy);   // positions outside the image are never consulted
+  const unsigned lt = (1u << lx) - 1u;
+  if (threadIdx.x == 0) { npairs = 0; nstarts = 0; }
+  const bool okx = x < iw, okw = x0 > 0, oke = x0 + TW < iw;
+  V up = V(), upW = V(), upE = V();
+  {
+    const int yu = y0 + wy * 4 - 1;
+    if (yu >= 0 && yu < ih) {
+      if (okx) up = f.load(x, yu);
+      upW = ccl_up1(up); upE = ccl_down1(up);
+      if (lx == 0 && okw) upW = f.load(x0 - 1, yu);
+      if (lx == 31 && oke) upE = f.load(x0 + TW, yu);
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int ly = wy + k * 8, y = y0 + ly, i = ly * TW + lx;
-    unsigned m = L_BG, full = L_BG;
-    if (x < iw && y < ih) {
-      const V *c = T + (ly + 1) * (TW + 2) + lx + 1;
-      full = f.link(c[0], c[-1], c[-(TW + 2) - 1], c[-(TW + 2)], c[-(TW + 2) + 1], x, y);
+    const int ly = wy * 4 + k, y = y0 + ly, i = ly * TW + lx;
+    V c = V(), w = V(), e = V();
+    if (y < ih) {
+      if (okx) c = f.load(x, y);
+      w = ccl_up1(c); e = ccl_down1(c);
+      if (lx == 0 && okw) w = f.load(x0 - 1, y);
+      if (lx == 31 && oke) e = f.load(x0 + TW, y);
+    }
+    unsigned m = L_BG;
+    if (okx && y < ih) {
+      const unsigned full = f.link(c, w, upW, up, upE, x, y);
       links[(size_t)y * iw + x] = (uint8_t)full;
       m = full;
       if (lx == 0) m &= ~(L_W | L_NW);                             // neighbours outside the tile are the seam kernel's business
@@ -153,35 +186,43 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
     const unsigned starts = ~__ballot_sync(0xffffffffu, (m & L_W) != 0);      // bit j set: pixel j starts a run
     const int first = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));        // nearest run start at or left of lx (bit 0 is always set)
     L[i] = ly * TW + first;
+    int base = 0;
+    if (lx == 0) base = atomicAdd(&nstarts, __popc(starts));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((starts >> lx) & 1u) starts_list[base + __popc(starts & lt)] = (unsigned short)i;
+    up = c; upW = w; upE = e;
   }
   __syncthreads();
-  // Stitch the runs of adjacent rows.  A union is skipped when a neighbouring link already implies it: the link to N is
-  // implied when the W neighbour has it too and both pairs are W-linked; the links to NW / NE are implied by the link to N
-  // when N is W-linked to them.  (Each skipped union follows from links that are themselves processed, so the components
-  // are unchanged - also for predicates that are not transitive.)  A uniform tile needs 31 unions instead of ~3000.
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int i = (wy + k * 8) * TW + lx;
+    const int i = (wy * 4 + k) * TW + lx;
     const unsigned m = M[i];
+    bool nN = false, nNW = false, nNE = false;
     if (m & (L_NW | L_N | L_NE)) {
       const unsigned mn = M[i - TW];
-      if ((m & L_N) && !((m & L_W) && (M[i - 1] & L_N) && (mn & L_W))) sm_unite(L, i, i - TW);
-      if ((m & L_NW) && !((m & L_N) && (mn & L_W))) sm_unite(L, i, i - TW - 1);
-      if ((m & L_NE) && !((m & L_N) && (M[i - TW + 1] & L_W))) sm_unite(L, i, i - TW + 1);
+      nN = (m & L_N) && !((m & L_W) && (M[i - 1] & L_N) && (mn & L_W));
+      nNW = (m & L_NW) && !((m & L_N) && (mn & L_W));
+      nNE = (m & L_NE) && !((m & L_N) && (M[i - TW + 1] & L_W));
     }
+    const unsigned bN = __ballot_sync(0xffffffffu, nN), bNW = __ballot_sync(0xffffffffu, nNW), bNE = __ballot_sync(0xffffffffu, nNE);
+    const int cN = __popc(bN), cNW = __popc(bNW), tot = cN + cNW + __popc(bNE);
+    if (tot == 0) continue;
+    int base = 0;
+    if (lx == 0) base = atomicAdd(&npairs, tot);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (nN) pairs[base + __popc(bN & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW);
+    if (nNW) pairs[base + cN + __popc(bNW & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW - 1);
+    if (nNE) pairs[base + cN + cNW + __popc(bNE & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW + 1);
   }
   __syncthreads();
-  // run starts look up their root first, then every pixel reads it through its run start (two hops)
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int i = (wy + k * 8) * TW + lx;
-    if (!(M[i] & L_W)) L[i] = sm_find(L, i);
-  }
+  for (int t = threadIdx.x, n = npairs; t < n; t += CCL_THREADS) { const unsigned pr = pairs[t]; sm_unite(L, (int)(pr >> 16), (int)(pr & 0xffffu)); }
+  __syncthreads();
+  for (int t = threadIdx.x, n = nstarts; t < n; t += CCL_THREADS) { const int i = starts_list[t]; L[i] = sm_find(L, i); }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int ly = wy + k * 8, y = y0 + ly, i = ly * TW + lx;
-    if (x < iw && y < ih) {
+    const int ly = wy * 4 + k, y = y0 + ly, i = ly * TW + lx;
+    if (okx && y < ih) {
       const int r = L[L[i]];
       label[(size_t)y * iw + x] = (y0 + (r >> 5)) * iw + x0 + (r & 31);
     }

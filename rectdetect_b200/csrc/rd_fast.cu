@@ -13,6 +13,7 @@
 //                       and direction, the pass1 / pass3 combinations are folded into the consumers.
 #include "rd_common.cuh"
 #include "rd_stageA.cuh"
+#include <mutex>
 #define RD_TABLE_QUAL static __device__ const
 #include "rd_tables.inc"
 
@@ -931,60 +932,108 @@ void rd_filter_masks_run(int8_t *weak, int *strong, const int *label, const int 
   RD_LAUNCH(kf_filter_masks, dim3(rd_cdiv(iw, 32), rd_cdiv(ih, 8), nb), b, 0, s, weak, strong, label, str, iw, ih, fs);
 }
 
-// quantize(24,24,24) + despeckle (oclrect.cl:207-244, oclrect.c:300-303): the 34x34 quantised tile lives in shared memory
+// quantize(24,24,24) + despeckle (oclrect.cl:207-244, oclrect.c:300-303): the 34x34 quantised tile lives in shared memory.
+// - quantize maps each channel through round(v * 24) / 24 in float and back to its integer code; with 4096 + 1024 possible
+//   codes that is a table, filled once per device by kq_tables with the very arithmetic of the operator kernel.
+// - despeckle picks, for an edge pixel, the 3x3 non-edge neighbour at the smallest distance() in Lab.  Unpacked channels
+//   are (code + 0.5) / 4096 or / 1024, so the differences are exact and the squared distance is N / 2^24 with the integer
+//   N = dl^2 + 16 da^2 + 16 db^2 (dl, da, db: code differences).  The canonical distance (float)sqrt((double)N / 2^24) is
+//   monotone in N, and below N = 2^20 two different N never round to the same float (the square roots are more than one
+//   float ulp apart), so the reference's "first neighbour with a strictly smaller distance" is the first neighbour with a
+//   strictly smaller N.  Pixels that see a larger N take the floating-point path.
+__device__ uint16_t g_quantL[4096], g_quantA[1024];
+__global__ void kq_tables() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4096) {
+    const float l = __fadd_rn(__fmul_rn((float)i, 1.0f / 4096), 0.5f / 4096);
+    g_quantL[i] = (uint16_t)rd_f2u_floor_sat(__fmul_rn(__fdiv_rn(roundf(__fmul_rn(l, 24.0f)), 24.0f), 4096.0f), 4095u);
+  }
+  if (i < 1024) {
+    const float a = __fadd_rn(__fmul_rn((float)i, 1.0f / 1024), 0.5f / 1024);
+    g_quantA[i] = (uint16_t)rd_f2u_floor_sat(__fmul_rn(__fdiv_rn(roundf(__fmul_rn(a, 24.0f)), 24.0f), 1024.0f), 1023u);
+  }
+}
 #define QD_T 32
 #define QD_W (QD_T + 2)
 __device__ __forceinline__ uint32_t quant24(uint32_t v) {
-  float l, a, b;
-  rd_unpacklab(v, l, a, b);
-  return rd_packlab(__fdiv_rn(roundf(__fmul_rn(l, 24.0f)), 24.0f), __fdiv_rn(roundf(__fmul_rn(a, 24.0f)), 24.0f), __fdiv_rn(roundf(__fmul_rn(b, 24.0f)), 24.0f));
+  return ((uint32_t)g_quantA[v >> 22] << 22) | ((uint32_t)g_quantA[(v >> 12) & 1023u] << 12) | (uint32_t)g_quantL[v & 4095u];
 }
 __global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, in, thin);
   __shared__ uint32_t q[QD_W * QD_W];
   __shared__ uint8_t e[QD_W * QD_W];                          // 1: edge pixel (thinned strength >= 1e-6), 2: outside the image
   const int bx = blockIdx.x * QD_T - 1, by = blockIdx.y * QD_T - 1;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < QD_W * QD_W; i += 256) {
-    const int gx = bx + i % QD_W, gy = by + i / QD_W;
-    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) {
-      const size_t p = (size_t)gy * iw + gx;
-      q[i] = quant24(in[p]);
-      e[i] = thin[p] >= 1e-6f ? 1 : 0;
-    } else { q[i] = 0; e[i] = 2; }
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  // warp -> tile rows wy, wy + 8, ...; lane -> column lane, lanes 0 / 1 also columns 32 / 33
+  for (int ty = wy; ty < QD_W; ty += 8) {
+    const int gy = by + ty;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int tx = lane + 32 * h;
+      if (tx >= QD_W) continue;
+      const int gx = bx + tx, i = ty * QD_W + tx;
+      if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) {
+        const size_t p = (size_t)gy * iw + gx;
+        q[i] = quant24(in[p]);
+        e[i] = thin[p] >= 1e-6f ? 1 : 0;
+      } else { q[i] = 0; e[i] = 2; }
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int tx = 1 + threadIdx.x, ty = 1 + threadIdx.y + k * 8;
+    const int tx = 1 + lane, ty = 1 + wy + k * 8;
     const int gx = bx + tx, gy = by + ty;
     if (gx >= iw || gy >= ih) continue;
     const int i = ty * QD_W + tx;
     uint32_t r = q[i];
     if (e[i] == 1) {
-      float dist = 1e+10f, l0, a0, b0;
-      double bestsq = 1e+300;
-      rd_unpacklab(r, l0, a0, b0);
+      const uint32_t c = r;
+      const int l0 = c & 4095u, a0 = (c >> 12) & 1023u, b0 = c >> 22;
+      unsigned best = 0xffffffffu, worst = 0;
 #pragma unroll
       for (int yy = -1; yy <= 1; yy++)
 #pragma unroll
         for (int xx = -1; xx <= 1; xx++) {
           const int j = i + yy * QD_W + xx;
           if (e[j] != 0) continue;                            // edge pixels and positions outside the image do not donate
-          float l1, a1, b1;
           const uint32_t v = q[j];
-          rd_unpacklab(v, l1, a1, b1);
-          // distance() = (float)sqrt(exact double sum) (canonical form).  The rounded root is monotone in the sum,
-          // so a sum that is not smaller than the best one so far cannot give a smaller distance: skip its square root.
-          const double dl = (double)__fsub_rn(l1, l0), da = (double)__fsub_rn(a1, a0), db = (double)__fsub_rn(b1, b0);
-          const double sq = __dadd_rn(__dadd_rn(__dmul_rn(dl, dl), __dmul_rn(da, da)), __dmul_rn(db, db));
-          if (!(sq < bestsq)) continue;
-          const float d = (float)__dsqrt_rn(sq);
-          if (d < dist) { r = v; dist = d; bestsq = sq; }
+          const int dl = (int)(v & 4095u) - l0, da = (int)((v >> 12) & 1023u) - a0, db = (int)(v >> 22) - b0;
+          const unsigned N = (unsigned)(dl * dl) + 16u * (unsigned)(da * da + db * db);
+          worst = max(worst, N);
+          if (N < best) { best = N; r = v; }
         }
+      if (worst >= (1u << 20)) {
+        // far-apart colours: distances may collide after rounding, follow the reference's float comparison
+        r = c;
+        float dist = 1e+10f, fl0, fa0, fb0;
+        rd_unpacklab(c, fl0, fa0, fb0);
+        for (int yy = -1; yy <= 1; yy++)
+          for (int xx = -1; xx <= 1; xx++) {
+            const int j = i + yy * QD_W + xx;
+            if (e[j] != 0) continue;
+            float l1, a1, b1;
+            const uint32_t v = q[j];
+            rd_unpacklab(v, l1, a1, b1);
+            const float d = rd_distance3(__fsub_rn(l1, fl0), __fsub_rn(a1, fa0), __fsub_rn(b1, fb0));
+            if (d < dist) { r = v; dist = d; }
+          }
+      }
     }
     out[(size_t)gy * iw + gx] = r;
   }
+}
+// fills the quantisation tables of the current device (once; called while an oclrect_t is created, before any schedule runs)
+void rd_quant_tables_init() {
+  static std::mutex mu;
+  static bool ready[64] = {false};
+  int dev = 0;
+  RD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  if (dev < 64 && ready[dev]) return;
+  RD_LAUNCH(kq_tables, 16, 256, 0, (cudaStream_t)0);
+  RD_CUDA(cudaDeviceSynchronize());
+  if (dev < 64) ready[dev] = true;
 }
 void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   RD_LAUNCH(kf_quant_despeckle, dim3(rd_cdiv(iw, QD_T), rd_cdiv(ih, QD_T), nb), dim3(32, 8), 0, s, out, in, thin, iw, ih, fs);

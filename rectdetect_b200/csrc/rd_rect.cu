@@ -33,6 +33,7 @@ void rd_edge_thin_run(float *thin, const float *blurL, const uint32_t *blurP, in
 void rd_strings1_run(uint8_t *out, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_filter_masks_run(int8_t *weak, int *strong, const int *label, const int *str, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_quant_tables_init();
 void rd_junction_mask_run(uint8_t *mask, int *junc, const int *strong, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_despeckle2_boundary_run(int *out, const int *label, const int *size, int thre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
@@ -644,6 +645,7 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
     o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(bb * nb, NULL, NULL);
     RD_CUDA(cudaEventCreateWithFlags(&o->events[p], cudaEventDisableTiming));
   }
+  rd_quant_tables_init();
   RD_CUDA(cudaDeviceSynchronize());
   return o;
 }
