@@ -275,8 +275,18 @@ __global__ void __launch_bounds__(EXS_WARPS * 32) kf_blb_extents_s(uint8_t *extH
 // different banks whatever their extents; the column sums live in a 16-row ring with one column per (lane, pixel).
 // All sums are kept modulo 2^64; a window sum is a difference of two of them and always fits its 20-bit field.
 #define S4_WARPS 4
-#define S4_PP 36
-struct S4Smem { blb_w P[2][4][S4_PP]; blb_w R[SB_RING][4][32]; };
+template <int NPX> struct S4Smem {
+  enum { AC = 4 / NPX, PP = 32 + 2 * AC + 2 };                    // apron columns per side; pitch of a plane of running sums
+  blb_w P[2][NPX][PP];
+  blb_w R[SB_RING][NPX][32];
+};
+template <int NPX> struct S4Vec;
+template <> struct S4Vec<4> { typedef uint4 T; };
+template <> struct S4Vec<2> { typedef uint2 T; };
+__device__ __forceinline__ void s4_get(const uint4 &v, uint32_t (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void s4_get(const uint2 &v, uint32_t (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ uint4 s4_make(const uint32_t (&r)[4]) { return make_uint4(r[0], r[1], r[2], r[3]); }
+__device__ __forceinline__ uint2 s4_make(const uint32_t (&r)[2]) { return make_uint2(r[0], r[1]); }
 // floor(c / w) = umulhi(2c, ceil(2^31 / w)) for c < 2^16, 1 <= w <= 10
 __constant__ const unsigned S4_M31[16] = {0u, 0x80000000u, 0x40000000u, 0x2aaaaaabu, 0x20000000u, 0x1999999au, 0x15555556u, 0x12492493u, 0x10000000u, 0x0e38e38fu, 0x0ccccccdu, 0u, 0u, 0u, 0u, 0u};
 __device__ __forceinline__ void s4_fields2(blb_w s, unsigned &f0, unsigned &f1, unsigned &f2) {      // the three fields, doubled
@@ -294,8 +304,24 @@ __device__ __forceinline__ uint32_t s4_mean_packed(blb_w s, unsigned m) {
   s4_fields2(s, f0, f1, f2);
   return (__umulhi(f2, m) << 22) | (__umulhi(f1, m) << 12) | __umulhi(f0, m);
 }
+// y pass for row yv of the lane's NPX columns: the sums behind rows yv - 5 .. yv + 5 are in the ring
+template <int NPX>
+__device__ __forceinline__ void s4_vrow(uint32_t (&res)[NPX], const blb_w (*R)[NPX][32], const unsigned *rcp, unsigned ev, int yv, int lane) {
+#pragma unroll
+  for (int k = 0; k < NPX; k++) {
+    const unsigned ek = (ev >> (8 * k)) & 255u, nu = ek & 15u, nd = ek >> 4;
+    const blb_w qa = R[(yv + 1) & (SB_RING - 1)][k][lane], qd = R[yv & (SB_RING - 1)][k][lane];
+    const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][k][lane]) + (R[(yv + nd) & (SB_RING - 1)][k][lane] - qd);
+    const unsigned ws = nu + nd;
+    res[k] = ws == 0 ? blb_pack(qa - qd) : s4_mean_packed(vs, rcp[ws]);
+  }
+}
+template <int NPX>
 __global__ void __launch_bounds__(S4_WARPS * 32) kf_blb_stream4(uint32_t *out, const uint32_t *in, const uint8_t *extH, const uint8_t *extV, int iw, int ih, int nb,
                                                                 int strips, int chunks, int ch, size_t fs) {
+  typedef S4Smem<NPX> Smem;
+  typedef typename S4Vec<NPX>::T Vec;
+  constexpr int AC = Smem::AC, SW = 32 * NPX;                     // strip width
   extern __shared__ __align__(16) unsigned char s4_raw[];
   __shared__ unsigned rcp[16];
   if (threadIdx.x < 16) rcp[threadIdx.x] = S4_M31[threadIdx.x];
@@ -303,104 +329,104 @@ __global__ void __launch_bounds__(S4_WARPS * 32) kf_blb_stream4(uint32_t *out, c
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int wid = blockIdx.x * S4_WARPS + wp;
   if (wid >= strips * chunks * nb) return;
-  S4Smem &sm = ((S4Smem *)s4_raw)[wp];
+  Smem &sm = ((Smem *)s4_raw)[wp];
   const int sx = wid % strips, cy = (wid / strips) % chunks, z = wid / (strips * chunks);
   rd_batch_off((size_t)z * fs, out, in, extH, extV);
-  const int x0 = sx * 128, x = x0 + 4 * lane;
+  const int x0 = sx * SW, x = x0 + NPX * lane;
   const bool okx = x < iw;
-  const bool okap = (lane == 0 && sx > 0) || (lane == 1 && x0 + 128 < iw);
-  const int q4 = iw >> 2, cx = x >> 2, cap = (lane == 0 ? x0 - 4 : x0 + 128) >> 2;
+  const bool okap = (lane == 0 && sx > 0) || (lane == 1 && x0 + SW < iw);
   const int y0 = cy * ch, y1 = min(y0 + ch, ih);
   const int first = max(y0 - BLB, 0), last = min(y1 + BLB, ih);
+  const Vec *inv = (const Vec *)in;
   const uint4 *in4 = (const uint4 *)in;
-  const uint32_t *eh4 = (const uint32_t *)extH, *ev4 = (const uint32_t *)extV;
-  uint4 *out4 = (uint4 *)out;
+  Vec *outv = (Vec *)out;
+  const int qv = iw / NPX, cx = x / NPX;                          // row pitch and column in vector units
+  const int q4 = iw >> 2, cap = (lane == 0 ? x0 - 4 : x0 + SW) >> 2;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  blb_w Q[4] = {0, 0, 0, 0};
+  Vec zerov;
+  memset(&zerov, 0, sizeof(zerov));
+  blb_w Q[NPX];
 #pragma unroll
-  for (int k = 0; k < 4; k++) sm.R[first & (SB_RING - 1)][k][lane] = 0;
+  for (int k = 0; k < NPX; k++) { Q[k] = 0; sm.R[first & (SB_RING - 1)][k][lane] = 0; }
+  auto load_ext = [&](const uint8_t *e, int row) -> unsigned {
+    if (NPX == 4) return ((const uint32_t *)e)[(size_t)row * qv + cx];
+    return ((const uint16_t *)e)[(size_t)row * qv + cx];
+  };
   // two rows of look-ahead in registers
-  uint4 v0 = zero4, v1 = zero4, a0 = zero4, a1 = zero4;
+  Vec v0 = zerov, v1 = zerov;
+  uint4 a0 = zero4, a1 = zero4;
   unsigned e0 = 0, e1 = 0;
   {
-    const size_t r0 = (size_t)first * q4, r1 = r0 + q4;
-    if (okx) { v0 = in4[r0 + cx]; e0 = eh4[r0 + cx]; }
-    if (okap) a0 = in4[r0 + cap];
+    if (okx) { v0 = inv[(size_t)first * qv + cx]; e0 = load_ext(extH, first); }
+    if (okap) a0 = in4[(size_t)first * q4 + cap];
     if (first + 1 < last) {
-      if (okx) { v1 = in4[r1 + cx]; e1 = eh4[r1 + cx]; }
-      if (okap) a1 = in4[r1 + cap];
+      if (okx) { v1 = inv[(size_t)(first + 1) * qv + cx]; e1 = load_ext(extH, first + 1); }
+      if (okap) a1 = in4[(size_t)(first + 1) * q4 + cap];
     }
   }
   for (int y = first; y < last; y++) {
-    const uint4 v = v0, ap = a0;
+    const Vec v = v0;
+    const uint4 ap = a0;
     const unsigned e = e0;
     v0 = v1; a0 = a1; e0 = e1;
-    v1 = zero4; a1 = zero4; e1 = 0;
+    v1 = zerov; a1 = zero4; e1 = 0;
     if (y + 2 < last) {
-      const size_t r2 = (size_t)(y + 2) * q4;
-      if (okx) { v1 = in4[r2 + cx]; e1 = eh4[r2 + cx]; }
-      if (okap) a1 = in4[r2 + cap];
+      if (okx) { v1 = inv[(size_t)(y + 2) * qv + cx]; e1 = load_ext(extH, y + 2); }
+      if (okap) a1 = in4[(size_t)(y + 2) * q4 + cap];
     }
     const int yv = y - BLB;
     const bool doV = yv >= y0 && okx;
     unsigned ev = 0;
-    if (doV) ev = ev4[(size_t)yv * q4 + cx];
-    // ---- x pass: running sums of the 136-pixel row
-    blb_w w[4] = {blb_spread(v.x), blb_spread(v.y), blb_spread(v.z), blb_spread(v.w)};
+    if (doV) ev = load_ext(extV, yv);
+    // ---- x pass: running sums of the row (4 apron pixels, 32 * NPX pixels, 4 apron pixels)
+    uint32_t pv[NPX];
+    s4_get(v, pv);
+    blb_w w[NPX], pc[NPX + 1];
+#pragma unroll
+    for (int k = 0; k < NPX; k++) w[k] = blb_spread(pv[k]);
+    blb_w tot = w[0];
+#pragma unroll
+    for (int k = 1; k < NPX; k++) tot += w[k];
     const blb_w aw0 = blb_spread(ap.x), aw1 = blb_spread(ap.y), aw2 = blb_spread(ap.z), aw3 = blb_spread(ap.w);
-    const blb_w s1 = w[0] + w[1], s2 = s1 + w[2], s3 = s2 + w[3];
     const blb_w as1 = aw0 + aw1, as2 = as1 + aw2, as3 = as2 + aw3;
-    const blb_w S = blb_scan_up(s3, lane, 5);
+    const blb_w S = blb_scan_up(tot, lane, 5);
     const blb_w T = __shfl_sync(0xffffffffu, S, 31), LA = __shfl_sync(0xffffffffu, as3, 0);
-    blb_w pc[5];                                                    // running sums in front of the lane's pixels 0..3 and behind pixel 3
-    pc[0] = LA + S - s3; pc[1] = pc[0] + w[0]; pc[2] = pc[0] + s1; pc[3] = pc[0] + s2; pc[4] = pc[0] + s3;
-    blb_w (*P)[S4_PP] = sm.P[y & 1];
+    pc[0] = LA + S - tot;                                           // running sum in front of the lane's first pixel
 #pragma unroll
-    for (int k = 0; k < 4; k++) P[k][lane + 1] = pc[k];
-    if (lane == 0) { P[0][0] = 0; P[1][0] = aw0; P[2][0] = as1; P[3][0] = as2; }
-    if (lane == 1) { const blb_w b = LA + T; P[0][33] = b; P[1][33] = b + aw0; P[2][33] = b + as1; P[3][33] = b + as2; P[0][34] = b + as3; }
+    for (int k = 0; k < NPX; k++) pc[k + 1] = pc[k] + w[k];
+    blb_w (*P)[Smem::PP] = sm.P[y & 1];
+#pragma unroll
+    for (int k = 0; k < NPX; k++) P[k][lane + AC] = pc[k];
+    // position i of the row lives in P[i % NPX][i / NPX]
+#define S4_P(i) P[(i) % NPX][(i) / NPX]
+    if (lane == 0) { S4_P(0) = 0; S4_P(1) = aw0; S4_P(2) = as1; S4_P(3) = as2; }
+    if (lane == 1) { const blb_w b = LA + T; S4_P(4 + SW) = b; S4_P(5 + SW) = b + aw0; S4_P(6 + SW) = b + as1; S4_P(7 + SW) = b + as2; S4_P(8 + SW) = b + as3; }
+#undef S4_P
     __syncwarp();
-    blb_w h[4];
+    blb_w h[NPX];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NPX; k++) {
       const unsigned ek = (e >> (8 * k)) & 255u, nl = ek & 15u, nr = ek >> 4;
-      const unsigned j1 = k + 5 - nl, j2 = k + 4 + nr;            // positions relative to the lane's column block
-      const blb_w hs = (pc[k + 1] - P[j1 & 3][lane + (j1 >> 2)]) + (P[j2 & 3][lane + (j2 >> 2)] - pc[k]);
+      const unsigned j1 = k + 5 - nl, j2 = k + 4 + nr;            // positions relative to the lane's first column
+      const blb_w hs = (pc[k + 1] - P[j1 % NPX][lane + j1 / NPX]) + (P[j2 % NPX][lane + j2 / NPX] - pc[k]);
       const unsigned ws = nl + nr;
       h[k] = ws == 0 ? w[k] : s4_mean_spread(hs, rcp[ws]);
     }
     // ---- y pass: column running sums in the ring; row yv = y - 4 is complete once the sums behind row y are known
-    blb_w (*R)[4][32] = sm.R;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { Q[k] += h[k]; R[(y + 1) & (SB_RING - 1)][k][lane] = Q[k]; }
+    for (int k = 0; k < NPX; k++) { Q[k] += h[k]; sm.R[(y + 1) & (SB_RING - 1)][k][lane] = Q[k]; }
     if (doV) {
-      uint32_t res[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const unsigned ek = (ev >> (8 * k)) & 255u, nu = ek & 15u, nd = ek >> 4;
-        const blb_w qa = R[(yv + 1) & (SB_RING - 1)][k][lane], qd = R[yv & (SB_RING - 1)][k][lane];
-        const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][k][lane]) + (R[(yv + nd) & (SB_RING - 1)][k][lane] - qd);
-        const unsigned ws = nu + nd;
-        res[k] = ws == 0 ? blb_pack(qa - qd) : s4_mean_packed(vs, rcp[ws]);
-      }
-      out4[(size_t)yv * q4 + cx] = make_uint4(res[0], res[1], res[2], res[3]);
+      uint32_t res[NPX];
+      s4_vrow<NPX>(res, sm.R, rcp, ev, yv, lane);
+      outv[(size_t)yv * qv + cx] = s4_make(res);
     }
   }
   // rows whose downward walk is cut by the bottom of the image rather than by the strip
   if (okx) {
-    blb_w (*R)[4][32] = sm.R;
     for (int yv = max(y0, last - BLB); yv < y1; yv++) {
-      const unsigned ev = ev4[(size_t)yv * q4 + cx];
-      uint32_t res[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const unsigned ek = (ev >> (8 * k)) & 255u, nu = ek & 15u, nd = ek >> 4;
-        const blb_w qa = R[(yv + 1) & (SB_RING - 1)][k][lane], qd = R[yv & (SB_RING - 1)][k][lane];
-        const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][k][lane]) + (R[(yv + nd) & (SB_RING - 1)][k][lane] - qd);
-        const unsigned ws = nu + nd;
-        res[k] = ws == 0 ? blb_pack(qa - qd) : s4_mean_packed(vs, rcp[ws]);
-      }
-      out4[(size_t)yv * q4 + cx] = make_uint4(res[0], res[1], res[2], res[3]);
+      uint32_t res[NPX];
+      s4_vrow<NPX>(res, sm.R, rcp, load_ext(extV, yv), yv, lane);
+      outv[(size_t)yv * qv + cx] = s4_make(res);
     }
   }
 }
@@ -430,15 +456,18 @@ void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int
   }
   const uint32_t *cur = src;
   if ((iw & 3) == 0) {
+    // Four pixels per lane: 18.3 KB of shared memory per warp, 12 warps per SM.  (Measured: the two-pixel instantiation
+    // - 24 warps per SM - is 10 % slower, 8.0 vs 7.2 us per 1280x720 iteration; the kernel is bound by instruction issue at
+    // ~170 instructions per pixel, not by latency, and the scan and apron cost more per pixel with narrower strips.)
+    constexpr int npx = 4;
     static bool attr = false;
-    const size_t smem = S4_WARPS * sizeof(S4Smem);
-    if (!attr) { RD_CUDA(cudaFuncSetAttribute(kf_blb_stream4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    // 12 warps per SM fit (18.25 KB of shared memory each)
-    const int strips = rd_cdiv(iw, 128), ch = rd_strip_height(strips, nb, ih, 12, 48, 1 << 20), chunks = rd_cdiv(ih, ch);
+    const size_t smem = S4_WARPS * sizeof(S4Smem<npx>);
+    if (!attr) { RD_CUDA(cudaFuncSetAttribute(kf_blb_stream4<npx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const int strips = rd_cdiv(iw, 32 * npx), ch = rd_strip_height(strips, nb, ih, 12, 48, 1 << 20), chunks = rd_cdiv(ih, ch);
     const int blocks = rd_cdiv(strips * chunks * nb, S4_WARPS);
     for (int i = 0; i < iters; i++) {
       uint32_t *o = ((iters - i) & 1) ? dst : pong;     // the last iteration lands in dst
-      RD_LAUNCH(kf_blb_stream4, blocks, S4_WARPS * 32, smem, s, o, cur, extH, extV, iw, ih, nb, strips, chunks, ch, fs);
+      RD_LAUNCH(kf_blb_stream4<npx>, blocks, S4_WARPS * 32, smem, s, o, cur, extH, extV, iw, ih, nb, strips, chunks, ch, fs);
       cur = o;
     }
     return;
