@@ -13,6 +13,7 @@
 //                       and direction, the pass1 / pass3 combinations are folded into the consumers.
 #include "rd_common.cuh"
 #include "rd_stageA.cuh"
+#include "rd_bits.cuh"
 #include <mutex>
 #define RD_TABLE_QUAL static __device__ const
 #include "rd_tables.inc"
@@ -867,76 +868,61 @@ void rd_edge_thin_run(float *thin, const float *blurL, const uint32_t *blurP, in
 // threshold_f_f / cast_i_f (oclrect.c:262-263) + simpleJunction + simpleConnect + stringify 0 + stringify 1
 // (oclrect.cl:74-135, oclrect.c:265-272) in one kernel on byte tiles in shared memory.  Output: the cleaned 0/1 string
 // image as a byte plane.  Each stage shrinks the valid region by its stencil radius: 40x40 edge tile -> 38 -> 36 -> 34 -> 32.
-#define ST_T 32
-#define ST_A 4
-#define ST_W (ST_T + 2 * ST_A)
-__device__ __forceinline__ bool st_inside(int gx, int gy, int iw, int ih, int border) { return gx >= border && gy >= border && gx < iw - border && gy < ih - border; }
-__global__ void __launch_bounds__(256) kf_strings1(uint8_t *out, const float *thin, int iw, int ih, size_t fs) {
+// Bit-plane tile (rd_bits.cuh), apron 4 = junction 1 + connect 1 + stringify 1 + 1.
+#define KB1_A 4
+#define KB1_R (BT_PR + 2 * KB1_A)
+struct ThinPos { __device__ __forceinline__ bool operator()(float t) const { return t > 0.0f; } };
+__global__ void __launch_bounds__(256) kb_strings1(uint8_t *out, const float *thin, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, thin);
-  __shared__ uint8_t a[ST_W * ST_W], b[ST_W * ST_W];
-  const int bx = blockIdx.x * ST_T - ST_A, by = blockIdx.y * ST_T - ST_A;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
+  __shared__ bt_plane pa[KB1_R], pz[KB1_R], pt[KB1_R];
+  const int bx0 = blockIdx.x * (32 * BT_PW), by0 = blockIdx.y * BT_PR, gy0 = by0 - KB1_A;
   // edge bitmap #1 : thin > 0 (0 outside the image)
-  for (int i = tid; i < ST_W * ST_W; i += 256) {
-    const int gx = bx + i % ST_W, gy = by + i / ST_W;
-    a[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih && thin[(size_t)gy * iw + gx] > 0.0f) ? 1 : 0;
-  }
+  bt_build(pa, thin, KB1_R, bx0, gy0, iw, ih, ThinPos());
   __syncthreads();
-  // simpleJunction (oclrect.cl:74): 1 + number of set neighbours, isolated pixels and the 1-px frame -> 0
-  for (int i = tid; i < ST_W * ST_W; i += 256) {
-    const int tx = i % ST_W, ty = i / ST_W;
-    uint8_t r = 0;
-    if (tx >= 1 && ty >= 1 && tx < ST_W - 1 && ty < ST_W - 1 && st_inside(bx + tx, by + ty, iw, ih, 1) && a[i]) {
-      const int c = 1 + a[i - 1] + a[i + 1] + a[i - ST_W] + a[i + ST_W] + a[i - ST_W - 1] + a[i - ST_W + 1] + a[i + ST_W - 1] + a[i + ST_W + 1];
-      r = c == 1 ? 0 : c;
+  // simpleJunction (oclrect.cl:74): 1 + number of set neighbours, isolated pixels and the 1-px frame -> 0.
+  // pz: value != 0, pt: value == 2 (exactly one neighbour)
+  BT_TASKS(KB1_R) {
+    BT_RC;
+    uint32_t nz = 0, eq2 = 0;
+    if (r >= 1 && r < KB1_R - 1) {
+      const int gy = gy0 + r, gx0 = bx0 + 32 * (c - 1);
+      const BtNb nb = bt_neighbours<false>(pa, r, c);
+      nz = nb.centre & nb.any & (bt_rowok(gy, ih, 1) ? bt_cols(gx0, iw, 1) : 0u);
+      eq2 = nz & ~nb.ge2;
     }
-    b[i] = r;
+    pz[r][c] = nz; pt[r][c] = eq2;
   }
   __syncthreads();
   // simpleConnect (oclrect.cl:97): fill one-pixel gaps next to end pixels (value 2); 2-px frame -> 0
-  for (int i = tid; i < ST_W * ST_W; i += 256) {
-    const int tx = i % ST_W, ty = i / ST_W;
-    uint8_t r = 0;
-    if (tx >= 2 && ty >= 2 && tx < ST_W - 2 && ty < ST_W - 2 && st_inside(bx + tx, by + ty, iw, ih, 2)) {
-      r = b[i] != 0;
-      if (!r) {
-        const int w = b[i - 1], e = b[i + 1], n = b[i - ST_W], s = b[i + ST_W];
-        const int nw = b[i - ST_W - 1], ne = b[i - ST_W + 1], sw = b[i + ST_W - 1], se = b[i + ST_W + 1];
-        r = (w == 2 && e != 0) || (w != 0 && e == 2) || (n == 2 && s != 0) || (n != 0 && s == 2) || (nw == 2 && se == 2) || (ne == 2 && sw == 2) ||
-            (e == 2 && sw == 2) || (w == 2 && se == 2) || (ne == 2 && s == 2) || (nw == 2 && s == 2);
-      }
+  BT_TASKS(KB1_R) {
+    BT_RC;
+    uint32_t res = 0;
+    if (r >= 2 && r < KB1_R - 2) {
+      const int gy = gy0 + r, gx0 = bx0 + 32 * (c - 1);
+      const Bt3 tn = bt_load3(pt, r - 1, c), tm = bt_load3(pt, r, c), ts = bt_load3(pt, r + 1, c), zm = bt_load3(pz, r, c);
+      const uint32_t wT = bt_w(tm, 1), eT = bt_e(tm, 1), nT = tn.c, sT = ts.c, nwT = bt_w(tn, 1), neT = bt_e(tn, 1), swT = bt_w(ts, 1), seT = bt_e(ts, 1);
+      const uint32_t wZ = bt_w(zm, 1), eZ = bt_e(zm, 1), nZ = pz[r - 1][c], sZ = pz[r + 1][c];
+      const uint32_t pat = (wT & eZ) | (wZ & eT) | (nT & sZ) | (nZ & sT) | (nwT & seT) | (neT & swT) | (eT & swT) | (wT & seT) | (neT & sT) | (nwT & sT);
+      res = (zm.c | pat) & (bt_rowok(gy, ih, 2) ? bt_cols(gx0, iw, 2) : 0u);
     }
-    a[i] = r;
+    pa[r][c] = res;
   }
   __syncthreads();
-  // stringify mod2 = 0 then 1 (oclrect.cl:123): checkerboard removal of L-corner pixels, 1-px frame copied
-#pragma unroll
-  for (int pass = 0; pass < 2; pass++) {
-    const uint8_t *src = pass == 0 ? a : b;
-    uint8_t *dst = pass == 0 ? b : a;
-    for (int i = tid; i < ST_W * ST_W; i += 256) {
-      const int tx = i % ST_W, ty = i / ST_W;
-      const int lo = 3 + pass, hi = ST_W - 3 - pass;
-      if (tx < lo || ty < lo || tx >= hi || ty >= hi) continue;
-      const int gx = bx + tx, gy = by + ty;
-      uint8_t r = src[i];
-      if (st_inside(gx, gy, iw, ih, 1) && ((gx + gy) & 1) == pass) {
-        const bool n = src[i - ST_W] != 0, s = src[i + ST_W] != 0, w = src[i - 1] != 0, e = src[i + 1] != 0;
-        if ((n || s) && (w || e)) r = 0;
-      }
-      dst[i] = r;
-    }
-    __syncthreads();
+  // stringify mod2 = 0 then 1 (oclrect.cl:123)
+  BT_TASKS(KB1_R) {
+    BT_RC;
+    pz[r][c] = (r >= 3 && r < KB1_R - 3) ? bt_stringify(pa, r, c, bx0 + 32 * (c - 1), gy0 + r, iw, ih, 0) : 0u;
   }
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int tx = ST_A + threadIdx.x, ty = ST_A + threadIdx.y + k * 8;
-    const int gx = bx + tx, gy = by + ty;
-    if (gx < iw && gy < ih) out[(size_t)gy * iw + gx] = a[ty * ST_W + tx];
+  __syncthreads();
+  BT_TASKS(KB1_R) {
+    BT_RC;
+    pa[r][c] = (r >= 4 && r < KB1_R - 4) ? bt_stringify(pz, r, c, bx0 + 32 * (c - 1), gy0 + r, iw, ih, 1) : 0u;
   }
+  __syncthreads();
+  bt_store_bytes(out, pa, KB1_A, bx0, by0, iw, ih);
 }
 void rd_strings1_run(uint8_t *out, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_LAUNCH(kf_strings1, dim3(rd_cdiv(iw, ST_T), rd_cdiv(ih, ST_T), nb), dim3(32, 8), 0, s, out, thin, iw, ih, fs);
+  RD_LAUNCH(kb_strings1, dim3(rd_cdiv(iw, 32 * BT_PW), rd_cdiv(ih, BT_PR), nb), 256, 0, s, out, thin, iw, ih, fs);
 }
 
 // filterStrength(500) + threshold_i_i + cast_c_i (oclrect.c:277-284) and filterStrength(2500) + threshold_i_i
@@ -1069,82 +1055,98 @@ void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin
 }
 
 // simpleJunction of the strong edges + clear + mkMergeMask0 + mkMergeMask1 (oclrect.cl:74, 246-287, oclrect.c:314-321).
-// The reference scatters constants around every junction-map pixel; here a CTA computes the junction map on its 32x32
-// tile plus an apron of 8 (the largest radius), scatters into a shared-memory mask and writes the centre.  Also writes
-// the junction values themselves into `junc`, which the region-size histogram then accumulates on top of.
-#define JM_T 32
-#define JM_A 8
-#define JM_W (JM_T + 2 * JM_A)
-// half-widths of the discs d^2 < 64 and d^2 < 16, and the |dx| range of the ring 16 <= d^2 < 36, per row offset |dy|
-__constant__ const int JM_D8[8] = {7, 7, 7, 7, 6, 6, 5, 3};
-__constant__ const int JM_D4[4] = {3, 3, 3, 2};
-__constant__ const int JM_RLO[6] = {4, 4, 4, 3, 0, 0};
-__constant__ const int JM_RHI[6] = {5, 5, 5, 5, 4, 3};
-__device__ __forceinline__ unsigned long long jm_span(int lo, int hi) { return ((1ull << (hi - lo + 1)) - 1ull) << lo; }   // bits lo..hi
-__global__ void __launch_bounds__(256) kf_junction_mask(uint8_t *mask, int *junc, const int *strong, int iw, int ih, size_t fs) {
+// The reference scatters constants around every junction-map pixel; here every output pixel gathers.  Also writes the
+// junction values themselves into `junc`, which the region-size histogram then accumulates on top of.
+// Bit-plane tile (rd_bits.cuh), apron 8 (the largest radius).  The discs and the ring are unions of horizontal spans, so
+// every source row is first dilated horizontally by each half-width that occurs, and an output row is the OR of the
+// matching dilated rows above and below it.
+#define KBJ_A 8
+#define KBJ_R (BT_PR + 2 * KBJ_A)
+struct IntPos { __device__ __forceinline__ bool operator()(int v) const { return v > 0; } };
+enum { JD_E7, JD_E6, JD_E5, JD_E3, JD_A4, JD_A3, JD_A2, JD_R45, JD_R35, JD_N };
+__global__ void __launch_bounds__(256) kb_junction_mask(uint8_t *mask, int *junc, const int *strong, int iw, int ih, size_t fs) {
   rd_batch_z(fs, mask, junc, strong);
-  __shared__ uint8_t sg[(JM_W + 2) * (JM_W + 2)];             // strong bitmap, one more pixel of apron for the 3x3 count
-  __shared__ uint8_t jn[JM_W * JM_W];
-  __shared__ unsigned long long rowA[JM_W], rowE[JM_W];       // per tile row: bit x set where the junction map is non-zero / equals 2
-  __shared__ int any;
-  const int bx = blockIdx.x * JM_T - JM_A, by = blockIdx.y * JM_T - JM_A;
-  const int lane = threadIdx.x, wy = threadIdx.y, tid = wy * 32 + lane;
-  const int SW = JM_W + 2;
-  if (tid == 0) any = 0;
-  for (int i = tid; i < SW * SW; i += 256) {
-    const int gx = bx - 1 + i % SW, gy = by - 1 + i / SW;
-    sg[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih && strong[(size_t)gy * iw + gx] > 0) ? 1 : 0;
+  __shared__ bt_plane pa[KBJ_R], pz[KBJ_R], pt[KBJ_R];
+  __shared__ bt_plane cnt[4][BT_PR];
+  __shared__ bt_plane dil[JD_N][KBJ_R];
+  const int bx0 = blockIdx.x * (32 * BT_PW), by0 = blockIdx.y * BT_PR, gy0 = by0 - KBJ_A;
+  bt_build(pa, strong, KBJ_R, bx0, gy0, iw, ih, IntPos());
+  __syncthreads();
+  // simpleJunction (oclrect.cl:74): pz = junction map != 0, pt = junction map == 2; the counts of the payload rows are kept
+  BT_TASKS(KBJ_R) {
+    BT_RC;
+    uint32_t nz = 0, eq2 = 0;
+    if (r >= 1 && r < KBJ_R - 1) {
+      const int gy = gy0 + r, gx0 = bx0 + 32 * (c - 1);
+      const BtNb nb = bt_neighbours<false>(pa, r, c);
+      nz = nb.centre & nb.any & (bt_rowok(gy, ih, 1) ? bt_cols(gx0, iw, 1) : 0u);
+      eq2 = nz & ~nb.ge2;
+      if (r >= KBJ_A && r < KBJ_A + BT_PR) {
+        uint32_t k[4];
+        bt_count8(pa, r, c, k);
+#pragma unroll
+        for (int b = 0; b < 4; b++) cnt[b][r - KBJ_A][c] = k[b];
+      }
+    }
+    pz[r][c] = nz; pt[r][c] = eq2;
   }
   __syncthreads();
-  // junction map of the apron-8 tile, one warp per row, and its two bit rows
-  for (int ty = wy; ty < JM_W; ty += 8) {
-    unsigned long long a = 0, e = 0;
+  // horizontal dilations of every row: sym[d] = pixels at distance exactly d to the left or right
+  BT_TASKS(KBJ_R) {
+    BT_RC;
+    const Bt3 e = bt_load3(pt, r, c), a = bt_load3(pz, r, c);
+    uint32_t es[8], as[6];
+    es[0] = e.c; as[0] = a.c;
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-      const int tx = lane + half * 32;
-      int r = 0;
-      if (tx < JM_W) {
-        const int gx = bx + tx, gy = by + ty, c = (ty + 1) * SW + tx + 1;
-        if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && sg[c]) {
-          const int n = 1 + sg[c - 1] + sg[c + 1] + sg[c - SW] + sg[c + SW] + sg[c - SW - 1] + sg[c - SW + 1] + sg[c + SW - 1] + sg[c + SW + 1];
-          r = n == 1 ? 0 : n;
+    for (int d = 1; d < 8; d++) es[d] = bt_w(e, d) | bt_e(e, d);
+#pragma unroll
+    for (int d = 1; d < 6; d++) as[d] = bt_w(a, d) | bt_e(a, d);
+    const uint32_t e3 = es[0] | es[1] | es[2] | es[3], e5 = e3 | es[4] | es[5], e6 = e5 | es[6], e7 = e6 | es[7];
+    const uint32_t a2 = as[0] | as[1] | as[2], a3 = a2 | as[3], a4 = a3 | as[4], r45 = as[4] | as[5], r35 = as[3] | r45;
+    dil[JD_E7][r][c] = e7; dil[JD_E6][r][c] = e6; dil[JD_E5][r][c] = e5; dil[JD_E3][r][c] = e3;
+    dil[JD_A4][r][c] = a4; dil[JD_A3][r][c] = a3; dil[JD_A2][r][c] = a2; dil[JD_R45][r][c] = r45; dil[JD_R35][r][c] = r35;
+  }
+  __syncthreads();
+  // mkMergeMask0 / mkMergeMask1 (oclrect.cl:246-287): ring 16 <= d^2 < 36 around junction-map pixels := 1, then
+  // disc d^2 < 64 around end pixels (== 2) and d^2 < 16 around the others := 0.  Half-widths per |dy|:
+  // disc 8: 7 7 7 7 6 6 5 3, disc 4: 3 3 3 2, ring: |dx| in [4,5] [4,5] [4,5] [3,5] [0,4] [0,3]
+  {
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int c = 1 + (lane >> 3);
+    for (int pr = wy; pr < BT_PR; pr += 8) {
+      const int gy = by0 + pr, r = KBJ_A + pr;
+      if (gy >= ih) break;
+      uint32_t zero = 0, one = 0;
+#pragma unroll
+      for (int dy = -7; dy <= 7; dy++) {
+        const int ad = dy < 0 ? -dy : dy;
+        zero |= dil[ad <= 3 ? JD_E7 : (ad <= 5 ? JD_E6 : (ad == 6 ? JD_E5 : JD_E3))][r + dy][c];
+        if (ad <= 3) zero |= dil[ad <= 2 ? JD_A3 : JD_A2][r + dy][c];
+        if (ad <= 5) one |= dil[ad <= 2 ? JD_R45 : (ad == 3 ? JD_R35 : (ad == 4 ? JD_A4 : JD_A3))][r + dy][c];
+      }
+      const uint32_t m = one & ~zero;
+      const int gx = bx0 + 4 * lane, sh = (lane & 7) * 4;
+      const uint32_t nz = pz[r][c] >> sh, k0 = cnt[0][pr][c] >> sh, k1 = cnt[1][pr][c] >> sh, k2 = cnt[2][pr][c] >> sh, k3 = cnt[3][pr][c] >> sh;
+      int jv[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        jv[k] = ((nz >> k) & 1u) ? 1 + (int)(((k0 >> k) & 1u) | (((k1 >> k) & 1u) << 1) | (((k2 >> k) & 1u) << 2) | (((k3 >> k) & 1u) << 3)) : 0;
+      const size_t p = (size_t)gy * iw + gx;
+      if ((iw & 3) == 0) {
+        if (gx < iw) {
+          *(uint32_t *)(mask + p) = bt_nibble_bytes(m, lane);
+          *(int4 *)(junc + p) = make_int4(jv[0], jv[1], jv[2], jv[3]);
         }
-        jn[ty * JM_W + tx] = (uint8_t)r;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (gx + k < iw) { mask[p + k] = (uint8_t)((m >> (sh + k)) & 1u); junc[p + k] = jv[k]; }
       }
-      a |= (unsigned long long)__ballot_sync(0xffffffffu, r != 0) << (half * 32);
-      e |= (unsigned long long)__ballot_sync(0xffffffffu, r == 2) << (half * 32);
-    }
-    if (lane == 0) { rowA[ty] = a; rowE[ty] = e; if (a) any = 1; }
-  }
-  __syncthreads();
-  const bool some = any != 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int tx = JM_A + lane, ty = JM_A + wy + k * 8;
-    const int gx = bx + tx, gy = by + ty;
-    int m = 0;
-    if (some) {
-      bool zero = false, one = false;
-#pragma unroll
-      for (int dy = -7; dy <= 7; dy++) { const int w = JM_D8[dy < 0 ? -dy : dy]; zero |= (rowE[ty + dy] & jm_span(tx - w, tx + w)) != 0; }
-#pragma unroll
-      for (int dy = -3; dy <= 3; dy++) { const int w = JM_D4[dy < 0 ? -dy : dy]; zero |= (rowA[ty + dy] & jm_span(tx - w, tx + w)) != 0; }
-#pragma unroll
-      for (int dy = -5; dy <= 5; dy++) {
-        const int ad = dy < 0 ? -dy : dy, lo = JM_RLO[ad], hi = JM_RHI[ad];
-        const unsigned long long sel = lo == 0 ? jm_span(tx - hi, tx + hi) : (jm_span(tx - hi, tx - lo) | jm_span(tx + lo, tx + hi));
-        one |= (rowA[ty + dy] & sel) != 0;
-      }
-      m = zero ? 0 : (one ? 1 : 0);
-    }
-    if (gx < iw && gy < ih) {
-      mask[(size_t)gy * iw + gx] = (uint8_t)m;
-      junc[(size_t)gy * iw + gx] = some ? jn[ty * JM_W + tx] : 0;
     }
   }
 }
 void rd_junction_mask_run(uint8_t *mask, int *junc, const int *strong, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_LAUNCH(kf_junction_mask, dim3(rd_cdiv(iw, JM_T), rd_cdiv(ih, JM_T), nb), dim3(32, 8), 0, s, mask, junc, strong, iw, ih, fs);
+  RD_LAUNCH(kb_junction_mask, dim3(rd_cdiv(iw, 32 * BT_PW), rd_cdiv(ih, BT_PR), nb), 256, 0, s, mask, junc, strong, iw, ih, fs);
 }
 
 // despeckle2(16) in its Jacobi form + markBoundary (oclrect.cl:348-390, oclrect.c:336-340): region labels with an apron

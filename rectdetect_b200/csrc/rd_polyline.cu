@@ -13,6 +13,7 @@
 //   - refine_pass3 computes all shared vertices from the unmodified list before writing any (Q5).
 #include "rd_common.cuh"
 #include "rd_stageA.cuh"
+#include "rd_bits.cuh"
 
 struct oclpolyline_t { uint32_t magic; int ordinal; };
 #define POLY_MAGIC 0x808eae03u
@@ -712,93 +713,87 @@ cl_event oclpolyline_execute(oclpolyline_t *thiz, cl_mem lsList, int lsListSize,
 //   - the foreground of the string labelling is gathered into a compact pixel list, and end finding, numbering, the
 //     loop breaker, size filter and relabelling only touch listed pixels (a few % of the frame) instead of sweeping planes;
 //   - ids are handed out in raster order of the root pixels by ranking the (few hundred) roots against each other.
-#define S2_T 32
-#define S2_A 6
-#define S2_W (S2_T + 2 * S2_A)
-__global__ void __launch_bounds__(256) kf_strings2(uint8_t *out, int *copyOut, int *list, const int *strong, int ring, int iw, int ih, size_t fs) {
+// Bit-plane tile (rd_bits.cuh), apron 6 = junction 1 + connect 2 + stringify 1 + 1 + removeBranch 1.
+#define KB2_A 6
+#define KB2_R (BT_PR + 2 * KB2_A)
+struct IntNonZero { __device__ __forceinline__ bool operator()(int v) const { return v != 0; } };
+__global__ void __launch_bounds__(256) kb_strings2(uint8_t *out, int *copyOut, int *list, const int *strong, int ring, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, copyOut, list, strong);
-  __shared__ uint8_t a[S2_W * S2_W], b[S2_W * S2_W];
-  const int bx = blockIdx.x * S2_T - S2_A, by = blockIdx.y * S2_T - S2_A;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) list[0] = 0;
-  for (int i = tid; i < S2_W * S2_W; i += 256) {
-    const int gx = bx + i % S2_W, gy = by + i / S2_W;
-    a[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih && strong[(size_t)gy * iw + gx] != 0) ? 1 : 0;
+  __shared__ bt_plane pa[KB2_R], pz[KB2_R], pt[KB2_R];
+  const int bx0 = blockIdx.x * (32 * BT_PW), by0 = blockIdx.y * BT_PR, gy0 = by0 - KB2_A;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) list[0] = 0;
+  {
+    // the copy for the next frame's strength accumulator is taken from the payload rows only (every pixel exactly once)
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    if (copyOut)
+      for (int pr = wy; pr < BT_PR; pr += 8) {
+        const int gy = by0 + pr;
+        if (gy >= ih) break;
+        for (int k = 0; k < BT_PW; k++) { const int gx = bx0 + 32 * k + lane; if (gx < iw) copyOut[(size_t)gy * iw + gx] = strong[(size_t)gy * iw + gx]; }
+      }
   }
+  bt_build(pa, strong, KB2_R, bx0, gy0, iw, ih, IntNonZero());
   __syncthreads();
-  // simpleJunction (oclpolyline.cl:66)
-  for (int i = tid; i < S2_W * S2_W; i += 256) {
-    const int tx = i % S2_W, ty = i / S2_W;
-    const int gx = bx + tx, gy = by + ty;
-    uint8_t r = 0;
-    if (tx >= 1 && ty >= 1 && tx < S2_W - 1 && ty < S2_W - 1 && gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && a[i]) {
-      const int c = 1 + a[i - 1] + a[i + 1] + a[i - S2_W] + a[i + S2_W] + a[i - S2_W - 1] + a[i - S2_W + 1] + a[i + S2_W - 1] + a[i + S2_W + 1];
-      r = c == 1 ? 0 : c;
+  // simpleJunction (oclpolyline.cl:66): pz = value != 0, pt = value == 2
+  BT_TASKS(KB2_R) {
+    BT_RC;
+    uint32_t nz = 0, eq2 = 0;
+    if (r >= 1 && r < KB2_R - 1) {
+      const int gy = gy0 + r, gx0 = bx0 + 32 * (c - 1);
+      const BtNb nb = bt_neighbours<false>(pa, r, c);
+      nz = nb.centre & nb.any & (bt_rowok(gy, ih, 1) ? bt_cols(gx0, iw, 1) : 0u);
+      eq2 = nz & ~nb.ge2;
     }
-    b[i] = r;
+    pz[r][c] = nz; pt[r][c] = eq2;
   }
   __syncthreads();
   // simpleConnect (oclpolyline.cl:89): bridges one-pixel gaps between two end pixels; the 2-px frame keeps what was there (`ring`)
-  for (int i = tid; i < S2_W * S2_W; i += 256) {
-    const int tx = i % S2_W, ty = i / S2_W;
-    const int gx = bx + tx, gy = by + ty;
-    uint8_t r = 0;
-    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) {
-      if (gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2) r = (uint8_t)ring;
-      else if (tx >= 3 && ty >= 3 && tx < S2_W - 3 && ty < S2_W - 3) {
-        r = b[i] != 0;
-        if (!r) {
-          const int W1 = S2_W, W2 = 2 * S2_W;
-          r = (b[i - 2] != 0 && b[i - 1] == 2 && b[i + 1] == 2 && b[i + 2] != 0) ||
-              (b[i - W2] != 0 && b[i - W1] == 2 && b[i + W1] == 2 && b[i + W2] != 0) ||
-              (b[i - W2 - 2] != 0 && b[i - W1 - 1] == 2 && b[i + W1 + 1] == 2 && b[i + W2 + 2] != 0) ||
-              (b[i - W2 + 2] != 0 && b[i - W1 + 1] == 2 && b[i + W1 - 1] == 2 && b[i + W2 - 2] != 0) ||
-              (b[i + 2] != 0 && b[i + 1] == 2 && b[i + W1 - 1] == 2 && b[i + W1 - 2] != 0) ||
-              (b[i - 2] != 0 && b[i - 1] == 2 && b[i + W1 + 1] == 2 && b[i + W1 + 2] != 0) ||
-              (b[i - W2 + 1] != 0 && b[i - W1 + 1] == 2 && b[i + W1] == 2 && b[i + W2] != 0) ||
-              (b[i - W2 - 1] != 0 && b[i - W1 - 1] == 2 && b[i + W1] == 2 && b[i + W2] != 0);
-        }
-      }
+  BT_TASKS(KB2_R) {
+    BT_RC;
+    uint32_t res = 0;
+    if (r >= 3 && r < KB2_R - 3) {
+      const int gy = gy0 + r, gx0 = bx0 + 32 * (c - 1);
+      const uint32_t inimg = (gy >= 0 && gy < ih) ? bt_cols(gx0, iw, 0) : 0u, in2 = bt_rowok(gy, ih, 2) ? bt_cols(gx0, iw, 2) : 0u;
+      const Bt3 z2n = bt_load3(pz, r - 2, c), zm = bt_load3(pz, r, c), zs = bt_load3(pz, r + 1, c), z2s = bt_load3(pz, r + 2, c);
+      const Bt3 tn = bt_load3(pt, r - 1, c), tm = bt_load3(pt, r, c), ts = bt_load3(pt, r + 1, c);
+      // Z(dx, dy) / T(dx, dy): the plane at (x + dx, y + dy)
+      const uint32_t p1 = bt_w(zm, 2) & bt_w(tm, 1) & bt_e(tm, 1) & bt_e(zm, 2);
+      const uint32_t p2 = z2n.c & tn.c & ts.c & z2s.c;
+      const uint32_t p3 = bt_w(z2n, 2) & bt_w(tn, 1) & bt_e(ts, 1) & bt_e(z2s, 2);
+      const uint32_t p4 = bt_e(z2n, 2) & bt_e(tn, 1) & bt_w(ts, 1) & bt_w(z2s, 2);
+      const uint32_t p5 = bt_e(zm, 2) & bt_e(tm, 1) & bt_w(ts, 1) & bt_w(zs, 2);
+      const uint32_t p6 = bt_w(zm, 2) & bt_w(tm, 1) & bt_e(ts, 1) & bt_e(zs, 2);
+      const uint32_t p7 = bt_e(z2n, 1) & bt_e(tn, 1) & ts.c & z2s.c;
+      const uint32_t p8 = bt_w(z2n, 1) & bt_w(tn, 1) & ts.c & z2s.c;
+      res = (in2 & (zm.c | p1 | p2 | p3 | p4 | p5 | p6 | p7 | p8)) | (ring ? (inimg & ~in2) : 0u);
     }
-    a[i] = r;
+    pa[r][c] = res;
   }
   __syncthreads();
   // stringify 0, 1 (oclpolyline.cl:112)
-#pragma unroll
-  for (int pass = 0; pass < 2; pass++) {
-    const uint8_t *src = pass == 0 ? a : b;
-    uint8_t *dst = pass == 0 ? b : a;
-    for (int i = tid; i < S2_W * S2_W; i += 256) {
-      const int tx = i % S2_W, ty = i / S2_W;
-      const int lo = 4 + pass, hi = S2_W - 4 - pass;
-      if (tx < lo || ty < lo || tx >= hi || ty >= hi) continue;
-      const int gx = bx + tx, gy = by + ty;
-      uint8_t r = src[i];
-      if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && ((gx + gy) & 1) == pass) {
-        const bool n = src[i - S2_W] != 0, s = src[i + S2_W] != 0, w = src[i - 1] != 0, e = src[i + 1] != 0;
-        if ((n || s) && (w || e)) r = 0;
-      }
-      dst[i] = r;
-    }
-    __syncthreads();
+  BT_TASKS(KB2_R) {
+    BT_RC;
+    pz[r][c] = (r >= 4 && r < KB2_R - 4) ? bt_stringify(pa, r, c, bx0 + 32 * (c - 1), gy0 + r, iw, ih, 0) : 0u;
   }
+  __syncthreads();
+  BT_TASKS(KB2_R) {
+    BT_RC;
+    pa[r][c] = (r >= 5 && r < KB2_R - 5) ? bt_stringify(pz, r, c, bx0 + 32 * (c - 1), gy0 + r, iw, ih, 1) : 0u;
+  }
+  __syncthreads();
   // removeBranch (oclpolyline.cl:126): only pixels with at most two neighbours stay
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int tx = S2_A + threadIdx.x, ty = S2_A + threadIdx.y + k * 8;
-    const int gx = bx + tx, gy = by + ty;
-    if (gx >= iw || gy >= ih) continue;
-    const int i = ty * S2_W + tx;
-    uint8_t r = 0;
-    if (gx >= 1 && gy >= 1 && gx < iw - 1 && gy < ih - 1 && a[i]) {
-      const int c = (a[i - 1] != 0) + (a[i + 1] != 0) + (a[i - S2_W] != 0) + (a[i + S2_W] != 0) + (a[i - S2_W - 1] != 0) + (a[i - S2_W + 1] != 0) +
-                    (a[i + S2_W - 1] != 0) + (a[i + S2_W + 1] != 0);
-      r = c <= 2 ? 1 : 0;
+  BT_TASKS(KB2_R) {
+    BT_RC;
+    uint32_t res = 0;
+    if (r >= KB2_A && r < KB2_R - KB2_A) {
+      const int gy = gy0 + r, gx0 = bx0 + 32 * (c - 1);
+      const BtNb nb = bt_neighbours<true>(pa, r, c);
+      res = nb.centre & ~nb.ge3 & (bt_rowok(gy, ih, 1) ? bt_cols(gx0, iw, 1) : 0u);
     }
-    const size_t p = (size_t)gy * iw + gx;
-    out[p] = r;
-    if (copyOut) copyOut[p] = strong[p];
+    pz[r][c] = res;
   }
+  __syncthreads();
+  bt_store_bytes(out, pz, KB2_A, bx0, by0, iw, ih);
 }
 
 // ---- list kernels: grid-stride over the compact list of string pixels (frame = blockIdx.y) ----
@@ -944,7 +939,7 @@ void rd_polyline_fast(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in,
   int *nextA = t3, *prevA = t4, *nextB = tmpBig, *prevB = tmpBig + n, *flags1 = tmpBig + 2 * (size_t)n;
   const dim3 lg(LIST_BLOCKS, nb);
   // step 1 : string clean-up, one kernel (also zeroes the list counter and copies the bitmap for the next frame)
-  RD_LAUNCH(kf_strings2, dim3(rd_cdiv(iw, S2_T), rd_cdiv(ih, S2_T), nb), dim3(32, 8), 0, s, str, copyOut, list, in, 1, iw, ih, fs);
+  RD_LAUNCH(kb_strings2, dim3(rd_cdiv(iw, 32 * BT_PW), rd_cdiv(ih, BT_PR), nb), 256, 0, s, str, copyOut, list, in, 1, iw, ih, fs);
   // step 2 : string id = smallest pixel index; foreground gathered into `list`
   rd_label8x_u8_list(lsIdOut, str, t1, list, 0, iw, ih, nb, fs, s);
   // step 3 : closed loops lose their root pixel
