@@ -23,8 +23,9 @@
 #define L_N 4
 #define L_NE 8
 #define L_BG 0x80
+#define L_ROOT 0x40                     // the pixel is the root of its component inside its tile
 
-// ---- link functors.  load(x, y) reads what the predicate needs to know about ONE pixel (each pixel of the tile and
+// ---- link functors.  load(p) reads what the predicate needs to know about ONE pixel (p = y * iw + x) (each pixel of the tile and
 // of its one-pixel apron above / beside is loaded once into shared memory); link(...) then decides, from the staged
 // values of a pixel (c) and of its W, NW, N, NE neighbours, which of the four belong to the same component. ----
 template <class PIX>
@@ -32,7 +33,7 @@ struct Link8x {                       // label8xMain_int_int: equal value, value
   typedef int V;
   const PIX *pix; int bgc, iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix); }
-  __device__ __forceinline__ V load(int x, int y) const { return (int)pix[(size_t)y * iw + x]; }
+  __device__ __forceinline__ V load(int p) const { return (int)pix[p]; }
   __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
     if (c == bgc) return L_BG;
     unsigned m = 0;
@@ -49,7 +50,7 @@ struct LinkPl {                       // labelpl_main: numbers (+1) both non-zer
   typedef int V;
   const int *num; int iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, num); }
-  __device__ __forceinline__ V load(int x, int y) const { return num[(size_t)y * iw + x]; }
+  __device__ __forceinline__ V load(int p) const { return num[p]; }
   __device__ __forceinline__ static bool con(int a, int b) { return b != 0 && abs(a - b) <= 1; }
   __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
     if (c == 0) return L_BG;
@@ -68,8 +69,7 @@ struct LinkMerge {                    // labelxPreprocess + labelMergeMain, cano
   struct V { uint32_t pix; uint32_t fl; };        // fl bit 0: mask != 0, bit 1: edge <= 0
   const uint32_t *pix; const MASK *mask; const int *edge; int iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix, mask, edge); }
-  __device__ __forceinline__ V load(int x, int y) const {
-    const size_t p = (size_t)y * iw + x;
+  __device__ __forceinline__ V load(int p) const {
     V v; v.pix = pix[p]; v.fl = (mask[p] != 0 ? 1u : 0u) | (edge[p] <= 0 ? 2u : 0u);
     return v;
   }
@@ -102,6 +102,13 @@ __device__ __forceinline__ int sm_find(volatile int *L, int x) {
     x = g;
     p = L[x];
   }
+  return x;
+}
+// read-only walk, for the phase in which every run start is being pointed at its root: a concurrent path-halving write
+// could put an older ancestor back over a root that was just stored
+__device__ __forceinline__ int sm_find_ro(const volatile int *L, int x) {
+  int p = L[x];
+  while (p != x) { x = p; p = L[x]; }
   return x;
 }
 __device__ __forceinline__ void sm_unite(int *L, int a, int b) {
@@ -152,31 +159,36 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
   const unsigned lt = (1u << lx) - 1u;
   if (threadIdx.x == 0) { npairs = 0; nstarts = 0; }
   const bool okx = x < iw, okw = x0 > 0, oke = x0 + TW < iw;
+  const bool fullTile = x0 + TW <= iw && y0 + TH <= ih;
+  int p = (y0 + wy * 4 - 1) * iw + x;                              // linear index of (x, row above the warp's first row)
   V up = V(), upW = V(), upE = V();
   {
     const int yu = y0 + wy * 4 - 1;
     if (yu >= 0 && yu < ih) {
-      if (okx) up = f.load(x, yu);
+      if (okx) up = f.load(p);
       upW = ccl_up1(up); upE = ccl_down1(up);
-      if (lx == 0 && okw) upW = f.load(x0 - 1, yu);
-      if (lx == 31 && oke) upE = f.load(x0 + TW, yu);
+      if (lx == 0 && okw) upW = f.load(p - 1);
+      if (lx == 31 && oke) upE = f.load(p + 1);
     }
   }
+  // what this thread has seen of the tile: bit 0 = not all background, bit 1 = not "one component hanging on the first pixel"
+  unsigned seen = fullTile ? 0u : 2u;
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int ly = wy * 4 + k, y = y0 + ly, i = ly * TW + lx;
+    p += iw;
     V c = V(), w = V(), e = V();
     if (y < ih) {
-      if (okx) c = f.load(x, y);
+      if (okx) c = f.load(p);
       w = ccl_up1(c); e = ccl_down1(c);
-      if (lx == 0 && okw) w = f.load(x0 - 1, y);
-      if (lx == 31 && oke) e = f.load(x0 + TW, y);
+      if (lx == 0 && okw) w = f.load(p - 1);
+      if (lx == 31 && oke) e = f.load(p + 1);
     }
     unsigned m = L_BG;
     if (okx && y < ih) {
       const unsigned full = f.link(c, w, upW, up, upE, x, y);
-      links[(size_t)y * iw + x] = (uint8_t)full;
+      links[p] = (uint8_t)full;
       m = full;
       if (lx == 0) m &= ~(L_W | L_NW);                             // neighbours outside the tile are the seam kernel's business
       if (lx == TW - 1) m &= ~L_NE;
@@ -190,9 +202,20 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
     if (lx == 0) base = atomicAdd(&nstarts, __popc(starts));
     base = __shfl_sync(0xffffffffu, base, 0);
     if ((starts >> lx) & 1u) starts_list[base + __popc(starts & lt)] = (unsigned short)i;
+    if (m != L_BG) seen |= 1u;
+    if ((m & L_BG) || starts != 1u || (ly > 0 && !(m & L_N))) seen |= 2u;
     up = c; upW = w; upE = e;
   }
-  __syncthreads();
+  const int notEmpty = __syncthreads_or((int)(seen & 1u)), notUniform = __syncthreads_or((int)(seen & 2u));
+  if (!notEmpty) return;                                           // nothing but background: the flatten kernel fills the tile
+  if (!notUniform) {
+    // a single run per row, every row linked to the one above: one component, rooted at the first pixel
+    const int root = y0 * iw + x0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) label[(y0 + wy * 4 + k) * iw + x] = root;
+    if (threadIdx.x == 0) links[root] |= L_ROOT;
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int i = (wy * 4 + k) * TW + lx;
@@ -217,14 +240,18 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
   __syncthreads();
   for (int t = threadIdx.x, n = npairs; t < n; t += CCL_THREADS) { const unsigned pr = pairs[t]; sm_unite(L, (int)(pr >> 16), (int)(pr & 0xffffu)); }
   __syncthreads();
-  for (int t = threadIdx.x, n = nstarts; t < n; t += CCL_THREADS) { const int i = starts_list[t]; L[i] = sm_find(L, i); }
+  for (int t = threadIdx.x, n = nstarts; t < n; t += CCL_THREADS) {
+    const int i = starts_list[t], r = sm_find_ro(L, i);
+    L[i] = r;
+    if (r == i && !(M[i] & L_BG)) links[(y0 + (i >> 5)) * iw + x0 + (i & 31)] |= L_ROOT;      // this CTA wrote the byte before the barriers
+  }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int ly = wy * 4 + k, y = y0 + ly, i = ly * TW + lx;
     if (okx && y < ih) {
       const int r = L[L[i]];
-      label[(size_t)y * iw + x] = (y0 + (r >> 5)) * iw + x0 + (r & 31);
+      label[y * iw + x] = (y0 + (r >> 5)) * iw + x0 + (r & 31);
     }
   }
 }
@@ -255,16 +282,30 @@ __global__ void __launch_bounds__(96) k_ccl_seams(int *label, const uint8_t *lin
   }
 }
 
-// final labels.  mode 0: background -> bgval, others -> root.
+// Final labels, in two steps.  k_ccl_roots: the tile roots (marked L_ROOT; a few per tile) walk to their final root and
+// remember it.  Every other pixel still points at its tile root - the seam unions only ever re-parent roots - so the
+// flatten kernels below need exactly one hop: label[label[p]].  (For a tile root, label[p] is already final and the final
+// root points at itself.)  Rewriting label[] in place is safe: a tile root is rewritten with the value it already holds.
+__global__ void k_ccl_roots(int *label, const uint8_t *links, int n, size_t fs) {
+  rd_batch_y(fs, label, links);
+  const int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (p4 >= n) return;
+  unsigned m4;
+  if (p4 + 3 < n) m4 = *(const uint32_t *)(links + p4);
+  else { m4 = 0; for (int k = 0; p4 + k < n; k++) m4 |= (unsigned)links[p4 + k] << (8 * k); }
+  if (!(m4 & 0x40404040u)) return;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if ((m4 >> (8 * k)) & L_ROOT) label[p4 + k] = rd_uf_find(label, p4 + k);
+}
+// background -> bgval, others -> root
 __global__ void k_ccl_flatten(int *label, const uint8_t *links, int bgval, int n, size_t fs) {
   rd_batch_y(fs, label, links);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (links[p] & L_BG) { label[p] = bgval; return; }
-  label[p] = rd_uf_find(label, p);
+  label[p] = __ldcg(label + __ldcg(label + p));
 }
-// The flatten above rewrites label[] while other threads still walk it; every intermediate value is an ancestor of
-// the pixel (parents only ever move towards the root), so concurrent walks stay correct.
 
 // flatten + compaction: foreground pixels are also appended to `list` (list[0] = count, entries from 1, any order)
 __global__ void k_ccl_flatten_list(int *label, const uint8_t *links, int *list, int bgval, int n, size_t fs) {
@@ -273,7 +314,7 @@ __global__ void k_ccl_flatten_list(int *label, const uint8_t *links, int *list, 
   bool fg = false;
   if (p < n) {
     if (links[p] & L_BG) label[p] = bgval;
-    else { label[p] = rd_uf_find(label, p); fg = true; }
+    else { label[p] = __ldcg(label + __ldcg(label + p)); fg = true; }
   }
   const unsigned m = __ballot_sync(0xffffffffu, fg);
   if (m == 0) return;
@@ -289,7 +330,7 @@ __global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   const int p = y * iw + x;
-  if (x > 0 && y > 0 && x < iw - 1 && y < ih - 1) { out[p] = rd_uf_find(label, p); return; }
+  if (x > 0 && y > 0 && x < iw - 1 && y < ih - 1) { out[p] = __ldcg(label + __ldcg(label + p)); return; }
   const uint32_t v = pix[p];
   int l = p;
   if (y > 0 && pix[p - iw] == v) l = p - iw;
@@ -301,6 +342,7 @@ template <class LinkFn>
 static void ccl_core(int *label, uint8_t *links, LinkFn f, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   RD_LAUNCH(k_ccl_tile<LinkFn>, rd_gz(dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH)), nb), CCL_THREADS, 0, s, label, links, f, iw, ih, fs);
   RD_LAUNCH(k_ccl_seams, dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH), nb), 96, 0, s, label, links, iw, ih, fs);
+  RD_LAUNCH(k_ccl_roots, rd_gy(rd_cdiv(rd_cdiv(iw * ih, 4), 256), nb), 256, 0, s, label, (const uint8_t *)links, iw * ih, fs);
 }
 
 // scratch: iw*ih bytes
