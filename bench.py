@@ -36,10 +36,21 @@ TAN_AOV = math.tan(math.radians(36.0))
 KERNEL_BYTES_PER_PX = {
     # production schedule
     "kf_bgr2plab4": 7, "kf_bgr2plab1": 7, "kf_iir_h3": 28, "kf_iir_mid3": 40, "kf_iir_v3": 36, "kf_iir_fin3": 52, "kf_edge_thin": 12,
-    "kf_strings1": 5, "k_ccl_tile<LinkFn>": 9, "k_ccl_seams": 1, "k_ccl_flatten": 9, "k_ccl_flatten_list": 9, "k_ccl_flatten_merge": 12,
-    "kr_calcStrength": 8, "kf_filter_masks": 9, "kf_blb_extents": 3, "kf_blb_stream": 10, "kf_quant_despeckle": 12, "kf_junction_mask": 9,
-    "kf_calcSize": 4, "kf_despeckle2_boundary": 8, "kf_strings2": 9, "k_clear4": 4, "k_clear": 4, "k_copy4": 8,
+    "kb_strings1": 5, "k_ccl_tile<LinkFn>": 9, "k_ccl_seams": 1, "k_ccl_roots": 1, "k_ccl_flatten": 9, "k_ccl_flatten_list": 9, "k_ccl_flatten_merge": 12,
+    "kr_calcStrength": 8, "kf_filter_masks": 9, "kf_blb_extents_s": 3, "kf_blb_stream4<npx>": 10, "kf_blb_stream": 10, "kf_quant_despeckle": 12,
+    "kb_junction_mask": 9, "kf_calcSize": 4, "kf_despeckle2_boundary": 8, "kb_strings2": 9, "k_clear4": 4, "k_clear": 4, "k_copy4": 8,
 }
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per FRAME of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json,
+    dram__bytes_read.sum + dram__bytes_write.sum per launch / frames per launch), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t["kernels"].get(kernel)
+        return (float(e["dram_bytes_per_frame"]), t.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 def synth_batch(iw, ih, first_seed, count, pinned):
@@ -143,8 +154,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--w", type=int, default=1280)
     ap.add_argument("--h", type=int, default=720)
-    ap.add_argument("--frames", type=int, default=192, help="frames per GPU per step")
-    ap.add_argument("--nctx", type=int, default=6, help="pipeline objects (streams) per GPU")
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--nctx", type=int, default=8, help="pipeline objects (streams) per GPU")
     ap.add_argument("--fpl", type=int, default=8, help="frames per kernel launch")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample")
@@ -221,9 +232,21 @@ def main():
     ms_val, launches, rects, _ = timed(True, args.steps)
     ms_e2e, _, rects_e2e, _ = timed(False, args.steps)
     clocks = sampler.finish() if sampler else None
-    # per-kernel device time (CUDA events on the launching streams) over the same steps, for the roofline of the top kernel;
-    # a separate pass so that the event records do not sit inside the headline timings
-    ms_prof, _, _, prof = timed(True, args.steps, profile=True)
+    wait_ms, tail_ms = batch.stage_ms()
+    # per-kernel device time for the roofline of the top kernel: CUDA events around every launch on the launching stream
+    # (rd_profile_*), in a separate pass over the same frames through ONE pipeline object, so that each kernel is timed
+    # alone on the device (in the headline passes the streams of the pipeline objects overlap) and the event records do not
+    # sit inside the headline timings
+    solo = rd.Batch(local_rank, iw, ih, nctx=1, frames_per_launch=args.fpl)
+    nsolo = min(hi - lo, 4 * args.fpl)
+    for _ in range(2):
+        solo.run(dev_frames.data_ptr(), frame_bytes, ws, nsolo, TAN_AOV, on_device=True, want_rects=False)
+    torch.cuda.synchronize()
+    rd.api.profile_start(None)
+    solo.run(dev_frames.data_ptr(), frame_bytes, ws, nsolo, TAN_AOV, on_device=True, want_rects=False)
+    torch.cuda.synchronize()
+    prof = rd.api.profile_stop()
+    solo.close()
 
     pix_per_step = total_frames * iw * ih
     value = pix_per_step * args.steps / (ms_val * 1e-3) / 1e6
@@ -242,11 +265,15 @@ def main():
         total_kernel_ms = sum(v[1] for v in prof.values())
         bpp = KERNEL_BYTES_PER_PX.get(tname)
         per_launch_ms = tms / tcnt
-        achieved = (bpp * iw * ih / (per_launch_ms * 1e-3) / 1e9) if bpp else None
+        fpl_eff = min(args.fpl, nsolo)
+        alg_bytes = (bpp * iw * ih * fpl_eff) if bpp else None
+        achieved = (alg_bytes / (per_launch_ms * 1e-3) / 1e9) if bpp else None
+        traffic_pf, traffic_src = ncu_traffic(tname)
         roofline = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": (bpp * iw * ih) if bpp else None,
-                    "avg_launch_us": per_launch_ms * 1e3, "share_of_kernel_time": tms / total_kernel_ms,
-                    "top5": [[k, v[0], round(v[1], 3)] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:5]],
+                    "traffic": (traffic_pf * fpl_eff) if traffic_pf else None, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "frames_per_launch": fpl_eff, "avg_launch_us": per_launch_ms * 1e3,
+                    "share_of_kernel_time": tms / total_kernel_ms, "kernel_time_us_per_frame": total_kernel_ms * 1e3 / nsolo,
+                    "top5_us_per_frame": [[k, round(v[1] * 1e3 / nsolo, 2)] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:5]],
                     "pipeline_algorithmic_bytes_per_px": 43, "pipeline_frac": (43.0 * value * 1e6 / 1e9) / peak}
         cpu = None
         if not args.no_cpu_baseline:
@@ -265,7 +292,8 @@ def main():
             "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": total_frames * 128 * 1024,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "rects_per_step": nrect, "value_and_e2e_rects_identical": bool(same), "profiled_pass_ms_per_step": ms_prof / args.steps,
+            "rects_per_step": nrect, "value_and_e2e_rects_identical": bool(same),
+            "host": {"driver_threads": args.nctx, "wait_for_device_ms_last_step": wait_ms, "host_tail_ms_last_step": tail_ms, "host_cores": os.cpu_count()},
         }
         print(json.dumps(line), flush=True)
     batch.close()

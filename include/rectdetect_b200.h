@@ -203,7 +203,8 @@ void rd_batch_run(rd_batch *b, const uint8_t *frames, size_t frame_stride, int w
 /* device-resident variant: frames already in device memory (read in place).  out == NULL runs the device stages and the
  * read-back of the compact record only (no host tail). */
 void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out);
-/* seconds spent per stage (A,B,C,D device time from CUDA events; tail = host) in the last rd_batch_run */
+/* host-side accounting of the last rd_batch_run, summed over the pipeline objects' driver threads: out_ms[0] = time spent
+ * waiting for the device, out_ms[4] = wall time of the host-tail phases (executeCPUTask); [1..3] are reserved (0) */
 void rd_batch_stage_ms(rd_batch *b, double out_ms[5]);
 
 #ifdef __cplusplus

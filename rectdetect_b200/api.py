@@ -268,6 +268,12 @@ class Batch:
             return None
         return [rects_from_ptr(p) for p in out]
 
+    def stage_ms(self):
+        """host-side accounting of the last run: (ms the driver threads waited for the device, ms of host-tail phases)"""
+        v = (C.c_double * 5)()
+        lib().rd_batch_stage_ms(self.h, v)
+        return float(v[0]), float(v[4])
+
     def close(self):
         if self.h:
             lib().rd_batch_destroy(self.h)

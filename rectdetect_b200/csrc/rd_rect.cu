@@ -11,6 +11,12 @@
 //     as executeCPUTask does (oclrect.c:1066-1098), the 15 sample points of every live line segment, and emits for
 //     each the region id under it and the vote-table entry of that (segment, region) pair.  The host tail then needs
 //     (n+1) x 416 bytes instead of the reference's 9 planes (33 MB at 1280x720).
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 #include "rd_common.cuh"
 #include "rd_stageA.cuh"
@@ -408,6 +414,7 @@ struct oclrect_t {
   int nextPageToEnqueue, nextPageToPoll;
   cudaEvent_t events[2];
   int pending[2];                       // number of frames in flight on the page
+  double wait_ms, tail_ms;              // host time spent waiting for the device / in executeCPUTask since the last reset
 };
 #define FIRST_CHUNK ((size_t)128 * 1024)
 
@@ -643,7 +650,7 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   for (int p = 0; p < 2; p++) {
     o->hostImg[p] = (uint8_t *)allocatePinnedMemory((size_t)iw * ih * 4 * nb, NULL, NULL);
     o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(bb * nb, NULL, NULL);
-    RD_CUDA(cudaEventCreateWithFlags(&o->events[p], cudaEventDisableTiming));
+    RD_CUDA(cudaEventCreateWithFlags(&o->events[p], cudaEventDisableTiming | cudaEventBlockingSync));   // waiting host threads sleep: the cores run host tails
   }
   rd_quant_tables_init();
   RD_CUDA(cudaDeviceSynchronize());
@@ -682,14 +689,89 @@ static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, 
   o->pending[page] = count;
 }
 
+// ---- host tails of a chunk run in parallel --------------------------------------------------------------------------
+// The tails of the frames of one chunk are independent (executeCPUTask reads one frame's record), and a chunk of frames
+// arrives at once, so the host threads that drive the pipelines hand them to a process-wide pool instead of walking them
+// one by one: tail throughput then scales with the host cores, not with the number of pipeline objects.
+class TailPool {
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  std::vector<std::thread> th_;
+  bool stop_ = false;
+  void loop() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        f = std::move(q_.front());
+        q_.pop_front();
+      }
+      f();
+    }
+  }
+ public:
+  explicit TailPool(int n) { for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); }); }
+  ~TailPool() {
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  // fn(0) .. fn(n-1), the caller takes part; returns when all are done
+  void run_all(int n, const std::function<void(int)> &fn) {
+    if (n <= 0) return;
+    int left = n - 1;
+    std::mutex dm;
+    std::condition_variable dcv;
+    if (n > 1) {
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        for (int i = 1; i < n; i++)
+          q_.push_back([&, i] {
+            fn(i);
+            std::lock_guard<std::mutex> dg(dm);
+            if (--left == 0) dcv.notify_one();
+          });
+      }
+      cv_.notify_all();
+    }
+    fn(0);
+    // help with whatever is queued (own or other chunks' tails) instead of sleeping
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        if (q_.empty()) break;
+        f = std::move(q_.front());
+        q_.pop_front();
+      }
+      f();
+    }
+    std::unique_lock<std::mutex> lk(dm);
+    dcv.wait(lk, [&] { return left == 0; });
+  }
+};
+static TailPool &tail_pool() {
+  static TailPool pool([] {
+    const char *e = getenv("RD_TAIL_THREADS");
+    int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return n < 1 ? 1 : (n > 64 ? 64 : n);
+  }());
+  return pool;
+}
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // executeCPUTask (oclrect.c:1049) on the read-back records of `page`; out[i] receives the list of frame i
 static void finish_page(oclrect_t *o, int page, double tanAOV, rect_t **out, int run_tail) {
   cudaStream_t s = rd_stream(o->queue);
   RD_CUDA(cudaSetDevice(o->ordinal));
+  const double t0 = now_ms();
   RD_CUDA(cudaEventSynchronize(o->events[page]));
   const int count = o->pending[page];
   o->pending[page] = 0;
-  if (!run_tail) { for (int i = 0; i < count; i++) if (out) out[i] = NULL; return; }
+  if (!run_tail) { for (int i = 0; i < count; i++) if (out) out[i] = NULL; o->wait_ms += now_ms() - t0; return; }
   bool more = false;
   for (int i = 0; i < count; i++) {
     unsigned char *hb = o->hostBlob[page] + (size_t)i * o->blobBytes;
@@ -701,24 +783,29 @@ static void finish_page(oclrect_t *o, int page, double tanAOV, rect_t **out, int
     }
   }
   if (more) RD_CUDA(cudaStreamSynchronize(s));
-  for (int i = 0; i < count; i++) {
+  const double t1 = now_ms();
+  o->wait_ms += t1 - t0;
+  auto one = [&](int i) {
     unsigned char *hb = o->hostBlob[page] + (size_t)i * o->blobBytes;
     const int n = ((int *)hb)[0], ng = ((int *)hb)[1];
     if (n > ng) {
       // more segments than the compact record holds: read back what the reference reads back and gather on the host
+      RD_CUDA(cudaSetDevice(o->ordinal));
       const size_t P = (size_t)o->iw * o->ih * 4, off = (size_t)i * o->fs;
       std::vector<unsigned char> ls((size_t)(n + 1) * sizeof(LS_t)), seg(P), votes(4 * P);
-      RD_CUDA(cudaMemcpyAsync(ls.data(), (char *)o->ioBig[0]->dptr + off, ls.size(), cudaMemcpyDeviceToHost, s));
-      RD_CUDA(cudaMemcpyAsync(seg.data(), (char *)o->iobuf[1]->dptr + off, P, cudaMemcpyDeviceToHost, s));
-      RD_CUDA(cudaMemcpyAsync(votes.data(), (char *)o->ioBig[1]->dptr + off, 4 * P, cudaMemcpyDeviceToHost, s));
-      RD_CUDA(cudaStreamSynchronize(s));
+      RD_CUDA(cudaMemcpy(ls.data(), (char *)o->ioBig[0]->dptr + off, ls.size(), cudaMemcpyDeviceToHost));
+      RD_CUDA(cudaMemcpy(seg.data(), (char *)o->iobuf[1]->dptr + off, P, cudaMemcpyDeviceToHost));
+      RD_CUDA(cudaMemcpy(votes.data(), (char *)o->ioBig[1]->dptr + off, 4 * P, cudaMemcpyDeviceToHost));
       out[i] = rd_rect_tail((const linesegment_t *)ls.data(), (const int32_t *)seg.data(), (const int32_t *)votes.data(), o->iw, o->ih, tanAOV);
-      continue;
+      return;
     }
     const linesegment_t *ls = (const linesegment_t *)(hb + 64);
     const rd_tail_sample *sm = (const rd_tail_sample *)(hb + 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7));
     out[i] = rd_tail_compact(ls, sm, o->iw, o->ih, tanAOV);
-  }
+  };
+  if (count == 1) one(0);
+  else tail_pool().run_all(count, one);
+  o->tail_ms += now_ms() - t1;
 }
 
 extern "C" {
@@ -827,7 +914,6 @@ void rd_rect_reduceLS(cl_mem out, cl_mem boundary, cl_mem lsid, int iw, int ih, 
 // polling N, vidrect.cpp:159-172), so the device stages overlap the host tails, and the nctx streams overlap each other.
 }  // extern "C" (reopened below)
 
-#include <thread>
 struct rd_batch {
   int device, iw, ih, nctx, fpl;
   std::vector<oclrect_t *> ctx;
@@ -890,6 +976,7 @@ void rd_batch_destroy(rd_batch *b) {
 }
 
 static void batch_run(rd_batch *b, const uint8_t *frames, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out, int kind, int run_tail) {
+  for (oclrect_t *o : b->ctx) { o->wait_ms = 0; o->tail_ms = 0; }
   const int nchunks = (nframes + b->fpl - 1) / b->fpl;
   const int nw = b->nctx < nchunks ? b->nctx : nchunks;
   std::vector<std::thread> th;
@@ -908,6 +995,9 @@ void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, 
   batch_run(b, (const uint8_t *)dframes, frame_stride, ws, nframes, tanAOV, out, 2, out != NULL);
 }
 
-void rd_batch_stage_ms(rd_batch *b, double out_ms[5]) { for (int i = 0; i < 5; i++) out_ms[i] = b->stage_ms[i]; }
+void rd_batch_stage_ms(rd_batch *b, double out_ms[5]) {
+  for (int i = 0; i < 5; i++) out_ms[i] = 0;
+  for (oclrect_t *o : b->ctx) { out_ms[0] += o->wait_ms; out_ms[4] += o->tail_ms; }
+}
 
 }  // extern "C"
