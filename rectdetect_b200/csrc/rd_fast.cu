@@ -794,18 +794,37 @@ struct TileMag {                     // Plane interface of rd_bicubic: the tile 
 };
 // Every tile is filled for ALL its positions with the value of the mirrored image position (the reference's border rule,
 // oclimgutil.cl:41-45), so the inner loops index with plain offsets and no coordinate is mirrored more than once.
+//  - The packed tile is unpacked once per staged pixel into three float tiles (each pixel is a neighbour of eight
+//    magnitude positions; unpacking inside rd_edge_plab_at did the conversion 8 x 3 times per position).
+//  - The 5x5 derivative taps with a zero coefficient are skipped: the accumulators start at +0 and a sum is -0 only when
+//    both operands are, so they are never -0 and adding the +-0 of a zero tap cannot change them.
+//  - Only local maxima along the gradient need the two outer NMS samples.  They are a third of the pixels, scattered over
+//    the warps, so they are queued (over the then dead Lab tiles) and finished densely, one per thread.
+struct EtQueued { unsigned short idx, pad; float vx, vy, am1, ap1; };
+#define ET_NPOS (ET_T * ET_T)
 __global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, size_t fs) {
   rd_batch_z(fs, thin, blurL, blurP);
-  __shared__ uint32_t sp[ET_PW * ET_PW];
+  // phase 1-2: three unpacked Lab tiles (apron 5); phase 3-4: the queue of local maxima
+  __shared__ __align__(16) unsigned char lab_or_queue[(3 * ET_PW * ET_PW * 4 > ET_NPOS * (int)sizeof(EtQueued)) ? 3 * ET_PW * ET_PW * 4 : ET_NPOS * (int)sizeof(EtQueued)];
   __shared__ float sm[ET_MW * ET_MW];
   __shared__ float sl[ET_LW * ET_LW];
+  __shared__ int nq;
+  float (*lab)[ET_PW * ET_PW] = (float (*)[ET_PW * ET_PW])lab_or_queue;
+  EtQueued *queue = (EtQueued *)lab_or_queue;
   const int bx = blockIdx.x * ET_T, by = blockIdx.y * ET_T;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  // stage the packed-Lab tile (apron 5) and the L tile (apron 2) at mirrored coordinates
+  if (tx == 0 && ty == 0) nq = 0;
+  // stage the packed-Lab tile (apron 5), unpacked, and the L tile (apron 2) at mirrored coordinates
   for (int r = ty; r < ET_PW; r += 8) {
     const size_t rb = (size_t)mirror_safe(by - ET_PA + r, ih) * iw;
-    sp[r * ET_PW + tx] = blurP[rb + mirror_safe(bx - ET_PA + tx, iw)];
-    if (tx < ET_PW - 32) sp[r * ET_PW + 32 + tx] = blurP[rb + mirror_safe(bx - ET_PA + 32 + tx, iw)];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int c = tx + 32 * h;
+      if (c >= ET_PW) continue;
+      float l, a, b;
+      rd_unpacklab(blurP[rb + mirror_safe(bx - ET_PA + c, iw)], l, a, b);
+      lab[0][r * ET_PW + c] = l; lab[1][r * ET_PW + c] = a; lab[2][r * ET_PW + c] = b;
+    }
   }
   for (int r = ty; r < ET_LW; r += 8) {
     const size_t rb = (size_t)mirror_safe(by - ET_LA + r, ih) * iw;
@@ -813,8 +832,8 @@ __global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *bl
     if (tx < ET_LW - 32) sl[r * ET_LW + 32 + tx] = blurL[rb + mirror_safe(bx - ET_LA + 32 + tx, iw)];
   }
   __syncthreads();
-  // edge magnitude on the apron-4 tile.  Position (gx, gy) of the tile stands for the image position (mirror(gx), mirror(gy));
-  // its 3x3 neighbourhood is taken around THAT position (the packed tile is indexed through the mirrored centre).
+  // edge magnitude (oclimgutil.cl:422-437) on the apron-4 tile.  Position (gx, gy) of the tile stands for the image position
+  // (mirror(gx), mirror(gy)); its 3x3 neighbourhood is taken around THAT position (the Lab tiles are indexed through the mirrored centre).
   for (int r = ty; r < ET_MW; r += 8) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -824,40 +843,74 @@ __global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *bl
       if (gx > iw + ET_MA - 1 || gy > ih + ET_MA - 1) continue;           // beyond the apron of the last in-image pixel: never read
       const int mx = rd_mirror1(gx, iw), my = rd_mirror1(gy, ih);
       // tile coordinates of the mirrored centre: the tile spans [bx-5, bx+36], and mirroring keeps a position within 5 of where it was
-      const uint32_t *q = sp + (my - (by - ET_PA)) * ET_PW + (mx - (bx - ET_PA));
-      sm[r * ET_MW + c] = rd_edge_plab_at(q[-ET_PW], q[-1], q[ET_PW], q[1], q[-ET_PW - 1], q[ET_PW + 1], q[-ET_PW + 1], q[ET_PW - 1]);
+      const int q = (my - (by - ET_PA)) * ET_PW + (mx - (bx - ET_PA));
+      float tot = 0.0f;
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const float *t = lab[ch] + q;
+        const float n = t[-ET_PW], w = t[-1], s = t[ET_PW], e = t[1], nw = t[-ET_PW - 1], se = t[ET_PW + 1], ne = t[-ET_PW + 1], sw = t[ET_PW - 1];
+        float d = __fsub_rn(__fsub_rn(__fadd_rn(n, w), s), e);
+        float acc = __fadd_rn(0.0f, __fmul_rn(__fsub_rn(nw, se), d));
+        d = __fsub_rn(__fadd_rn(__fsub_rn(n, w), e), s);
+        acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(ne, sw), d));
+        const float pos = acc > 0.0f ? acc : 0.0f;
+        tot = ch == 0 ? pos : __fadd_rn(tot, pos);
+      }
+      sm[r * ET_MW + c] = tot > 0.0f ? __fsqrt_rn(tot) : 0.0f;
     }
   }
   __syncthreads();
   const TileMag mag = {sm, bx - ET_MA, by - ET_MA};
+  constexpr float V5[25] = {-4.667f, -4.083f, 0.0f, 4.083f, 4.667f, -10.024f, -0.963f, 0.0f, 0.963f, 10.024f, -14.120f, 3.622f, 0.0f, -3.622f, 14.120f,
+                            -10.024f, -0.963f, 0.0f, 0.963f, 10.024f, -4.667f, -4.083f, 0.0f, 4.083f, 4.667f};                    // RD_V5C
+  const unsigned lane = tx, ltmask = (1u << lane) - 1u;
 #pragma unroll 1
   for (int k = 0; k < 4; k++) {
     const int x = bx + tx, y = by + ty + k * 8;
-    if (x >= iw || y >= ih) continue;
-    float vx = 0, vy = 0;
-    const float *lc = sl + (y - (by - ET_LA)) * ET_LW + (x - (bx - ET_LA));
+    bool want = false;
+    float2 v = make_float2(0.0f, 0.0f);
+    float am1 = 0.0f, ap1 = 0.0f;
+    if (x < iw && y < ih) {
+      float vx = 0, vy = 0;
+      const float *lc = sl + (y - (by - ET_LA)) * ET_LW + (x - (bx - ET_LA));
 #pragma unroll
-    for (int yy = -2; yy <= 2; yy++)
+      for (int yy = -2; yy <= 2; yy++)
 #pragma unroll
-      for (int xx = -2; xx <= 2; xx++) {
-        const float s = lc[yy * ET_LW + xx];
-        vx = __fadd_rn(vx, __fmul_rn(RD_V5C[(xx + 2) + (yy + 2) * 5], s));
-        vy = __fadd_rn(vy, __fmul_rn(RD_V5C[(yy + 2) + (xx + 2) * 5], s));
-      }
-    const float2 v = rd_edgevec_normalise(vx, vy);
-    // thinthres: the outer samples only matter where the pixel is a local maximum along the gradient
-    const float fx = (float)x, fy = (float)y;
-    const float a0 = mag.at(x, y);
-    const float am1 = rd_bicubic(mag, __fsub_rn(fx, v.x), __fsub_rn(fy, v.y));
-    const float ap1 = rd_bicubic(mag, __fadd_rn(fx, v.x), __fadd_rn(fy, v.y));
-    float r = 0.0f;
-    if (am1 <= a0 && a0 >= ap1) {
-      const float vx2 = __fmul_rn(2.0f, v.x), vy2 = __fmul_rn(2.0f, v.y);
-      const float am2 = rd_bicubic(mag, __fsub_rn(fx, vx2), __fsub_rn(fy, vy2));
-      const float ap2 = rd_bicubic(mag, __fadd_rn(fx, vx2), __fadd_rn(fy, vy2));
-      r = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(am2, am1), a0), ap1), ap2);
+        for (int xx = -2; xx <= 2; xx++) {
+          const float s = lc[yy * ET_LW + xx];
+          if (V5[(xx + 2) + (yy + 2) * 5] != 0.0f) vx = __fadd_rn(vx, __fmul_rn(V5[(xx + 2) + (yy + 2) * 5], s));
+          if (V5[(yy + 2) + (xx + 2) * 5] != 0.0f) vy = __fadd_rn(vy, __fmul_rn(V5[(yy + 2) + (xx + 2) * 5], s));
+        }
+      v = rd_edgevec_normalise(vx, vy);
+      // thinthres: the outer samples only matter where the pixel is a local maximum along the gradient
+      const float fx = (float)x, fy = (float)y;
+      const float a0 = mag.at(x, y);
+      am1 = rd_bicubic(mag, __fsub_rn(fx, v.x), __fsub_rn(fy, v.y));
+      ap1 = rd_bicubic(mag, __fadd_rn(fx, v.x), __fadd_rn(fy, v.y));
+      want = am1 <= a0 && a0 >= ap1;
+      if (!want) thin[(size_t)y * iw + x] = 0.0f;
     }
-    thin[(size_t)y * iw + x] = r;
+    const unsigned b = __ballot_sync(0xffffffffu, want);
+    if (b) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&nq, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (want) {
+        EtQueued e;
+        e.idx = (unsigned short)((ty + k * 8) * ET_T + tx); e.pad = 0; e.vx = v.x; e.vy = v.y; e.am1 = am1; e.ap1 = ap1;
+        queue[base + __popc(b & ltmask)] = e;
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = ty * 32 + tx, n = nq; t < n; t += 256) {
+    const EtQueued e = queue[t];
+    const int x = bx + (e.idx & (ET_T - 1)), y = by + (e.idx >> 5);
+    const float fx = (float)x, fy = (float)y;
+    const float vx2 = __fmul_rn(2.0f, e.vx), vy2 = __fmul_rn(2.0f, e.vy);
+    const float am2 = rd_bicubic(mag, __fsub_rn(fx, vx2), __fsub_rn(fy, vy2));
+    const float ap2 = rd_bicubic(mag, __fadd_rn(fx, vx2), __fadd_rn(fy, vy2));
+    thin[(size_t)y * iw + x] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(am2, e.am1), mag.at(x, y)), e.ap1), ap2);
   }
 }
 void rd_edge_thin_run(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
