@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
     const int first = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));        // nearest run start at or left of lx (bit 0 is always set)
     L[i] = ly * TW + first;
     int base = 0;
-    if (lx == 0) base = atomicAdd(&nstarts, __popc(starts));
+    if (lx == 0) base = rd_smem_fetch_add(&nstarts, __popc(starts));
     base = __shfl_sync(0xffffffffu, base, 0);
     if ((starts >> lx) & 1u) starts_list[base + __popc(starts & lt)] = (unsigned short)i;
     if (m != L_BG) seen |= 1u;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
     const int cN = __popc(bN), cNW = __popc(bNW), tot = cN + cNW + __popc(bNE);
     if (tot == 0) continue;
     int base = 0;
-    if (lx == 0) base = atomicAdd(&npairs, tot);
+    if (lx == 0) base = rd_smem_fetch_add(&npairs, tot);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (nN) pairs[base + __popc(bN & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW);
     if (nNW) pairs[base + cN + __popc(bNW & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW - 1);

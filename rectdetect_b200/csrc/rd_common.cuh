@@ -112,6 +112,15 @@ __device__ __forceinline__ float rd_distance3(float dx, float dy, float dz) {
 __constant__ const int RD_RX[8] = {1, 1, 0, -1, -1, -1, 0, 1};   // oclrect.cl:12, oclpolyline.cl:63
 __constant__ const int RD_RY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 
+// shared-memory fetch-and-add issued by ONE elected lane.  (Written as PTX: for atomicAdd() the compiler emits its own
+// warp-aggregation sequence - match, ballot, leader election, ~30 instructions - around every call, which is pure overhead
+// when the caller has already aggregated the warp's contribution.)
+__device__ __forceinline__ int rd_smem_fetch_add(int *p, int v) {
+  int old;
+  asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
+}
+
 // ---- union-find with "the smaller index is the root" : every CCL of the path is built on it ----
 __device__ __forceinline__ int rd_uf_find(const int *L, int x) {
   int p = __ldcg(L + x);          // L2 reads: parents are updated by atomics from other SMs

@@ -677,25 +677,35 @@ __global__ void __launch_bounds__(128) kf_iir_v3(float *vf0, float *vf1, float *
   else for (int y = ih + warm; y >= ih; y--) st.step1(h[(size_t)rd_mirror1(y, ih) * iw], c);
   const int y0 = dir == 0 ? 0 : ih - 1;                          // first real row; row k of the walk is y0 + k*sgn
   const int nblk = ih >> 3;
+  // running pointers: row k of the walk is hp[k * step] (64-bit index arithmetic per element cost a quarter of the kernel)
+  const ptrdiff_t step = (ptrdiff_t)sgn * iw;
+  const float *hp = h + (size_t)y0 * iw;
+  float *op = o + (size_t)y0 * iw;
   float cur[8], nxt[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) cur[j] = j < ih ? h[(size_t)(y0 + j * sgn) * iw] : 0.0f;
+  for (int j = 0; j < 8; j++) cur[j] = j < ih ? hp[j * step] : 0.0f;
   for (int b = 0; b < nblk; b++) {
     const int k0 = b * 8;
+    if (k0 + 16 <= ih) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) { const int k = k0 + 8 + j; nxt[j] = k < ih ? h[(size_t)(y0 + k * sgn) * iw] : 0.0f; }
+      for (int j = 0; j < 8; j++) nxt[j] = hp[(8 + j) * step];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) nxt[j] = k0 + 8 + j < ih ? hp[(8 + j) * step] : 0.0f;
+    }
     float out[8];
     st.step8(cur, out, c);
 #pragma unroll
-    for (int j = 0; j < 8; j++) o[(size_t)(y0 + (k0 + j) * sgn) * iw] = out[j];
+    for (int j = 0; j < 8; j++) op[j * step] = out[j];
 #pragma unroll
     for (int j = 0; j < 8; j++) cur[j] = nxt[j];
+    hp += 8 * step; op += 8 * step;
   }
   for (int k = nblk * 8, j = 0; k < ih; k++, j++) {               // ragged tail (ih % 8 rows): cur[] holds them
     float v = 0.0f;
 #pragma unroll
     for (int q = 0; q < 8; q++) if (q == j) v = cur[q];
-    o[(size_t)(y0 + k * sgn) * iw] = st.step1(v, c);
+    op[j * step] = st.step1(v, c);
   }
 }
 // pass3 (oclimgutil.cl:629) for the three channels + pack_plab (oclimgutil.cl:325): blurred L plane and blurred packed Lab;
@@ -893,7 +903,7 @@ __global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *bl
     const unsigned b = __ballot_sync(0xffffffffu, want);
     if (b) {
       int base = 0;
-      if (lane == 0) base = atomicAdd(&nq, __popc(b));
+      if (lane == 0) base = rd_smem_fetch_add(&nq, __popc(b));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (want) {
         EtQueued e;
