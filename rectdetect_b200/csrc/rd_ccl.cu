@@ -123,70 +123,71 @@ __device__ __forceinline__ void sm_unite(int *L, int a, int b) {
   }
 }
 
+// out of line: unions are rare events in the row sweep below, which is unrolled 32 times
+__device__ __noinline__ void sm_unite_rare(int *L, int a, int b) { sm_unite(L, a, b); }
+
 // neighbour exchange inside a warp for the staged values (int, or the two words of LinkMerge::V)
 __device__ __forceinline__ int ccl_up1(int v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ int ccl_down1(int v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 template <class V> __device__ __forceinline__ V ccl_up1(V v) { V r; r.pix = __shfl_up_sync(0xffffffffu, v.pix, 1); r.fl = __shfl_up_sync(0xffffffffu, v.fl, 1); return r; }
 template <class V> __device__ __forceinline__ V ccl_down1(V v) { V r; r.pix = __shfl_down_sync(0xffffffffu, v.pix, 1); r.fl = __shfl_down_sync(0xffffffffu, v.fl, 1); return r; }
 
-// One CTA per 32x32 tile; warp w owns the four consecutive tile rows 4w .. 4w+3, lane = column.
-//  1. The predicate inputs are loaded once per pixel (coalesced) and handed to the neighbours by shuffles: a warp keeps the
-//     row above in registers, lanes 0 / 31 fetch the columns beside the tile.  The link masks go to the byte plane and to
-//     shared memory; horizontal runs are resolved with a ballot (every pixel starts out pointing at the first pixel of its
-//     run), so the union-find only has to stitch runs of adjacent rows together.
-//  2. The unions that are still needed are appended to a list in shared memory, skipping every link that another link
-//     implies: the link to N is implied when the W neighbour has it too and both pairs are W-linked; the links to NW / NE
-//     are implied by the link to N when N is W-linked to them.  (Each skipped union follows from links that are themselves
-//     processed, so the components are unchanged - also for predicates that are not transitive.)  A uniform tile needs 31
-//     unions instead of ~3000.
-//  3. The list is processed densely, one union per thread (the unions of a row are few and scattered, and walking them in
-//     place left most lanes of a warp idle), then the run starts - also gathered in a list - look up their roots, and every
-//     pixel reads its root through its run start (two hops).
-#define CCL_MAXPAIRS (3 * TW * TH)
+// One WARP per 32x32 tile (eight tiles per CTA), lane = column, rows top to bottom - the classic two-pass labelling with the
+// first pass done a row at a time by a warp:
+//  - the predicate inputs are loaded once per pixel (coalesced, one row ahead) and handed to the neighbours by shuffles;
+//    the row above stays in registers, lanes 0 / 31 fetch the columns beside the tile; the link masks go to the byte plane;
+//  - a horizontal run is a ballot away; every pixel takes the smallest provisional label among the pixels of the row above
+//    it is linked to (its own index if there is none), and one redux.sync.min per run gives the run its label.  A run
+//    that starts a component therefore gets its first pixel's index - the smallest index of the component so far;
+//  - only where a run joins DIFFERENT labels from above (the bottom of a "U") is a union recorded, in a union-find over the
+//    provisional labels kept in the tile's label array itself (A[i] = label of pixel i <= i, a forest by construction).
+//    These events are rare, so the row loop is almost branch-free - the previous kernel spent most of its time in the
+//    unions of every run overlap;
+//  - second pass: every pixel follows A[] to its root (depth 1 unless unions happened), roots are marked L_ROOT.
+// Links towards pixels outside the tile are left to the seam kernel.
+#define CCL_WARPS 8
 template <class LinkFn>
-__global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *links, LinkFn f, int iw, int ih, size_t fs) {
+__global__ void __launch_bounds__(CCL_WARPS * 32) k_ccl_tile(int *label, uint8_t *links, LinkFn f, int iw, int ih, int tilesX, int tiles, size_t fs) {
   rd_batch_z(fs, label, links);
   f.shift((size_t)blockIdx.z * fs);
   typedef typename LinkFn::V V;
-  __shared__ int L[TW * TH];
-  __shared__ uint8_t M[TW * TH];
-  __shared__ unsigned pairs[CCL_MAXPAIRS];
-  __shared__ unsigned short starts_list[TW * TH];
-  __shared__ int npairs, nstarts;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  __shared__ int A_all[CCL_WARPS][TW * TH];
+  const int lx = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * CCL_WARPS + wp;
+  if (tile >= tiles) return;
+  int *A = A_all[wp];
+  const int x0 = (tile % tilesX) * TW, y0 = (tile / tilesX) * TH;
   const int x = x0 + lx;
-  const unsigned lt = (1u << lx) - 1u;
-  if (threadIdx.x == 0) { npairs = 0; nstarts = 0; }
   const bool okx = x < iw, okw = x0 > 0, oke = x0 + TW < iw;
-  const bool fullTile = x0 + TW <= iw && y0 + TH <= ih;
-  int p = (y0 + wy * 4 - 1) * iw + x;                              // linear index of (x, row above the warp's first row)
+  const int rows = min(TH, ih - y0);
+  int p = y0 * iw + x;                                             // linear index of (x, y0)
   V up = V(), upW = V(), upE = V();
-  {
-    const int yu = y0 + wy * 4 - 1;
-    if (yu >= 0 && yu < ih) {
-      if (okx) up = f.load(p);
-      upW = ccl_up1(up); upE = ccl_down1(up);
-      if (lx == 0 && okw) upW = f.load(p - 1);
-      if (lx == 31 && oke) upE = f.load(p + 1);
-    }
+  if (y0 > 0) {
+    if (okx) up = f.load(p - iw);
+    upW = ccl_up1(up); upE = ccl_down1(up);
+    if (lx == 0 && okw) upW = f.load(p - iw - 1);
+    if (lx == 31 && oke) upE = f.load(p - iw + 1);
   }
-  // what this thread has seen of the tile: bit 0 = not all background, bit 1 = not "one component hanging on the first pixel"
-  unsigned seen = fullTile ? 0u : 2u;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int ly = wy * 4 + k, y = y0 + ly, i = ly * TW + lx;
-    p += iw;
-    V c = V(), w = V(), e = V();
-    if (y < ih) {
-      if (okx) c = f.load(p);
-      w = ccl_up1(c); e = ccl_down1(c);
-      if (lx == 0 && okw) w = f.load(p - 1);
-      if (lx == 31 && oke) e = f.load(p + 1);
+  // row 0, loaded ahead
+  V cn = V(), wn = V(), en = V();
+  if (okx) cn = f.load(p);
+  if (lx == 0 && okw) wn = f.load(p - 1);
+  if (lx == 31 && oke) en = f.load(p + 1);
+  int prevLab = 0;
+  unsigned fgbits = 0;                                             // bit ly: my pixel of row ly is foreground
+  for (int ly = 0; ly < rows; ly++, p += iw) {
+    const int y = y0 + ly, i = ly * TW + lx;
+    const V c = cn;
+    V w = ccl_up1(c), e = ccl_down1(c);
+    if (lx == 0) w = wn;
+    if (lx == 31) e = en;
+    if (ly + 1 < rows) {                                           // next row
+      if (okx) cn = f.load(p + iw);
+      if (lx == 0 && okw) wn = f.load(p + iw - 1);
+      if (lx == 31 && oke) en = f.load(p + iw + 1);
     }
     unsigned m = L_BG;
-    if (okx && y < ih) {
+    if (okx) {
       const unsigned full = f.link(c, w, upW, up, upE, x, y);
       links[p] = (uint8_t)full;
       m = full;
@@ -194,65 +195,42 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_tile(int *label, uint8_t *l
       if (lx == TW - 1) m &= ~L_NE;
       if (ly == 0) m &= ~(L_NW | L_N | L_NE);
     }
-    M[i] = (uint8_t)m;
     const unsigned starts = ~__ballot_sync(0xffffffffu, (m & L_W) != 0);      // bit j set: pixel j starts a run
-    const int first = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));        // nearest run start at or left of lx (bit 0 is always set)
-    L[i] = ly * TW + first;
-    int base = 0;
-    if (lx == 0) base = rd_smem_fetch_add(&nstarts, __popc(starts));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if ((starts >> lx) & 1u) starts_list[base + __popc(starts & lt)] = (unsigned short)i;
-    if (m != L_BG) seen |= 1u;
-    if ((m & L_BG) || starts != 1u || (ly > 0 && !(m & L_N))) seen |= 2u;
+    const int labW = __shfl_up_sync(0xffffffffu, prevLab, 1), labE = __shfl_down_sync(0xffffffffu, prevLab, 1);
+    int lab = i;
+    if (!(m & L_BG)) {
+      int v = i;
+      if (m & L_N) v = min(v, prevLab);
+      if (m & L_NW) v = min(v, labW);
+      if (m & L_NE) v = min(v, labE);
+      const int s = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));          // first lane of my run (bit 0 of `starts` is always set)
+      const unsigned right = lx == 31 ? 0u : (starts & (0xffffffffu << (lx + 1)));
+      const int e1 = right ? __ffs(right) - 1 : 32;                           // one past its last lane
+      const unsigned runmask = (e1 == 32 ? 0xffffffffu : ((1u << e1) - 1u)) & (0xffffffffu << s);
+      lab = __reduce_min_sync(runmask, v);
+      // the run joins everything it is linked to above: whatever carries another label is united with the run's label
+      if ((m & L_N) && prevLab != lab) sm_unite_rare(A, prevLab, lab);
+      if ((m & L_NW) && labW != lab) sm_unite_rare(A, labW, lab);
+      if ((m & L_NE) && labE != lab) sm_unite_rare(A, labE, lab);
+      A[i] = lab;
+      fgbits |= 1u << ly;
+    }
+    __syncwarp();
+    // carry the CURRENT root of the label down: after two labels have been united, the rows below would otherwise keep
+    // meeting the stale pair and ask for the same union again (every diagonal step of a thin string joins the two
+    // background sides through the 8-neighbourhood)
+    if (!(m & L_BG)) { const int r = A[lab]; if (r != lab) lab = sm_find_ro(A, r); }
+    prevLab = lab;
     up = c; upW = w; upE = e;
   }
-  const int notEmpty = __syncthreads_or((int)(seen & 1u)), notUniform = __syncthreads_or((int)(seen & 2u));
-  if (!notEmpty) return;                                           // nothing but background: the flatten kernel fills the tile
-  if (!notUniform) {
-    // a single run per row, every row linked to the one above: one component, rooted at the first pixel
-    const int root = y0 * iw + x0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) label[(y0 + wy * 4 + k) * iw + x] = root;
-    if (threadIdx.x == 0) links[root] |= L_ROOT;
-    return;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int i = (wy * 4 + k) * TW + lx;
-    const unsigned m = M[i];
-    bool nN = false, nNW = false, nNE = false;
-    if (m & (L_NW | L_N | L_NE)) {
-      const unsigned mn = M[i - TW];
-      nN = (m & L_N) && !((m & L_W) && (M[i - 1] & L_N) && (mn & L_W));
-      nNW = (m & L_NW) && !((m & L_N) && (mn & L_W));
-      nNE = (m & L_NE) && !((m & L_N) && (M[i - TW + 1] & L_W));
-    }
-    const unsigned bN = __ballot_sync(0xffffffffu, nN), bNW = __ballot_sync(0xffffffffu, nNW), bNE = __ballot_sync(0xffffffffu, nNE);
-    const int cN = __popc(bN), cNW = __popc(bNW), tot = cN + cNW + __popc(bNE);
-    if (tot == 0) continue;
-    int base = 0;
-    if (lx == 0) base = rd_smem_fetch_add(&npairs, tot);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (nN) pairs[base + __popc(bN & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW);
-    if (nNW) pairs[base + cN + __popc(bNW & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW - 1);
-    if (nNE) pairs[base + cN + cNW + __popc(bNE & lt)] = ((unsigned)i << 16) | (unsigned)(i - TW + 1);
-  }
-  __syncthreads();
-  for (int t = threadIdx.x, n = npairs; t < n; t += CCL_THREADS) { const unsigned pr = pairs[t]; sm_unite(L, (int)(pr >> 16), (int)(pr & 0xffffu)); }
-  __syncthreads();
-  for (int t = threadIdx.x, n = nstarts; t < n; t += CCL_THREADS) {
-    const int i = starts_list[t], r = sm_find_ro(L, i);
-    L[i] = r;
-    if (r == i && !(M[i] & L_BG)) links[(y0 + (i >> 5)) * iw + x0 + (i & 31)] |= L_ROOT;      // this CTA wrote the byte before the barriers
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int ly = wy * 4 + k, y = y0 + ly, i = ly * TW + lx;
-    if (okx && y < ih) {
-      const int r = L[L[i]];
-      label[y * iw + x] = (y0 + (r >> 5)) * iw + x0 + (r & 31);
-    }
+  // second pass: roots
+  p = y0 * iw + x;
+  for (int ly = 0; ly < rows; ly++, p += iw) {
+    const int i = ly * TW + lx;
+    if (!((fgbits >> ly) & 1u)) continue;
+    const int r = sm_find_ro(A, i);
+    label[p] = (y0 + (r >> 5)) * iw + x0 + (r & 31);
+    if (r == i) links[p] |= L_ROOT;
   }
 }
 
@@ -340,7 +318,8 @@ __global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *
 
 template <class LinkFn>
 static void ccl_core(int *label, uint8_t *links, LinkFn f, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_LAUNCH(k_ccl_tile<LinkFn>, rd_gz(dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH)), nb), CCL_THREADS, 0, s, label, links, f, iw, ih, fs);
+  const int tilesX = rd_cdiv(iw, TW), tiles = tilesX * rd_cdiv(ih, TH);
+  RD_LAUNCH(k_ccl_tile<LinkFn>, dim3(rd_cdiv(tiles, CCL_WARPS), 1, nb), CCL_WARPS * 32, 0, s, label, links, f, iw, ih, tilesX, tiles, fs);
   RD_LAUNCH(k_ccl_seams, dim3(rd_cdiv(iw, TW), rd_cdiv(ih, TH), nb), 96, 0, s, label, links, iw, ih, fs);
   RD_LAUNCH(k_ccl_roots, rd_gy(rd_cdiv(rd_cdiv(iw * ih, 4), 256), nb), 256, 0, s, label, (const uint8_t *)links, iw * ih, fs);
 }
