@@ -137,7 +137,7 @@ template <class V> __device__ __forceinline__ V ccl_down1(V v) { V r; r.pix = __
 //  - the predicate inputs are loaded once per pixel (coalesced, one row ahead) and handed to the neighbours by shuffles;
 //    the row above stays in registers, lanes 0 / 31 fetch the columns beside the tile; the link masks go to the byte plane;
 //  - a horizontal run is a ballot away; every pixel takes the smallest provisional label among the pixels of the row above
-//    it is linked to (its own index if there is none), and one redux.sync.min per run gives the run its label.  A run
+//    it is linked to (its own index if there is none), and a segmented min-scan gives the run its label.  A run
 //    that starts a component therefore gets its first pixel's index - the smallest index of the component so far;
 //  - only where a run joins DIFFERENT labels from above (the bottom of a "U") is a union recorded, in a union-find over the
 //    provisional labels kept in the tile's label array itself (A[i] = label of pixel i <= i, a forest by construction).
@@ -197,17 +197,23 @@ __global__ void __launch_bounds__(CCL_WARPS * 32) k_ccl_tile(int *label, uint8_t
     }
     const unsigned starts = ~__ballot_sync(0xffffffffu, (m & L_W) != 0);      // bit j set: pixel j starts a run
     const int labW = __shfl_up_sync(0xffffffffu, prevLab, 1), labE = __shfl_down_sync(0xffffffffu, prevLab, 1);
-    int lab = i;
+    // smallest label among the pixels of the row above this pixel is linked to (its own index if none), then the smallest
+    // of the run: a segmented min-scan towards the right and a broadcast from the run's last lane.  (redux.sync with one
+    // member mask per run is serialised run by run; the scan costs the same whatever the row looks like.)
+    int v = i;
+    if (m & L_N) v = min(v, prevLab);
+    if (m & L_NW) v = min(v, labW);
+    if (m & L_NE) v = min(v, labE);
+    const int s = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));            // first lane of my run (bit 0 of `starts` is always set)
+    const unsigned right = lx == 31 ? 0u : (starts & (0xffffffffu << (lx + 1)));
+    const int last = right ? __ffs(right) - 2 : 31;                           // its last lane
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lx - d >= s) v = min(v, t);
+    }
+    const int lab = __shfl_sync(0xffffffffu, v, last);
     if (!(m & L_BG)) {
-      int v = i;
-      if (m & L_N) v = min(v, prevLab);
-      if (m & L_NW) v = min(v, labW);
-      if (m & L_NE) v = min(v, labE);
-      const int s = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));          // first lane of my run (bit 0 of `starts` is always set)
-      const unsigned right = lx == 31 ? 0u : (starts & (0xffffffffu << (lx + 1)));
-      const int e1 = right ? __ffs(right) - 1 : 32;                           // one past its last lane
-      const unsigned runmask = (e1 == 32 ? 0xffffffffu : ((1u << e1) - 1u)) & (0xffffffffu << s);
-      lab = __reduce_min_sync(runmask, v);
       // the run joins everything it is linked to above: whatever carries another label is united with the run's label
       if ((m & L_N) && prevLab != lab) sm_unite_rare(A, prevLab, lab);
       if ((m & L_NW) && labW != lab) sm_unite_rare(A, labW, lab);
@@ -219,8 +225,8 @@ __global__ void __launch_bounds__(CCL_WARPS * 32) k_ccl_tile(int *label, uint8_t
     // carry the CURRENT root of the label down: after two labels have been united, the rows below would otherwise keep
     // meeting the stale pair and ask for the same union again (every diagonal step of a thin string joins the two
     // background sides through the 8-neighbourhood)
-    if (!(m & L_BG)) { const int r = A[lab]; if (r != lab) lab = sm_find_ro(A, r); }
     prevLab = lab;
+    if (!(m & L_BG)) { const int r = A[lab]; if (r != lab) prevLab = sm_find_ro(A, r); }
     up = c; upW = w; upE = e;
   }
   // second pass: roots
