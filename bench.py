@@ -2,14 +2,15 @@
 """bench.py - throughput of the rectangle-detection hot path on B200 (one process per GPU).
 
 metric  : Mpix/s = frames/s x iw x ih, BGR frame -> rect_t list (BASELINE.json)
-step    : one batch of --frames 1280x720 synthetic frames per GPU (config "vidrect 1280x720 synthetic stream, AOV 72,
+step    : one batch of --frames (default 256) 1280x720 synthetic frames per GPU (config "vidrect 1280x720 synthetic stream, AOV 72,
           batched on 1xB200"); frames of a batch are independent and are sharded across ranks (weak scaling, no data-path
           collective; one gather of the rect lists to rank 0 per step).
 value   : frames already resident in HBM; every device stage, the compact read-back and the host tail run (rect lists
           are produced on the host), plus the rect-list gather for N > 1.
 e2e     : the same through the C-ABI batch call with frames in pinned HOST memory (H2D copies inside the timed region).
-roofline: the kernel with the largest share of device time (per-kernel CUDA-event timing on the launching streams, in
-          the library, during the timed value steps) against the measured HBM copy bandwidth.
+roofline: the kernel with the largest share of device time against the measured HBM copy bandwidth.  Per-kernel times come
+          from CUDA events around every launch on the launching stream (in the library), in a separate pass through ONE
+          pipeline object so that each kernel is timed alone; per-stage (A/B/C/D) totals of the same pass are reported too.
 --impl reference : the CPU oracle (restatement of the reference's OpenCL kernels and launch schedule; the reference itself
           needs an OpenCL ICD + OpenCV that this image lacks) on all host cores, bounded sample per step.
 """
@@ -155,7 +156,7 @@ def main():
     ap.add_argument("--w", type=int, default=1280)
     ap.add_argument("--h", type=int, default=720)
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
-    ap.add_argument("--nctx", type=int, default=8, help="pipeline objects (streams) per GPU")
+    ap.add_argument("--nctx", type=int, default=16, help="pipeline objects (streams) per GPU")
     ap.add_argument("--fpl", type=int, default=8, help="frames per kernel launch")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample")
@@ -242,11 +243,17 @@ def main():
     for _ in range(2):
         solo.run(dev_frames.data_ptr(), frame_bytes, ws, nsolo, TAN_AOV, on_device=True, want_rects=False)
     torch.cuda.synchronize()
-    rd.api.profile_start(None)
+    rd.api.profile_start(None, stages=True)
     solo.run(dev_frames.data_ptr(), frame_bytes, ws, nsolo, TAN_AOV, on_device=True, want_rects=False)
     torch.cuda.synchronize()
-    prof = rd.api.profile_stop()
+    prof_staged = rd.api.profile_stop()
     solo.close()
+    prof, stage_ms = {}, {}
+    for k, (c, ms) in prof_staged.items():
+        st, name = k.split("/", 1)
+        pc, pm = prof.get(name, (0, 0.0))
+        prof[name] = (pc + c, pm + ms)
+        stage_ms[st] = stage_ms.get(st, 0.0) + ms
 
     pix_per_step = total_frames * iw * ih
     value = pix_per_step * args.steps / (ms_val * 1e-3) / 1e6
@@ -275,6 +282,16 @@ def main():
                     "share_of_kernel_time": tms / total_kernel_ms, "kernel_time_us_per_frame": total_kernel_ms * 1e3 / nsolo,
                     "top5_us_per_frame": [[k, round(v[1] * 1e3 / nsolo, 2)] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:5]],
                     "pipeline_algorithmic_bytes_per_px": 43, "pipeline_frac": (43.0 * value * 1e6 / 1e9) / peak}
+        # per-stage roofline: algorithmic bytes per pixel A 11, B 16, C 8 (+56 B per segment), D 8 (+20 B per
+        # vote pair); the list terms are <1 % of a frame and are left out, so the fractions are slightly conservative
+        stage_bpp = {"A": 11, "B": 16, "C": 8, "D": 8}
+        stages = {}
+        for st in sorted(stage_ms):
+            us = stage_ms[st] * 1e3 / nsolo
+            gbs = stage_bpp.get(st, 0) * iw * ih / (us * 1e-6) / 1e9 if us > 0 else None
+            stages[st] = {"us_per_frame": round(us, 2), "algorithmic_bytes_per_px": stage_bpp.get(st), "achieved_gbs": round(gbs, 1) if gbs else None,
+                          "frac_of_hbm_peak": round(gbs / peak, 4) if gbs else None}
+        roofline["stages"] = stages
         cpu = None
         if not args.no_cpu_baseline:
             v, cores, secs = cpu_oracle_mpix(iw, ih, [1000 + i for i in range(args.cpu_frames)])

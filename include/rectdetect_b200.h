@@ -160,7 +160,8 @@ int    rd_device_count(void);                                    /* 0 when no CU
 const char *rd_version(void);
 int    rd_kernel_launches(void);                                 /* kernels launched by this library so far (process-wide counter) */
 /* per-kernel device time from CUDA events recorded on the launching stream around each launch.
- * mode 1: every kernel, mode 2: only kernels whose name contains `select`.  rd_profile_stop waits for the device and
+ * mode 1: every kernel, mode 2: only kernels whose name contains `select`, mode 3: every kernel, names prefixed with the
+ * stage of the production schedule ("A/", "B/", "C/", "D/").  rd_profile_stop waits for the device and
  * returns one "kernel_name launches total_ms" line per kernel (string owned by the library, valid until the next call). */
 void   rd_profile_start(int mode, const char *select);
 const char *rd_profile_stop(void);

@@ -119,9 +119,10 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def profile_start(select=None):
-    """time every kernel (select=None) or only kernels whose name contains `select`, with CUDA events on their stream"""
-    lib().rd_profile_start(1 if select is None else 2, (select or "").encode())
+def profile_start(select=None, stages=False):
+    """time every kernel (select=None) or only kernels whose name contains `select`, with CUDA events on their stream;
+    stages=True prefixes every name with the stage of the production schedule ("A/kf_iir_h3")"""
+    lib().rd_profile_start(3 if stages else (1 if select is None else 2), (select or "").encode())
 
 
 def profile_stop():

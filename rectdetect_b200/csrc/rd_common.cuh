@@ -49,6 +49,7 @@ extern std::atomic<int> g_rd_launches;
 extern std::atomic<int> g_rd_prof_mode;
 int rd_prof_begin(const char *name, cudaStream_t s);
 void rd_prof_end(int slot, cudaStream_t s);
+void rd_prof_stage(const char *tag);      // stage tag of the calling thread (string literal), used by profile mode 3
 
 static inline cudaStream_t rd_stream(cl_command_queue q) {
   if (!q) exitf(-1, "rectdetect_b200: NULL command queue\n");

@@ -525,6 +525,7 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   const size_t fs = o->fs;
   cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
   // Stage A (oclrect.c:245-263)
+  rd_prof_stage("A");
   rd_bgr2plab_run(PU(buf[0]), din, din_fs, iw, ih, ws, nb, fs, s);
   STAGE(1);
   rd_iirblur3_run(PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), PU(buf[1]), PU(buf[0]), PF(ioBig[1]), PF(ioBig[0]), o->P / 4, 2, iw, ih, nb, fs, s);
@@ -532,6 +533,7 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   rd_edge_thin_run(PF(buf[2]), PF(tmp[1]), PU(buf[1]), iw, ih, nb, fs, s);
   STAGE(3);
   // Stage B (oclrect.c:265-342)
+  rd_prof_stage("B");
   rd_strings1_run((uint8_t *)tmp[0]->dptr, PF(buf[2]), iw, ih, nb, fs, s);
   STAGE(4);
   rd_label8x_u8(PI(buf[1]), (const uint8_t *)tmp[0]->dptr, tmp[4]->dptr, -1, iw, ih, nb, fs, s);
@@ -553,10 +555,12 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[4]->dptr, -1, iw, ih, nb, fs, s);
   STAGE(12);
   // Stage C (oclrect.c:361).  The clean-up kernel also copies the bitmap into buf3, where the next frame's strengths accumulate.
+  rd_prof_stage("C");
   rd_polyline_fast((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(tmp[5]), PI(buf[3]), PI(ioBig[1]), PI(tmp[0]), PI(tmp[1]), PI(tmp[2]), PI(tmp[3]), PI(tmp[4]),
                    PI(buf[5]), 4.0f, 20, iw, ih, nb, fs, s);
   STAGE(13);
   // Stage D (oclrect.c:365-367) and the compact read-back record
+  rd_prof_stage("D");
   const int nentry = n * 4 / 5;
   rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
   RD_LAUNCH(kr_reduceLS_list<0>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);   // tmp2: the polyline stage's pixel list

@@ -280,9 +280,14 @@ std::string g_prof_select;
 std::string g_prof_report;
 }
 
-int rd_prof_begin(const char *name, cudaStream_t s) {
+thread_local const char *g_rd_prof_stage = "";
+void rd_prof_stage(const char *tag) { g_rd_prof_stage = tag ? tag : ""; }
+
+int rd_prof_begin(const char *kname, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_prof_mutex);
-  if (g_rd_prof_mode.load() == 2 && strstr(name, g_prof_select.c_str()) == NULL) return -1;
+  if (g_rd_prof_mode.load() == 2 && strstr(kname, g_prof_select.c_str()) == NULL) return -1;
+  // mode 3: the name carries the pipeline stage the calling thread is in ("A/kf_iir_h3"), for per-stage totals
+  const std::string name = g_rd_prof_mode.load() == 3 ? std::string(g_rd_prof_stage) + "/" + kname : std::string(kname);
   auto it = g_prof_index.find(name);
   int idx;
   if (it == g_prof_index.end()) { idx = (int)g_prof_names.size(); g_prof_names.push_back(name); g_prof_index[name] = idx; }
@@ -301,7 +306,7 @@ void rd_prof_end(int slot, cudaStream_t s) {
 }
 
 extern "C" {
-// mode 0 off, 1 all kernels, 2 kernels whose name contains `select`
+// mode 0 off, 1 all kernels, 2 kernels whose name contains `select`, 3 all kernels with the stage tag in the name
 void rd_profile_start(int mode, const char *select) {
   std::lock_guard<std::mutex> lk(g_prof_mutex);
   g_prof_select = select ? select : "";
