@@ -276,11 +276,17 @@ __global__ void __launch_bounds__(EXS_WARPS * 32) kf_blb_extents_s(uint8_t *extH
 // different banks whatever their extents; the column sums live in a 16-row ring with one column per (lane, pixel).
 // All sums are kept modulo 2^64; a window sum is a difference of two of them and always fits its 20-bit field.
 #define S4_WARPS 4
+// The y pass of row yv looks at the column sums behind rows yv - 4 .. yv + 5, so a ring of S4_RING = 10 rows is enough
+// (10 KB per warp instead of 16 with a power-of-two depth: 16 warps per SM instead of 12, and room for other kernels'
+// CTAs beside them).  Slots are addressed relative to the newest row, `top` = slot of row yv + 5: row yv + 5 - k lives
+// in slot top - k (+ S4_RING if negative).
+#define S4_RING 10
 template <int NPX> struct S4Smem {
   enum { AC = 4 / NPX, PP = 32 + 2 * AC + 2 };                    // apron columns per side; pitch of a plane of running sums
   blb_w P[2][NPX][PP];
-  blb_w R[SB_RING][NPX][32];
+  blb_w R[S4_RING][NPX][32];
 };
+__device__ __forceinline__ int s4_slot(int top, int k) { const int t = top - k; return t < 0 ? t + S4_RING : t; }
 template <int NPX> struct S4Vec;
 template <> struct S4Vec<4> { typedef uint4 T; };
 template <> struct S4Vec<2> { typedef uint2 T; };
@@ -305,14 +311,15 @@ __device__ __forceinline__ uint32_t s4_mean_packed(blb_w s, unsigned m) {
   s4_fields2(s, f0, f1, f2);
   return (__umulhi(f2, m) << 22) | (__umulhi(f1, m) << 12) | __umulhi(f0, m);
 }
-// y pass for row yv of the lane's NPX columns: the sums behind rows yv - 5 .. yv + 5 are in the ring
+// y pass for row yv of the lane's NPX columns: the sums behind rows yv - 4 .. yv + 5 are in the ring; top = slot of row yv + 5
 template <int NPX>
-__device__ __forceinline__ void s4_vrow(uint32_t (&res)[NPX], const blb_w (*R)[NPX][32], const unsigned *rcp, unsigned ev, int yv, int lane) {
+__device__ __forceinline__ void s4_vrow(uint32_t (&res)[NPX], const blb_w (*R)[NPX][32], const unsigned *rcp, unsigned ev, int top, int lane) {
+  const int sa = s4_slot(top, 4), sd = s4_slot(top, 5);            // rows yv + 1, yv
 #pragma unroll
   for (int k = 0; k < NPX; k++) {
     const unsigned ek = (ev >> (8 * k)) & 255u, nu = ek & 15u, nd = ek >> 4;
-    const blb_w qa = R[(yv + 1) & (SB_RING - 1)][k][lane], qd = R[yv & (SB_RING - 1)][k][lane];
-    const blb_w vs = (qa - R[(yv + 1 - nu) & (SB_RING - 1)][k][lane]) + (R[(yv + nd) & (SB_RING - 1)][k][lane] - qd);
+    const blb_w qa = R[sa][k][lane], qd = R[sd][k][lane];
+    const blb_w vs = (qa - R[s4_slot(top, 4 + (int)nu)][k][lane]) + (R[s4_slot(top, 5 - (int)nd)][k][lane] - qd);
     const unsigned ws = nu + nd;
     res[k] = ws == 0 ? blb_pack(qa - qd) : s4_mean_packed(vs, rcp[ws]);
   }
@@ -347,8 +354,9 @@ __global__ void __launch_bounds__(S4_WARPS * 32) kf_blb_stream4(uint32_t *out, c
   Vec zerov;
   memset(&zerov, 0, sizeof(zerov));
   blb_w Q[NPX];
+  int slot = first % S4_RING;                                     // slot of the row whose column sums were stored last
 #pragma unroll
-  for (int k = 0; k < NPX; k++) { Q[k] = 0; sm.R[first & (SB_RING - 1)][k][lane] = 0; }
+  for (int k = 0; k < NPX; k++) { Q[k] = 0; sm.R[slot][k][lane] = 0; }
   auto load_ext = [&](const uint8_t *e, int row) -> unsigned {
     if (NPX == 4) return ((const uint32_t *)e)[(size_t)row * qv + cx];
     return ((const uint16_t *)e)[(size_t)row * qv + cx];
@@ -415,10 +423,12 @@ __global__ void __launch_bounds__(S4_WARPS * 32) kf_blb_stream4(uint32_t *out, c
     }
     // ---- y pass: column running sums in the ring; row yv = y - 4 is complete once the sums behind row y are known
 #pragma unroll
-    for (int k = 0; k < NPX; k++) { Q[k] += h[k]; sm.R[(y + 1) & (SB_RING - 1)][k][lane] = Q[k]; }
+    slot = slot + 1 == S4_RING ? 0 : slot + 1;                     // row y + 1 = yv + 5
+#pragma unroll
+    for (int k = 0; k < NPX; k++) { Q[k] += h[k]; sm.R[slot][k][lane] = Q[k]; }
     if (doV) {
       uint32_t res[NPX];
-      s4_vrow<NPX>(res, sm.R, rcp, ev, yv, lane);
+      s4_vrow<NPX>(res, sm.R, rcp, ev, slot, lane);
       outv[(size_t)yv * qv + cx] = s4_make(res);
     }
   }
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(S4_WARPS * 32) kf_blb_stream4(uint32_t *out, c
   if (okx) {
     for (int yv = max(y0, last - BLB); yv < y1; yv++) {
       uint32_t res[NPX];
-      s4_vrow<NPX>(res, sm.R, rcp, load_ext(extV, yv), yv, lane);
+      s4_vrow<NPX>(res, sm.R, rcp, load_ext(extV, yv), (yv + 5) % S4_RING, lane);
       outv[(size_t)yv * qv + cx] = s4_make(res);
     }
   }
@@ -457,14 +467,14 @@ void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int
   }
   const uint32_t *cur = src;
   if ((iw & 3) == 0) {
-    // Four pixels per lane: 18.3 KB of shared memory per warp, 12 warps per SM.  (Measured: the two-pixel instantiation
-    // - 24 warps per SM - is 10 % slower, 8.0 vs 7.2 us per 1280x720 iteration; the kernel is bound by instruction issue at
+    // Four pixels per lane: 12.3 KB of shared memory per warp, 16 warps per SM.  (Measured: the two-pixel instantiation
+    // - twice the warps per SM - is 10 % slower, 8.0 vs 7.2 us per 1280x720 iteration; the kernel is bound by instruction issue at
     // ~170 instructions per pixel, not by latency, and the scan and apron cost more per pixel with narrower strips.)
     constexpr int npx = 4;
     static bool attr = false;
     const size_t smem = S4_WARPS * sizeof(S4Smem<npx>);
     if (!attr) { RD_CUDA(cudaFuncSetAttribute(kf_blb_stream4<npx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    const int strips = rd_cdiv(iw, 32 * npx), ch = rd_strip_height(strips, nb, ih, 12, 48, 1 << 20), chunks = rd_cdiv(ih, ch);
+    const int strips = rd_cdiv(iw, 32 * npx), ch = rd_strip_height(strips, nb, ih, 16, 48, 1 << 20), chunks = rd_cdiv(ih, ch);
     const int blocks = rd_cdiv(strips * chunks * nb, S4_WARPS);
     for (int i = 0; i < iters; i++) {
       uint32_t *o = ((iters - i) & 1) ? dst : pong;     // the last iteration lands in dst
