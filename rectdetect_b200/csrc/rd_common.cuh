@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <functional>
 #include "../../include/rectdetect_b200.h"
 
 struct rd_cl_platform { int unused; };
@@ -148,6 +149,8 @@ void rd_label8x(int *label, const int *pix, void *scratch /* iw*ih bytes */, int
 // host tail (rd_tail.cpp) on the compact read-back record (see rd_rect.cu : tail_gather)
 struct rd_tail_sample { int32_t segid; int32_t vote[5]; };            // vote = the table entry the (ls,segid) pair hashes to
 #define RD_TAIL_NSAMPLE 15
-rect_t *rd_tail_compact(const linesegment_t *ls /* n+1 entries */, const rd_tail_sample *samples /* (n+1)*15 */, int iw, int ih, double tanAOV);
+typedef void (*rd_parallel_for_t)(int n, const std::function<void(int)> &fn);     // fn(0) .. fn(n-1), returns when all are done
+rect_t *rd_tail_compact(const linesegment_t *ls /* n+1 entries */, const rd_tail_sample *samples /* (n+1)*15 */, int iw, int ih, double tanAOV,
+                        rd_parallel_for_t pfor /* NULL: serial */);
 
 #endif

@@ -765,6 +765,7 @@ static TailPool &tail_pool() {
   }());
   return pool;
 }
+static void tail_parallel_for(int n, const std::function<void(int)> &fn) { tail_pool().run_all(n, fn); }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // executeCPUTask (oclrect.c:1049) on the read-back records of `page`; out[i] receives the list of frame i
@@ -805,7 +806,7 @@ static void finish_page(oclrect_t *o, int page, double tanAOV, rect_t **out, int
     }
     const linesegment_t *ls = (const linesegment_t *)(hb + 64);
     const rd_tail_sample *sm = (const rd_tail_sample *)(hb + 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7));
-    out[i] = rd_tail_compact(ls, sm, o->iw, o->ih, tanAOV);
+    out[i] = rd_tail_compact(ls, sm, o->iw, o->ih, tanAOV, count == 1 ? tail_parallel_for : (rd_parallel_for_t)NULL);   // a lone frame spreads its candidates
   };
   if (count == 1) one(0);
   else tail_pool().run_all(count, one);

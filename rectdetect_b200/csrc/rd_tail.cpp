@@ -10,10 +10,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
 #include <vector>
 #include "../../include/rectdetect_b200.h"
 
 struct rd_tail_sample { int32_t segid; int32_t vote[5]; };
+typedef void (*rd_parallel_for_t)(int n, const std::function<void(int)> &fn);   // as in rd_common.cuh
 #define RD_TAIL_NSAMPLE 15
 
 namespace {
@@ -387,21 +389,20 @@ bool toCorners(std::vector<Edge> &es) {                                         
 }
 
 // the candidate test shared by both loops of executeCPUTask (oclrect.c:1134-1160, 1190-1216)
-void tryQuad(std::vector<Edge> es, uint32_t status, int iw, int ih, double tanAOV, std::vector<rect_t> &out) {
+bool tryQuad(std::vector<Edge> es, uint32_t status, int iw, int ih, double tanAOV, rect_t &r) {
   dropShort(es, 0.05f);
   es = keepOuter(es);
   const double len0 = totalLength(es);
   es = keepLongest(es, 4);
   sortByAngle(es, weightedCentre(es));
-  if (!toCorners(es)) return;
+  if (!toCorners(es)) return false;
   const double len1 = totalLength(es);
-  if (nearlyTriangle(es, 0.001) || es.size() < 4 || len1 / len0 > 2 || !convex(es)) return;
-  rect_t r;
+  if (nearlyTriangle(es, 0.001) || es.size() < 4 || len1 / len0 > 2 || !convex(es)) return false;
   memset(&r, 0, sizeof(r));
   estimatePose(es.data(), weightedCentre(es), iw, ih, tanAOV, &r);
   r.status = status;
   if (looksLikeAScreen(r)) r.status |= 1;
-  out.push_back(r);
+  return true;
 }
 
 inline int bucketOf(uint64_t key) { return (int)((key ^ (key >> 10) ^ (key >> 20) ^ (key >> 30)) & 1023); }   // helper.c:129-131
@@ -409,9 +410,12 @@ inline int bucketOf(uint64_t key) { return (int)((key ^ (key >> 10) ^ (key >> 20
 }  // namespace
 
 // executeCPUTask on the compact record.  ls: n+1 entries (entry 0 = header); samples: (n+1) x 15.
-rect_t *rd_tail_compact(const linesegment_t *ls, const rd_tail_sample *samples, int iw, int ih, double tanAOV) {
+// The candidates are independent (each ends in a pose estimation, which is where the time goes); `pfor`, when given, runs
+// them in parallel - the results are collected in candidate order either way, so the list does not depend on it.
+rect_t *rd_tail_compact(const linesegment_t *ls, const rd_tail_sample *samples, int iw, int ih, double tanAOV, rd_parallel_for_t pfor) {
   const int n = *(const int32_t *)ls;
-  std::vector<rect_t> found;
+  struct Candidate { std::vector<Edge> es; uint32_t status; };
+  std::vector<Candidate> cands;
 
   // (i) regions each live segment touches, grouped by region in ArrayMap iteration order (bucket, then first insertion)
   struct Region { int segid; std::vector<int> lsids; std::vector<const int32_t *> votes; };
@@ -445,7 +449,7 @@ rect_t *rd_tail_compact(const linesegment_t *ls, const rd_tail_sample *samples, 
         if (!clipToBox(x0, y0, x1, y1, iw - v[1], ih - v[3], v[2], v[4])) continue;
         es.push_back(Edge{{x0, y0}, {x1, y1}});
       }
-      tryQuad(es, 0, iw, ih, tanAOV, found);
+      cands.push_back(Candidate{std::move(es), 0u});
     }
 
   // (iii) one candidate per polyline chain, from its segments longer than 32 px
@@ -456,12 +460,20 @@ rect_t *rd_tail_compact(const linesegment_t *ls, const rd_tail_sample *samples, 
       const P2 a = {ls[j].x0, ls[j].y0}, b = {ls[j].x1, ls[j].y1};
       if (dist2(a, b) > 32.0 * 32.0) es.push_back(Edge{a, b});
     }
-    tryQuad(es, 2, iw, ih, tanAOV, found);
+    cands.push_back(Candidate{std::move(es), 2u});
   }
 
-  rect_t *out = (rect_t *)calloc(found.size() + 1, sizeof(rect_t));
-  for (size_t i = 0; i < found.size(); i++) out[i + 1] = found[i];
-  out[0].nItems = (int)found.size() + 1;
+  std::vector<rect_t> rects(cands.size());
+  std::vector<char> ok(cands.size(), 0);
+  auto one = [&](int i) { ok[i] = tryQuad(cands[i].es, cands[i].status, iw, ih, tanAOV, rects[i]) ? 1 : 0; };
+  if (pfor && cands.size() > 1) pfor((int)cands.size(), one);
+  else for (size_t i = 0; i < cands.size(); i++) one((int)i);
+  size_t nfound = 0;
+  for (size_t i = 0; i < cands.size(); i++) nfound += ok[i];
+  rect_t *out = (rect_t *)calloc(nfound + 1, sizeof(rect_t));
+  size_t k = 1;
+  for (size_t i = 0; i < cands.size(); i++) if (ok[i]) out[k++] = rects[i];
+  out[0].nItems = (int)nfound + 1;
   return out;
 }
 
@@ -495,5 +507,5 @@ extern "C" rect_t *rd_rect_tail(const linesegment_t *ls, const int32_t *segid, c
   const int n = *(const int32_t *)ls;
   std::vector<rd_tail_sample> sm((size_t)(n + 1) * RD_TAIL_NSAMPLE);
   rd_tail_gather_host(ls, segid, votes, iw, ih, sm.data());
-  return rd_tail_compact(ls, sm.data(), iw, ih, tanAOV);
+  return rd_tail_compact(ls, sm.data(), iw, ih, tanAOV, NULL);
 }
