@@ -55,6 +55,22 @@ def test_production_schedule_stage_planes_bit_exact(rd, gpu_dev, iw, ih, seed):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("iw,ih", [(641, 479), (130, 97), (96, 64), (1284, 724), (257, 511), (48, 40)])
+def test_production_schedule_odd_sizes(rd, gpu_dev, iw, ih):
+    # widths that are not multiples of 4 / 32 / 128 (scalar fall-backs of the vectorised kernels, ragged tiles and strips),
+    # frames smaller than a tile; tools/gpu_stress_parity.py runs the full sweep (profiles/r02c_stress_parity_48_cases.txt)
+    seed = 31
+    bad = [r for r in parity.compare_fast_stages(iw, ih, seed, sorted(parity.FAST_STAGES), rd, gpu_dev) if r[2] != 0]
+    assert not bad, bad
+    img = ol.synth_frame(iw, ih, seed)
+    o, g = ol.OracleRect(iw, ih), rd.OclRect(gpu_dev, iw, ih)
+    for _ in range(2):                               # second pass: carried-over strength accumulator
+        ok, why = parity.rects_close(o.execute_once(img, parity.TAN_AOV), g.execute_once(img, parity.TAN_AOV))
+        assert ok, why
+    g.close()
+    o.close()
+
+
 def test_row_stride_wider_than_the_image(rd, gpu_dev):
     iw, ih = 300, 200
     bad = [r for r in parity.compare_steps(iw, ih, 11, [1, 8, 21], rd, gpu_dev, ws=4 * iw - 3) if r[2] != 0]
