@@ -422,7 +422,6 @@ __global__ void __launch_bounds__(S4_WARPS * 32) kf_blb_stream4(uint32_t *out, c
       h[k] = ws == 0 ? w[k] : s4_mean_spread(hs, rcp[ws]);
     }
     // ---- y pass: column running sums in the ring; row yv = y - 4 is complete once the sums behind row y are known
-#pragma unroll
     slot = slot + 1 == S4_RING ? 0 : slot + 1;                     // row y + 1 = yv + 5
 #pragma unroll
     for (int k = 0; k < NPX; k++) { Q[k] += h[k]; sm.R[slot][k][lane] = Q[k]; }

@@ -14,6 +14,7 @@
 #include "rd_common.cuh"
 #include "rd_stageA.cuh"
 #include "rd_bits.cuh"
+#include <cooperative_groups.h>
 
 struct oclpolyline_t { uint32_t magic; int ordinal; };
 #define POLY_MAGIC 0x808eae03u
@@ -31,7 +32,15 @@ static_assert(sizeof(LS_t) == 56 && sizeof(LSX_t) == 56, "list entries are 56 by
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
 #define IS_BORDER1 (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1)
 // kernels over the compact list of labelled pixels: grid-stride loop, `continue` instead of `return`
-#define PLIST_LOOP const int pcount_ = plist[0]; for (int k_ = threadIdx.x; k_ < pcount_; k_ += blockDim.x)
+// The list kernel (kp_polyline_list) runs one thread-block CLUSTER per frame: its passes are grid-stride loops over the
+// cluster's threads, separated by cluster barriers (hardware barrier.cluster with release / acquire ordering of the global
+// lists they exchange).
+#define PL_CLUSTER 8
+#define PL_THREADS 512
+__device__ __forceinline__ int pl_tid() { return (int)(cooperative_groups::this_cluster().block_rank() * blockDim.x + threadIdx.x); }
+__device__ __forceinline__ int pl_nt() { return (int)(cooperative_groups::this_cluster().num_blocks() * blockDim.x); }
+#define PLIST_LOOP const int pcount_ = plist[0]; for (int k_ = pl_tid(), nt_ = pl_nt(); k_ < pcount_; k_ += nt_)
+#define PL_SEG_LOOP(count) for (int g = pl_tid() + 1, nt_ = pl_nt(); g <= (count); g += nt_)
 #define PLIST_XY const int p0 = plist[k_ + 1]; const int x = p0 % iw, y = p0 / iw; (void)x; (void)y
 #define LIST_BLOCKS 32
 
@@ -332,7 +341,7 @@ __device__ __forceinline__ void closestPoint(float vx, float vy, float wx, float
 __device__ __forceinline__ void d_mkpl_init(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const int *table, int *flags, int maxIter) {
   const int cap2 = min(cap, lsListSize / (int)sizeof(LS_t));
   const int K = min(table[0], cap2 - 1);
-  const int t = (int)threadIdx.x, nt = (int)blockDim.x;
+  const int t = pl_tid(), nt = pl_nt();
   if (t < maxIter + 1) flags[t] = t == 0 ? 1 : 0;
   int *raw = (int *)gp;
   for (int i = t; i < (K + 1) * 14; i += nt) raw[i] = 0;
@@ -365,7 +374,7 @@ __device__ __forceinline__ void d_mkpl_pass0b(LS_t *gp, int lsListSize, int *aux
 // one thread per list entry: turn the start / end pixel indices into coordinates
 __device__ __forceinline__ void d_mkpl_pass0c(LS_t *gp, const int *aux, int cap, int iw) {
   const int count = min(*(const int *)gp, cap - 1);
-  for (int g = (int)threadIdx.x + 1; g <= count; g += (int)blockDim.x) {
+  PL_SEG_LOOP(count) {
     const int sp = aux[g] - 1, ep = aux[cap + g];
     if (sp >= 0) { gp[g].x0 = (float)(sp % iw); gp[g].y0 = (float)(sp / iw); gp[g].level = 0; }
     if (ep >= 0 && ep != 0x7fffffff) { gp[g].x1 = (float)(ep % iw); gp[g].y1 = (float)(ep / iw); gp[g].polyid = g; }
@@ -408,15 +417,16 @@ __device__ __forceinline__ void d_mkpl_pass2a(const LS_t *gp, int lsListSize, in
     atomicMin(winner + g, p0);
   }
 }
-// pass2b: single CTA; decides the splits of this iteration, numbers the new entries by a prefix sum over the
+// pass2b: ONE CTA (rank 0 of the cluster); decides the splits of this iteration, numbers the new entries by a prefix sum over the
 // parent id and rewrites the list.  Also resets winner[] for the next iteration.
 __device__ __forceinline__ void d_mkpl_pass2b(LS_t *gp, int lsListSize, int *winner, const int *numberin, const int *flags, int nIter, float minerror, int iw) {
   __shared__ int wsum[32];
   __shared__ int carry, total;
   const int count = *(const int *)gp;
   if (threadIdx.x == 0) carry = count;
+  if (threadIdx.x < 32) wsum[threadIdx.x] = 0;
   __syncthreads();
-  for (int base = 1; base <= count; base += 1024) {
+  for (int base = 1; base <= count; base += PL_THREADS) {
     const int g = base + threadIdx.x;
     bool split = false;
     int px = 0, py = 0, n = 0, maxDist = 0, gr = 0, endIndex = 0, polyid = 0;
@@ -444,7 +454,7 @@ __device__ __forceinline__ void d_mkpl_pass2b(LS_t *gp, int lsListSize, int *win
     if (lane == 0) wsum[w] = __popc(b);
     __syncthreads();
     if (threadIdx.x < 32) {
-      const int v = wsum[threadIdx.x];
+      const int v = threadIdx.x < PL_THREADS / 32 ? wsum[threadIdx.x] : 0;
       int vi = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, vi, o); if (threadIdx.x >= o) vi += t; }
@@ -486,7 +496,7 @@ __device__ __forceinline__ void d_mkpl_pass3(const LS_t *gp, int lsListSize, con
 // ---------------------------------------------------------------------------- refine (oclpolyline.cl:680-809)
 __device__ __forceinline__ void d_refine_pass0(LSX_t *lsx, const LS_t *ls) {
   const int count_ = *(const int *)ls;
-  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
+  PL_SEG_LOOP(count_) {
   if (ls[g].polyid == 0) continue;
   LSX_t v;
   v.dirSEx = (short)(int)__fsub_rn(ls[g].x1, ls[g].x0);          // convert_short2: truncation (Q18)
@@ -519,7 +529,7 @@ __device__ __forceinline__ void d_refine_pass1(LSX_t *lsx, const LS_t *ls, const
 }
 __device__ __forceinline__ void d_refine_pass2(const LSX_t *lsx, LS_t *ls) {
   const int count_ = *(const int *)ls;
-  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
+  PL_SEG_LOOP(count_) {
   if (ls[g].polyid == 0) continue;
   const float mx00 = (float)lsx[g].mx00, mx01 = (float)lsx[g].mx01, mx11 = (float)lsx[g].mx11, my0 = (float)lsx[g].my0, my1 = (float)lsx[g].my1;
   float rdet = __fsub_rn(__fmul_rn(mx00, mx11), __fmul_rn(mx01, mx01));
@@ -537,7 +547,7 @@ __device__ __forceinline__ void d_refine_pass2(const LSX_t *lsx, LS_t *ls) {
 // pass3a computes the vertex g shares with its right neighbour from the unmodified list; pass3b writes it to both
 __device__ __forceinline__ void d_refine_pass3a(float2 *vtx, const LS_t *ls) {
   const int count_ = *(const int *)ls;
-  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
+  PL_SEG_LOOP(count_) {
   float2 r = make_float2(__int_as_float(0x7fc00000), 0.0f);     // NaN = nothing to write
   if (ls[g].polyid != 0 && ls[g].rightPtr != 0) {
     const int h = ls[g].rightPtr;
@@ -559,7 +569,7 @@ __device__ __forceinline__ void d_refine_pass3a(float2 *vtx, const LS_t *ls) {
 }
 __device__ __forceinline__ void d_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot) {
   const int count_ = *(const int *)ls;
-  for (int g = (int)threadIdx.x + 1; g <= count_; g += (int)blockDim.x) {
+  PL_SEG_LOOP(count_) {
   (void)rightPtrSnapshot;
   const float2 r = vtx[g];
   if (r.x != r.x) {
@@ -572,38 +582,42 @@ __device__ __forceinline__ void d_refine_pass3b(const float2 *vtx, LS_t *ls, con
   }
 }
 
-// mkpl (oclpolyline.c:186-216) + refine (oclpolyline.c:299-306) for one frame per CTA.
-__global__ void __launch_bounds__(1024) kp_polyline_list(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const int *table, int *flags, int *dist,
-                                                         const int *numberin, int *labelinout, const int *plist, LSX_t *lsx, float2 *vtx, float minerror, int iw, size_t fs) {
-  rd_batch_x(fs, gp, aux, winner, table, flags, dist, numberin, labelinout, plist, lsx, vtx);
+// mkpl (oclpolyline.c:186-216) + refine (oclpolyline.c:299-306) for one frame per thread-block cluster.
+#define PL_SYNC cluster.sync()
+__global__ void __cluster_dims__(PL_CLUSTER, 1, 1) __launch_bounds__(PL_THREADS)
+kp_polyline_list(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const int *table, int *flags, int *dist,
+                 const int *numberin, int *labelinout, const int *plist, LSX_t *lsx, float2 *vtx, float minerror, int iw, size_t fs) {
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  rd_batch_off((size_t)(blockIdx.x / PL_CLUSTER) * fs, gp, aux, winner, table, flags, dist, numberin, labelinout, plist, lsx, vtx);
+  const bool lead = cluster.block_rank() == 0;
   const int N = 16;
   d_mkpl_init(gp, lsListSize, aux, winner, cap, table, flags, N);
-  __syncthreads();
+  PL_SYNC;
   d_mkpl_pass0a(gp, lsListSize, aux, cap, numberin, labelinout, plist, iw);
-  __syncthreads();
+  PL_SYNC;
   d_mkpl_pass0b(gp, lsListSize, aux, cap, numberin, labelinout, plist, iw);
-  __syncthreads();
+  PL_SYNC;
   d_mkpl_pass0c(gp, aux, cap, iw);
-  __syncthreads();
+  PL_SYNC;
   for (int it = 1; it < N; it++) {
-    if (flags[it - 1] == 0) break;                 // nothing moved in the previous round: every later round is a no-op too
+    if (*(volatile int *)(flags + it - 1) == 0) break;   // nothing moved in the previous round: every later round is a no-op too
     d_mkpl_pass1(gp, lsListSize, dist, labelinout, plist, flags, it, iw);
-    __syncthreads();
+    PL_SYNC;
     d_mkpl_pass2a(gp, lsListSize, winner, dist, labelinout, plist, flags, it, iw);
-    __syncthreads();
-    d_mkpl_pass2b(gp, lsListSize, winner, numberin, flags, it, minerror, iw);
-    __syncthreads();
+    PL_SYNC;
+    if (lead) d_mkpl_pass2b(gp, lsListSize, winner, numberin, flags, it, minerror, iw);
+    PL_SYNC;
     d_mkpl_pass3(gp, lsListSize, numberin, labelinout, plist, flags, it, iw);
-    __syncthreads();
+    PL_SYNC;
   }
   d_refine_pass0(lsx, gp);
-  __syncthreads();
+  PL_SYNC;
   d_refine_pass1(lsx, gp, labelinout, plist, iw);
-  __syncthreads();
+  PL_SYNC;
   d_refine_pass2(lsx, gp);
-  __syncthreads();
+  PL_SYNC;
   d_refine_pass3a(vtx, gp);
-  __syncthreads();
+  PL_SYNC;
   d_refine_pass3b(vtx, gp, (const int *)NULL);
 }
 
@@ -665,7 +679,7 @@ void rd_polyline_run(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, 
   {
     const int cap = lsListSize / (int)sizeof(LS_t);
     int *aux = tmpBig + n + 8, *winner = aux + 2 * (size_t)cap;
-    RD_LAUNCH(kp_polyline_list, dim3(nb), 1024, 0, s, lsList, lsListSize, aux, winner, cap, table, tmp4, tmp3, tmp2, lsIdOut, plist, (LSX_t *)tmpBig,
+    RD_LAUNCH(kp_polyline_list, dim3(nb * PL_CLUSTER), PL_THREADS, 0, s, lsList, lsListSize, aux, winner, cap, table, tmp4, tmp3, tmp2, lsIdOut, plist, (LSX_t *)tmpBig,
               (float2 *)tmp3, minerror, iw, fs);
   }
   (void)tmp5;
@@ -976,7 +990,7 @@ void rd_polyline_fast(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in,
   {
     const int cap = lsListSize / (int)sizeof(LS_t);
     int *aux = tmpBig + n + 8, *winner = aux + 2 * (size_t)cap;
-    RD_LAUNCH(kp_polyline_list, dim3(nb), 1024, 0, s, lsList, lsListSize, aux, winner, cap, table, t5, t4, number, lsIdOut, list, (LSX_t *)tmpBig, (float2 *)t4,
+    RD_LAUNCH(kp_polyline_list, dim3(nb * PL_CLUSTER), PL_THREADS, 0, s, lsList, lsListSize, aux, winner, cap, table, t5, t4, number, lsIdOut, list, (LSX_t *)tmpBig, (float2 *)t4,
               minerror, iw, fs);
   }
 }
