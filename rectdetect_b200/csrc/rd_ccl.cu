@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(CCL_WARPS * 32) k_ccl_tile(int *label, uint8_t
       if (lx == TW - 1) m &= ~L_NE;
       if (ly == 0) m &= ~(L_NW | L_N | L_NE);
     }
+    if (__ballot_sync(0xffffffffu, !(m & L_BG)) == 0) { up = c; upW = w; upE = e; continue; }   // nothing but background in this row
     const unsigned starts = ~__ballot_sync(0xffffffffu, (m & L_W) != 0);      // bit j set: pixel j starts a run
     const int labW = __shfl_up_sync(0xffffffffu, prevLab, 1), labE = __shfl_down_sync(0xffffffffu, prevLab, 1);
     // smallest label among the pixels of the row above this pixel is linked to (its own index if none), then the smallest
