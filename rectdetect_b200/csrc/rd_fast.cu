@@ -1050,8 +1050,11 @@ __global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const u
   rd_batch_z(fs, out, in, thin);
   __shared__ uint32_t q[QD_W * QD_W];
   __shared__ uint8_t e[QD_W * QD_W];                          // 1: edge pixel (thinned strength >= 1e-6), 2: outside the image
+  __shared__ unsigned short queue[QD_T * QD_T];
+  __shared__ int nq;
   const int bx = blockIdx.x * QD_T - 1, by = blockIdx.y * QD_T - 1;
   const int lane = threadIdx.x, wy = threadIdx.y;
+  if (lane == 0 && wy == 0) nq = 0;
   // warp -> tile rows wy, wy + 8, ...; lane -> column lane, lanes 0 / 1 also columns 32 / 33
   for (int ty = wy; ty < QD_W; ty += 8) {
     const int gy = by + ty;
@@ -1068,45 +1071,59 @@ __global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const u
     }
   }
   __syncthreads();
+  // non-edge pixels keep their quantised colour; the edge pixels (a third of the frame, scattered over every warp) are
+  // queued and searched densely, one per thread
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int tx = 1 + lane, ty = 1 + wy + k * 8;
     const int gx = bx + tx, gy = by + ty;
-    if (gx >= iw || gy >= ih) continue;
     const int i = ty * QD_W + tx;
-    uint32_t r = q[i];
-    if (e[i] == 1) {
-      const uint32_t c = r;
-      const int l0 = c & 4095u, a0 = (c >> 12) & 1023u, b0 = c >> 22;
-      unsigned best = 0xffffffffu, worst = 0;
+    const bool inside = gx < iw && gy < ih;
+    const bool edge = inside && e[i] == 1;
+    if (inside && !edge) out[(size_t)gy * iw + gx] = q[i];
+    const unsigned b = __ballot_sync(0xffffffffu, edge);
+    if (b) {
+      int base = 0;
+      if (lane == 0) base = rd_smem_fetch_add(&nq, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (edge) queue[base + __popc(b & ((1u << lane) - 1u))] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  for (int t = wy * 32 + lane, n = nq; t < n; t += 256) {
+    const int i = queue[t];
+    const int gx = bx + i % QD_W, gy = by + i / QD_W;
+    const uint32_t c = q[i];
+    uint32_t r = c;
+    const int l0 = c & 4095u, a0 = (c >> 12) & 1023u, b0 = c >> 22;
+    unsigned best = 0xffffffffu, worst = 0;
 #pragma unroll
+    for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+      for (int xx = -1; xx <= 1; xx++) {
+        const int j = i + yy * QD_W + xx;
+        if (e[j] != 0) continue;                              // edge pixels and positions outside the image do not donate
+        const uint32_t v = q[j];
+        const int dl = (int)(v & 4095u) - l0, da = (int)((v >> 12) & 1023u) - a0, db = (int)(v >> 22) - b0;
+        const unsigned N = (unsigned)(dl * dl) + 16u * (unsigned)(da * da + db * db);
+        worst = max(worst, N);
+        if (N < best) { best = N; r = v; }
+      }
+    if (worst >= (1u << 20)) {
+      // far-apart colours: distances may collide after rounding, follow the reference's float comparison
+      r = c;
+      float dist = 1e+10f, fl0, fa0, fb0;
+      rd_unpacklab(c, fl0, fa0, fb0);
       for (int yy = -1; yy <= 1; yy++)
-#pragma unroll
         for (int xx = -1; xx <= 1; xx++) {
           const int j = i + yy * QD_W + xx;
-          if (e[j] != 0) continue;                            // edge pixels and positions outside the image do not donate
+          if (e[j] != 0) continue;
+          float l1, a1, b1;
           const uint32_t v = q[j];
-          const int dl = (int)(v & 4095u) - l0, da = (int)((v >> 12) & 1023u) - a0, db = (int)(v >> 22) - b0;
-          const unsigned N = (unsigned)(dl * dl) + 16u * (unsigned)(da * da + db * db);
-          worst = max(worst, N);
-          if (N < best) { best = N; r = v; }
+          rd_unpacklab(v, l1, a1, b1);
+          const float d = rd_distance3(__fsub_rn(l1, fl0), __fsub_rn(a1, fa0), __fsub_rn(b1, fb0));
+          if (d < dist) { r = v; dist = d; }
         }
-      if (worst >= (1u << 20)) {
-        // far-apart colours: distances may collide after rounding, follow the reference's float comparison
-        r = c;
-        float dist = 1e+10f, fl0, fa0, fb0;
-        rd_unpacklab(c, fl0, fa0, fb0);
-        for (int yy = -1; yy <= 1; yy++)
-          for (int xx = -1; xx <= 1; xx++) {
-            const int j = i + yy * QD_W + xx;
-            if (e[j] != 0) continue;
-            float l1, a1, b1;
-            const uint32_t v = q[j];
-            rd_unpacklab(v, l1, a1, b1);
-            const float d = rd_distance3(__fsub_rn(l1, fl0), __fsub_rn(a1, fa0), __fsub_rn(b1, fb0));
-            if (d < dist) { r = v; dist = d; }
-          }
-      }
     }
     out[(size_t)gy * iw + gx] = r;
   }
@@ -1232,47 +1249,66 @@ __global__ void __launch_bounds__(256) kf_despeckle2_boundary(int *out, const in
   __shared__ int sl[DB_W * DB_W];
   __shared__ int ss[DB_W * DB_W];
   __shared__ int sd[DB_W * DB_W];
+  __shared__ unsigned rowU[DB_W];                              // bit c: the five absorbed labels around payload column c of this row are equal
   const int bx = blockIdx.x * DB_T - DB_A, by = blockIdx.y * DB_T - DB_A;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < DB_W * DB_W; i += 256) {
-    const int gx = bx + i % DB_W, gy = by + i / DB_W;
-    int l = -1, sz = 0;
-    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) { l = label[(size_t)gy * iw + gx]; sz = size[l]; }
-    sl[i] = l; ss[i] = sz;
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  // warp -> tile rows wy, wy + 8, ...; lane -> column lane, lanes 0..5 also columns 32..37
+  for (int ty = wy; ty < DB_W; ty += 8) {
+    const int gy = by + ty;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int tx = lane + 32 * h;
+      if (tx >= DB_W) continue;
+      const int gx = bx + tx;
+      int l = -1, sz = 0;
+      if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) { l = label[(size_t)gy * iw + gx]; sz = size[l]; }
+      sl[ty * DB_W + tx] = l; ss[ty * DB_W + tx] = sz;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < DB_W * DB_W; i += 256) {
-    const int tx = i % DB_W, ty = i / DB_W;
-    const int gx = bx + tx, gy = by + ty;
-    int res = sl[i];
-    if (tx >= 1 && ty >= 1 && tx < DB_W - 1 && ty < DB_W - 1 && gx >= 0 && gx < iw && gy >= 0 && gy < ih && !(ss[i] > thre)) {
-      int maxSize = 0;
+  // despeckle2 (Jacobi): a pixel of a small region takes the label of the largest region among its 3x3 neighbours
+  for (int ty = wy; ty < DB_W; ty += 8) {
+    const int gy = by + ty;
 #pragma unroll
-      for (int yy = -1; yy <= 1; yy++)
+    for (int h = 0; h < 2; h++) {
+      const int tx = lane + 32 * h;
+      if (tx >= DB_W) continue;
+      const int gx = bx + tx, i = ty * DB_W + tx;
+      int res = sl[i];
+      if (tx >= 1 && ty >= 1 && tx < DB_W - 1 && ty < DB_W - 1 && gx >= 0 && gx < iw && gy >= 0 && gy < ih && !(ss[i] > thre)) {
+        int maxSize = 0;
 #pragma unroll
-        for (int xx = -1; xx <= 1; xx++) {
-          if (gx + xx < 0 || gx + xx >= iw || gy + yy < 0 || gy + yy >= ih) continue;
-          const int j = i + yy * DB_W + xx;
-          if (ss[j] > maxSize) { maxSize = ss[j]; res = sl[j]; }
-        }
+        for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+          for (int xx = -1; xx <= 1; xx++) {
+            if (gx + xx < 0 || gx + xx >= iw || gy + yy < 0 || gy + yy >= ih) continue;
+            const int j = i + yy * DB_W + xx;
+            if (ss[j] > maxSize) { maxSize = ss[j]; res = sl[j]; }
+          }
+      }
+      sd[i] = res;
     }
-    sd[i] = res;
+  }
+  __syncthreads();
+  // markBoundary: the 5x5 neighbourhood is uniform iff each of its five rows is uniform and the five row centres agree
+  for (int ty = 1 + wy; ty < DB_W - 1; ty += 8) {
+    const int i = ty * DB_W + DB_A + lane, c = sd[i];
+    const bool u = sd[i - 2] == c && sd[i - 1] == c && sd[i + 1] == c && sd[i + 2] == c;
+    const unsigned b = __ballot_sync(0xffffffffu, u);
+    if (lane == 0) rowU[ty] = b;
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int tx = DB_A + threadIdx.x, ty = DB_A + threadIdx.y + k * 8;
+    const int tx = DB_A + lane, ty = DB_A + wy + k * 8;
     const int gx = bx + tx, gy = by + ty;
     if (gx >= iw || gy >= ih) continue;
     int r = -1;
     if (!(gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2)) {
       const int i = ty * DB_W + tx, c0 = sd[i];
-      bool nearEdge = false;
-#pragma unroll
-      for (int yy = -2; yy <= 2; yy++)
-#pragma unroll
-        for (int xx = -2; xx <= 2; xx++) nearEdge |= sd[i + yy * DB_W + xx] != c0;
-      if (nearEdge) r = c0;
+      const unsigned uni = rowU[ty - 2] & rowU[ty - 1] & rowU[ty] & rowU[ty + 1] & rowU[ty + 2];
+      const bool same = ((uni >> lane) & 1u) && sd[i - 2 * DB_W] == c0 && sd[i - DB_W] == c0 && sd[i + DB_W] == c0 && sd[i + 2 * DB_W] == c0;
+      if (!same) r = c0;
     }
     out[(size_t)gy * iw + gx] = r;
   }
