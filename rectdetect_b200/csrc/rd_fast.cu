@@ -1249,66 +1249,47 @@ __global__ void __launch_bounds__(256) kf_despeckle2_boundary(int *out, const in
   __shared__ int sl[DB_W * DB_W];
   __shared__ int ss[DB_W * DB_W];
   __shared__ int sd[DB_W * DB_W];
-  __shared__ unsigned rowU[DB_W];                              // bit c: the five absorbed labels around payload column c of this row are equal
   const int bx = blockIdx.x * DB_T - DB_A, by = blockIdx.y * DB_T - DB_A;
-  const int lane = threadIdx.x, wy = threadIdx.y;
-  // warp -> tile rows wy, wy + 8, ...; lane -> column lane, lanes 0..5 also columns 32..37
-  for (int ty = wy; ty < DB_W; ty += 8) {
-    const int gy = by + ty;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int tx = lane + 32 * h;
-      if (tx >= DB_W) continue;
-      const int gx = bx + tx;
-      int l = -1, sz = 0;
-      if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) { l = label[(size_t)gy * iw + gx]; sz = size[l]; }
-      sl[ty * DB_W + tx] = l; ss[ty * DB_W + tx] = sz;
-    }
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < DB_W * DB_W; i += 256) {
+    const int gx = bx + i % DB_W, gy = by + i / DB_W;
+    int l = -1, sz = 0;
+    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) { l = label[(size_t)gy * iw + gx]; sz = size[l]; }
+    sl[i] = l; ss[i] = sz;
   }
   __syncthreads();
-  // despeckle2 (Jacobi): a pixel of a small region takes the label of the largest region among its 3x3 neighbours
-  for (int ty = wy; ty < DB_W; ty += 8) {
-    const int gy = by + ty;
+  for (int i = tid; i < DB_W * DB_W; i += 256) {
+    const int tx = i % DB_W, ty = i / DB_W;
+    const int gx = bx + tx, gy = by + ty;
+    int res = sl[i];
+    if (tx >= 1 && ty >= 1 && tx < DB_W - 1 && ty < DB_W - 1 && gx >= 0 && gx < iw && gy >= 0 && gy < ih && !(ss[i] > thre)) {
+      int maxSize = 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int tx = lane + 32 * h;
-      if (tx >= DB_W) continue;
-      const int gx = bx + tx, i = ty * DB_W + tx;
-      int res = sl[i];
-      if (tx >= 1 && ty >= 1 && tx < DB_W - 1 && ty < DB_W - 1 && gx >= 0 && gx < iw && gy >= 0 && gy < ih && !(ss[i] > thre)) {
-        int maxSize = 0;
+      for (int yy = -1; yy <= 1; yy++)
 #pragma unroll
-        for (int yy = -1; yy <= 1; yy++)
-#pragma unroll
-          for (int xx = -1; xx <= 1; xx++) {
-            if (gx + xx < 0 || gx + xx >= iw || gy + yy < 0 || gy + yy >= ih) continue;
-            const int j = i + yy * DB_W + xx;
-            if (ss[j] > maxSize) { maxSize = ss[j]; res = sl[j]; }
-          }
-      }
-      sd[i] = res;
+        for (int xx = -1; xx <= 1; xx++) {
+          if (gx + xx < 0 || gx + xx >= iw || gy + yy < 0 || gy + yy >= ih) continue;
+          const int j = i + yy * DB_W + xx;
+          if (ss[j] > maxSize) { maxSize = ss[j]; res = sl[j]; }
+        }
     }
-  }
-  __syncthreads();
-  // markBoundary: the 5x5 neighbourhood is uniform iff each of its five rows is uniform and the five row centres agree
-  for (int ty = 1 + wy; ty < DB_W - 1; ty += 8) {
-    const int i = ty * DB_W + DB_A + lane, c = sd[i];
-    const bool u = sd[i - 2] == c && sd[i - 1] == c && sd[i + 1] == c && sd[i + 2] == c;
-    const unsigned b = __ballot_sync(0xffffffffu, u);
-    if (lane == 0) rowU[ty] = b;
+    sd[i] = res;
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int tx = DB_A + lane, ty = DB_A + wy + k * 8;
+    const int tx = DB_A + threadIdx.x, ty = DB_A + threadIdx.y + k * 8;
     const int gx = bx + tx, gy = by + ty;
     if (gx >= iw || gy >= ih) continue;
     int r = -1;
     if (!(gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2)) {
       const int i = ty * DB_W + tx, c0 = sd[i];
-      const unsigned uni = rowU[ty - 2] & rowU[ty - 1] & rowU[ty] & rowU[ty + 1] & rowU[ty + 2];
-      const bool same = ((uni >> lane) & 1u) && sd[i - 2 * DB_W] == c0 && sd[i - DB_W] == c0 && sd[i + DB_W] == c0 && sd[i + 2 * DB_W] == c0;
-      if (!same) r = c0;
+      bool nearEdge = false;
+#pragma unroll
+      for (int yy = -2; yy <= 2; yy++)
+#pragma unroll
+        for (int xx = -2; xx <= 2; xx++) nearEdge |= sd[i + yy * DB_W + xx] != c0;
+      if (nearEdge) r = c0;
     }
     out[(size_t)gy * iw + gx] = r;
   }
