@@ -169,6 +169,9 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # the ranks of one node share its cores: each gets its slice for the host-tail pool (read when the pool is created)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("RD_TAIL_THREADS", str(max(2, (os.cpu_count() or 8) // max(1, local_world))))
 
     import torch
     import torch.distributed as dist
@@ -310,7 +313,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "rects_per_step": nrect, "value_and_e2e_rects_identical": bool(same),
-            "host": {"driver_threads": args.nctx, "wait_for_device_ms_last_step": wait_ms, "host_tail_ms_last_step": tail_ms, "host_cores": os.cpu_count()},
+            "host": {"driver_threads": args.nctx, "tail_pool_threads": int(os.environ["RD_TAIL_THREADS"]), "wait_for_device_ms_last_step": wait_ms, "host_tail_ms_last_step": tail_ms, "host_cores": os.cpu_count()},
         }
         print(json.dumps(line), flush=True)
     batch.close()
