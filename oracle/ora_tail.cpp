@@ -1,5 +1,7 @@
 // ora_tail.cpp - CPU oracle, host tail: restatement of executeCPUTask and its helpers
 // (oclrect.c:385-1226, vec234.h, egbuf.h, helper.c:124-267).  TEST INFRASTRUCTURE ONLY (see rd_oracle.h).
+// PINNED: checked bit for bit (order and every field) against the reference's own executeCPUTask compiled from
+// /root/reference (oracle/_ref/librd_ref_tail.so, tests/test_ref_tail.py) and against reference-generated fixtures.
 // Everything is IEEE double in the order the reference writes it.  CANONICAL (Q20): the qsort calls are
 // replaced by stable sorts (glibc's qsort is a stable merge sort for these sizes).
 #include <vector>
