@@ -7,13 +7,16 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * The product library never links, imports or calls anything in this directory.
  *
- * PARITY STATUS: "parity unpinned".  The reference has no tests, golden vectors or fixtures
- *  and cannot run in this image (no OpenCL ICD, no CL/cl.h), so
- * this oracle is pinned only by (a) closed-form known-answer tests written for it
- * (tests/test_oracle_kat.py), (b) the LUT check against the reference source/pinned digests
- * (tools/gen_tables.py --check) and (c) an independent CCL cross-check (scipy).  Where the
+ * PARITY STATUS: device stages "parity unpinned", host tail PINNED.  The reference has no tests, golden
+ * vectors or fixtures and its device side cannot run in this image (OpenCL C kernels,
+ * no ICD), so the restatement of the kernels and schedules is pinned only by (a) closed-form
+ * known-answer tests written for it (tests/test_oracle_kat.py), (b) the LUT check against the reference
+ * source/pinned digests (tools/gen_tables.py --check) and (c) an independent CCL cross-check (scipy).  The
+ * host tail IS checked against the reference itself: oracle/_ref/librd_ref_tail.so is the reference's own
+ * oclrect.c + helper.c compiled here (Makefile target _ref, ref_tail_wrap.c), and ora_tail.cpp reproduces its
+ * executeCPUTask bit for bit (tests/test_ref_tail.py, tests/golden/ref_tail_golden.json).  Where the
  * reference is schedule-dependent (data races, atomic arrival order, bounded label passes) the
- * oracle fixes ONE canonical outcome; each such choice is marked "CANONICAL" in rd_oracle.cpp
+ * oracle fixes ONE canonical outcome; each such choice is marked "CANONICAL" in the sources
  * and listed in DESIGN.md section "Canonical semantics".
  */
 #ifndef RD_ORACLE_H
