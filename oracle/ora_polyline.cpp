@@ -1,5 +1,6 @@
 // ora_polyline.cpp - CPU oracle, Stage C: restatement of oclpolyline.cl and of oclpolyline_execute
 // (oclpolyline.c:154-309).  TEST INFRASTRUCTURE ONLY (see rd_oracle.h).
+#include <algorithm>
 #include <vector>
 #include "ora_internal.h"
 
@@ -384,8 +385,9 @@ static void k_mkpl_pass1(LS_t *gp, int lsListSize, int32_t *tmp, const int32_t *
 
 // ---- oclpolyline.cl:543-615.  `old` is the copy made by the host before this launch (oclpolyline.c:207),
 // `nw` the live list.  CANONICAL (Q4/Q8): at most one split per segment and iteration - the arg-max pixel,
-// the first in raster order on an exact tie - and the new ids are handed out in increasing order of the
-// parent id (the reference: atomic_inc arrival order; both are outcomes the reference can produce). ----
+// the first in raster order on an exact tie - and the new ids are handed out in raster order of the splitting
+// pixels: the reference's atomic_inc arrival order when its work-items run in raster order, so that the ids are the
+// ones oracle/_ref/librd_ref.so (the reference's own kernel, sequential schedule) produces. ----
 static void k_mkpl_pass2(LS_t *nw, const LS_t *old, int lsListSize, const int32_t *tmp, const int32_t *numberin, const int32_t *labelin,
                          const int32_t *flags, int nIter, float minerror, int iw, int ih) {
   if (flags[nIter - 1] == 0) return;
@@ -403,9 +405,11 @@ static void k_mkpl_pass2(LS_t *nw, const LS_t *old, int lsListSize, const int32_
       if (winner[g] >= 0) { g_stats.mkpl_ties++; continue; }
       winner[g] = p0;
     }
-  for (int g = 1; g <= count; g++) {
-    const int p0 = winner[g];
-    if (p0 < 0) continue;
+  std::vector<std::pair<int32_t, int32_t>> order;   // (splitting pixel, segment)
+  for (int g = 1; g <= count; g++) if (winner[g] >= 0) order.emplace_back(winner[g], g);
+  std::sort(order.begin(), order.end());
+  for (const auto &pg : order) {
+    const int p0 = pg.first, g = pg.second;
     const int x = p0 % iw, y = p0 / iw, n = numberin[p0];
     const LS_t *gp = old;
     if (gp[g].endIndex - gp[g].startIndex < MINNINDEX - 1) continue;
@@ -530,19 +534,20 @@ static void k_refine_pass2(const LSX_t *lsx, LS_t *ls) {
   }
 }
 
-// ---- oclpolyline.cl:772-809.  CANONICAL (Q5): Jacobi - all reads see the list as it was at launch.
-// Each endpoint is written by exactly one work-item (g writes its own end and the start of rightPtr). ----
+// ---- oclpolyline.cl:772-809.  The kernel rewrites the vertex a segment shares with its right neighbour IN PLACE, so what a
+// work-item reads depends on which neighbours ran before it.  CANONICAL (Q5): the work-items in id order (the schedule of
+// oracle/_ref/librd_ref.so): g sees its own start as already moved by its left neighbour l iff l < g, and its right
+// neighbour's end as already moved iff h < g. ----
 static void k_refine_pass3(LS_t *ls) {
   const int count = *(const int32_t *)ls;
-  std::vector<LS_t> snap(ls, ls + count + 1);
   for (int g = 1; g <= count; g++) {
-    if (snap[g].polyid == 0) continue;
-    const int h = snap[g].rightPtr;
+    if (ls[g].polyid == 0) continue;
+    const int h = ls[g].rightPtr;
     if (h == 0) continue;
-    float v0 = snap[g].x0, v1 = snap[g].y0, v2 = snap[g].x1, v3 = snap[g].y1;
-    float u0 = snap[h].x0, u1 = snap[h].y0, u2 = snap[h].x1, u3 = snap[h].y1;
+    float v0 = ls[g].x0, v1 = ls[g].y0, v2 = ls[g].x1, v3 = ls[g].y1;
+    float u0 = ls[h].x0, u1 = ls[h].y0, u2 = ls[h].x1, u3 = ls[h].y1;
     float d = (v2 - v0) * (u3 - u1) - (v3 - v1) * (u2 - u0);
-    float mx = (snap[g].x1 + snap[h].x0) * 0.5f, my = (snap[g].y1 + snap[h].y0) * 0.5f;
+    float mx = (v2 + u0) * 0.5f, my = (v3 + u1) * 0.5f;
     if ((double)fabsf(d) < 1e-6) {                                              // Q15
       ls[g].x1 = ls[h].x0 = mx; ls[g].y1 = ls[h].y0 = my;
       continue;
@@ -550,7 +555,7 @@ static void k_refine_pass3(LS_t *ls) {
     float n = (v1 - u1) * (u2 - u0) - (v0 - u0) * (u3 - u1);
     float q = n / d;
     float wx = v0 + q * (v2 - v0), wy = v1 + q * (v3 - v1);
-    if (hypot_c(wx - snap[g].x1, wy - snap[g].y1) > 10 && hypot_c(wx - snap[h].x0, wy - snap[h].y0) > 10) {
+    if (hypot_c(wx - v2, wy - v3) > 10 && hypot_c(wx - u0, wy - u1) > 10) {
       ls[g].x1 = ls[h].x0 = mx; ls[g].y1 = ls[h].y0 = my;
       continue;
     }

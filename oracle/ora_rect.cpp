@@ -284,11 +284,11 @@ static void k_markBoundary(int32_t *out, const int32_t *in, int iw, int ih) {
 }
 
 // ---- oclrect.cl:427-464 : the vote table.  slot = ((lsid*bid) & 0x7fffffff) % nentry, no probing ----
-// CANONICAL (Q19): when several lsid want one slot the smallest lsid owns it (the reference: whoever's
-// atomic_cmpxchg lands first); every hit of the owner is recorded (the reference drops the one hit that
-// performed the claim, oclrect.cl:451-456, which is again arrival-order dependent).
+// CANONICAL (Q19): the reference's own rule with its work-items in raster order (the schedule of oracle/_ref/librd_ref.so):
+// the first pixel in raster order that hits an empty slot claims it for its lsid (the reference: whoever's
+// atomic_cmpxchg lands first), and the very hit that performs the claim is NOT recorded (oclrect.cl:449-456: the
+// cmpxchg returns 0, which is not lsid) - so the claiming pixel counts only if its window hits the slot again.
 static void k_reduceLS(int32_t *out, const int32_t *boundaryin, const int32_t *lsidin, int iw, int ih, int nentry) {
-  // phase 1: owners
   for (int y = 1; y < ih - 1; y++)
     for (int x = 1; x < iw - 1; x++) {
       const int lsid = lsidin[y * iw + x];
@@ -300,29 +300,9 @@ static void k_reduceLS(int32_t *out, const int32_t *boundaryin, const int32_t *l
           const int bid = boundaryin[(y + yy) * iw + x + xx];
           if (bid <= 0) continue;
           const int hash = (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry);
-          int cur = out[hash * 5 + 0];
-          if (cur == 0) { out[hash * 5 + 0] = lsid; g_stats.vote_slots++; }
-          else if (cur != lsid) {
-            g_stats.vote_collisions++;
-            if (lsid < cur) out[hash * 5 + 0] = lsid;
-          }
-        }
-      }
-    }
-  // phase 2: bounding boxes of where the owner touches the region
-  for (int y = 1; y < ih - 1; y++)
-    for (int x = 1; x < iw - 1; x++) {
-      const int lsid = lsidin[y * iw + x];
-      if (lsid <= 0) continue;
-      for (int yy = -3; yy <= 3; yy++) {
-        if (y + yy < 0 || ih <= y + yy) continue;
-        for (int xx = -3; xx <= 3; xx++) {
-          if (x + xx < 0 || iw <= x + xx) continue;
-          const int bid = boundaryin[(y + yy) * iw + x + xx];
-          if (bid <= 0) continue;
-          const int hash = (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry);
-          if (out[hash * 5 + 0] != lsid) continue;
           int *e = &out[hash * 5];
+          if (e[0] == 0) { e[0] = lsid; g_stats.vote_slots++; continue; }
+          if (e[0] != lsid) { g_stats.vote_collisions++; continue; }
           if (iw - x > e[1]) e[1] = iw - x;
           if (x > e[2]) e[2] = x;
           if (ih - y > e[3]) e[3] = ih - y;

@@ -20,6 +20,19 @@ void *rd_ref_rect_buffer(oclrect_t *thiz, const char *name) {
   if (!strncmp(name, "ioBig", 5) && name[5] >= '0' && name[5] < '2') return rd_ref_mem_ptr(thiz->ioBig[name[5] - '0']);
   return NULL;
 }
+/* back to the state init_oclrect leaves: every device plane zero (the reference keeps state across frames in buf[3], Q1).
+ * The reference's helper layer hands out at most 1000 kernel ids per process (oclhelper.c KERNELIDMAX), 19 per
+ * init_oclrect, so the tests reuse one object per frame size instead of creating fresh ones. */
+size_t rd_ref_mem_bytes(cl_mem m);
+void rd_ref_rect_reset(oclrect_t *thiz) {
+  assert(thiz->magic == MAGIC);
+  for (int i = 0; i < NBUF; i++) memset(rd_ref_mem_ptr(thiz->buf[i]), 0, rd_ref_mem_bytes(thiz->buf[i]));
+  for (int i = 0; i < NTMP; i++) memset(rd_ref_mem_ptr(thiz->tmp[i]), 0, rd_ref_mem_bytes(thiz->tmp[i]));
+  for (int i = 0; i < 2; i++) {
+    memset(rd_ref_mem_ptr(thiz->iobuf[i]), 0, rd_ref_mem_bytes(thiz->iobuf[i]));
+    memset(rd_ref_mem_ptr(thiz->ioBig[i]), 0, rd_ref_mem_bytes(thiz->ioBig[i]));
+  }
+}
 /* the device half of oclrect_executeOnce (oclrect.c:1230-1246): genGPUTask on page 0, waited for */
 void rd_ref_gen_gpu_task(oclrect_t *thiz, uint8_t *img, int ws) {
   cl_event ev = genGPUTask(thiz, img, 0, ws, thiz->queue, NULL);

@@ -417,71 +417,69 @@ __device__ __forceinline__ void d_mkpl_pass2a(const LS_t *gp, int lsListSize, in
     atomicMin(winner + g, p0);
   }
 }
-// pass2b: ONE CTA (rank 0 of the cluster); decides the splits of this iteration, numbers the new entries by a prefix sum over the
-// parent id and rewrites the list.  Also resets winner[] for the next iteration.
+// pass2b: ONE CTA (rank 0 of the cluster); decides the splits of this iteration, numbers the new entries in raster order of
+// the splitting pixels (the reference's atomic_inc arrival order when its work-items run in raster order, oclpolyline.cl:585)
+// and rewrites the list.  Also resets winner[] for the next iteration.
+#define PL_SPLITCAP 2048
+__device__ __forceinline__ bool d_mkpl_splits(const LS_t &o, int px, int py, float minerror) {
+  if (o.endIndex - o.startIndex < MINNINDEX - 1) return false;
+  if (o.startCount > 1 || o.endCount > 1) return false;
+  const int maxDist = o.maxDist;
+  if (maxDist < ((int)__fmul_rn(minerror, 65536.0f))) return false;
+  if ((float)maxDist < __fmul_rn(__fmul_rn(minerror, 3.0f), 65536.0f) &&
+      __fdiv_rn(__fmul_rn((float)maxDist, (float)maxDist), distanceSqu(o.x0, o.y0, o.x1, o.y1)) < 100000.0f) return false;
+  if (distanceSqu((float)px, (float)py, o.x0, o.y0) < (float)(MINEDGELEN * MINEDGELEN)) return false;
+  if (distanceSqu((float)px, (float)py, o.x1, o.y1) < (float)(MINEDGELEN * MINEDGELEN)) return false;
+  return true;
+}
 __device__ __forceinline__ void d_mkpl_pass2b(LS_t *gp, int lsListSize, int *winner, const int *numberin, const int *flags, int nIter, float minerror, int iw) {
-  __shared__ int wsum[32];
-  __shared__ int carry, total;
+  __shared__ int spix[PL_SPLITCAP];
+  __shared__ int nsplit;
   const int count = *(const int *)gp;
-  if (threadIdx.x == 0) carry = count;
-  if (threadIdx.x < 32) wsum[threadIdx.x] = 0;
+  if (threadIdx.x == 0) nsplit = 0;
   __syncthreads();
+  // phase A: winner[g] keeps the splitting pixel of the segments that split, "none" otherwise
   for (int base = 1; base <= count; base += PL_THREADS) {
     const int g = base + threadIdx.x;
+    if (g > count || ls_overflow(g, lsListSize)) continue;
+    const int p0 = winner[g];
     bool split = false;
-    int px = 0, py = 0, n = 0, maxDist = 0, gr = 0, endIndex = 0, polyid = 0;
-    float x1 = 0, y1 = 0;
-    if (g <= count && !ls_overflow(g, lsListSize)) {
-      const int p0 = winner[g];
-      winner[g] = 0x7fffffff;
+    if (p0 != 0x7fffffff) {
       const LS_t o = gp[g];
-      if (p0 != 0x7fffffff && o.polyid != 0) {
-        px = p0 % iw; py = p0 / iw; n = numberin[p0];
-        maxDist = o.maxDist; gr = o.rightPtr; endIndex = o.endIndex; polyid = o.polyid; x1 = o.x1; y1 = o.y1;
-        split = true;
-        if (o.endIndex - o.startIndex < MINNINDEX - 1) split = false;
-        if (o.startCount > 1 || o.endCount > 1) split = false;
-        if (maxDist < ((int)__fmul_rn(minerror, 65536.0f))) split = false;
-        if (split && (float)maxDist < __fmul_rn(__fmul_rn(minerror, 3.0f), 65536.0f) &&
-            __fdiv_rn(__fmul_rn((float)maxDist, (float)maxDist), distanceSqu(o.x0, o.y0, o.x1, o.y1)) < 100000.0f) split = false;
-        if (distanceSqu((float)px, (float)py, o.x0, o.y0) < (float)(MINEDGELEN * MINEDGELEN)) split = false;
-        if (distanceSqu((float)px, (float)py, o.x1, o.y1) < (float)(MINEDGELEN * MINEDGELEN)) split = false;
-      }
+      split = o.polyid != 0 && d_mkpl_splits(o, p0 % iw, p0 / iw, minerror);
     }
-    // block-wide exclusive prefix sum of the split flags
-    const unsigned b = __ballot_sync(0xffffffffu, split);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) wsum[w] = __popc(b);
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int v = threadIdx.x < PL_THREADS / 32 ? wsum[threadIdx.x] : 0;
-      int vi = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, vi, o); if (threadIdx.x >= o) vi += t; }
-      wsum[threadIdx.x] = vi - v;
-      if (threadIdx.x == 31) total = vi;
-    }
-    __syncthreads();
-    const int rank = wsum[w] + __popc(b & ((1u << lane) - 1));
-    const int base_id = carry;
-    __syncthreads();
-    if (threadIdx.x == 0) carry = base_id + total;
     if (split) {
-      const int gn = base_id + rank + 1;
-      if (!ls_overflow(gn, lsListSize)) {
-        LS_t nw;
-        nw.x0 = (float)px; nw.y0 = (float)py; nw.x1 = x1; nw.y1 = y1;
-        nw.startIndex = n; nw.endIndex = endIndex; nw.leftPtr = g; nw.rightPtr = gr;
-        nw.startCount = 0; nw.endCount = 0; nw.maxDist = 0; nw.polyid = polyid; nw.npix = 0; nw.level = maxDist;
-        gp[gn] = nw;
-        winner[gn] = 0x7fffffff;
-        gp[g].endIndex = n; gp[g].x1 = (float)px; gp[g].y1 = (float)py; gp[g].rightPtr = gn; gp[g].maxDist = 0;
-        if (gr != 0) gp[gr].leftPtr = gn;
-      }
-    }
-    __syncthreads();
+      const int k = atomicAdd(&nsplit, 1);
+      if (k < PL_SPLITCAP) spix[k] = p0;
+    } else winner[g] = 0x7fffffff;
   }
-  if (threadIdx.x == 0) *(int *)gp = carry;
+  __syncthreads();
+  const int S = nsplit;
+  // phase B: id of a new entry = count + 1 + number of splitting pixels in front of its own in raster order
+  for (int base = 1; base <= count; base += PL_THREADS) {
+    const int g = base + threadIdx.x;
+    if (g > count || ls_overflow(g, lsListSize)) continue;
+    const int p0 = winner[g];
+    if (p0 == 0x7fffffff) continue;
+    int rank = 0;
+    if (S <= PL_SPLITCAP) { for (int k = 0; k < S; k++) rank += spix[k] < p0; }
+    else { for (int h = 1; h <= count; h++) rank += winner[h] < p0; }
+    const int gn = count + rank + 1;
+    if (ls_overflow(gn, lsListSize)) continue;
+    const LS_t o = gp[g];
+    const int px = p0 % iw, py = p0 / iw, n = numberin[p0], gr = o.rightPtr;
+    LS_t nw;
+    nw.x0 = (float)px; nw.y0 = (float)py; nw.x1 = o.x1; nw.y1 = o.y1;
+    nw.startIndex = n; nw.endIndex = o.endIndex; nw.leftPtr = g; nw.rightPtr = gr;
+    nw.startCount = 0; nw.endCount = 0; nw.maxDist = 0; nw.polyid = o.polyid; nw.npix = 0; nw.level = o.maxDist;
+    gp[gn] = nw;
+    winner[gn] = 0x7fffffff;
+    gp[g].endIndex = n; gp[g].x1 = (float)px; gp[g].y1 = (float)py; gp[g].rightPtr = gn; gp[g].maxDist = 0;
+    if (gr != 0) gp[gr].leftPtr = gn;
+  }
+  __syncthreads();
+  for (int g = 1 + threadIdx.x; g <= count; g += PL_THREADS) if (!ls_overflow(g, lsListSize)) winner[g] = 0x7fffffff;
+  if (threadIdx.x == 0) *(int *)gp = count + S;
 }
 __device__ __forceinline__ void d_mkpl_pass3(const LS_t *gp, int lsListSize, const int *numberin, int *labelinout, const int *plist, int *flags, int nIter, int iw) {
   PLIST_LOOP {
@@ -544,41 +542,49 @@ __device__ __forceinline__ void d_refine_pass2(const LSX_t *lsx, LS_t *ls) {
   ls[g].y1 = __fadd_rn(ls[g].y1, __fmul_rn(vy, as01));
   }
 }
-// pass3a computes the vertex g shares with its right neighbour from the unmodified list; pass3b writes it to both
-__device__ __forceinline__ void d_refine_pass3a(float2 *vtx, const LS_t *ls) {
-  const int count_ = *(const int *)ls;
-  PL_SEG_LOOP(count_) {
-  float2 r = make_float2(__int_as_float(0x7fc00000), 0.0f);     // NaN = nothing to write
-  if (ls[g].polyid != 0 && ls[g].rightPtr != 0) {
-    const int h = ls[g].rightPtr;
-    const float v0 = ls[g].x0, v1 = ls[g].y0, v2 = ls[g].x1, v3 = ls[g].y1;
-    const float u0 = ls[h].x0, u1 = ls[h].y0, u2 = ls[h].x1, u3 = ls[h].y1;
-    const float d = __fsub_rn(__fmul_rn(__fsub_rn(v2, v0), __fsub_rn(u3, u1)), __fmul_rn(__fsub_rn(v3, v1), __fsub_rn(u2, u0)));
-    const float mx = __fmul_rn(__fadd_rn(v2, u0), 0.5f), my = __fmul_rn(__fadd_rn(v3, u1), 0.5f);
-    if ((double)fabsf(d) < 1e-6) r = make_float2(mx, my);
-    else {
-      const float n = __fsub_rn(__fmul_rn(__fsub_rn(v1, u1), __fsub_rn(u2, u0)), __fmul_rn(__fsub_rn(v0, u0), __fsub_rn(u3, u1)));
-      const float q = __fdiv_rn(n, d);
-      const float wx = __fadd_rn(v0, __fmul_rn(q, __fsub_rn(v2, v0))), wy = __fadd_rn(v1, __fmul_rn(q, __fsub_rn(v3, v1)));
-      if (rd_hypot(__fsub_rn(wx, v2), __fsub_rn(wy, v3)) > 10.0f && rd_hypot(__fsub_rn(wx, u0), __fsub_rn(wy, u1)) > 10.0f) r = make_float2(mx, my);
-      else r = make_float2(wx, wy);
+// refine_pass3 (oclpolyline.cl:772-809) rewrites the vertex a segment shares with its right neighbour IN PLACE: what a
+// work-item reads depends on which of its neighbours ran before it.  Canonical (Q5) = the work-items in id order: g sees its
+// own start as moved by its left neighbour l iff l < g, and the end of its right neighbour h as moved iff h < g (and h has a
+// right neighbour itself).  Neighbouring segments are therefore always ordered by a dependency, dependencies point to smaller
+// ids, and a chain of them is a run of increasing ids along a polyline, i.e. at most one per split round: ONE CTA evaluates
+// the list level by level, in place (`state`: 0 = waiting, 1 = done).
+__device__ __forceinline__ void d_refine_pass3(LS_t *ls, int *state) {
+  __shared__ int pending;
+  const int count = *(const int *)ls;
+  for (int g = 1 + threadIdx.x; g <= count; g += blockDim.x) state[g] = (ls[g].polyid == 0 || ls[g].rightPtr == 0) ? 1 : 0;
+  __syncthreads();
+  for (int round = 0; round <= count; round++) {
+    if (threadIdx.x == 0) pending = 0;
+    __syncthreads();
+    // who can run: judged on the states left by the previous round
+    for (int g = 1 + threadIdx.x; g <= count; g += blockDim.x) {
+      if (state[g] != 0) continue;
+      const int l = ls[g].leftPtr, h = ls[g].rightPtr;
+      const bool ready = !(l != 0 && l < g && state[l] != 1) && !(h < g && ls[h].rightPtr != 0 && state[h] != 1);
+      if (ready) state[g] = 2; else pending = 1;
     }
-  }
-  vtx[g] = r;
-  }
-}
-__device__ __forceinline__ void d_refine_pass3b(const float2 *vtx, LS_t *ls, const int *rightPtrSnapshot) {
-  const int count_ = *(const int *)ls;
-  PL_SEG_LOOP(count_) {
-  (void)rightPtrSnapshot;
-  const float2 r = vtx[g];
-  if (r.x != r.x) {
-    // distinguish "no right neighbour" from a genuinely NaN vertex: recompute the guard
-    if (ls[g].polyid == 0 || ls[g].rightPtr == 0) continue;
-  }
-  const int h = ls[g].rightPtr;
-  ls[g].x1 = r.x; ls[g].y1 = r.y;
-  ls[h].x0 = r.x; ls[h].y0 = r.y;
+    __syncthreads();
+    for (int g = 1 + threadIdx.x; g <= count; g += blockDim.x) {
+      if (state[g] != 2) continue;
+      const int h = ls[g].rightPtr;
+      const float v0 = ls[g].x0, v1 = ls[g].y0, v2 = ls[g].x1, v3 = ls[g].y1;
+      const float u0 = ls[h].x0, u1 = ls[h].y0, u2 = ls[h].x1, u3 = ls[h].y1;
+      const float d = __fsub_rn(__fmul_rn(__fsub_rn(v2, v0), __fsub_rn(u3, u1)), __fmul_rn(__fsub_rn(v3, v1), __fsub_rn(u2, u0)));
+      const float mx = __fmul_rn(__fadd_rn(v2, u0), 0.5f), my = __fmul_rn(__fadd_rn(v3, u1), 0.5f);
+      float rx = mx, ry = my;
+      if (!((double)fabsf(d) < 1e-6)) {
+        const float n = __fsub_rn(__fmul_rn(__fsub_rn(v1, u1), __fsub_rn(u2, u0)), __fmul_rn(__fsub_rn(v0, u0), __fsub_rn(u3, u1)));
+        const float q = __fdiv_rn(n, d);
+        const float wx = __fadd_rn(v0, __fmul_rn(q, __fsub_rn(v2, v0))), wy = __fadd_rn(v1, __fmul_rn(q, __fsub_rn(v3, v1)));
+        if (!(rd_hypot(__fsub_rn(wx, v2), __fsub_rn(wy, v3)) > 10.0f && rd_hypot(__fsub_rn(wx, u0), __fsub_rn(wy, u1)) > 10.0f)) { rx = wx; ry = wy; }
+      }
+      ls[g].x1 = rx; ls[g].y1 = ry;
+      ls[h].x0 = rx; ls[h].y0 = ry;
+      state[g] = 1;
+    }
+    __syncthreads();
+    if (pending == 0) break;
+    __syncthreads();
   }
 }
 
@@ -616,9 +622,7 @@ kp_polyline_list(LS_t *gp, int lsListSize, int *aux, int *winner, int cap, const
   PL_SYNC;
   d_refine_pass2(lsx, gp);
   PL_SYNC;
-  d_refine_pass3a(vtx, gp);
-  PL_SYNC;
-  d_refine_pass3b(vtx, gp, (const int *)NULL);
+  if (lead) d_refine_pass3(gp, (int *)vtx);
 }
 
 // ---------------------------------------------------------------------------- the schedule (oclpolyline.c:218-309)

@@ -278,15 +278,29 @@ __global__ void kr_markBoundary(int *out, const int *in, int iw, int ih, size_t 
 }
 
 // ---------------------------------------------------------------------------- oclrect.cl:427-464 : the vote table
-// slot = ((lsid*bid) & 0x7fffffff) % nentry, no probing.  Canonical: the smallest lsid that wants a slot
-// owns it and all of its hits are recorded.  Phase 0 claims, phase 1 accumulates the four maxima.
+// slot = ((lsid*bid) & 0x7fffffff) % nentry, no probing.  Canonical = the reference's kernel with its
+// work-items in raster order: the first pixel in raster order that hits a slot claims it for its lsid, and the hit that
+// performs the claim is not recorded (the atomic_cmpxchg returns 0, oclrect.cl:449-456), so the claiming pixel counts only
+// if its window hits the slot a second time.  Phase 0 claims (slot word 0 = 0x7fffffff - smallest pixel index, by
+// atomicMax on the cleared table), phase 1 accumulates the four maxima of the owner's hits, phase 2 replaces the claim key
+// by the owner's lsid.  Keys are > any lsid (lsid < iw*ih*16/56).
+#define RLS_KEY(p0) (0x7fffffff - (p0))
+__device__ __forceinline__ int rls_hash(int lsid, int bid, int nentry) { return (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry); }
+// how often the 7x7 window of (x, y) hits `slot`
+__device__ __noinline__ int rls_hits(const int *boundaryin, int lsid, int slot, int x, int y, int iw, int ih, int nentry) {
+  int c = 0;
+  for (int yy = -3; yy <= 3; yy++) {
+    if (y + yy < 0 || ih <= y + yy) continue;
+    for (int xx = -3; xx <= 3; xx++) {
+      if (x + xx < 0 || iw <= x + xx) continue;
+      const int bid = boundaryin[(y + yy) * iw + x + xx];
+      if (bid > 0 && rls_hash(lsid, bid, nentry) == slot) c++;
+    }
+  }
+  return c;
+}
 template <int PHASE>
-__global__ void kr_reduceLS(int *out, const int *boundaryin, const int *lsidin, int iw, int ih, int nentry, size_t fs) {
-  rd_batch_z(fs, out, boundaryin, lsidin);
-  XY2D;
-  if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return;
-  const int lsid = lsidin[p0];
-  if (lsid <= 0) return;
+__device__ __forceinline__ void rls_pixel(int *out, const int *boundaryin, const int *lsidin, int p0, int x, int y, int lsid, int iw, int ih, int nentry) {
   int lastbid = 0;
   for (int yy = -3; yy <= 3; yy++) {
     if (y + yy < 0 || ih <= y + yy) continue;
@@ -295,27 +309,36 @@ __global__ void kr_reduceLS(int *out, const int *boundaryin, const int *lsidin, 
       const int bid = boundaryin[(y + yy) * iw + x + xx];
       if (bid <= 0 || bid == lastbid) continue;          // consecutive repeats of a region hit the same slot with the same values
       lastbid = bid;
-      const int hash = (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry);
+      const int hash = rls_hash(lsid, bid, nentry);
       int *e = out + (size_t)hash * 5;
       if (PHASE == 0) {
-        int cur = *(volatile int *)e;
-        while (cur == 0 || lsid < cur) {
-          const int prev = atomicCAS(e, cur, lsid);
-          if (prev == cur) break;
-          cur = prev;
-        }
-      } else {
-        if (e[0] != lsid) continue;
+        atomicMax(e, RLS_KEY(p0));
+      } else if (PHASE == 1) {
+        const int q = RLS_KEY(e[0]);                      // the claiming pixel
+        if (q != p0) { if (lsidin[q] != lsid) continue; }
+        else if (rls_hits(boundaryin, lsid, hash, x, y, iw, ih, nentry) < 2) continue;
         atomicMax(e + 1, iw - x);
         atomicMax(e + 2, x);
         atomicMax(e + 3, ih - y);
         atomicMax(e + 4, y);
+      } else {
+        const int k = *(volatile int *)e;                 // several pixels may finalise one slot: all write the same value
+        if (k > 0x3fffffff) *(volatile int *)e = lsidin[RLS_KEY(k)];
       }
     }
   }
 }
+template <int PHASE>
+__global__ void kr_reduceLS(int *out, const int *boundaryin, const int *lsidin, int iw, int ih, int nentry, size_t fs) {
+  rd_batch_z(fs, out, boundaryin, lsidin);
+  XY2D;
+  if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) return;
+  const int lsid = lsidin[p0];
+  if (lsid <= 0) return;
+  rls_pixel<PHASE>(out, boundaryin, lsidin, p0, x, y, lsid, iw, ih, nentry);
+}
 
-// The same two phases over the compact list of string pixels the polyline stage leaves behind (list[0] = count): only
+// The same phases over the compact list of string pixels the polyline stage leaves behind (list[0] = count): only
 // pixels that carry a segment id vote, and they are a few percent of the frame.
 template <int PHASE>
 __global__ void kr_reduceLS_list(int *out, const int *boundaryin, const int *lsidin, const int *list, int iw, int ih, int nentry, size_t fs) {
@@ -326,32 +349,7 @@ __global__ void kr_reduceLS_list(int *out, const int *boundaryin, const int *lsi
     if (x <= 0 || y <= 0 || x >= iw - 1 || y >= ih - 1) continue;
     const int lsid = lsidin[p0];
     if (lsid <= 0) continue;
-    int lastbid = 0;
-    for (int yy = -3; yy <= 3; yy++) {
-      if (y + yy < 0 || ih <= y + yy) continue;
-      for (int xx = -3; xx <= 3; xx++) {
-        if (x + xx < 0 || iw <= x + xx) continue;
-        const int bid = boundaryin[(y + yy) * iw + x + xx];
-        if (bid <= 0 || bid == lastbid) continue;
-        lastbid = bid;
-        const int hash = (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry);
-        int *e = out + (size_t)hash * 5;
-        if (PHASE == 0) {
-          int cur = *(volatile int *)e;
-          while (cur == 0 || lsid < cur) {
-            const int prev = atomicCAS(e, cur, lsid);
-            if (prev == cur) break;
-            cur = prev;
-          }
-        } else {
-          if (e[0] != lsid) continue;
-          atomicMax(e + 1, iw - x);
-          atomicMax(e + 2, x);
-          atomicMax(e + 3, ih - y);
-          atomicMax(e + 4, y);
-        }
-      }
-    }
+    rls_pixel<PHASE>(out, boundaryin, lsidin, p0, x, y, lsid, iw, ih, nentry);
   }
 }
 
@@ -504,6 +502,7 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
   RD_LAUNCH(kr_reduceLS<0>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
   RD_LAUNCH(kr_reduceLS<1>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS<2>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
   STEP(21);
   // step 22 : compact read-back record instead of the reference's three big copies (oclrect.c:371-376)
   RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
@@ -565,6 +564,7 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
   RD_LAUNCH(kr_reduceLS_list<0>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);   // tmp2: the polyline stage's pixel list
   RD_LAUNCH(kr_reduceLS_list<1>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS_list<2>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
   RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
 }
 
@@ -907,6 +907,7 @@ void rd_rect_reduceLS(cl_mem out, cl_mem boundary, cl_mem lsid, int iw, int ih, 
   QS;
   RD_LAUNCH(kr_reduceLS<0>, rd_gz(G2, nb), RB, 0, s, PI(out), PI(boundary), PI(lsid), iw, ih, nentry, fs);
   RD_LAUNCH(kr_reduceLS<1>, rd_gz(G2, nb), RB, 0, s, PI(out), PI(boundary), PI(lsid), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS<2>, rd_gz(G2, nb), RB, 0, s, PI(out), PI(boundary), PI(lsid), iw, ih, nentry, fs);
 }
 
 

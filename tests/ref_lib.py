@@ -18,6 +18,7 @@ from oracle_lib import LS_DTYPE, RECT_DTYPE, ROOT
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "librd_ref.so")
 REF_SRC = "/root/reference/oclrect.c"
 _lib = None
+_default_ctx = None
 vp, ci, cf, cd = C.c_void_p, C.c_int, C.c_float, C.c_double
 
 
@@ -38,7 +39,7 @@ def lib():
             "init_oclimgutil": (vp, [vp, vp]), "init_oclpolyline": (vp, [vp, vp]), "init_oclrect": (vp, [vp, vp, vp, vp, vp, ci, ci]),
             "dispose_oclrect": (None, [vp]), "dispose_oclimgutil": (None, [vp]), "dispose_oclpolyline": (None, [vp]),
             "oclrect_executeOnce": (vp, [vp, vp, ci, cd]), "oclrect_enqueueTask": (None, [vp, vp, ci]), "oclrect_pollTask": (vp, [vp, cd]),
-            "rd_ref_rect_buffer": (vp, [vp, C.c_char_p]), "rd_ref_gen_gpu_task": (None, [vp, vp, ci]), "rd_ref_cpu_task": (vp, [vp, cd]),
+            "rd_ref_rect_buffer": (vp, [vp, C.c_char_p]), "rd_ref_rect_reset": (None, [vp]), "rd_ref_gen_gpu_task": (None, [vp, vp, ci]), "rd_ref_cpu_task": (vp, [vp, cd]),
             "rd_ref_mem_ptr": (vp, [vp]), "rd_ref_free": (None, [vp]),
             "rd_ref_set_threads": (None, [ci]), "rd_ref_get_threads": (ci, []), "rd_ref_launches": (C.c_long, []),
             "rd_ref_trace_reset": (None, []), "rd_ref_trace_name": (C.c_char_p, [C.c_long]), "rd_ref_set_launch_limit": (None, [C.c_long]),
@@ -121,18 +122,31 @@ class RefContext:
         self._mems = []
 
 
+_pool = {}
+
+
 class RefRect:
-    """the reference's oclrect_t (oclrect.c:41-135) - init_oclrect / oclrect_executeOnce / enqueue / poll"""
+    """the reference's oclrect_t (oclrect.c:41-135) - init_oclrect / oclrect_executeOnce / enqueue / poll.
+    The reference hands out at most 1000 kernel ids per process (oclhelper.c KERNELIDMAX; 19 per init_oclrect), so closed
+    objects go back to a pool and come out again with every device plane zeroed (= the state after init_oclrect)."""
 
     def __init__(self, iw, ih, ctx=None):
-        self.ctx = ctx or RefContext()
+        global _default_ctx
+        if ctx is None:
+            ctx = _default_ctx = _default_ctx or RefContext()
+        self.ctx = ctx
         self.L = self.ctx.L
         self.iw, self.ih = iw, ih
-        self.h = self.L.init_oclrect(self.ctx.imgutil, self.ctx.polyline, self.ctx.device, self.ctx.context, self.ctx.queue, iw, ih)
+        free = _pool.setdefault((id(self.ctx), iw, ih), [])
+        if free:
+            self.h = free.pop()
+            self.L.rd_ref_rect_reset(self.h)
+        else:
+            self.h = self.L.init_oclrect(self.ctx.imgutil, self.ctx.polyline, self.ctx.device, self.ctx.context, self.ctx.queue, iw, ih)
 
     def close(self):
         if self.h:
-            self.L.dispose_oclrect(self.h)
+            _pool[(id(self.ctx), self.iw, self.ih)].append(self.h)
             self.h = None
 
     def execute_once(self, img, tan_aov, ws=None):
