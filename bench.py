@@ -11,8 +11,9 @@ e2e     : the same through the C-ABI batch call with frames in pinned HOST memor
 roofline: the kernel with the largest share of device time against the measured HBM copy bandwidth.  Per-kernel times come
           from CUDA events around every launch on the launching stream (in the library), in a separate pass through ONE
           pipeline object so that each kernel is timed alone; per-stage (A/B/C/D) totals of the same pass are reported too.
---impl reference : the CPU oracle (restatement of the reference's OpenCL kernels and launch schedule; the reference itself
-          needs an OpenCL ICD + OpenCV that this image lacks) on all host cores, bounded sample per step.
+--impl reference : THE REFERENCE ITSELF on the host cores - oracle/_ref/librd_ref.so = its unmodified host code and its OpenCL C
+          kernels compiled as C++ (oracle/Makefile target _ref), one instance per core on a bounded sample of the stream per step;
+          the CPU oracle port is timed beside it (cpu_port).
 """
 import argparse
 import json
@@ -118,29 +119,67 @@ def cpu_oracle_mpix(iw, ih, seeds, threads=None):
     return len(frames) * iw * ih / dt / 1e6, cores, dt
 
 
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "librd_ref.so")
+REF_KIND = ("the reference itself (oracle/_ref/librd_ref.so: its unmodified host code + its OpenCL C kernels compiled as C++ with g++ -O2, "
+            "220 launches per frame, oclrect_enqueueTask/pollTask), one single-threaded instance per host core, the stream split among them")
+
+
+def cpu_reference_mpix(iw, ih, first_seed, frames, workers=None):
+    """THE REFERENCE on the host cores: `workers` processes (all cores by default), each running the reference's own pipeline
+    on its share of `frames` frames (tests/ref_worker.py); wall time from the common start to the last "done".
+    -> (Mpix/s, workers, seconds)"""
+    workers = max(1, min(workers or os.cpu_count() or 1, frames))
+    share = [frames // workers + (1 if i < frames % workers else 0) for i in range(workers)]
+    procs, seed = [], first_seed
+    for n in share:
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), str(iw), str(ih), str(seed), str(n)],
+                                      stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")))
+        seed += n
+    for p in procs:
+        if p.stdout.readline().strip() != "ready":
+            raise RuntimeError("reference worker failed to start")
+    t0 = time.perf_counter()
+    for p in procs:
+        p.stdin.write("go\n")
+        p.stdin.flush()
+    for p in procs:
+        if not p.stdout.readline().startswith("done"):
+            raise RuntimeError("reference worker failed")
+    dt = time.perf_counter() - t0
+    for p in procs:
+        p.wait()
+    return frames * iw * ih / dt / 1e6, workers, dt
+
+
 def run_reference(args, rank, world):
-    """--impl reference: rank 0 times the CPU oracle, the other ranks exit without work"""
+    """--impl reference: rank 0 times the reference's own CPU run (oracle/_ref/librd_ref.so; the oracle port when that library
+    is absent), the other ranks exit without work"""
     if rank != 0:
         return
     iw, ih = args.w, args.h
     sample = args.ref_frames
+    have_ref = os.path.exists(REF_SO)
+    run = (lambda first, n: cpu_reference_mpix(iw, ih, first, n)) if have_ref else (lambda first, n: cpu_oracle_mpix(iw, ih, [first + i for i in range(n)]))
     for _ in range(args.warmup):
-        cpu_oracle_mpix(iw, ih, [1000])
-    t0 = time.perf_counter()
-    vals = []
+        run(1000, min(sample, os.cpu_count() or 1))
+    vals, secs = [], []
     for s in range(args.steps):
-        v, cores, _ = cpu_oracle_mpix(iw, ih, [1000 + s * sample + i for i in range(sample)])
+        v, cores, sec = run(1000 + s * sample, sample)
         vals.append(v)
-    dt = time.perf_counter() - t0
-    value = float(np.mean(vals))
+        secs.append(sec)
+    dt = float(np.sum(secs))                      # the timed regions (worker start-up and warm-up frames are outside)
+    value = sample * iw * ih * args.steps / dt / 1e6
+    port_v, port_cores, _ = cpu_oracle_mpix(iw, ih, [1000 + i for i in range(min(sample, 8))])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32 (f64 host tail)",
         "data": "synthetic",
         "config": {"workload": "vidrect %dx%d synthetic stream, AOV 72, full imgutil->polyline->rect pipeline" % (iw, ih), "frames_per_step": sample,
                    "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                         "sample": "%d frames of the workload per step (CPU oracle: OpenMP restatement of the reference's OpenCL schedule; the reference itself needs an OpenCL ICD + OpenCV, absent here)" % sample},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "reference" if have_ref else "port",
+                         "sample": "%d frames of the workload per step; %s" % (sample, REF_KIND if have_ref else "CPU oracle (OpenMP restatement); oracle/_ref/librd_ref.so not found")},
+        "cpu_port": {"value": port_v, "unit": "Mpix/s", "cores": port_cores, "kind": "port",
+                     "sample": "the CPU oracle (tuned OpenMP restatement of the same schedule with exact connected components) on the same frames, for comparison"},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -158,8 +197,8 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--nctx", type=int, default=16, help="pipeline objects (streams) per GPU")
     ap.add_argument("--fpl", type=int, default=8, help="frames per kernel launch")
-    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
-    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample")
+    ap.add_argument("--ref-frames", type=int, default=os.cpu_count() or 8, help="frames per step of the CPU reference arm (default: one per host core)")
+    ap.add_argument("--cpu-frames", type=int, default=2 * (os.cpu_count() or 8), help="frames of the cpu_baseline sample (default: two per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -297,9 +336,15 @@ def main():
         roofline["stages"] = stages
         cpu = None
         if not args.no_cpu_baseline:
-            v, cores, secs = cpu_oracle_mpix(iw, ih, [1000 + i for i in range(args.cpu_frames)])
-            cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                   "sample": "%d frames of the same stream, %.1f s (CPU oracle = OpenMP restatement of the reference's OpenCL kernels + schedule + host tail)" % (args.cpu_frames, secs)}
+            if os.path.exists(REF_SO):
+                v, cores, secs = cpu_reference_mpix(iw, ih, 1000, args.cpu_frames)
+                cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "reference", "sample": "%d frames of the same stream, %.1f s; %s" % (args.cpu_frames, secs, REF_KIND)}
+            else:
+                v, cores, secs = cpu_oracle_mpix(iw, ih, [1000 + i for i in range(args.cpu_frames)])
+                cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                       "sample": "%d frames of the same stream, %.1f s (CPU oracle = OpenMP restatement of the reference's OpenCL kernels + schedule + host tail)" % (args.cpu_frames, secs)}
+            pv, pc, ps = cpu_oracle_mpix(iw, ih, [1000 + i for i in range(min(args.cpu_frames, 16))])
+            cpu["port"] = {"value": pv, "unit": "Mpix/s", "cores": pc, "kind": "port", "sample": "CPU oracle (OpenMP restatement) on %d frames, %.1f s" % (min(args.cpu_frames, 16), ps)}
         nrect = sum(len(r) for r in rects) if rects else 0
         same = rects is not None and rects_e2e is not None and all(a.tobytes() == b.tobytes() for a, b in zip(rects, rects_e2e))
         line = {

@@ -286,22 +286,25 @@ __global__ void kr_markBoundary(int *out, const int *in, int iw, int ih, size_t 
 // by the owner's lsid.  Keys are > any lsid (lsid < iw*ih*16/56).
 #define RLS_KEY(p0) (0x7fffffff - (p0))
 __device__ __forceinline__ int rls_hash(int lsid, int bid, int nentry) { return (int)((((unsigned)lsid * (unsigned)bid) & 0x7fffffffu) % (unsigned)nentry); }
-// how often the 7x7 window of (x, y) hits `slot`
-__device__ __noinline__ int rls_hits(const int *boundaryin, int lsid, int slot, int x, int y, int iw, int ih, int nentry) {
+// does the 7x7 window of (x, y) hit `slot` at least twice?  (only asked for the one pixel that claimed the slot, and only when
+// the hit at hand has no equal right-hand neighbour in the window)
+__device__ __noinline__ bool rls_hits_twice(const int *boundaryin, int lsid, int bid0, int slot, int x, int y, int iw, int ih, int nentry) {
   int c = 0;
   for (int yy = -3; yy <= 3; yy++) {
     if (y + yy < 0 || ih <= y + yy) continue;
     for (int xx = -3; xx <= 3; xx++) {
       if (x + xx < 0 || iw <= x + xx) continue;
       const int bid = boundaryin[(y + yy) * iw + x + xx];
-      if (bid > 0 && rls_hash(lsid, bid, nentry) == slot) c++;
+      if (bid <= 0) continue;
+      if (bid == bid0 || rls_hash(lsid, bid, nentry) == slot) { if (++c == 2) return true; }
     }
   }
-  return c;
+  return false;
 }
 template <int PHASE>
 __device__ __forceinline__ void rls_pixel(int *out, const int *boundaryin, const int *lsidin, int p0, int x, int y, int lsid, int iw, int ih, int nentry) {
-  int lastbid = 0;
+  int lastbid = 0, twiceSlot = -1;
+  bool twice = false;
   for (int yy = -3; yy <= 3; yy++) {
     if (y + yy < 0 || ih <= y + yy) continue;
     for (int xx = -3; xx <= 3; xx++) {
@@ -316,7 +319,14 @@ __device__ __forceinline__ void rls_pixel(int *out, const int *boundaryin, const
       } else if (PHASE == 1) {
         const int q = RLS_KEY(e[0]);                      // the claiming pixel
         if (q != p0) { if (lsidin[q] != lsid) continue; }
-        else if (rls_hits(boundaryin, lsid, hash, x, y, iw, ih, nentry) < 2) continue;
+        else {                                            // this pixel made the claim: it counts only if it hits the slot twice
+          if (hash != twiceSlot) {
+            twiceSlot = hash;
+            twice = (xx < 3 && x + xx + 1 < iw && boundaryin[(y + yy) * iw + x + xx + 1] == bid) ||
+                    rls_hits_twice(boundaryin, lsid, bid, hash, x, y, iw, ih, nentry);
+          }
+          if (!twice) continue;
+        }
         atomicMax(e + 1, iw - x);
         atomicMax(e + 2, x);
         atomicMax(e + 3, ih - y);

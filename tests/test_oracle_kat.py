@@ -220,6 +220,28 @@ def test_oracle_pipeline_matches_golden(g):
             assert d[k] == g[k], k
 
 
+# ------------------------------------------------------------------ fixtures generated by THE REFERENCE (tools/make_ref_device_golden.py)
+REF_DEVICE_GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_device_golden.json")))
+# plane -> (oracle stop step, oracle buffer)
+REF_DEVICE_PLANES = {"plab": (1, "buf0"), "thin_strength_f32": (7, "buf1"), "edge_bitmap1": (8, "tmp1"), "string_labels": (10, "buf2"),
+                     "blurred_plab": (13, "buf4"), "quantised_plab": (14, "buf4"), "strong_edge": (15, "buf3"), "lsid": (20, "buf0"), "ls": (20, "ioBig0")}
+
+
+@pytest.mark.parametrize("g", REF_DEVICE_GOLDEN, ids=lambda g: "%dx%d-s%d" % (g["iw"], g["ih"], g["seed"]))
+def test_oracle_matches_reference_generated_planes(g):
+    """SHA-256 of planes the reference's own kernels produced here (oracle/_ref/librd_ref.so): packed Lab, thinned edge strength
+    (floats), edge bitmap, string labels, blurred / quantised colours, strong-edge bitmap, segment-id map, polyline vertex list"""
+    import hashlib
+    iw, ih = g["iw"], g["ih"]
+    img = ol.synth_frame(iw, ih, g["seed"])
+    for name, (step, buf) in REF_DEVICE_PLANES.items():
+        o = ol.OracleRect(iw, ih)
+        o.gpu_task(img, stop_step=step)
+        a = o.ls_list().view(np.int32) if name == "ls" else o.buffer(buf)[: iw * ih]
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == g["sha"][name], name
+        o.close()
+
+
 def test_oracle_detects_the_planted_quads():
     iw, ih, seed = 1280, 720, 2
     img, quads = ol.synth_frame(iw, ih, seed, with_truth=True)
