@@ -7,17 +7,27 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * The product library never links, imports or calls anything in this directory.
  *
- * PARITY STATUS: device stages "parity unpinned", host tail PINNED.  The reference has no tests, golden
- * vectors or fixtures and its device side cannot run in this image (OpenCL C kernels,
- * no ICD), so the restatement of the kernels and schedules is pinned only by (a) closed-form
- * known-answer tests written for it (tests/test_oracle_kat.py), (b) the LUT check against the reference
- * source/pinned digests (tools/gen_tables.py --check) and (c) an independent CCL cross-check (scipy).  The
- * host tail IS checked against the reference itself: oracle/_ref/librd_ref_tail.so is the reference's own
- * oclrect.c + helper.c compiled here (Makefile target _ref, ref_tail_wrap.c), and ora_tail.cpp reproduces its
- * executeCPUTask bit for bit (tests/test_ref_tail.py, tests/golden/ref_tail_golden.json).  Where the
- * reference is schedule-dependent (data races, atomic arrival order, bounded label passes) the
- * oracle fixes ONE canonical outcome; each such choice is marked "CANONICAL" in the sources
- * and listed in DESIGN.md section "Canonical semantics".
+ * PARITY STATUS: PINNED TO THE REFERENCE RUNNING HERE, except two kernels whose result depends on the order of the
+ * reference's own work-items.  The reference ships no tests, golden vectors or fixtures and no
+ * OpenCL runtime exists in this image, but the reference itself does run: `make _ref` compiles its host code
+ * (helper.c, oclhelper.c, oclimgutil.c, oclpolyline.c, oclrect.c - unmodified, from /root/reference) together with its
+ * three OpenCL C kernel files compiled as C++ (cl_translate.py rewrites only the vector-literal syntax, cl_compat.h supplies
+ * the OpenCL C built-ins) over a synchronous host runtime (ref_cl_rt.cpp) into oracle/_ref/librd_ref.so; every NDRange runs
+ * its work-items in raster order on one thread - one legal schedule of the reference.  Against it (tests/test_ref_device.py,
+ * tests/golden/ref_device_golden.json):
+ *   - Stage A and Stage B up to the merge mask (genGPUTask steps 1-16): every plane bit-exact, floats included;
+ *   - Stage C (oclpolyline_execute, all 116 launches): every plane, the segment-id map and the LS_t list bit-exact;
+ *   - calcSize, markBoundary, label8x, reduceLS (vote table) on identical inputs: bit-exact;
+ *   - executeCPUTask (host tail): bit-exact (tests/test_ref_tail.py, tests/golden/ref_tail_golden.json);
+ *   - labelMergeMain (Q6') and despeckle2 (Q3) are ORDER DEPENDENT in the reference (directed adopt rule gated on the
+ *     current labels; in-place neighbourhood update).  The oracle fixes a deterministic outcome for each (components of
+ *     the symmetric closure; Jacobi) whose relation to the sequential schedule is tested (coarsening, < 1 % of the
+ *     pixels); with those two kernels swapped for the reference's the oracle reproduces the reference's region map
+ *     bit-exactly.
+ * Every other place where the reference is schedule-dependent (atomic arrival order, in-place races, vote-slot claims)
+ * is resolved the way the raster-order schedule resolves it; each is marked "CANONICAL" in the sources and listed in
+ * DESIGN.md section "Canonical semantics".  Vendor-defined OpenCL built-ins (rsqrt, hypot, distance, FP contraction) follow
+ * the choices stated there (Q14-Q18) in the oracle, in cl_compat.h and in the CUDA kernels alike.
  */
 #ifndef RD_ORACLE_H
 #define RD_ORACLE_H
