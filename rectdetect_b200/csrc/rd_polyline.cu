@@ -420,7 +420,9 @@ __device__ __forceinline__ void d_mkpl_pass2a(const LS_t *gp, int lsListSize, in
 // pass2b: ONE CTA (rank 0 of the cluster); decides the splits of this iteration, numbers the new entries in raster order of
 // the splitting pixels (the reference's atomic_inc arrival order when its work-items run in raster order, oclpolyline.cl:585)
 // and rewrites the list.  Also resets winner[] for the next iteration.
-#define PL_SPLITCAP 2048
+#ifndef PL_SPLITCAP
+#define PL_SPLITCAP 2048   // splitting pixels of one round ranked out of shared memory; more than that: ranked against winner[] in global memory
+#endif
 __device__ __forceinline__ bool d_mkpl_splits(const LS_t &o, int px, int py, float minerror) {
   if (o.endIndex - o.startIndex < MINNINDEX - 1) return false;
   if (o.startCount > 1 || o.endCount > 1) return false;
