@@ -335,7 +335,7 @@ def main():
                           "frac_of_hbm_peak": round(gbs / peak, 4) if gbs else None}
         roofline["stages"] = stages
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is timed at N = 1 only
             if os.path.exists(REF_SO):
                 v, cores, secs = cpu_reference_mpix(iw, ih, 1000, args.cpu_frames)
                 cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "reference", "sample": "%d frames of the same stream, %.1f s; %s" % (args.cpu_frames, secs, REF_KIND)}
