@@ -129,11 +129,13 @@ def cpu_reference_mpix(iw, ih, first_seed, frames, workers=None):
     on its share of `frames` frames (tests/ref_worker.py); wall time from the common start to the last "done".
     -> (Mpix/s, workers, seconds)"""
     workers = max(1, min(workers or os.cpu_count() or 1, frames))
+    if os.path.exists("/root/reference/oclrect.c"):          # build container: make sure oracle/_ref is current, once, before the workers start
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
     share = [frames // workers + (1 if i < frames % workers else 0) for i in range(workers)]
     procs, seed = [], first_seed
     for n in share:
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), str(iw), str(ih), str(seed), str(n)],
-                                      stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")))
+                                      stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=dict(os.environ, OMP_NUM_THREADS="1", RD_REF_NO_BUILD="1")))
         seed += n
     for p in procs:
         if p.stdout.readline().strip() != "ready":
@@ -183,10 +185,29 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    # libraries print to stdout behind Python's back (NCCL: "NCCL version ..." from the first communicator): keep fd 1 for the
+    # JSON line alone and send everything else to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -360,7 +381,7 @@ def main():
             "rects_per_step": nrect, "value_and_e2e_rects_identical": bool(same),
             "host": {"driver_threads": args.nctx, "tail_pool_threads": int(os.environ["RD_TAIL_THREADS"]), "wait_for_device_ms_last_step": wait_ms, "host_tail_ms_last_step": tail_ms, "host_cores": os.cpu_count()},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     batch.close()
     if world > 1:
         dist.barrier()

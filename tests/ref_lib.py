@@ -27,11 +27,17 @@ def available():
     return os.path.exists(REF_SO) or os.path.exists(REF_SRC)
 
 
+def build():
+    """(re)build oracle/_ref from /root/reference where that exists (this container); elsewhere the prebuilt files are used.
+    RD_REF_NO_BUILD=1 skips it (set for the worker processes of bench.py, whose parent has built already)."""
+    if os.path.exists(REF_SRC) and not os.environ.get("RD_REF_NO_BUILD"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+
+
 def lib():
     global _lib
     if _lib is None:
-        if os.path.exists(REF_SRC):
-            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+        build()
         L = C.CDLL(REF_SO)
         sig = {
             "simpleGetDevice": (vp, [ci]), "simpleCreateContext": (vp, [vp]), "clCreateCommandQueue": (vp, [vp, vp, C.c_uint64, vp]),
