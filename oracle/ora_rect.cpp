@@ -267,6 +267,25 @@ static void k_despeckle2(int32_t *labelinout, const int32_t *sizein, int thre, i
     }
 }
 
+// ---- oclrect.cl:348-371 with the work-items in raster order, in place: what oracle/_ref/librd_ref.so computes.  NOT part of the
+// canonical schedule (Q3 is Jacobi, above); kept as an operator so that the distance between the two is measurable
+// (tools/ref_vs_oracle_sweep.py) and as the checker for the row-scan formulation planned in DESIGN.md section 8. ----
+static void k_despeckle2_raster(int32_t *labelinout, const int32_t *sizein, int thre, int iw, int ih) {
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      if (sizein[labelinout[p0]] > thre) continue;
+      int maxSize = 0, maxLabel = labelinout[p0];
+      for (int yy = -1; yy <= 1; yy++)
+        for (int xx = -1; xx <= 1; xx++)
+          if (0 <= x + xx && x + xx < iw && 0 <= y + yy && y + yy < ih) {
+            const int p1 = (y + yy) * iw + x + xx;
+            if (sizein[labelinout[p1]] > maxSize) { maxSize = sizein[labelinout[p1]]; maxLabel = labelinout[p1]; }
+          }
+      labelinout[p0] = maxLabel;
+    }
+}
+
 // ---- oclrect.cl:373-390 (the `edge` argument is unused by the kernel) ----
 static void k_markBoundary(int32_t *out, const int32_t *in, int iw, int ih) {
 #pragma omp parallel for schedule(static)
@@ -340,6 +359,7 @@ void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int 
 void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { labelMerge(label, pix, mask, edge, iw, ih); }
 void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih) { k_calcSize(out, label, iw, ih); }
 void ora_rect_despeckle2(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih) { k_despeckle2(labelinout, size, thre, iw, ih); }
+void ora_rect_despeckle2_raster(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih) { k_despeckle2_raster(labelinout, size, thre, iw, ih); }
 void ora_rect_markBoundary(int32_t *out, const int32_t *in, int iw, int ih) { k_markBoundary(out, in, iw, ih); }
 void ora_rect_reduceLS(int32_t *out, const int32_t *boundary, const int32_t *lsid, int iw, int ih, int nentry) { k_reduceLS(out, boundary, lsid, iw, ih, nentry); }
 

@@ -162,6 +162,9 @@ def test_stage_b_tail_kernels_on_identical_inputs(ctx, iw, ih, seed):
     lab_r, lab_o = d["label"].copy(), d["label"].copy()
     k_d2(iw, ih, P(lab_r), P(size_r), 16, iw, ih)
     L.ora_rect_despeckle2(P(lab_o), P(size_o), 16, iw, ih)
+    lab_s = d["label"].copy()
+    L.ora_rect_despeckle2_raster(P(lab_s), P(size_o), 16, iw, ih)    # the oracle's raster-order operator (not in the schedule)
+    assert np.array_equal(lab_r, lab_s)
     small = size_o[d["label"]] <= 16
     assert np.array_equal(lab_r[~small], lab_o[~small])              # only pixels of small regions may change at all
     assert np.array_equal(lab_r[~small], d["label"][~small])
