@@ -102,6 +102,8 @@ void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih);
 void ora_rect_despeckle2(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih);
 /* the same kernel with its work-items in raster order, in place (the reference's sequential schedule); not in the canonical schedule */
 void ora_rect_despeckle2_raster(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih);
+/* the raster recurrence truncated at dependency depth K (K = 1: the canonical Jacobi form); not in the canonical schedule */
+void ora_rect_despeckle2_sweeps(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih, int K);
 void ora_rect_markBoundary(int32_t *out, const int32_t *in, int iw, int ih);
 void ora_rect_reduceLS(int32_t *out, const int32_t *boundary, const int32_t *lsid, int iw, int ih, int nentry);
 

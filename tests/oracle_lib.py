@@ -68,7 +68,7 @@ def oracle():
             "ora_rect_quantize": (None, [vp, vp, i, i, i, i, i]), "ora_rect_despeckle": (None, [vp, vp, vp, i, i]),
             "ora_rect_mkMergeMask0": (None, [vp, vp, i, i]), "ora_rect_mkMergeMask1": (None, [vp, vp, i, i]),
             "ora_rect_labelMerge": (None, [vp, vp, vp, vp, i, i]),
-            "ora_rect_calcSize": (None, [vp, vp, i, i]), "ora_rect_despeckle2": (None, [vp, vp, i, i, i]), "ora_rect_despeckle2_raster": (None, [vp, vp, i, i, i]),
+            "ora_rect_calcSize": (None, [vp, vp, i, i]), "ora_rect_despeckle2": (None, [vp, vp, i, i, i]), "ora_rect_despeckle2_raster": (None, [vp, vp, i, i, i]), "ora_rect_despeckle2_sweeps": (None, [vp, vp, i, i, i, i]),
             "ora_rect_markBoundary": (None, [vp, vp, i, i]), "ora_rect_reduceLS": (None, [vp, vp, vp, i, i, i]),
             "ora_polyline_execute": (None, [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, f, i, i, i, i]),
             "ora_rect_create": (vp, [i, i]), "ora_rect_destroy": (None, [vp]),

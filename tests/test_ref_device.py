@@ -165,6 +165,27 @@ def test_stage_b_tail_kernels_on_identical_inputs(ctx, iw, ih, seed):
     lab_s = d["label"].copy()
     L.ora_rect_despeckle2_raster(P(lab_s), P(size_o), 16, iw, ih)    # the oracle's raster-order operator (not in the schedule)
     assert np.array_equal(lab_r, lab_s)
+    # the recurrence truncated at depth K: K = 1 is the canonical Jacobi form; every pixel whose chain of small causal
+    # neighbours is shorter than K already has its raster label; the distance to the raster result shrinks with K
+    small2 = (size_o[d["label"]] <= 16).reshape(ih, iw)
+    depth = np.zeros((ih, iw), np.int32)                             # length of the longest chain of small causal neighbours
+    for y in range(ih):
+        for x in np.flatnonzero(small2[y]):
+            m = 0
+            for yy, xx in ((-1, -1), (-1, 0), (-1, 1), (0, -1)):
+                if 0 <= y + yy and 0 <= x + xx < iw and small2[y + yy, x + xx]:
+                    m = max(m, depth[y + yy, x + xx])
+            depth[y, x] = m + 1
+    dist = []
+    for K in (1, 2, 4):
+        lab_k = d["label"].copy()
+        L.ora_rect_despeckle2_sweeps(P(lab_k), P(size_o), 16, iw, ih, K)
+        if K == 1:
+            assert np.array_equal(lab_k, lab_o)
+        exact = (depth.ravel() <= K)
+        assert np.array_equal(lab_k[exact], lab_r[exact]), K
+        dist.append(int((lab_k != lab_r).sum()))
+    assert dist[0] >= dist[1] >= dist[2] and dist[2] < dist[0]
     small = size_o[d["label"]] <= 16
     assert np.array_equal(lab_r[~small], lab_o[~small])              # only pixels of small regions may change at all
     assert np.array_equal(lab_r[~small], d["label"][~small])
