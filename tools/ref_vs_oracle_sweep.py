@@ -3,7 +3,7 @@
 (incl. widths that are not multiples of 32, frames smaller than the blur / window radii), row strides wider than the image,
 blank frames and many seeds.  Per case: which of the order-independent planes are bit-exact after the full genGPUTask, how far
 the region map is off (labelMergeMain / despeckle2 are order dependent), the vote table on identical inputs, and how the
-rectangle lists compare.   usage: ref_vs_oracle_sweep.py [quick]   (needs a built librd_ref.so)"""
+rectangle lists compare.   usage: ref_vs_oracle_sweep.py [quick|big]   (needs a built librd_ref.so)"""
 import ctypes as C
 import math
 import os
@@ -18,11 +18,14 @@ import ref_lib as rl  # noqa: E402
 from test_ref_device import _match_rects  # noqa: E402
 
 TAN = math.tan(math.radians(36.0))
-quick = len(sys.argv) > 1
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+big = len(sys.argv) > 1 and sys.argv[1] == "big"          # configs 4 and 5 of BASELINE.json: 1920x1080 seed 2000, 3840x2160 seed 5
 sizes = [(640, 480), (641, 479), (322, 200), (130, 97), (96, 64), (48, 40), (257, 511), (1000, 562), (1280, 720)]
 seeds = [31] if quick else [31, 32, 33]
 cases = [(iw, ih, s, None, False) for iw, ih in sizes for s in seeds]
 cases += [(640, 360, 41, 4 * 640 - 3, False), (333, 217, 42, 3 * 333 + 5, False), (320, 240, 0, None, True)]
+if big:
+    cases = [(1920, 1080, 2000, None, False), (1920, 1080, 2001, None, False), (3840, 2160, 5, None, False)]
 k_votes = rl.kernel_direct("rect", "reduceLS")
 k_votes.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
 rl.set_threads(1)
