@@ -122,12 +122,34 @@ def test_reference_poly_program_runs_on_the_reference_library(tmp_path):
     assert os.path.exists(os.path.join(cwd, "output.png"))
 
 
-def _poly_lines(img, iw, ih):
+@pytest.mark.skipif(not _have("vidpoly_ref"), reason="oracle/_ref/apps not built (needs /root/reference)")
+def test_reference_vidpoly_program_runs_on_the_reference_library(tmp_path):
+    """vidpoly.cpp (vidpoly.cpp:150-215: the poly pipeline per frame with strength 2000, minerror 1, sizeThre 10, all its
+    device buffers reused from frame to frame without clearing) on librd_ref.so: every frame draws the segments the oracle
+    computes for that frame from FRESH buffers - nothing in the L2 path depends on what an earlier frame left behind"""
+    cwd = str(tmp_path)
+    iw, ih, nf = 320, 240, 3
+    frames = [ol.synth_frame(iw, ih, 4000 + i) for i in range(nf)]
+    write_stream(os.path.join(cwd, "in.rdv"), frames, iw, ih)
+    _, per_frame, _ = run_app("vidpoly_ref", [0, "in.rdv", "out.rdv"], cwd)
+    assert len(per_frame) == nf
+    for k in range(nf):
+        L = _poly_list(frames[k], iw, ih, 1.0, 10, 2000)
+        want = [(int(L["x0"][i]), int(L["y0"][i]), int(L["x1"][i]), int(L["y1"][i]), 255, 255, 255, 1) for i in range(1, len(L))]   # no polyid test (vidpoly.cpp:196-203)
+        assert len(want) > 3 and same_drawing(per_frame[k], want), k
+
+
+def _poly_list(img, iw, ih, minerror, size_thre, strength):
     n = iw * ih
     lsid, ls = np.zeros(n, np.int32), np.zeros(4 * n, np.int32)
-    ol.oracle().ora_poly_frame(img.ctypes.data, img.shape[-1], iw, ih, 1.0, 20, 500, lsid.ctypes.data, ls.ctypes.data, None)
+    ol.oracle().ora_poly_frame(img.ctypes.data, img.shape[-1], iw, ih, minerror, size_thre, strength, lsid.ctypes.data, ls.ctypes.data, None)
     cnt = int(ls[0])
-    L = ls[: 14 * (cnt + 1)].view(np.uint8).view(ol.LS_DTYPE)
+    return ls[: 14 * (cnt + 1)].view(np.uint8).view(ol.LS_DTYPE)
+
+
+def _poly_lines(img, iw, ih):
+    L = _poly_list(img, iw, ih, 1.0, 20, 500)
+    cnt = len(L) - 1
     want = []
     for i in range(1, cnt + 1):                                                    # poly.cpp:138-154
         if L["polyid"][i] == 0 or L["leftPtr"][i] > 0:
