@@ -107,14 +107,14 @@ def test_elementwise_and_colour_operators(ctx, iw, ih):
 @pytest.mark.parametrize("iw,ih", SIZES)
 def test_recursive_gaussian_all_radii(ctx, iw, ih):
     """oclimgutil_iirblur_f_f (oclimgutil.c:243-273: 2 clears + 6 passes) for every coefficient row the table holds that the
-    frame is large enough for: the recurrences start r + 9 samples outside the frame and fold that lead-in back with
-    mirror1 / repeat1 (oclimgutil.cl:47-56), which is only meaningful while r + 9 stays well inside the frame (the path
-    uses r = 2)"""
+    frame is large enough for: the anti-causal recurrences start at index iw + r + 9 (oclimgutil.cl:569, :618) and fold that
+    lead-in back with mirror1 (oclimgutil.cl:47), which stays inside the plane only while r <= min(iw, ih) - 11 - beyond
+    that the reference itself reads out of bounds (the path uses r = 2 on frames of at least 13 x 13)"""
     L, LO = ctx.L, ol.oracle()
     rng = np.random.default_rng(7)
     n = iw * ih
     src = rng.random(n, dtype=np.float32)
-    for r in range(0, min(32, min(iw, ih) - 11)):
+    for r in range(0, min(32, min(iw, ih) - 10)):
         mo, mi, t0, t1 = ctx.mem(4 * n), ctx.mem(4 * n, src), ctx.mem(4 * n), ctx.mem(4 * n)
         L.oclimgutil_iirblur_f_f(ctx.imgutil, mo, mi, t0, t1, r, iw, ih, ctx.queue, None)
         out, a, b = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
