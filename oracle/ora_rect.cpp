@@ -247,30 +247,10 @@ static void k_calcSize(int32_t *out, const int32_t *label, int iw, int ih) {
   }
 }
 
-// ---- oclrect.cl:348-371.  CANONICAL (Q3): Jacobi - every pixel reads the labels as they were at launch ----
+// ---- oclrect.cl:348-371.  The kernel updates the labels in place, so its outcome depends on the order of the work-items.
+// CANONICAL (Q3): raster order - the schedule of the reference run here (oracle/_ref/librd_ref.so), bit-identical to it
+// (tests/test_ref_device.py).  A pixel sees the new labels of its NW / N / NE / W neighbours and the old ones elsewhere. ----
 static void k_despeckle2(int32_t *labelinout, const int32_t *sizein, int thre, int iw, int ih) {
-  std::vector<int32_t> snap(labelinout, labelinout + (size_t)iw * ih);
-  const int32_t *L = snap.data();
-#pragma omp parallel for schedule(static)
-  for (int y = 0; y < ih; y++)
-    for (int x = 0; x < iw; x++) {
-      const int p0 = y * iw + x;
-      if (sizein[L[p0]] > thre) continue;
-      int maxSize = 0, maxLabel = L[p0];
-      for (int yy = -1; yy <= 1; yy++)
-        for (int xx = -1; xx <= 1; xx++)
-          if (0 <= x + xx && x + xx < iw && 0 <= y + yy && y + yy < ih) {
-            const int p1 = (y + yy) * iw + x + xx;
-            if (sizein[L[p1]] > maxSize) { maxSize = sizein[L[p1]]; maxLabel = L[p1]; }
-          }
-      labelinout[p0] = maxLabel;
-    }
-}
-
-// ---- oclrect.cl:348-371 with the work-items in raster order, in place: what oracle/_ref/librd_ref.so computes.  NOT part of the
-// canonical schedule (Q3 is Jacobi, above); kept as an operator so that the distance between the two is measurable
-// (tools/ref_vs_oracle_sweep.py) and as the checker for the row-scan formulation planned in DESIGN.md section 8. ----
-static void k_despeckle2_raster(int32_t *labelinout, const int32_t *sizein, int thre, int iw, int ih) {
   for (int y = 0; y < ih; y++)
     for (int x = 0; x < iw; x++) {
       const int p0 = y * iw + x;
@@ -284,34 +264,6 @@ static void k_despeckle2_raster(int32_t *labelinout, const int32_t *sizein, int 
           }
       labelinout[p0] = maxLabel;
     }
-}
-
-// ---- the raster-order recurrence of despeckle2 truncated at dependency depth K: sweep k re-evaluates every small-region pixel
-// with the labels of its four causal neighbours (UL, U, UR, L) taken from sweep k-1 and the other five from the input.
-// K = 1 is the canonical Jacobi form; a pixel whose chain of small causal neighbours is shorter than K gets exactly the label
-// the raster schedule gives it.  NOT part of the canonical schedule: the candidate for replacing Q3. ----
-static void k_despeckle2_sweeps(int32_t *labelinout, const int32_t *sizein, int thre, int iw, int ih, int K) {
-  const size_t n = (size_t)iw * ih;
-  std::vector<int32_t> old(labelinout, labelinout + n), prev(old), next(old);
-  for (int k = 0; k < K; k++) {
-#pragma omp parallel for schedule(static)
-    for (int y = 0; y < ih; y++)
-      for (int x = 0; x < iw; x++) {
-        const int p0 = y * iw + x;
-        if (sizein[old[p0]] > thre) continue;
-        int maxSize = 0, maxLabel = old[p0];
-        for (int yy = -1; yy <= 1; yy++)
-          for (int xx = -1; xx <= 1; xx++)
-            if (0 <= x + xx && x + xx < iw && 0 <= y + yy && y + yy < ih) {
-              const int p1 = (y + yy) * iw + x + xx;
-              const int l = (yy < 0 || (yy == 0 && xx < 0)) ? prev[p1] : old[p1];
-              if (sizein[l] > maxSize) { maxSize = sizein[l]; maxLabel = l; }
-            }
-        next[p0] = maxLabel;
-      }
-    prev = next;
-  }
-  memcpy(labelinout, prev.data(), n * sizeof(int32_t));
 }
 
 // ---- oclrect.cl:373-390 (the `edge` argument is unused by the kernel) ----
@@ -387,8 +339,6 @@ void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int 
 void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { labelMerge(label, pix, mask, edge, iw, ih); }
 void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih) { k_calcSize(out, label, iw, ih); }
 void ora_rect_despeckle2(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih) { k_despeckle2(labelinout, size, thre, iw, ih); }
-void ora_rect_despeckle2_raster(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih) { k_despeckle2_raster(labelinout, size, thre, iw, ih); }
-void ora_rect_despeckle2_sweeps(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih, int K) { k_despeckle2_sweeps(labelinout, size, thre, iw, ih, K); }
 void ora_rect_markBoundary(int32_t *out, const int32_t *in, int iw, int ih) { k_markBoundary(out, in, iw, ih); }
 void ora_rect_reduceLS(int32_t *out, const int32_t *boundary, const int32_t *lsid, int iw, int ih, int nentry) { k_reduceLS(out, boundary, lsid, iw, ih, nentry); }
 

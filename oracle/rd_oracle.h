@@ -7,8 +7,8 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * The product library never links, imports or calls anything in this directory.
  *
- * PARITY STATUS: PINNED TO THE REFERENCE RUNNING HERE, except two kernels whose result depends on the order of the
- * reference's own work-items.  The reference ships no tests, golden vectors or fixtures and no
+ * PARITY STATUS: PINNED TO THE REFERENCE RUNNING HERE, except one kernel (labelMergeMain) whose result depends on the order
+ * of the reference's own work-items in a way no deterministic rule reproduces.  The reference ships no tests, golden vectors or fixtures and no
  * OpenCL runtime exists in this image, but the reference itself does run: `make _ref` compiles its host code
  * (helper.c, oclhelper.c, oclimgutil.c, oclpolyline.c, oclrect.c - unmodified, from /root/reference) together with its
  * three OpenCL C kernel files compiled as C++ (cl_translate.py rewrites only the vector-literal syntax, cl_compat.h supplies
@@ -19,11 +19,12 @@
  *   - Stage C (oclpolyline_execute, all 116 launches): every plane, the segment-id map and the LS_t list bit-exact;
  *   - calcSize, markBoundary, label8x, reduceLS (vote table) on identical inputs: bit-exact;
  *   - executeCPUTask (host tail): bit-exact (tests/test_ref_tail.py, tests/golden/ref_tail_golden.json);
- *   - labelMergeMain (Q6') and despeckle2 (Q3) are ORDER DEPENDENT in the reference (directed adopt rule gated on the
- *     current labels; in-place neighbourhood update).  The oracle fixes a deterministic outcome for each (components of
- *     the symmetric closure; Jacobi) whose relation to the sequential schedule is tested (coarsening, < 1 % of the
- *     pixels); with those two kernels swapped for the reference's the oracle reproduces the reference's region map
- *     bit-exactly.
+ *   - despeckle2 (Q3) updates its labels in place: the oracle evaluates it in raster order, i.e. exactly as the reference run
+ *     does - bit-exact on identical inputs;
+ *   - labelMergeMain (Q6') is ORDER DEPENDENT in the reference (directed adopt rule gated on the current labels).  The
+ *     oracle fixes a deterministic outcome (components of the symmetric closure of the adopt rule) whose relation to the
+ *     sequential schedule is tested (coarsening, < 1 % of the pixels); with that one kernel swapped for the reference's
+ *     the oracle reproduces the reference's region map bit-exactly.
  * Every other place where the reference is schedule-dependent (atomic arrival order, in-place races, vote-slot claims)
  * is resolved the way the raster-order schedule resolves it; each is marked "CANONICAL" in the sources and listed in
  * DESIGN.md section "Canonical semantics".  Vendor-defined OpenCL built-ins (rsqrt, hypot, distance, FP contraction) follow
@@ -99,11 +100,8 @@ void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int 
 /* labelxPreprocess + labelMergeMain x8 -> CANONICAL converged symmetric merge */
 void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);
 void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih);
+/* in place, work-items in raster order (CANONICAL Q3 = the reference run) */
 void ora_rect_despeckle2(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih);
-/* the same kernel with its work-items in raster order, in place (the reference's sequential schedule); not in the canonical schedule */
-void ora_rect_despeckle2_raster(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih);
-/* the raster recurrence truncated at dependency depth K (K = 1: the canonical Jacobi form); not in the canonical schedule */
-void ora_rect_despeckle2_sweeps(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih, int K);
 void ora_rect_markBoundary(int32_t *out, const int32_t *in, int iw, int ih);
 void ora_rect_reduceLS(int32_t *out, const int32_t *boundary, const int32_t *lsid, int iw, int ih, int nentry);
 

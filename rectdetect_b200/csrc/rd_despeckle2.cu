@@ -1,0 +1,193 @@
+// rd_despeckle2.cu - despeckle2 (oclrect.cl:348-371, oclrect.c:336) with the reference's in-place semantics under its raster
+// schedule, exactly, and markBoundary (oclrect.cl:373-390) behind it.  See rd_despeckle2.cuh for the formulation.
+//
+//   kd2_pre  : fully parallel, one CTA per image row.  Pixels of large regions are final (copied to `dst`); every small-region
+//              pixel gets its static record (best known candidate + which causal neighbours are small), compacted per row in
+//              ascending x into three list planes, row y at offset y * iw.  rowcnt[y] = number of small pixels of the row.
+//   kd2_seq  : the dependent part, one WARP per frame walking the rows top-down, 32 list entries per step.  Everything on the
+//              critical path lives in shared memory / registers: the (label, size) pairs the previous row's small pixels ended
+//              up with (rowbuf, two rows), the composed maps of a run of small pixels (warp shuffle scan, as many doubling steps
+//              as the longest run of the chunk needs), the carry into the next chunk.  The list records are streamed into a
+//              shared-memory ring D2_RING chunks ahead with cp.async, so the HBM/L2 latency is off the critical path.
+//              Cost: ~0.15 us per chunk, ih + (small pixels)/32 chunks per frame; frames of a batch run side by side.
+//   kf_markBoundary : tile kernel on the final labels.
+#include "rd_common.cuh"
+#include "rd_despeckle2.cuh"
+#include <mutex>
+
+#define D2P_THREADS 256
+__global__ void __launch_bounds__(D2P_THREADS) kd2_pre(int *dst, int *list, int *recL, int *recS, int *rowcnt, const int *label, const int *size, int thre,
+                                                       int iw, int ih, size_t fs) {
+  rd_batch_y(fs, dst, list, recL, recS, rowcnt, label, size);
+  __shared__ int wsum[D2P_THREADS / 32];
+  __shared__ int base;
+  const int y = blockIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const size_t row = (size_t)y * iw;
+  for (int x0 = 0; x0 < iw; x0 += D2P_THREADS) {
+    const int x = x0 + threadIdx.x;
+    bool small = false;
+    int rec = 0, bl = 0, bs = 0;
+    if (x < iw) {
+      const int l = label[row + x];
+      small = !(size[l] > thre);
+      if (!small) dst[row + x] = l;
+      else rec = d2_static(x, y, label, size, thre, iw, ih, bl, bs);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, small);
+    if (lane == 0) wsum[wp] = __popc(b);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < wp; w++) off += wsum[w];
+    if (small) {
+      const size_t o = row + off + __popc(b & ((1u << lane) - 1u));
+      list[o] = rec; recL[o] = bl; recS[o] = bs;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = base; for (int w = 0; w < D2P_THREADS / 32; w++) t += wsum[w]; base = t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowcnt[y] = base;
+}
+
+#define D2_RING 8
+#define D2_SMEM_MAX (200 * 1024)
+__device__ __forceinline__ void d2_cp_async4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void d2_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void d2_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(D2_RING - 1) : "memory"); }
+
+// rowbuf_g != NULL: the two-row buffer lives in global memory (frames too wide for shared memory)
+__global__ void __launch_bounds__(32) kd2_seq(int *dst, const int *list, const int *recL, const int *recS, const int *rowcnt, int2 *rowbuf_g, int iw, int ih,
+                                              size_t fs) {
+  rd_batch_x(fs, dst, list, recL, recS, rowcnt);
+  if (rowbuf_g) rd_batch_x(fs, rowbuf_g);
+  extern __shared__ __align__(16) int d2_smem[];
+  int *ring = d2_smem;                                        // [D2_RING][3][32]
+  int *cnt = ring + D2_RING * 3 * 32;                         // [ih]
+  int2 *rowbuf = rowbuf_g ? rowbuf_g : (int2 *)(cnt + ((ih + 1) & ~1));   // [2][iw]
+  const int lane = threadIdx.x;
+  for (int i = lane; i < ih; i += 32) cnt[i] = rowcnt[i];
+  __syncwarp();
+  // fetch cursor (warp-uniform): the next chunk to stream in is entries [fc, fc + 32) of row fy
+  int fy = 0, fc = 0;
+  while (fy < ih && cnt[fy] == 0) fy++;
+  auto fetch = [&](int stage) {
+    if (fy < ih) {
+      const int j = fc + lane;
+      if (j < cnt[fy]) {
+        const size_t o = (size_t)fy * iw + j;
+        int *r = ring + stage * 96 + lane;
+        d2_cp_async4(r, list + o); d2_cp_async4(r + 32, recL + o); d2_cp_async4(r + 64, recS + o);
+      }
+      fc += D2_CHUNK;
+      if (fc >= cnt[fy]) { fc = 0; do fy++; while (fy < ih && cnt[fy] == 0); }
+    }
+    d2_cp_commit();
+  };
+  for (int s = 0; s < D2_RING; s++) fetch(s);
+  int py = 0, pc = 0, stage = 0;
+  while (py < ih && cnt[py] == 0) py++;
+  int carryL = 0, carryS = 0;
+  while (py < ih) {
+    d2_cp_wait();
+    __syncwarp();
+    const int n = cnt[py];
+    const bool valid = pc + lane < n;
+    const int *r = ring + stage * 96 + lane;
+    const int rec = valid ? r[0] : 0;
+    int bl = valid ? r[32] : 0, bs = valid ? r[64] : 0;
+    __syncwarp();
+    fetch(stage);
+    stage = stage + 1 == D2_RING ? 0 : stage + 1;
+    const int x = rec & 0xffff, dyn = (rec >> 20) & 15;
+    int code = (rec >> 16) & 15;
+    const int2 *above = rowbuf + (size_t)((py + 1) & 1) * iw;
+    if (dyn & 1) { const int2 v = above[x - 1]; d2_take(bl, bs, code, v.x, v.y, 1); }
+    if (dyn & 2) { const int2 v = above[x]; d2_take(bl, bs, code, v.x, v.y, 2); }
+    if (dyn & 4) { const int2 v = above[x + 1]; d2_take(bl, bs, code, v.x, v.y, 3); }
+    int T = D2_HEAD;
+    if (dyn & 8) T = d2_threshold(bs, code);
+    if (lane == 0 && T != D2_HEAD) {                          // the run continues from the previous chunk
+      if (carryS >= T) { bl = carryL; bs = carryS; }
+      T = D2_HEAD;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      if (__all_sync(0xffffffffu, T == D2_HEAD)) break;
+      const int lL = __shfl_up_sync(0xffffffffu, bl, d), lS = __shfl_up_sync(0xffffffffu, bs, d), lT = __shfl_up_sync(0xffffffffu, T, d);
+      if (lane >= d && T != D2_HEAD) d2_compose(bl, bs, T, lL, lS, lT);
+    }
+    if (valid) {
+      dst[(size_t)py * iw + x] = bl;
+      rowbuf[(size_t)(py & 1) * iw + x] = make_int2(bl, bs);
+    }
+    carryL = __shfl_sync(0xffffffffu, bl, 31); carryS = __shfl_sync(0xffffffffu, bs, 31);
+    pc += D2_CHUNK;
+    if (pc >= n) { pc = 0; do py++; while (py < ih && cnt[py] == 0); }
+    if (rowbuf_g) __threadfence_block();
+    __syncwarp();
+  }
+}
+
+// markBoundary (oclrect.cl:373-390): a pixel keeps its region label if its 5x5 window holds another label; 2-px frame -> -1
+#define MB_T 32
+#define MB_A 2
+#define MB_W (MB_T + 2 * MB_A)
+__global__ void __launch_bounds__(256) kf_markBoundary(int *out, const int *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
+  __shared__ int sd[MB_W * MB_W];
+  const int bx = blockIdx.x * MB_T - MB_A, by = blockIdx.y * MB_T - MB_A;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < MB_W * MB_W; i += 256) {
+    const int gx = bx + i % MB_W, gy = by + i / MB_W;
+    sd[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih) ? in[(size_t)gy * iw + gx] : -1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int tx = MB_A + threadIdx.x, ty = MB_A + threadIdx.y + k * 8;
+    const int gx = bx + tx, gy = by + ty;
+    if (gx >= iw || gy >= ih) continue;
+    int r = -1;
+    if (!(gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2)) {
+      const int i = ty * MB_W + tx, c0 = sd[i];
+      bool nearEdge = false;
+#pragma unroll
+      for (int yy = -2; yy <= 2; yy++)
+#pragma unroll
+        for (int xx = -2; xx <= 2; xx++) nearEdge |= sd[i + yy * MB_W + xx] != c0;
+      if (nearEdge) r = c0;
+    }
+    out[(size_t)gy * iw + gx] = r;
+  }
+}
+
+// dst = despeckle2(label) (dst != label; label is left untouched).  list / recL / recS: scratch planes of iw*ih ints each;
+// rowcnt: ih ints; rowbuf: 2*iw int2 of scratch, only used when the frame is too wide for shared memory.
+void rd_despeckle2_run(int *dst, const int *label, const int *size, int *list, int *recL, int *recS, int *rowcnt, int2 *rowbuf, int thre, int iw, int ih,
+                       int nb, size_t fs, cudaStream_t s) {
+  if (iw > 0xffff) exitf(-1, "rectdetect_b200: despeckle2: frames wider than 65535 pixels are not supported\n");
+  RD_LAUNCH(kd2_pre, dim3(ih, nb), D2P_THREADS, 0, s, dst, list, recL, recS, rowcnt, label, size, thre, iw, ih, fs);
+  const size_t fixed = (size_t)D2_RING * 96 * 4 + (size_t)((ih + 1) & ~1) * 4, full = fixed + (size_t)2 * iw * sizeof(int2);
+  const bool in_smem = full <= D2_SMEM_MAX;
+  const size_t smem = in_smem ? full : fixed;
+  if (smem > D2_SMEM_MAX) exitf(-1, "rectdetect_b200: despeckle2: frame too tall (%d rows)\n", ih);
+  if (smem > 48 * 1024) {                             // opt in once per device
+    static std::mutex mu;
+    static bool ready[64] = {false};
+    int dev = 0;
+    RD_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(mu);
+    if (dev >= 64 || !ready[dev]) {
+      RD_CUDA(cudaFuncSetAttribute(kd2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_MAX));
+      if (dev < 64) ready[dev] = true;
+    }
+  }
+  RD_LAUNCH(kd2_seq, nb, 32, smem, s, dst, list, recL, recS, rowcnt, in_smem ? (int2 *)NULL : rowbuf, iw, ih, fs);
+}
+void rd_markBoundary_run(int *out, const int *in, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_LAUNCH(kf_markBoundary, dim3(rd_cdiv(iw, MB_T), rd_cdiv(ih, MB_T), nb), dim3(32, 8), 0, s, out, in, iw, ih, fs);
+}

@@ -1238,62 +1238,3 @@ __global__ void __launch_bounds__(256) kb_junction_mask(uint8_t *mask, int *junc
 void rd_junction_mask_run(uint8_t *mask, int *junc, const int *strong, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   RD_LAUNCH(kb_junction_mask, dim3(rd_cdiv(iw, 32 * BT_PW), rd_cdiv(ih, BT_PR), nb), 256, 0, s, mask, junc, strong, iw, ih, fs);
 }
-
-// despeckle2(16) in its Jacobi form + markBoundary (oclrect.cl:348-390, oclrect.c:336-340): region labels with an apron
-// of 3 and their sizes are staged; the absorbed labels are formed on the apron-2 tile, the boundary test on the centre.
-#define DB_T 32
-#define DB_A 3
-#define DB_W (DB_T + 2 * DB_A)
-__global__ void __launch_bounds__(256) kf_despeckle2_boundary(int *out, const int *label, const int *size, int thre, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, out, label, size);
-  __shared__ int sl[DB_W * DB_W];
-  __shared__ int ss[DB_W * DB_W];
-  __shared__ int sd[DB_W * DB_W];
-  const int bx = blockIdx.x * DB_T - DB_A, by = blockIdx.y * DB_T - DB_A;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < DB_W * DB_W; i += 256) {
-    const int gx = bx + i % DB_W, gy = by + i / DB_W;
-    int l = -1, sz = 0;
-    if (gx >= 0 && gx < iw && gy >= 0 && gy < ih) { l = label[(size_t)gy * iw + gx]; sz = size[l]; }
-    sl[i] = l; ss[i] = sz;
-  }
-  __syncthreads();
-  for (int i = tid; i < DB_W * DB_W; i += 256) {
-    const int tx = i % DB_W, ty = i / DB_W;
-    const int gx = bx + tx, gy = by + ty;
-    int res = sl[i];
-    if (tx >= 1 && ty >= 1 && tx < DB_W - 1 && ty < DB_W - 1 && gx >= 0 && gx < iw && gy >= 0 && gy < ih && !(ss[i] > thre)) {
-      int maxSize = 0;
-#pragma unroll
-      for (int yy = -1; yy <= 1; yy++)
-#pragma unroll
-        for (int xx = -1; xx <= 1; xx++) {
-          if (gx + xx < 0 || gx + xx >= iw || gy + yy < 0 || gy + yy >= ih) continue;
-          const int j = i + yy * DB_W + xx;
-          if (ss[j] > maxSize) { maxSize = ss[j]; res = sl[j]; }
-        }
-    }
-    sd[i] = res;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int tx = DB_A + threadIdx.x, ty = DB_A + threadIdx.y + k * 8;
-    const int gx = bx + tx, gy = by + ty;
-    if (gx >= iw || gy >= ih) continue;
-    int r = -1;
-    if (!(gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2)) {
-      const int i = ty * DB_W + tx, c0 = sd[i];
-      bool nearEdge = false;
-#pragma unroll
-      for (int yy = -2; yy <= 2; yy++)
-#pragma unroll
-        for (int xx = -2; xx <= 2; xx++) nearEdge |= sd[i + yy * DB_W + xx] != c0;
-      if (nearEdge) r = c0;
-    }
-    out[(size_t)gy * iw + gx] = r;
-  }
-}
-void rd_despeckle2_boundary_run(int *out, const int *label, const int *size, int thre, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_LAUNCH(kf_despeckle2_boundary, dim3(rd_cdiv(iw, DB_T), rd_cdiv(ih, DB_T), nb), dim3(32, 8), 0, s, out, label, size, thre, iw, ih, fs);
-}

@@ -41,7 +41,9 @@ void rd_filter_masks_run(int8_t *weak, int *strong, const int *label, const int 
 void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_quant_tables_init();
 void rd_junction_mask_run(uint8_t *mask, int *junc, const int *strong, int iw, int ih, int nb, size_t fs, cudaStream_t s);
-void rd_despeckle2_boundary_run(int *out, const int *label, const int *size, int thre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_despeckle2_run(int *dst, const int *label, const int *size, int *list, int *recL, int *recS, int *rowcnt, int2 *rowbuf, int thre, int iw, int ih,
+                       int nb, size_t fs, cudaStream_t s);
+void rd_markBoundary_run(int *out, const int *in, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_polyline_fast(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *copyOut, int *tmpBig, int *t0, int *t1, int *t2, int *t3, int *t4, int *t5,
@@ -243,24 +245,6 @@ __global__ void kr_calcSize(int *out, const int *label, int n, size_t fs) {
   const int l = label[i];
   if (l != -1) atomicAdd(out + l, 1);
 }
-// Jacobi form of despeckle2: reads the labels as they were at launch (`snap`), writes `out`
-__global__ void kr_despeckle2(int *out, const int *snap, const int *sizein, int thre, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, out, snap, sizein);
-  XY2D;
-  const int l0 = snap[p0];
-  int res = l0;
-  if (!(sizein[l0] > thre)) {
-    int maxSize = 0;
-    for (int yy = -1; yy <= 1; yy++)
-      for (int xx = -1; xx <= 1; xx++)
-        if (0 <= x + xx && x + xx < iw && 0 <= y + yy && y + yy < ih) {
-          const int l1 = snap[(y + yy) * iw + x + xx];
-          const int s1 = sizein[l1];
-          if (s1 > maxSize) { maxSize = s1; res = l1; }
-        }
-  }
-  out[p0] = res;
-}
 __global__ void kr_markBoundary(int *out, const int *in, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, in);
   XY2D;
@@ -414,7 +398,8 @@ struct oclrect_t {
   unsigned char *dbase;                 // nb arenas, fs bytes apart
   size_t fs, P;                         // arena stride, plane pitch (bytes)
   cl_mem buf[6], tmp[6], iobuf[2], ioBig[2];   // non-owning handles on the buffers of arena 0
-  unsigned char *dblob;                 // read-back record of arena 0
+  unsigned char *dblob[2];              // read-back records of arena 0, one per pipeline page (a record is read back in two parts; the
+                                        // second part is copied while the next task already runs, so the pages must not share one)
   size_t blobBytes;
   int maxLS;
   uint8_t *hostImg[2];                  // pinned: frame staging, nb x P per page (hostiobuf[page][0] of the reference)
@@ -438,7 +423,7 @@ __global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, in
 
 // genGPUTask (oclrect.c:235-381) without the copies.  Step numbers follow SURVEY.md section 10.1; stop_step = k > 0
 // returns after step k (for the intermediate-parity tests), 0 runs everything.
-static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int stop_step, int nb, cudaStream_t s) {
+static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int stop_step, int nb, cudaStream_t s, int page = 0) {
   const int iw = o->iw, ih = o->ih, n = iw * ih, g1 = rd_cdiv(n, 256);
   const size_t fs = o->fs;
   cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
@@ -494,10 +479,11 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   // step 17 : colour regions (work plane tmp4, link bytes tmp5: both dead until the polyline stage rewrites them)
   rd_labelMerge(PI(buf[5]), PI(tmp[4]), PU(buf[4]), PI(tmp[1]), PI(buf[2]), tmp[5]->dptr, iw, ih, nb, fs, s);
   STEP(17);
-  // step 18 : region sizes on top of the junction map (Q2), small regions absorbed (Jacobi: snapshot in tmp4)
+  // step 18 : region sizes on top of the junction map (Q2), small regions absorbed in place in raster order (rd_despeckle2.cu;
+  // input snapshot in tmp4, list planes tmp2 / tmp3 / tmp5, row counts tmp1, wide-frame row buffer ioBig0: all dead here)
   rd_calcSize_run(PI(tmp[0]), PI(buf[5]), iw, ih, nb, fs, s);
   rd_k_copy(PI(tmp[4]), PI(buf[5]), n, nb, fs, s);
-  RD_LAUNCH(kr_despeckle2, rd_gz(G2, nb), RB, 0, s, PI(buf[5]), PI(tmp[4]), PI(tmp[0]), 16, iw, ih, fs);
+  rd_despeckle2_run(PI(buf[5]), PI(tmp[4]), PI(tmp[0]), PI(tmp[2]), PI(tmp[3]), PI(tmp[5]), PI(tmp[1]), (int2 *)ioBig[0]->dptr, 16, iw, ih, nb, fs, s);
   STEP(18);
   // step 19 : boundary bands and their components -> segid map
   RD_LAUNCH(kr_markBoundary, rd_gz(G2, nb), RB, 0, s, PI(tmp[1]), PI(buf[5]), iw, ih, fs);
@@ -515,7 +501,7 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   RD_LAUNCH(kr_reduceLS<2>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
   STEP(21);
   // step 22 : compact read-back record instead of the reference's three big copies (oclrect.c:371-376)
-  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
+  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob[page], o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
 #undef STEP
 }
 
@@ -528,7 +514,7 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
 //   iobuf1 region-boundary (segid) map   ioBig0 blur scratch -> segment list   ioBig1 blur scratch -> polyline scratch -> vote table
 // stop_stage > 0 ends the schedule after that stage (tests compare the planes of the production schedule stage by stage,
 // tests/parity.py FAST_STAGES); 0 runs everything.
-static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int nb, cudaStream_t s, int stop_stage = 0) {
+static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int nb, cudaStream_t s, int stop_stage = 0, int page = 0) {
 #define STAGE(k) do { if (stop_stage == (k)) return; } while (0)
   const int iw = o->iw, ih = o->ih, n = iw * ih;
   const size_t fs = o->fs;
@@ -559,7 +545,9 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   rd_labelMerge_u8(PI(buf[4]), PI(buf[5]), PU(tmp[2]), (const uint8_t *)tmp[3]->dptr, PI(tmp[5]), tmp[4]->dptr, iw, ih, nb, fs, s);
   STAGE(10);
   rd_calcSize_run(PI(tmp[0]), PI(buf[4]), iw, ih, nb, fs, s);
-  rd_despeckle2_boundary_run(PI(tmp[1]), PI(buf[4]), PI(tmp[0]), 16, iw, ih, nb, fs, s);
+  // despeckle2 in raster order: final labels -> buf5; list planes buf1 / buf2 / tmp2, row counts tmp3 (all dead here)
+  rd_despeckle2_run(PI(buf[5]), PI(buf[4]), PI(tmp[0]), PI(buf[1]), PI(buf[2]), PI(tmp[2]), PI(tmp[3]), (int2 *)ioBig[0]->dptr, 16, iw, ih, nb, fs, s);
+  rd_markBoundary_run(PI(tmp[1]), PI(buf[5]), iw, ih, nb, fs, s);
   STAGE(11);
   rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[4]->dptr, -1, iw, ih, nb, fs, s);
   STAGE(12);
@@ -575,7 +563,7 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   RD_LAUNCH(kr_reduceLS_list<0>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);   // tmp2: the polyline stage's pixel list
   RD_LAUNCH(kr_reduceLS_list<1>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
   RD_LAUNCH(kr_reduceLS_list<2>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
-  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob, o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
+  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob[page], o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
 }
 
 // ---- fused / specialised Stage A kernels of the rect pipeline ----
@@ -650,7 +638,7 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   o->maxLS = (int)((bb - 128) / (sizeof(LS_t) + RD_TAIL_NSAMPLE * sizeof(rd_tail_sample))) - 1;
   const int cap = (int)((size_t)iw * ih * 16 / sizeof(LS_t)) - 1;
   if (o->maxLS > cap) o->maxLS = cap;
-  o->fs = 22 * P + bb;
+  o->fs = 22 * P + 2 * bb;
   o->P = P;
   RD_CUDA(cudaMalloc((void **)&o->dbase, o->fs * nb));
   // CANONICAL (Q1): memory the reference never initialises reads as zero on the first frame
@@ -660,7 +648,8 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   for (int i = 0; i < 6; i++) { o->tmp[i] = rd_wrap_device_memory(q, P); q += P; }
   for (int i = 0; i < 2; i++) { o->iobuf[i] = rd_wrap_device_memory(q, P); q += P; }
   for (int i = 0; i < 2; i++) { o->ioBig[i] = rd_wrap_device_memory(q, 4 * P); q += 4 * P; }
-  o->dblob = q;
+  o->dblob[0] = q;
+  o->dblob[1] = q + bb;
   for (int p = 0; p < 2; p++) {
     o->hostImg[p] = (uint8_t *)allocatePinnedMemory((size_t)iw * ih * 4 * nb, NULL, NULL);
     o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(bb * nb, NULL, NULL);
@@ -696,9 +685,9 @@ static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, 
     din_fs = frame_stride;
   }
   if (fresh) RD_CUDA(cudaMemset2DAsync(o->buf[3]->dptr, o->fs, 0, (size_t)iw * ih * 4, count, s));
-  gpu_task_fast(o, din, din_fs, ws, count, s);
+  gpu_task_fast(o, din, din_fs, ws, count, s, 0, page);
   const size_t chunk = o->blobBytes < FIRST_CHUNK ? o->blobBytes : FIRST_CHUNK;
-  RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], o->blobBytes, o->dblob, o->fs, chunk, count, cudaMemcpyDeviceToHost, s));
+  RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], o->blobBytes, o->dblob[page], o->fs, chunk, count, cudaMemcpyDeviceToHost, s));
   RD_CUDA(cudaEventRecord(o->events[page], s));
   o->pending[page] = count;
 }
@@ -793,7 +782,7 @@ static void finish_page(oclrect_t *o, int page, double tanAOV, rect_t **out, int
     const int n = ((int *)hb)[0], ng = ((int *)hb)[1];
     const size_t need = blob_need(ng);
     if (n <= ng && need > FIRST_CHUNK) {
-      RD_CUDA(cudaMemcpyAsync(hb + FIRST_CHUNK, o->dblob + (size_t)i * o->fs + FIRST_CHUNK, need - FIRST_CHUNK, cudaMemcpyDeviceToHost, s));
+      RD_CUDA(cudaMemcpyAsync(hb + FIRST_CHUNK, o->dblob[page] + (size_t)i * o->fs + FIRST_CHUNK, need - FIRST_CHUNK, cudaMemcpyDeviceToHost, s));
       more = true;
     }
   }
@@ -909,8 +898,14 @@ void rd_rect_labelMerge(cl_mem label, cl_mem pix, cl_mem mask, cl_mem edge, int 
 void rd_rect_calcSize(cl_mem out, cl_mem label, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_calcSize, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, PI(out), PI(label), iw * ih, fs); }
 void rd_rect_despeckle2(cl_mem io, cl_mem size, cl_mem scratch, int thre, int iw, int ih, cl_command_queue q) {
   QS;
+  const size_t n = (size_t)iw * ih;
+  int *w = NULL;                                   // three list planes, the row counts, the wide-frame row buffer
+  RD_CUDA(cudaMallocAsync((void **)&w, (3 * n + ih + 4 * (size_t)iw + 4) * sizeof(int), s));
   rd_k_copy(PI(scratch), PI(io), iw * ih, 1, 0, s);
-  RD_LAUNCH(kr_despeckle2, rd_gz(G2, nb), RB, 0, s, PI(io), PI(scratch), PI(size), thre, iw, ih, fs);
+  int *rowbuf = w + 3 * n + ih;
+  rowbuf += ((uintptr_t)rowbuf & 4) ? 1 : 0;
+  rd_despeckle2_run(PI(io), PI(scratch), PI(size), w, w + n, w + 2 * n, w + 3 * n, (int2 *)rowbuf, thre, iw, ih, nb, fs, s);
+  RD_CUDA(cudaFreeAsync(w, s));
 }
 void rd_rect_markBoundary(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_markBoundary, rd_gz(G2, nb), RB, 0, s, PI(out), PI(in), iw, ih, fs); }
 void rd_rect_reduceLS(cl_mem out, cl_mem boundary, cl_mem lsid, int iw, int ih, int nentry, cl_command_queue q) {

@@ -68,7 +68,7 @@ def oracle():
             "ora_rect_quantize": (None, [vp, vp, i, i, i, i, i]), "ora_rect_despeckle": (None, [vp, vp, vp, i, i]),
             "ora_rect_mkMergeMask0": (None, [vp, vp, i, i]), "ora_rect_mkMergeMask1": (None, [vp, vp, i, i]),
             "ora_rect_labelMerge": (None, [vp, vp, vp, vp, i, i]),
-            "ora_rect_calcSize": (None, [vp, vp, i, i]), "ora_rect_despeckle2": (None, [vp, vp, i, i, i]), "ora_rect_despeckle2_raster": (None, [vp, vp, i, i, i]), "ora_rect_despeckle2_sweeps": (None, [vp, vp, i, i, i, i]),
+            "ora_rect_calcSize": (None, [vp, vp, i, i]), "ora_rect_despeckle2": (None, [vp, vp, i, i, i]),
             "ora_rect_markBoundary": (None, [vp, vp, i, i]), "ora_rect_reduceLS": (None, [vp, vp, vp, i, i, i]),
             "ora_polyline_execute": (None, [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, f, i, i, i, i]),
             "ora_rect_create": (vp, [i, i]), "ora_rect_destroy": (None, [vp]),
@@ -92,6 +92,18 @@ def oracle():
 
 
 from rectdetect_b200.synth import synth_frame, synth_lib  # noqa: E402,F401  (the generator is workload input, not oracle)
+
+
+def dense_frame(iw, ih, seed, tiles_x=4, tiles_y=4):
+    """a frame tiled from tiles_x x tiles_y independent synthetic frames: many more rectangles / line segments than
+    synth_frame gives (used to exercise the large read-back records; 1280x720 in 5x5 tiles has > 400 segments)"""
+    tw, th = iw // tiles_x, ih // tiles_y
+    img = np.full((ih, 3 * iw), 128, np.uint8)
+    for ty in range(tiles_y):
+        for tx in range(tiles_x):
+            t = synth_frame(tw, th, seed * 100 + ty * tiles_x + tx)
+            img[ty * th:(ty + 1) * th, 3 * tx * tw:3 * (tx + 1) * tw] = t[:, :3 * tw]
+    return img
 
 
 def rects_from_ptr(p, free=True):

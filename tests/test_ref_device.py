@@ -157,50 +157,14 @@ def test_stage_b_tail_kernels_on_identical_inputs(ctx, iw, ih, seed):
     k_size(iw, ih, P(size_r), P(d["label"]), iw, ih)
     L.ora_rect_calcSize(P(size_o), P(d["label"]), iw, ih)
     assert np.array_equal(size_r, size_o)
-    # despeckle2: in place.  Sequential raster order lets a speckle dissolve in one sweep (a pixel sees its already
-    # re-labelled upper / left neighbours); the canonical Jacobi form re-labels only the pixels that touch a large region.
+    # despeckle2: in place; the oracle evaluates it in raster order, exactly like the reference run (Q3)
     lab_r, lab_o = d["label"].copy(), d["label"].copy()
     k_d2(iw, ih, P(lab_r), P(size_r), 16, iw, ih)
     L.ora_rect_despeckle2(P(lab_o), P(size_o), 16, iw, ih)
-    lab_s = d["label"].copy()
-    L.ora_rect_despeckle2_raster(P(lab_s), P(size_o), 16, iw, ih)    # the oracle's raster-order operator (not in the schedule)
-    assert np.array_equal(lab_r, lab_s)
-    # the recurrence truncated at depth K: K = 1 is the canonical Jacobi form; every pixel whose chain of small causal
-    # neighbours is shorter than K already has its raster label; the distance to the raster result shrinks with K
-    small2 = (size_o[d["label"]] <= 16).reshape(ih, iw)
-    depth = np.zeros((ih, iw), np.int32)                             # length of the longest chain of small causal neighbours
-    for y in range(ih):
-        for x in np.flatnonzero(small2[y]):
-            m = 0
-            for yy, xx in ((-1, -1), (-1, 0), (-1, 1), (0, -1)):
-                if 0 <= y + yy and 0 <= x + xx < iw and small2[y + yy, x + xx]:
-                    m = max(m, depth[y + yy, x + xx])
-            depth[y, x] = m + 1
-    dist = []
-    for K in (1, 2, 4):
-        lab_k = d["label"].copy()
-        L.ora_rect_despeckle2_sweeps(P(lab_k), P(size_o), 16, iw, ih, K)
-        if K == 1:
-            assert np.array_equal(lab_k, lab_o)
-        exact = (depth.ravel() <= K)
-        assert np.array_equal(lab_k[exact], lab_r[exact]), K
-        dist.append(int((lab_k != lab_r).sum()))
-    assert dist[0] >= dist[1] >= dist[2] and dist[2] < dist[0]
+    assert np.array_equal(lab_r, lab_o)
     small = size_o[d["label"]] <= 16
-    assert np.array_equal(lab_r[~small], lab_o[~small])              # only pixels of small regions may change at all
-    assert np.array_equal(lab_r[~small], d["label"][~small])
-    assert (lab_r != lab_o).mean() < 0.01
-    # the recurrence "upper / left neighbours new, the others old" iterated from the Jacobi result to its fixed point IS the
-    # sequential result (checked on the changed pixels' first sweep: every pixel whose 4 causal neighbours are large regions
-    # already agrees)
-    causal_small = np.zeros((ih, iw), bool)
-    s2 = small.reshape(ih, iw)
-    causal_small[1:, 1:] |= s2[:-1, :-1]
-    causal_small[1:, :] |= s2[:-1, :]
-    causal_small[1:, :-1] |= s2[:-1, 1:]
-    causal_small[:, 1:] |= s2[:, :-1]
-    indep = small & ~causal_small.ravel()
-    assert np.array_equal(lab_r[indep], lab_o[indep])
+    assert np.array_equal(lab_r[~small], d["label"][~small])         # only pixels of small regions may change at all
+    assert small.any() and (lab_r != d["label"]).any()
     # markBoundary + label8x (bgc = -1) -> the segid map, from the oracle's labels
     bnd_r, bnd_o = np.zeros(n, np.int32), np.zeros(n, np.int32)
     k_mb(iw, ih, P(bnd_r), P(lab_o), P(d["edge"]), iw, ih)
@@ -215,9 +179,9 @@ def test_stage_b_tail_kernels_on_identical_inputs(ctx, iw, ih, seed):
 
 
 @pytest.mark.parametrize("iw,ih,seed", [(640, 480, 2), (640, 480, 12)])
-def test_region_map_is_the_references_once_the_two_order_dependent_kernels_are_swapped(ctx, iw, ih, seed):
-    """reference labelMergeMain + reference despeckle2 (sequential schedule) inside the ORACLE's Stage B reproduce the
-    reference's segid map bit-exactly: nothing else in the stage deviates"""
+def test_region_map_is_the_references_once_the_order_dependent_kernel_is_swapped(ctx, iw, ih, seed):
+    """reference labelMergeMain (sequential schedule) inside the ORACLE's Stage B reproduces the reference's segid map
+    bit-exactly: nothing else in the stage deviates (despeckle2 is the oracle's own)"""
     L = ol.oracle()
     n = iw * ih
     img, d = _oracle_stage_b_inputs(iw, ih, seed)
@@ -228,9 +192,7 @@ def test_region_map_is_the_references_once_the_two_order_dependent_kernels_are_s
     lab = _ref_label_merge(d, iw, ih)[-1]
     size = d["junction"].copy()
     L.ora_rect_calcSize(P(size), P(lab), iw, ih)
-    k_d2 = rl.kernel_direct("rect", "despeckle2")
-    k_d2.argtypes = [ci, ci, vp, vp, ci, ci, ci]
-    k_d2(iw, ih, P(lab), P(size), 16, iw, ih)
+    L.ora_rect_despeckle2(P(lab), P(size), 16, iw, ih)
     bnd, seg, tmp = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
     L.ora_rect_markBoundary(P(bnd), P(lab), iw, ih)
     L.ora_label8x_int_int(P(seg), P(bnd), P(tmp), -1, iw, ih)

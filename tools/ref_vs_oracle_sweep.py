@@ -2,8 +2,8 @@
 """CPU sweep: the oracle against THE REFERENCE ITSELF (oracle/_ref/librd_ref.so, raster-order schedule) over frame sizes
 (incl. widths that are not multiples of 32, frames smaller than the blur / window radii), row strides wider than the image,
 blank frames and many seeds.  Per case: which of the order-independent planes are bit-exact after the full genGPUTask, how far
-the region map is off (labelMergeMain / despeckle2 are order dependent), the vote table on identical inputs, and how the
-rectangle lists compare.   usage: ref_vs_oracle_sweep.py [quick|big]   (needs a built librd_ref.so)"""
+the region map is off (labelMergeMain is order dependent: the one remaining canonical substitute), the vote table on identical
+inputs, and how the rectangle lists compare.   usage: ref_vs_oracle_sweep.py [quick|big]   (needs a built librd_ref.so)"""
 import ctypes as C
 import math
 import os
@@ -31,30 +31,10 @@ k_votes.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_in
 rl.set_threads(1)
 t0 = time.time()
 bad = tot_r = tot_m = 0
-print("%-26s %-58s %-12s %-7s %-22s %s" % ("case", "bit-exact planes (plab thin strong quant lsid ls)", "segid off", "votes", "rects ref/ora/matched",
-                                            "what if despeckle2 ran in raster order: segid off, rects matched"))
+print("%-26s %-58s %-12s %-7s %s" % ("case", "bit-exact planes (plab thin strong quant lsid ls)", "segid off", "votes", "rects ref/ora/matched"))
 LO = ol.oracle()
 
 
-def what_if_raster_despeckle2(img, stride, iw, ih, o_full, ref_segid, ref_rects):
-    """the oracle's Stage B with its despeckle2 replaced by the raster-order operator; everything else canonical"""
-    n = iw * ih
-    o = ol.OracleRect(iw, ih)
-    o.gpu_task(img, stride, 17)
-    lab, size = o.buffer("buf5").copy(), o.buffer("tmp0").copy()
-    o.close()
-    LO.ora_rect_calcSize(size.ctypes.data, lab.ctypes.data, iw, ih)
-    LO.ora_rect_despeckle2_raster(lab.ctypes.data, size.ctypes.data, 16, iw, ih)
-    bnd, seg, tmp, votes = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(4 * n, np.int32)
-    LO.ora_rect_markBoundary(bnd.ctypes.data, lab.ctypes.data, iw, ih)
-    LO.ora_label8x_int_int(seg.ctypes.data, bnd.ctypes.data, tmp.ctypes.data, -1, iw, ih)
-    lsid, ls = o_full.buffer("buf0").copy(), o_full.buffer("ioBig0").copy()
-    LO.ora_rect_reduceLS(votes.ctypes.data, seg.ctypes.data, lsid.ctypes.data, iw, ih, n * 4 // 5)
-    rects = ol.rects_from_ptr(LO.ora_tail(ls.ctypes.data, seg.ctypes.data, votes.ctypes.data, iw, ih, TAN))
-    return float((seg != ref_segid).mean()), _match_rects(ref_rects, rects), len(rects)
-
-
-tot_w = 0
 for iw, ih, seed, ws, blank in cases:
     n = iw * ih
     img = np.full((ih, 3 * iw), 128, np.uint8) if blank else ol.synth_frame(iw, ih, seed, ws=ws)
@@ -86,12 +66,9 @@ for iw, ih, seed, ws, blank in cases:
     tot_m += m
     ok = all(flags) and votes_ok
     bad += 0 if ok else 1
-    w_off, w_m, w_n = what_if_raster_despeckle2(img, stride, iw, ih, o, r.buffer("iobuf1"), a)
-    tot_w += w_m
-    print("%-26s %-58s %-12s %-7s %-22s %.3f %%, %d/%d" % ("%dx%d s%d%s%s" % (iw, ih, seed, " ws%d" % ws if ws else "", " blank" if blank else ""),
+    print("%-26s %-58s %-12s %-7s %s" % ("%dx%d s%d%s%s" % (iw, ih, seed, " ws%d" % ws if ws else "", " blank" if blank else ""),
                                                      " ".join("yes" if f else "NO " for f in flags), "%.3f %%" % (100 * seg_off), "yes" if votes_ok else "NO",
-                                                     "%d/%d/%d" % (len(a), len(b), m), 100 * w_off, w_m, max(len(a), w_n)))
+                                                     "%d/%d/%d" % (len(a), len(b), m)))
     r.close()
     o.close()
-print("%d cases, %d with a plane that is not bit-exact; rectangles: %d of %d matched within 1e-4 (%d with a raster-order despeckle2); %.0f s"
-      % (len(cases), bad, tot_m, tot_r, tot_w, time.time() - t0))
+print("%d cases, %d with a plane that is not bit-exact; rectangles: %d of %d matched within 1e-4; %.0f s" % (len(cases), bad, tot_m, tot_r, time.time() - t0))
