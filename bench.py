@@ -229,10 +229,6 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    # the ranks of one node share its cores: each gets its slice for the host-tail pool (read when the pool is created)
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("RD_TAIL_THREADS", str(max(2, (os.cpu_count() or 8) // max(1, local_world))))
-
     import torch
     import torch.distributed as dist
     import rectdetect_b200 as rd
@@ -347,7 +343,7 @@ def main():
                     "pipeline_algorithmic_bytes_per_px": 43, "pipeline_frac": (43.0 * value * 1e6 / 1e9) / peak}
         # per-stage roofline: algorithmic bytes per pixel A 11, B 16, C 8 (+56 B per segment), D 8 (+20 B per
         # vote pair); the list terms are <1 % of a frame and are left out, so the fractions are slightly conservative
-        stage_bpp = {"A": 11, "B": 16, "C": 8, "D": 8}
+        stage_bpp = {"A": 11, "B": 16, "C": 8, "D": 8, "T": 0}
         stages = {}
         for st in sorted(stage_ms):
             us = stage_ms[st] * 1e3 / nsolo
@@ -371,15 +367,16 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i32 (f64 host tail)", "data": "synthetic",
+            "dtype": "f32+i32 (f64 device tail)", "data": "synthetic",
             "config": {"workload": "vidrect %dx%d synthetic stream (seeds 1000+i), AOV 72, full imgutil->polyline->rect pipeline, batched" % (iw, ih),
                        "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "frames_per_launch": args.fpl, "parallelism": "frames x%d" % world,
                        "l2": "inputs larger than L2 (%d MB of frames + %d x 81 MB working sets per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx * args.fpl)},
-            "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": total_frames * 128 * 1024,
+            "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": total_frames * 16 * 1024,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "rects_per_step": nrect, "value_and_e2e_rects_identical": bool(same),
-            "host": {"driver_threads": args.nctx, "tail_pool_threads": int(os.environ["RD_TAIL_THREADS"]), "wait_for_device_ms_last_step": wait_ms, "host_tail_ms_last_step": tail_ms, "host_cores": os.cpu_count()},
+            "host": {"driver_threads": args.nctx, "wait_for_device_ms_last_step": wait_ms, "host_list_copy_ms_last_step": tail_ms, "host_cores": os.cpu_count(),
+                     "host_tail": "none: executeCPUTask runs on the device (rd_gtail.cu)"},
         }
         emit(line)
     batch.close()

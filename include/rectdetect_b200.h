@@ -178,7 +178,7 @@ void rd_rect_mkMergeMask0(cl_mem out, cl_mem junction, int iw, int ih, cl_comman
 void rd_rect_mkMergeMask1(cl_mem inout, cl_mem junction, int iw, int ih, cl_command_queue q);              /* oclrect.cl:263 */
 void rd_rect_labelMerge(cl_mem label, cl_mem pix, cl_mem mask, cl_mem edge, int iw, int ih, cl_command_queue q); /* oclrect.cl:289-334 + oclrect.c:325-331, converged */
 void rd_rect_calcSize(cl_mem out, cl_mem label, int iw, int ih, cl_command_queue q);                       /* oclrect.cl:336 */
-void rd_rect_despeckle2(cl_mem labelinout, cl_mem size, cl_mem scratch, int thre, int iw, int ih, cl_command_queue q); /* oclrect.cl:348 (Jacobi) */
+void rd_rect_despeckle2(cl_mem labelinout, cl_mem size, cl_mem scratch, int thre, int iw, int ih, cl_command_queue q); /* oclrect.cl:348, in place, work-items in raster order */
 void rd_rect_markBoundary(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q);                      /* oclrect.cl:373 */
 void rd_rect_reduceLS(cl_mem out, cl_mem boundary, cl_mem lsid, int iw, int ih, int nentry, cl_command_queue q); /* oclrect.cl:427 */
 
@@ -188,8 +188,12 @@ cl_mem rd_oclrect_buffer(struct oclrect_t *thiz, const char *name);
 /* run genGPUTask's device schedule only (no read-back, no host tail); stop_step > 0: the operator-level replay stopped at
  * that step of SURVEY.md 10.1; 0: the production schedule; < 0: the production schedule stopped after stage -stop_step */
 void   rd_oclrect_run_device(struct oclrect_t *thiz, const uint8_t *imgData, int ws, int stop_step);
-/* executeCPUTask (oclrect.c:1049) on host arrays: ls = list incl. header, segid = plane, votes = int[nentry][5] */
+/* executeCPUTask (oclrect.c:1049) on host arrays: ls = list incl. header, segid = plane, votes = int[nentry][5].  Pure host code,
+ * kept as the checker of the device tail (the pipeline itself runs executeCPUTask on the device, rd_gtail.cu) */
 rect_t *rd_rect_tail(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, double tanAOV);
+/* executeCPUTask (oclrect.c:1049) as a device operator on caller-owned buffers (the three read-backs of oclrect.c:371-376 as
+ * cl_mems): segment list incl. header, region map, vote table.  Synchronous; returns a malloc()ed list, element 0 = header */
+rect_t *rd_rect_tail_device(cl_mem lsList, cl_mem segid, cl_mem votes, int iw, int ih, double tanAOV, cl_command_queue q);
 void   rd_free(void *p);
 
 /* Frame-batch engine: `nctx` pipeline objects on one device, each with its own stream, buffers for
@@ -201,11 +205,11 @@ typedef struct rd_batch rd_batch;
 rd_batch *rd_batch_create(int device, int iw, int ih, int nctx, int frames_per_launch);
 void rd_batch_destroy(rd_batch *b);
 void rd_batch_run(rd_batch *b, const uint8_t *frames, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out);
-/* device-resident variant: frames already in device memory (read in place).  out == NULL runs the device stages and the
- * read-back of the compact record only (no host tail). */
+/* device-resident variant: frames already in device memory (read in place).  out == NULL runs everything on the device but
+ * builds no host lists. */
 void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out);
 /* host-side accounting of the last rd_batch_run, summed over the pipeline objects' driver threads: out_ms[0] = time spent
- * waiting for the device, out_ms[4] = wall time of the host-tail phases (executeCPUTask); [1..3] are reserved (0) */
+ * waiting for the device, out_ms[4] = wall time spent copying the read-back records into rect_t lists; [1..3] are reserved (0) */
 void rd_batch_stage_ms(rd_batch *b, double out_ms[5]);
 
 #ifdef __cplusplus

@@ -90,7 +90,7 @@ def lib():
         "rd_rect_calcSize": (None, [vp, vp, i, i, vp]), "rd_rect_despeckle2": (None, [vp, vp, vp, i, i, i, vp]),
         "rd_rect_markBoundary": (None, [vp, vp, i, i, vp]), "rd_rect_reduceLS": (None, [vp, vp, vp, i, i, i, vp]),
         "rd_oclrect_buffer": (vp, [vp, C.c_char_p]), "rd_oclrect_run_device": (None, [vp, vp, i, i]),
-        "rd_rect_tail": (vp, [vp, vp, vp, i, i, d]),
+        "rd_rect_tail": (vp, [vp, vp, vp, i, i, d]), "rd_rect_tail_device": (vp, [vp, vp, vp, i, i, d, vp]),
         "rd_batch_create": (vp, [i, i, i, i, i]), "rd_batch_destroy": (None, [vp]),
         "rd_batch_run": (None, [vp, vp, sz, i, i, d, vp]), "rd_batch_run_device": (None, [vp, vp, sz, i, i, d, vp]),
         "rd_batch_stage_ms": (None, [vp, vp]),
@@ -287,3 +287,19 @@ def rect_tail(ls, segid, votes, iw, ih, tan_aov):
     segid = np.ascontiguousarray(segid, np.int32)
     votes = np.ascontiguousarray(votes, np.int32)
     return rects_from_ptr(lib().rd_rect_tail(_p(ls), _p(segid), _p(votes), iw, ih, tan_aov))
+
+
+def rect_tail_device(dev, ls, segid, votes, iw, ih, tan_aov):
+    """executeCPUTask (oclrect.c:1049) on the device (rd_gtail.cu) from host arrays: uploads them and runs the operator"""
+    n = iw * ih
+    mls, mseg, mvotes = dev.buffer(nbytes=16 * n), dev.buffer(nbytes=4 * n), dev.buffer(nbytes=16 * n)
+    raw = np.zeros(4 * n, np.int32)
+    src = np.ascontiguousarray(ls).view(np.int32).ravel()
+    raw[: src.size] = src
+    mls.write(raw)
+    mseg.write(np.ascontiguousarray(segid, np.int32))
+    mvotes.write(np.ascontiguousarray(votes, np.int32))
+    r = rects_from_ptr(lib().rd_rect_tail_device(mls.h, mseg.h, mvotes.h, iw, ih, tan_aov, dev.queue))
+    for m in (mls, mseg, mvotes):
+        m.release()
+    return r

@@ -7,13 +7,10 @@
 // top of the junction map) and the stale frame that oclpolyline.cl's simpleConnect leaves in its output are
 // reproduced by construction.  What differs from the reference, on purpose:
 //   - the bounded label propagation loops are exact connected components (rd_ccl.cu);
-//   - nothing big is read back: a gather kernel (k_tail_gather) evaluates, on the device and in IEEE double exactly
-//     as executeCPUTask does (oclrect.c:1066-1098), the 15 sample points of every live line segment, and emits for
-//     each the region id under it and the vote-table entry of that (segment, region) pair.  The host tail then needs
-//     (n+1) x 416 bytes instead of the reference's 9 planes (33 MB at 1280x720).
+//   - nothing big is read back: executeCPUTask (oclrect.c:1049-1226) runs on the device too (rd_gtail.cu), in IEEE double in
+//     the reference's order of operations, so a frame costs one small D2H copy - its rect_t list - instead of the
+//     reference's 9 planes (33 MB at 1280x720), and no host core touches it.
 #include <chrono>
-#include <condition_variable>
-#include <deque>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -48,7 +45,8 @@ void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int i
 void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_polyline_fast(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *copyOut, int *tmpBig, int *t0, int *t1, int *t2, int *t3, int *t4, int *t5,
                       float minerror, int sizeThre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
-void rd_tail_gather_host(const linesegment_t *ls, const int32_t *segid, const int32_t *votes, int iw, int ih, rd_tail_sample *out);
+void rd_gtail_run(unsigned char *blob, size_t blobBytes, const linesegment_t *ls, const int *segid, const int *votes, int *table, unsigned char *scratch,
+                  size_t scratchBytes, int iw, int ih, double tanAOV, int phases, int nb, size_t fs, cudaStream_t s);
 
 #define XY2D const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y; if (x >= iw || y >= ih) return; const int p0 = y * iw + x
 static const dim3 RB(32, getenv("RD_BY") ? atoi(getenv("RD_BY")) : 8);
@@ -347,45 +345,6 @@ __global__ void kr_reduceLS_list(int *out, const int *boundaryin, const int *lsi
   }
 }
 
-// ---------------------------------------------------------------------------- read-back record for the host tail
-// Blob layout: [0] int n, [1] int n_gathered, ... 64-byte header; LS_t[n_g+1] at byte 64; rd_tail_sample[(n_g+1)*15] behind it
-// (8-byte aligned).  n_g = min(n, maxLS).  Double arithmetic exactly as oclrect.c:1069-1084 (no FMA, IEEE sqrt/div).
-__global__ void k_tail_gather(unsigned char *blob, int maxLS, const LS_t *ls, const int *segidMap, const int *votes, int iw, int ih, int nentry, size_t fs) {
-  rd_batch_y(fs, blob, ls, segidMap, votes);
-  const int n = *(const int *)ls;
-  const int ng = min(max(n, 0), maxLS);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { ((int *)blob)[0] = n; ((int *)blob)[1] = ng; }
-  if (i > ng) return;
-  LS_t *ols = (LS_t *)(blob + 64);
-  rd_tail_sample *osm = (rd_tail_sample *)(blob + 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7));
-  const LS_t e = ls[i];
-  ols[i] = e;
-  rd_tail_sample *sm = osm + (size_t)i * RD_TAIL_NSAMPLE;
-  for (int k = 0; k < RD_TAIL_NSAMPLE; k++) { sm[k].segid = 0; for (int j = 0; j < 5; j++) sm[k].vote[j] = 0; }
-  if (i == 0 || e.polyid == 0) return;
-  const double x0 = rint((double)e.x0), y0 = rint((double)e.y0), x1 = rint((double)e.x1), y1 = rint((double)e.y1);
-  const double dx = __dsub_rn(x1, x0), dy = __dsub_rn(y1, y0);
-  const double len2 = __dadd_rn(__dadd_rn(0.0, __dmul_rn(dx, dx)), __dmul_rn(dy, dy));
-  const double inv = __ddiv_rn(1.0, __dadd_rn(__dsqrt_rn(len2), 1e-20));          // normalize2, vec234.h
-  const double ndx = __dmul_rn(dx, inv), ndy = __dmul_rn(dy, inv);
-  const double vdx = -ndy, vdy = ndx;
-  int k = 0;
-  for (int j = 0; j < 3; j++)
-    for (int dist = -2; dist <= 2; dist++, k++) {
-      const double t = __ddiv_rn(__dadd_rn((double)j, 0.5), 3.0);
-      const double px = __dadd_rn(x0, __dmul_rn(dx, t)), py = __dadd_rn(y0, __dmul_rn(dy, t));
-      const double cx = __dadd_rn(px, __dmul_rn(vdx, (double)dist)), cy = __dadd_rn(py, __dmul_rn(vdy, (double)dist));
-      const int x = (int)__dadd_rn(cx, 0.5), y = (int)__dadd_rn(cy, 0.5);
-      if (x < 0 || x >= iw || y < 0 || y >= ih) continue;
-      const int segid = segidMap[x + y * iw];
-      if (segid <= 0) continue;
-      const int hash = (int)((((unsigned)i * (unsigned)segid) & 0x7fffffffu) % (unsigned)nentry);
-      sm[k].segid = segid;
-      for (int q = 0; q < 5; q++) sm[k].vote[q] = votes[(size_t)hash * 5 + q];
-    }
-}
-
 // ============================================================================ the oclrect_t object
 // One object owns `nb` frame arenas (nb = 1 for the reference's single-frame API, oclrect.h:17-23; more for the batch
 // engine).  An arena holds every device buffer of one frame with the reference's buffer plan (oclrect.c:120-135):
@@ -398,18 +357,23 @@ struct oclrect_t {
   unsigned char *dbase;                 // nb arenas, fs bytes apart
   size_t fs, P;                         // arena stride, plane pitch (bytes)
   cl_mem buf[6], tmp[6], iobuf[2], ioBig[2];   // non-owning handles on the buffers of arena 0
-  unsigned char *dblob[2];              // read-back records of arena 0, one per pipeline page (a record is read back in two parts; the
-                                        // second part is copied while the next task already runs, so the pages must not share one)
+  unsigned char *dblob[2];              // read-back records of arena 0, one per pipeline page: 64-byte header + rect_t list (first half), the
+                                        // quadrilaterals / pose results of the device tail (second half, rd_gtail.cu).  A record may be read
+                                        // - or its pose phase re-run - while the next task already runs, so the pages do not share one
   size_t blobBytes;
-  int maxLS;
+  int *tailTable;                       // 2 ints per region id, zero between frames (rd_gtail.cu)
   uint8_t *hostImg[2];                  // pinned: frame staging, nb x P per page (hostiobuf[page][0] of the reference)
-  unsigned char *hostBlob[2];           // pinned: read-back records, nb x blobBytes per page
+  unsigned char *hostBlob[2];           // pinned: read-back records (first chunk of each), nb x hostBlobStride per page
   int nextPageToEnqueue, nextPageToPoll;
   cudaEvent_t events[2];
+  cudaStream_t copyq;                   // second-chunk copies of long rect lists (must not queue behind the next task)
   int pending[2];                       // number of frames in flight on the page
-  double wait_ms, tail_ms;              // host time spent waiting for the device / in executeCPUTask since the last reset
+  double pageTan[2];                    // tanAOV the pose phase of the page was enqueued with (NaN: not yet run)
+  double lastTan;                       // tanAOV of the last poll: oclrect_enqueueTask has no tanAOV argument (oclrect.h:21-22), so the pose
+                                        // phase runs ahead with this one and is repeated at poll time if the caller asks for another
+  double wait_ms, tail_ms;              // host time spent waiting for the device / assembling the lists since the last reset
 };
-#define FIRST_CHUNK ((size_t)128 * 1024)
+#define FIRST_CHUNK ((size_t)16 * 1024)  // header + 90 rectangles; longer lists take a second copy
 
 static inline int *PI(cl_mem m) { return (int *)m->dptr; }
 static inline float *PF(cl_mem m) { return (float *)m->dptr; }
@@ -421,9 +385,17 @@ __global__ void k_edgevec_r(float2 *dst, const float *in, int iw, int ih, size_t
 __global__ void k_edge_plab_r(float *out, const uint32_t *in, int iw, int ih, size_t fs);
 __global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, int iw, int ih, size_t fs);
 
+// executeCPUTask (oclrect.c:1049-1226) on the device.  Inputs where both schedules leave them: segment list ioBig0, region map iobuf1,
+// vote table ioBig1.  Work space: the eight planes buf4 .. tmp5 (contiguous in the arena, dead by now).  The pose phase needs tanAOV;
+// without one (NaN) only the quadrilaterals are prepared and the pose phase runs at poll time.
+static void device_tail(oclrect_t *o, int page, double tanAOV, int nb, cudaStream_t s) {
+  rd_gtail_run(o->dblob[page], o->blobBytes, (const linesegment_t *)o->ioBig[0]->dptr, PI(o->iobuf[1]), PI(o->ioBig[1]), o->tailTable,
+               (unsigned char *)o->buf[4]->dptr, 8 * o->P, o->iw, o->ih, tanAOV, tanAOV == tanAOV ? 3 : 1, nb, o->fs, s);
+}
+
 // genGPUTask (oclrect.c:235-381) without the copies.  Step numbers follow SURVEY.md section 10.1; stop_step = k > 0
 // returns after step k (for the intermediate-parity tests), 0 runs everything.
-static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int stop_step, int nb, cudaStream_t s, int page = 0) {
+static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int stop_step, int nb, cudaStream_t s, int page = 0, double tanAOV = NAN) {
   const int iw = o->iw, ih = o->ih, n = iw * ih, g1 = rd_cdiv(n, 256);
   const size_t fs = o->fs;
   cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
@@ -500,8 +472,8 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   RD_LAUNCH(kr_reduceLS<1>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
   RD_LAUNCH(kr_reduceLS<2>, rd_gz(G2, nb), RB, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), iw, ih, nentry, fs);
   STEP(21);
-  // step 22 : compact read-back record instead of the reference's three big copies (oclrect.c:371-376)
-  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob[page], o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
+  // step 22 : instead of the reference's three big copies (oclrect.c:371-376) the tail runs here (scratch: buf4 .. tmp5, all dead)
+  device_tail(o, page, tanAOV, nb, s);
 #undef STEP
 }
 
@@ -514,7 +486,7 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
 //   iobuf1 region-boundary (segid) map   ioBig0 blur scratch -> segment list   ioBig1 blur scratch -> polyline scratch -> vote table
 // stop_stage > 0 ends the schedule after that stage (tests compare the planes of the production schedule stage by stage,
 // tests/parity.py FAST_STAGES); 0 runs everything.
-static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int nb, cudaStream_t s, int stop_stage = 0, int page = 0) {
+static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, int nb, cudaStream_t s, int stop_stage = 0, int page = 0, double tanAOV = NAN) {
 #define STAGE(k) do { if (stop_stage == (k)) return; } while (0)
   const int iw = o->iw, ih = o->ih, n = iw * ih;
   const size_t fs = o->fs;
@@ -563,7 +535,8 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   RD_LAUNCH(kr_reduceLS_list<0>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);   // tmp2: the polyline stage's pixel list
   RD_LAUNCH(kr_reduceLS_list<1>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
   RD_LAUNCH(kr_reduceLS_list<2>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
-  RD_LAUNCH(k_tail_gather, rd_gy(rd_cdiv(o->maxLS + 1, 128), nb), 128, 0, s, o->dblob[page], o->maxLS, (const LS_t *)ioBig[0]->dptr, PI(iobuf[1]), PI(ioBig[1]), iw, ih, nentry, fs);
+  rd_prof_stage("T");
+  device_tail(o, page, tanAOV, nb, s);
 }
 
 // ---- fused / specialised Stage A kernels of the rect pipeline ----
@@ -617,7 +590,7 @@ __global__ void k_thinthres_r(float *out, const float *in, const float2 *vec, in
 
 static void chk(oclrect_t *t) { if (!t || t->magic != RECT_MAGIC) exitf(-1, "rectdetect_b200: bad oclrect_t\n"); }
 
-static size_t blob_need(int ng) { return 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7) + (size_t)(ng + 1) * RD_TAIL_NSAMPLE * sizeof(rd_tail_sample); }
+static size_t blob_need(int nrect) { return 64 + (size_t)nrect * sizeof(rect_t); }
 
 static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int ih, int nb) {
   if (rd_device_count() <= 0) exitf(-1, "rectdetect_b200: no CUDA device; there is no CPU fallback\n");
@@ -635,10 +608,8 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   if (bb < ((size_t)1 << 20)) bb = (size_t)1 << 20;
   bb = (bb + 255) & ~(size_t)255;
   o->blobBytes = bb;
-  o->maxLS = (int)((bb - 128) / (sizeof(LS_t) + RD_TAIL_NSAMPLE * sizeof(rd_tail_sample))) - 1;
-  const int cap = (int)((size_t)iw * ih * 16 / sizeof(LS_t)) - 1;
-  if (o->maxLS > cap) o->maxLS = cap;
-  o->fs = 22 * P + 2 * bb;
+  o->fs = 24 * P + 2 * bb;
+  o->lastTan = o->pageTan[0] = o->pageTan[1] = NAN;
   o->P = P;
   RD_CUDA(cudaMalloc((void **)&o->dbase, o->fs * nb));
   // CANONICAL (Q1): memory the reference never initialises reads as zero on the first frame
@@ -648,11 +619,13 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   for (int i = 0; i < 6; i++) { o->tmp[i] = rd_wrap_device_memory(q, P); q += P; }
   for (int i = 0; i < 2; i++) { o->iobuf[i] = rd_wrap_device_memory(q, P); q += P; }
   for (int i = 0; i < 2; i++) { o->ioBig[i] = rd_wrap_device_memory(q, 4 * P); q += 4 * P; }
+  o->tailTable = (int *)q; q += 2 * P;
   o->dblob[0] = q;
   o->dblob[1] = q + bb;
+  RD_CUDA(cudaStreamCreateWithFlags(&o->copyq, cudaStreamNonBlocking));
   for (int p = 0; p < 2; p++) {
     o->hostImg[p] = (uint8_t *)allocatePinnedMemory((size_t)iw * ih * 4 * nb, NULL, NULL);
-    o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(bb * nb, NULL, NULL);
+    o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(FIRST_CHUNK * nb, NULL, NULL);
     RD_CUDA(cudaEventCreateWithFlags(&o->events[p], cudaEventDisableTiming | cudaEventBlockingSync));   // waiting host threads sleep: the cores run host tails
   }
   rd_quant_tables_init();
@@ -660,12 +633,12 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   return o;
 }
 
-// `count` frames (<= nb), frame i at img + i*frame_stride -> device, run the schedule, queue the first chunk of every
-// read-back record.  src_kind 0: pageable host memory (staged through the pinned page, oclrect.c:1235/1256),
+// `count` frames (<= nb), frame i at img + i*frame_stride -> device, run the schedule incl. the device tail, queue the first chunk of
+// every read-back record.  src_kind 0: pageable host memory (staged through the pinned page, oclrect.c:1235/1256),
 // 1: pinned host memory (copied to the device directly), 2: device memory (the schedule reads it in place).
 // fresh != 0 clears the one buffer that carries state from the previous frame (buf3) so that every frame is
-// processed as by a newly created object.
-static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, int ws, int page, int src_kind, int fresh, int count) {
+// processed as by a newly created object.  tanAOV = NaN: not known yet (oclrect_enqueueTask before the first poll).
+static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, int ws, int page, int src_kind, int fresh, int count, double tanAOV) {
   const int iw = o->iw, ih = o->ih;
   if (ws < 3 * iw || (size_t)ws * ih > (size_t)iw * ih * 4) exitf(-1, "rectdetect_b200: row stride %d not in [3*iw, 4*iw]\n", ws);
   if (count < 1 || count > o->nb) exitf(-1, "rectdetect_b200: %d frames do not fit an object built for %d\n", count, o->nb);
@@ -685,130 +658,51 @@ static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, 
     din_fs = frame_stride;
   }
   if (fresh) RD_CUDA(cudaMemset2DAsync(o->buf[3]->dptr, o->fs, 0, (size_t)iw * ih * 4, count, s));
-  gpu_task_fast(o, din, din_fs, ws, count, s, 0, page);
-  const size_t chunk = o->blobBytes < FIRST_CHUNK ? o->blobBytes : FIRST_CHUNK;
-  RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], o->blobBytes, o->dblob[page], o->fs, chunk, count, cudaMemcpyDeviceToHost, s));
+  gpu_task_fast(o, din, din_fs, ws, count, s, 0, page, tanAOV);
+  o->pageTan[page] = tanAOV;
+  if (tanAOV == tanAOV) RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], FIRST_CHUNK, o->dblob[page], o->fs, FIRST_CHUNK, count, cudaMemcpyDeviceToHost, s));
   RD_CUDA(cudaEventRecord(o->events[page], s));
   o->pending[page] = count;
 }
 
-// ---- host tails of a chunk run in parallel --------------------------------------------------------------------------
-// The tails of the frames of one chunk are independent (executeCPUTask reads one frame's record), and a chunk of frames
-// arrives at once, so the host threads that drive the pipelines hand them to a process-wide pool instead of walking them
-// one by one: tail throughput then scales with the host cores, not with the number of pipeline objects.
-class TailPool {
-  std::mutex mu_;
-  std::condition_variable cv_;
-  std::deque<std::function<void()>> q_;
-  std::vector<std::thread> th_;
-  bool stop_ = false;
-  void loop() {
-    for (;;) {
-      std::function<void()> f;
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
-        if (q_.empty()) return;
-        f = std::move(q_.front());
-        q_.pop_front();
-      }
-      f();
-    }
-  }
- public:
-  explicit TailPool(int n) { for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); }); }
-  ~TailPool() {
-    { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
-    cv_.notify_all();
-    for (auto &t : th_) t.join();
-  }
-  // fn(0) .. fn(n-1), the caller takes part; returns when all are done
-  void run_all(int n, const std::function<void(int)> &fn) {
-    if (n <= 0) return;
-    int left = n - 1;
-    std::mutex dm;
-    std::condition_variable dcv;
-    if (n > 1) {
-      {
-        std::lock_guard<std::mutex> g(mu_);
-        for (int i = 1; i < n; i++)
-          q_.push_back([&, i] {
-            fn(i);
-            std::lock_guard<std::mutex> dg(dm);
-            if (--left == 0) dcv.notify_one();
-          });
-      }
-      cv_.notify_all();
-    }
-    fn(0);
-    // help with whatever is queued (own or other chunks' tails) instead of sleeping
-    for (;;) {
-      std::function<void()> f;
-      {
-        std::lock_guard<std::mutex> g(mu_);
-        if (q_.empty()) break;
-        f = std::move(q_.front());
-        q_.pop_front();
-      }
-      f();
-    }
-    std::unique_lock<std::mutex> lk(dm);
-    dcv.wait(lk, [&] { return left == 0; });
-  }
-};
-static TailPool &tail_pool() {
-  static TailPool pool([] {
-    const char *e = getenv("RD_TAIL_THREADS");
-    int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return n < 1 ? 1 : (n > 64 ? 64 : n);
-  }());
-  return pool;
-}
-static void tail_parallel_for(int n, const std::function<void(int)> &fn) { tail_pool().run_all(n, fn); }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// executeCPUTask (oclrect.c:1049) on the read-back records of `page`; out[i] receives the list of frame i
-static void finish_page(oclrect_t *o, int page, double tanAOV, rect_t **out, int run_tail) {
+// waits for the page and turns its read-back records into rect_t lists (malloc()ed, element 0 = header, oclrect.c:1219-1225);
+// out[i] receives the list of frame i.  If the pose phase has not run with this tanAOV it is run now (its inputs live in the record).
+static void finish_page(oclrect_t *o, int page, double tanAOV, rect_t **out, int want_lists) {
   cudaStream_t s = rd_stream(o->queue);
   RD_CUDA(cudaSetDevice(o->ordinal));
   const double t0 = now_ms();
-  RD_CUDA(cudaEventSynchronize(o->events[page]));
   const int count = o->pending[page];
-  o->pending[page] = 0;
-  if (!run_tail) { for (int i = 0; i < count; i++) if (out) out[i] = NULL; o->wait_ms += now_ms() - t0; return; }
-  bool more = false;
-  for (int i = 0; i < count; i++) {
-    unsigned char *hb = o->hostBlob[page] + (size_t)i * o->blobBytes;
-    const int n = ((int *)hb)[0], ng = ((int *)hb)[1];
-    const size_t need = blob_need(ng);
-    if (n <= ng && need > FIRST_CHUNK) {
-      RD_CUDA(cudaMemcpyAsync(hb + FIRST_CHUNK, o->dblob[page] + (size_t)i * o->fs + FIRST_CHUNK, need - FIRST_CHUNK, cudaMemcpyDeviceToHost, s));
-      more = true;
-    }
+  if (want_lists && memcmp(&o->pageTan[page], &tanAOV, sizeof(double)) != 0) {
+    RD_CUDA(cudaStreamWaitEvent(o->copyq, o->events[page], 0));
+    rd_gtail_run(o->dblob[page], o->blobBytes, NULL, NULL, NULL, NULL, NULL, 0, o->iw, o->ih, tanAOV, 2, count, o->fs, o->copyq);
+    RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], FIRST_CHUNK, o->dblob[page], o->fs, FIRST_CHUNK, count, cudaMemcpyDeviceToHost, o->copyq));
+    RD_CUDA(cudaStreamSynchronize(o->copyq));
+    o->pageTan[page] = tanAOV;
+  } else {
+    RD_CUDA(cudaEventSynchronize(o->events[page]));
   }
-  if (more) RD_CUDA(cudaStreamSynchronize(s));
+  o->pending[page] = 0;
+  if (!want_lists) { for (int i = 0; i < count; i++) if (out) out[i] = NULL; o->wait_ms += now_ms() - t0; return; }
   const double t1 = now_ms();
   o->wait_ms += t1 - t0;
-  auto one = [&](int i) {
-    unsigned char *hb = o->hostBlob[page] + (size_t)i * o->blobBytes;
-    const int n = ((int *)hb)[0], ng = ((int *)hb)[1];
-    if (n > ng) {
-      // more segments than the compact record holds: read back what the reference reads back and gather on the host
-      RD_CUDA(cudaSetDevice(o->ordinal));
-      const size_t P = (size_t)o->iw * o->ih * 4, off = (size_t)i * o->fs;
-      std::vector<unsigned char> ls((size_t)(n + 1) * sizeof(LS_t)), seg(P), votes(4 * P);
-      RD_CUDA(cudaMemcpy(ls.data(), (char *)o->ioBig[0]->dptr + off, ls.size(), cudaMemcpyDeviceToHost));
-      RD_CUDA(cudaMemcpy(seg.data(), (char *)o->iobuf[1]->dptr + off, P, cudaMemcpyDeviceToHost));
-      RD_CUDA(cudaMemcpy(votes.data(), (char *)o->ioBig[1]->dptr + off, 4 * P, cudaMemcpyDeviceToHost));
-      out[i] = rd_rect_tail((const linesegment_t *)ls.data(), (const int32_t *)seg.data(), (const int32_t *)votes.data(), o->iw, o->ih, tanAOV);
-      return;
+  bool more = false;
+  for (int i = 0; i < count; i++) {
+    const unsigned char *hb = o->hostBlob[page] + (size_t)i * FIRST_CHUNK;
+    const int nrect = ((const int *)hb)[1], err = ((const int *)hb)[2];
+    if (err) exitf(-1, "rectdetect_b200: the device tail ran out of %s (frame with %d line segments)\n", err == 2 ? "read-back record space" : "work space", ((const int *)hb)[0]);
+    rect_t *r = (rect_t *)calloc((size_t)nrect + 1, sizeof(rect_t));
+    r[0].nItems = nrect + 1;
+    const size_t need = blob_need(nrect), have = need < FIRST_CHUNK ? need : FIRST_CHUNK;
+    memcpy(r + 1, hb + 64, have - 64);
+    if (need > FIRST_CHUNK) {                                   // long list: the rest straight from the page's device record
+      RD_CUDA(cudaMemcpyAsync((unsigned char *)(r + 1) + (FIRST_CHUNK - 64), o->dblob[page] + (size_t)i * o->fs + FIRST_CHUNK, need - FIRST_CHUNK, cudaMemcpyDeviceToHost, o->copyq));
+      more = true;
     }
-    const linesegment_t *ls = (const linesegment_t *)(hb + 64);
-    const rd_tail_sample *sm = (const rd_tail_sample *)(hb + 64 + (((size_t)(ng + 1) * sizeof(LS_t) + 7) & ~(size_t)7));
-    out[i] = rd_tail_compact(ls, sm, o->iw, o->ih, tanAOV, count == 1 ? tail_parallel_for : (rd_parallel_for_t)NULL);   // a lone frame spreads its candidates
-  };
-  if (count == 1) one(0);
-  else tail_pool().run_all(count, one);
+    out[i] = r;
+  }
+  if (more) RD_CUDA(cudaStreamSynchronize(o->copyq));
   o->tail_ms += now_ms() - t1;
 }
 
@@ -826,6 +720,7 @@ void dispose_oclrect(struct oclrect_t *o) {
   for (int i = 0; i < 2; i++) { clReleaseMemObject(o->iobuf[i]); clReleaseMemObject(o->ioBig[i]); }
   RD_CUDA(cudaFree(o->dbase));
   for (int p = 0; p < 2; p++) { freePinnedMemory(o->hostImg[p], NULL, NULL); freePinnedMemory(o->hostBlob[p], NULL, NULL); RD_CUDA(cudaEventDestroy(o->events[p])); }
+  RD_CUDA(cudaStreamDestroy(o->copyq));
   o->magic = 0;
   free(o);
 }
@@ -833,7 +728,8 @@ void dispose_oclrect(struct oclrect_t *o) {
 rect_t *oclrect_executeOnce(struct oclrect_t *o, uint8_t *imgData, int ws, const double tanAOV) {   // oclrect.c:1230
   chk(o);
   if (o->pending[0]) exitf(-1, "rectdetect_b200: oclrect_executeOnce while a task is pending on page 0\n");
-  enqueue_page(o, imgData, 0, ws, 0, 0, 0, 1);
+  enqueue_page(o, imgData, 0, ws, 0, 0, 0, 1, tanAOV);
+  o->lastTan = tanAOV;
   rect_t *r = NULL;
   finish_page(o, 0, tanAOV, &r, 1);
   return r;
@@ -844,7 +740,7 @@ void oclrect_enqueueTask(struct oclrect_t *o, uint8_t *imgData, int ws) {       
   const int page = 1 & o->nextPageToEnqueue;
   o->nextPageToEnqueue++;
   if (o->pending[page]) exitf(-1, "rectdetect_b200: oclrect_enqueueTask with two tasks already in flight\n");   // assert(events[page]==NULL)
-  enqueue_page(o, imgData, 0, ws, page, 0, 0, 1);
+  enqueue_page(o, imgData, 0, ws, page, 0, 0, 1, o->lastTan);
 }
 
 rect_t *oclrect_pollTask(struct oclrect_t *o, const double tanAOV) {                                // oclrect.c:1263
@@ -853,6 +749,7 @@ rect_t *oclrect_pollTask(struct oclrect_t *o, const double tanAOV) {            
   o->nextPageToPoll++;
   if (!o->pending[page]) exitf(-1, "rectdetect_b200: oclrect_pollTask without a pending task\n");
   rect_t *r = NULL;
+  o->lastTan = tanAOV;
   finish_page(o, page, tanAOV, &r, 1);
   return r;
 }
@@ -907,6 +804,28 @@ void rd_rect_despeckle2(cl_mem io, cl_mem size, cl_mem scratch, int thre, int iw
   rd_despeckle2_run(PI(io), PI(scratch), PI(size), w, w + n, w + 2 * n, w + 3 * n, (int2 *)rowbuf, thre, iw, ih, nb, fs, s);
   RD_CUDA(cudaFreeAsync(w, s));
 }
+// executeCPUTask (oclrect.c:1049) on caller-owned device buffers: the device tail as an operator.  Returns a malloc()ed list.
+rect_t *rd_rect_tail_device(cl_mem lsList, cl_mem segid, cl_mem votes, int iw, int ih, double tanAOV, cl_command_queue q) {
+  cudaStream_t s = rd_stream(q);
+  const size_t P = (((size_t)iw * ih * 4) + 255) & ~(size_t)255;
+  size_t bb = (size_t)iw * ih * 2;
+  if (bb < ((size_t)1 << 20)) bb = (size_t)1 << 20;
+  unsigned char *w = NULL;                         // table (2P, zero), work space (8P), record
+  RD_CUDA(cudaMallocAsync((void **)&w, 10 * P + bb, s));
+  RD_CUDA(cudaMemsetAsync(w, 0, 2 * P, s));
+  unsigned char *blob = w + 10 * P;
+  rd_gtail_run(blob, bb, (const linesegment_t *)lsList->dptr, PI(segid), PI(votes), (int *)w, w + 2 * P, 8 * P, iw, ih, tanAOV, 3, 1, 0, s);
+  int hdr[16];
+  RD_CUDA(cudaMemcpyAsync(hdr, blob, sizeof(hdr), cudaMemcpyDeviceToHost, s));
+  RD_CUDA(cudaStreamSynchronize(s));
+  if (hdr[2]) exitf(-1, "rectdetect_b200: the device tail ran out of %s (frame with %d line segments)\n", hdr[2] == 2 ? "read-back record space" : "work space", hdr[0]);
+  rect_t *r = (rect_t *)calloc((size_t)hdr[1] + 1, sizeof(rect_t));
+  r[0].nItems = hdr[1] + 1;
+  if (hdr[1] > 0) RD_CUDA(cudaMemcpyAsync(r + 1, blob + 64, (size_t)hdr[1] * sizeof(rect_t), cudaMemcpyDeviceToHost, s));
+  RD_CUDA(cudaFreeAsync(w, s));
+  RD_CUDA(cudaStreamSynchronize(s));
+  return r;
+}
 void rd_rect_markBoundary(cl_mem out, cl_mem in, int iw, int ih, cl_command_queue q) { QS; RD_LAUNCH(kr_markBoundary, rd_gz(G2, nb), RB, 0, s, PI(out), PI(in), iw, ih, fs); }
 void rd_rect_reduceLS(cl_mem out, cl_mem boundary, cl_mem lsid, int iw, int ih, int nentry, cl_command_queue q) {
   QS;
@@ -955,7 +874,7 @@ static void batch_worker(rd_batch *b, int c, const uint8_t *frames, size_t frame
   for (int ch = c; ch < nchunks; ch += b->nctx) {
     const int f0 = ch * b->fpl;
     const int cnt = (nframes - f0) < b->fpl ? (nframes - f0) : b->fpl;
-    enqueue_page(o, frames + (size_t)f0 * frame_stride, frame_stride, ws, page, kind, 1, cnt);
+    enqueue_page(o, frames + (size_t)f0 * frame_stride, frame_stride, ws, page, kind, 1, cnt, tanAOV);
     if (prev >= 0) finish(prev, prevPage);
     prev = ch; prevPage = page; page ^= 1;
   }

@@ -1,10 +1,17 @@
-"""Host replay of the exact despeckle2 kernels (CPU): kd2_pre / kd2_seq of rectdetect_b200/csrc/rd_despeckle2.cu are built from
+"""Host replays of CUDA kernels whose logic is shared with the host through a header (CPU tests, no GPU needed).
+
+1. The exact despeckle2 kernels: kd2_pre / kd2_seq of rectdetect_b200/csrc/rd_despeckle2.cu are built from
 the pure functions in rd_despeckle2.cuh (static record, merge of the row above, threshold map, composition of two maps);
 tests/emu_despeckle2x.cpp replays the kernels' structure around them - per-row compaction, 32-entry chunks, the doubling scan over
 the lanes, the carry between chunks, the two-row buffer.  What the replay produces must equal the oracle's raster-order
 despeckle2 (= the reference kernel run sequentially, tests/test_ref_device.py) on pipeline planes of every frame size and on
 adversarial random planes (long runs of small regions, ties, zero and negative sizes) - a check of the formulation that
-needs no GPU (the -m gpu tests then check the kernels themselves)."""
+needs no GPU (the -m gpu tests then check the kernels themselves).
+
+2. The device tail (executeCPUTask on the GPU, rectdetect_b200/csrc/rd_gtail.cu): its logic is rd_gtail.cuh; tests/emu_gtail.cpp runs
+the per-item kernels as loops and the warp-per-candidate kernel with its 32 lanes as fibers (every ballot / shuffle / syncwarp
+is a rendezvous, so a missing synchronisation shows up as a wrong answer).  The rect_t lists must equal the oracle's tail - and
+through it the reference's own executeCPUTask (tests/test_ref_tail.py) - byte for byte, in the same order."""
 import ctypes as C
 import os
 import subprocess
@@ -70,3 +77,67 @@ def test_replay_equals_the_oracle_on_random_planes(emu, iw, ih, nlab, thre, seed
     got = np.full(n, -99, np.int32)
     emu.emu_despeckle2x(P(got), P(lab), P(size), thre, iw, ih)
     assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------ device tail
+GT_SO = os.path.join(ROOT, "tests", "_emu", "libemu_gtail.so")
+
+
+@pytest.fixture(scope="module")
+def emu_tail():
+    os.makedirs(os.path.dirname(GT_SO), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-o", GT_SO,
+                           os.path.join(ROOT, "tests", "emu_gtail.cpp")])
+    E = C.CDLL(GT_SO)
+    E.emu_gtail.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    return E
+
+
+def _emu_tail(E, ls, seg, votes, iw, ih, tan):
+    out, st = np.zeros(8192, ol.RECT_DTYPE), np.zeros(4, np.int32)
+    n = E.emu_gtail(P(out), len(out), P(ls), P(seg), P(votes), iw, ih, tan, P(st))
+    assert n >= 0, n
+    return out[:n], st
+
+
+@pytest.mark.parametrize("iw,ih,seed,dense,aov", [(640, 480, 1, 0, 36.0), (333, 217, 7, 0, 36.0), (641, 479, 32, 0, 25.0), (1280, 720, 1000, 0, 36.0),
+                                                   (1280, 720, 7, 1, 36.0), (640, 360, 1001, 0, 50.0), (48, 40, 32, 0, 36.0)])
+def test_device_tail_replay_equals_the_oracle_tail(emu_tail, iw, ih, seed, dense, aov):
+    import math
+    tan = math.tan(math.radians(aov))
+    img = ol.dense_frame(iw, ih, seed, 5, 5) if dense else ol.synth_frame(iw, ih, seed)
+    o = ol.OracleRect(iw, ih)
+    want = o.execute_once(img, tan)
+    ls, seg, votes = o.buffer("ioBig0").copy(), o.buffer("iobuf1").copy(), o.buffer("ioBig1").copy()
+    o.close()
+    got, st = _emu_tail(emu_tail, ls, seg, votes, iw, ih, tan)
+    assert got.tobytes() == want.tobytes(), (len(got), len(want), st.tolist())
+    if iw >= 333:
+        assert len(want) > 0 and st[3] == len(want)
+
+
+def test_device_tail_replay_with_vote_collisions_and_dead_segments(emu_tail):
+    """a vote table whose slots are partly owned by other segments or empty (hash collisions, oclrect.c:1116-1121), dead list entries,
+    and an empty list"""
+    import math
+    tan = math.tan(math.radians(36.0))
+    iw, ih = 640, 480
+    o = ol.OracleRect(iw, ih)
+    o.execute_once(ol.dense_frame(iw, ih, 3, 3, 3), tan)
+    ls, seg, votes = o.buffer("ioBig0").copy(), o.buffer("iobuf1").copy(), o.buffer("ioBig1").copy()
+    o.close()
+    rng = np.random.default_rng(11)
+    v = votes.reshape(-1, 5)
+    occ = np.flatnonzero(v[:, 0] > 0)
+    v[occ[rng.random(len(occ)) < 0.15], 0] += 1                   # owned by "another segment": unclipped
+    v[occ[rng.random(len(occ)) < 0.10]] = 0                       # empty slot: the pair contributes nothing
+    n = int(ls[0])
+    lsv = ls.view(np.uint8)[: 56 * (n + 1)].view(ol.LS_DTYPE)
+    lsv["polyid"][1 + rng.choice(n, n // 10, replace=False)] = 0  # dead entries
+    LO = ol.oracle()
+    want = ol.rects_from_ptr(LO.ora_tail(P(ls), P(seg), P(votes), iw, ih, tan))
+    got, st = _emu_tail(emu_tail, ls, seg, votes, iw, ih, tan)
+    assert got.tobytes() == want.tobytes() and len(want) > 3
+    ls[0] = 0
+    got, _ = _emu_tail(emu_tail, ls, seg, votes, iw, ih, tan)
+    assert len(got) == 0

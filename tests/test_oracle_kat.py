@@ -245,6 +245,7 @@ def test_oracle_matches_reference_generated_planes(g):
 def test_oracle_detects_the_planted_quads():
     iw, ih, seed = 1280, 720, 2
     img, quads = ol.synth_frame(iw, ih, seed, with_truth=True)
+    ol.oracle().ora_reset_stats()                    # the counters are process-wide
     o = ol.OracleRect(iw, ih)
     rects = o.execute_once(img, math.tan(math.radians(36.0)))
     screens = rects[(rects["status"] & 1) == 1]
