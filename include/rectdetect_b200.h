@@ -69,6 +69,12 @@ char *getDeviceName(cl_device_id device);                 /* oclhelper.h:16 : ma
 cl_device_id simpleGetDevice(int did);                    /* oclhelper.h:17 : did < 0 lists devices and exits */
 int simpleGetDevices(cl_device_id *devices, int maxDevices);   /* oclhelper.h:18 */
 cl_context simpleCreateContext(cl_device_id device);      /* oclhelper.h:19 */
+int simpleBuildProgram(cl_program program, cl_device_id device, const char *optionString);           /* oclhelper.h:20 : link stubs - no OpenCL   */
+void simpleSetKernelArg(cl_kernel kernel, const char *format, ...);                                   /* oclhelper.h:21   program / kernel objects  */
+cl_event runKernel1D(cl_command_queue queue, cl_kernel kernel, int kernelID, size_t ws1, int nev, ...);            /* :22   exist in this library;   */
+cl_event runKernel2D(cl_command_queue queue, cl_kernel kernel, int kernelID, size_t ws1, size_t ws2, int nev, ...); /* :23  calling one ends the     */
+cl_event runKernel1Dx(cl_command_queue queue, cl_kernel kernel, int kernelID, size_t ws1, const cl_event *events);  /* :24  process                  */
+cl_event runKernel2Dx(cl_command_queue queue, cl_kernel kernel, int kernelID, size_t ws1, size_t ws2, const cl_event *events); /* :25 */
 void waitForEvent(cl_event ev);                           /* oclhelper.h:27 : cudaEventSynchronize, no 15 ms polling */
 void clearPlan(void);                                     /* oclhelper.h:29-34 : the work-group autotuner has no CUDA */
 int loadPlan(const char *fn, cl_device_id device);        /*   counterpart; loadPlan returns 0 ("plan found") so   */
@@ -81,6 +87,9 @@ void freePinnedMemory(void *p, cl_context context, cl_command_queue queue);     
 int getNextKernelID(void);                                /* oclhelper.h:39 */
 
 void exitf(int code, const char *mes, ...);               /* helper.h:12 */
+char *readFileAsStr(const char *fn, int maxSize);         /* helper.h:13 : malloc()ed contents */
+char *readFileAsStrN(const char **fn);                    /* helper.h:14 : NULL-terminated list of files, concatenated */
+void String_trim(char *str);                              /* helper.h:17 */
 int64_t currentTimeMillis(void);                          /* helper.h:15 */
 void sleepMillis(int ms);                                 /* helper.h:16 */
 ArrayMap *initArrayMap(void);                             /* helper.h:23-31 : uint64 -> void* map, 1024 buckets */
@@ -91,6 +100,8 @@ void *ArrayMap_put(ArrayMap *thiz, uint64_t key, void *value);
 void *ArrayMap_get(ArrayMap *thiz, uint64_t key);
 uint64_t *ArrayMap_keyArray(ArrayMap *thiz);
 void **ArrayMap_valueArray(ArrayMap *thiz);
+uint64_t ArrayMap_getKey(ArrayMap *thiz, int idx);        /* helper.h:30-31 : declared by the reference but defined nowhere in it; here: the idx-th */
+void *ArrayMap_getValue(ArrayMap *thiz, int idx);         /*                  entry in keyArray order */
 
 /* ------------------------------------------------------------------------------------------------------
  * L2 - image operators (oclimgutil.h:74-100).  Every operator is an asynchronous enqueue on `queue`'s stream.

@@ -194,6 +194,134 @@ static void k_thinthres(float *out, const float *in, const float *vxy, int iw, i
     }
 }
 
+// ---- the operators no configured path of the reference enqueues (visualisers and alternative edge kernels): restated so that the
+// whole L2 surface (oclimgutil.h:74-100) has a checker; pinned to the reference's kernels in tests/test_ref_operators.py ----
+static inline int floor_clamp(float v, int lo, int hi) {             // clamp(convert_int_rtn(v), lo, hi); NaN -> lo
+  if (!(v >= (float)lo)) return lo;
+  if (v >= (float)hi) return hi;
+  return (int)floorf(v);
+}
+static inline float icfunc(float ft) {                                 // oclimgutil.cl:136-142
+  if (ft > 0.20689270648f) return ft * ft * ft;
+  return (ft - 16.0f / 116) * (1.0f / 7.787f);
+}
+// oclimgutil.cl:146-178 (lab2srgb) after unpacklab; u[0..2] = B, G, R
+static inline void plab2srgb(uint32_t plab, uint8_t u[3]) {
+  const float xn = 0.950456f, zn = 1.088754f;
+  float l, a, b;
+  unpacklab(plab, l, a, b);
+  l *= 256; a *= 256; b *= 256;
+  float cy;
+  if (l > 0.20689270648f) {
+    cy = (l + 16) * (1.0f / 116.0f);
+    cy = cy * cy * cy;
+  } else {
+    cy = l * (1.0f / 903.3f);
+  }
+  const float fy = (RD_CFUNC[floor_clamp(cy * 1024, 0, 1023)] + 9039) * (1.0f / 65536.0f);
+  const float fz = fy - (b - 128) * (1.0f / 200.0f);
+  const float fx = fy + (a - 128) * (1.0f / 500.0f);
+  const float cx = icfunc(fx) * xn;
+  const float cz = icfunc(fz) * zn;
+  const float r = cx * 3.240479f + cy * -1.537150f + cz * -0.498535f;
+  const float g = cx * -0.969256f + cy * 1.875991f + cz * 0.041556f;
+  const float bl = cx * 0.055648f + cy * -0.204043f + cz * 1.057311f;
+  u[2] = RD_L2S[floor_clamp(r * 1024, 0, 1023)];
+  u[1] = RD_L2S[floor_clamp(g * 1024, 0, 1023)];
+  u[0] = RD_L2S[floor_clamp(bl * 1024, 0, 1023)];
+}
+// oclimgutil.cl:264-273
+static void k_plab2bgr(uint8_t *out, const uint32_t *in, int iw, int ih, int ws) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) plab2srgb(in[y * iw + x], out + (size_t)y * ws + x * 3);
+}
+// oclimgutil.cl:283-289
+static void k_convert_bgr_lumaf(uint8_t *out, const float *in, float f, int iw, int ih, int ws) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      uint8_t *o = out + (size_t)y * ws + x * 3;
+      o[0] = o[1] = o[2] = (uint8_t)floor_clamp(in[y * iw + x] * f * 255, 0, 255);
+    }
+}
+// oclimgutil.cl:291-322
+static void k_convert_bgr_labeli(uint8_t *out, const int32_t *in, int bgc, int iw, int ih, int ws) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      uint8_t *o = out + (size_t)y * ws + x * 3;
+      const int c = in[y * iw + x];
+      if (c == bgc) { o[0] = o[1] = o[2] = 0; continue; }
+      const int g = (int)((uint32_t)c * 1103515245u + 12345u);
+      o[2] = (uint8_t)((((g & (7 << 0)) << 5) | 31) & 255);
+      o[1] = (uint8_t)((((g & (7 << 3)) << 2) | 31) & 255);
+      o[0] = (uint8_t)((((g & (7 << 6)) >> 1) | 31) & 255);
+    }
+}
+// oclimgutil.cl:439-452
+static void k_edge_f_f(float *out, const float *in, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      float sum = 0, t;
+      t = in[mirror(x, y - 1, iw, ih)] + in[mirror(x - 1, y, iw, ih)] - in[mirror(x, y + 1, iw, ih)] - in[mirror(x + 1, y, iw, ih)];
+      sum += (in[mirror(x - 1, y - 1, iw, ih)] - in[mirror(x + 1, y + 1, iw, ih)]) * t;
+      t = in[mirror(x, y - 1, iw, ih)] - in[mirror(x - 1, y, iw, ih)] + in[mirror(x + 1, y, iw, ih)] - in[mirror(x, y + 1, iw, ih)];
+      sum += (in[mirror(x + 1, y - 1, iw, ih)] - in[mirror(x - 1, y + 1, iw, ih)]) * t;
+      out[y * iw + x] = sqrtf(sum > 0.0f ? sum : 0.0f);                // sqrt(max(0.0f, sum)); fmax semantics: NaN -> 0
+    }
+}
+// oclimgutil.cl:473-491
+static void k_thincubic(float *out, const float *in, const float *vxy, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      const float vx = vxy[p0 * 2 + 0], vy = vxy[p0 * 2 + 1];
+      const float am2 = bicubic(in, x - 2 * vx, y - 2 * vy, iw, ih);
+      const float am1 = bicubic(in, x - 1 * vx, y - 1 * vy, iw, ih);
+      const float a0 = in[p0];
+      const float ap1 = bicubic(in, x + 1 * vx, y + 1 * vy, iw, ih);
+      const float ap2 = bicubic(in, x + 2 * vx, y + 2 * vy, iw, ih);
+      const float C = 0.99f;
+      out[p0] = (am2 * C <= a0 && am1 * C <= a0 && a0 >= ap1 * C && a0 >= ap2 * C) ? (am2 + am1 + a0 + ap1 + ap2) : 0;
+    }
+}
+// oclimgutil.cl:354-393 : the gradient direction of the Lab channel with the strongest gradient, oriented like the L gradient
+static void k_edgevec_plab(float *dst, const uint32_t *in, int iw, int ih) {
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      float vx3[3] = {0, 0, 0}, vy3[3] = {0, 0, 0};
+      for (int yy = -2; yy <= 2; yy++)
+        for (int xx = -2; xx <= 2; xx++) {
+          float s[3];
+          unpacklab(in[mirror(x + xx, y + yy, iw, ih)], s[0], s[1], s[2]);
+          for (int c = 0; c < 3; c++) {
+            vx3[c] += V5C[(xx + 2) + (yy + 2) * 5] * s[c];
+            vy3[c] += V5C[(yy + 2) + (xx + 2) * 5] * s[c];
+          }
+        }
+      float iv3[3];
+      for (int c = 0; c < 3; c++) iv3[c] = vx3[c] * vx3[c] + vy3[c] * vy3[c];
+      float ivlen, vx, vy;
+      if (iv3[0] >= iv3[1] && iv3[0] >= iv3[2]) { ivlen = iv3[0]; vx = vx3[0]; vy = vy3[0]; }
+      else if (iv3[1] >= iv3[2]) { ivlen = iv3[1]; vx = vx3[1]; vy = vy3[1]; }
+      else { ivlen = iv3[2]; vx = vx3[2]; vy = vy3[2]; }
+      if ((double)iv3[0] >= 1e-6 && (vx3[0] * vx + vy3[0] * vy < 0)) { vx = -vx; vy = -vy; }       // Q15: double comparison
+      if ((double)ivlen > 1e-10) {
+        ivlen = 1.0f / sqrtf(ivlen);                                   // CANONICAL rsqrt (Q17)
+        vx *= ivlen; vy *= ivlen;
+      } else {
+        vx = vy = 0.70710678118f;
+      }
+      dst[p0 * 2 + 0] = vx;
+      dst[p0 * 2 + 1] = vy;
+    }
+}
+
 // ---- oclimgutil.cl:542-637 : recursive Gaussian.  One chain per row / column, serial inside. ----
 struct Taps {
   float iv[8], tv[8];
@@ -418,6 +546,12 @@ void ora_iirblur_f_f(float *obuf, const float *ibuf, float *tmp0, float *tmp1, i
 }
 
 void ora_edgevec_f2_f(float *out_xy, const float *in, int iw, int ih) { k_edgevec_f(out_xy, in, iw, ih); }
+void ora_edgevec_f2_plab(float *out_xy, const uint32_t *in, int iw, int ih) { k_edgevec_plab(out_xy, in, iw, ih); }
+void ora_edge_f_f(float *out, const float *in, int iw, int ih) { k_edge_f_f(out, in, iw, ih); }
+void ora_thincubic_f_f_f2(float *out, const float *in, const float *vxy, int iw, int ih) { k_thincubic(out, in, vxy, iw, ih); }
+void ora_convert_bgr_plab(uint8_t *out, const uint32_t *in, int iw, int ih, int ws) { k_plab2bgr(out, in, iw, ih, ws); }     /* Q9: the names are swapped */
+void ora_convert_bgr_lumaf(uint8_t *out, const float *in, float f, int iw, int ih, int ws) { k_convert_bgr_lumaf(out, in, f, iw, ih, ws); }
+void ora_convert_bgr_labeli(uint8_t *out, const int32_t *in, int bgc, int iw, int ih, int ws) { k_convert_bgr_labeli(out, in, bgc, iw, ih, ws); }
 void ora_edge_f_plab(float *out, const uint32_t *in, int iw, int ih) { k_edge_plab(out, in, iw, ih); }
 void ora_thinthres_f_f_f2(float *out, const float *in, const float *vxy, int iw, int ih) { k_thinthres(out, in, vxy, iw, ih); }
 

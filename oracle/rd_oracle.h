@@ -80,6 +80,13 @@ void ora_unpack_f_f_f_plab(float *o0, float *o1, float *o2, const uint32_t *in, 
 void ora_pack_plab_f_f_f(uint32_t *out, const float *i0, const float *i1, const float *i2, int iw, int ih);
 void ora_iirblur_f_f(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih);
 void ora_edgevec_f2_f(float *out_xy, const float *in, int iw, int ih);
+/* operators no configured path enqueues (oclimgutil.h:86-94): visualisers, alternative edge / thinning kernels */
+void ora_edgevec_f2_plab(float *out_xy, const uint32_t *in, int iw, int ih);                      /* oclimgutil.cl:354 */
+void ora_edge_f_f(float *out, const float *in, int iw, int ih);                                   /* oclimgutil.cl:439 */
+void ora_thincubic_f_f_f2(float *out, const float *in, const float *vxy, int iw, int ih);         /* oclimgutil.cl:473 */
+void ora_convert_bgr_plab(uint8_t *out, const uint32_t *in, int iw, int ih, int ws);              /* oclimgutil.cl:264 plab2bgr (Q9) */
+void ora_convert_bgr_lumaf(uint8_t *out, const float *in, float f, int iw, int ih, int ws);       /* oclimgutil.cl:283 */
+void ora_convert_bgr_labeli(uint8_t *out, const int32_t *in, int bgc, int iw, int ih, int ws);    /* oclimgutil.cl:291 */
 void ora_edge_f_plab(float *out, const uint32_t *in, int iw, int ih);
 void ora_thinthres_f_f_f2(float *out, const float *in, const float *vxy, int iw, int ih);
 /* CANONICAL: converged labels.  Returns number of sequential passes the reference kernel needed. */

@@ -67,7 +67,10 @@ def lib():
         "oclimgutil_iirblur_f_f": (vp, [vp, vp, vp, vp, vp, i, i, i] + op_tail),
         "oclimgutil_edgevec_f2_f": (vp, [vp, vp, vp, i, i] + op_tail),
         "oclimgutil_edge_f_plab": (vp, [vp, vp, vp, i, i] + op_tail),
-        "oclimgutil_thinthres_f_f_f2": (vp, [vp, vp, vp, vp, i, i] + op_tail),
+        "oclimgutil_thinthres_f_f_f2": (vp, [vp, vp, vp, vp, i, i] + op_tail), "oclimgutil_thincubic_f_f_f2": (vp, [vp, vp, vp, vp, i, i] + op_tail),
+        "oclimgutil_edgevec_f2_plab": (vp, [vp, vp, vp, i, i] + op_tail), "oclimgutil_edge_f_f": (vp, [vp, vp, vp, i, i] + op_tail),
+        "oclimgutil_convert_bgr_plab": (vp, [vp, vp, vp, i, i, i] + op_tail), "oclimgutil_convert_bgr_lumaf": (vp, [vp, vp, vp, f, i, i, i] + op_tail),
+        "oclimgutil_convert_bgr_labeli": (vp, [vp, vp, vp, i, i, i, i] + op_tail),
         "oclimgutil_label8x_int_int": (vp, [vp, vp, vp, vp, i, i, i] + op_tail),
         "oclimgutil_calcStrength": (vp, [vp, vp, vp, vp, i, i] + op_tail),
         "oclimgutil_filterStrength": (vp, [vp, vp, vp, i, i, i] + op_tail),

@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(GTQ_WARPS * 32) kt_quad(GtArgs a0) {
 __global__ void __launch_bounds__(64) kt_pose(GtArgs a0, double tanAOV) {
   const GtArgs a = gt_frame(a0, blockIdx.y);
   const GtLayout L = gt_layout_of(a, gt_hdr_of(a)->n);           // (not gt_count: the segment list may belong to the next frame by now)
-  if (!L.ok || L.hdr->err) return;
+  if (!L.okPersist || L.hdr->err) return;
   const int nv = L.hdr->nvalid;
-  for (int t = blockIdx.x * 64 + threadIdx.x; t < 2 * nv; t += gridDim.x * 64) {
+  for (int t = blockIdx.x * 64 + threadIdx.x; t < ((nv + 31) >> 5) * 64; t += gridDim.x * 64) {
     // the two variants of one quadrilateral sit 32 threads apart, so a warp runs ONE variant on 32 quadrilaterals
     const int blk = t >> 6, within = t & 63, v = blk * 32 + (within & 31), mode = within < 32 ? 1 : 0;
     if (v >= nv) continue;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) kt_finish(GtArgs a0, double tanAOV) {
   GtRect *out = (GtRect *)(a.blob + 64);
   const int cap = (int)((((a.blobBytes / 2) & ~(size_t)15) - 64) / sizeof(GtRect));
   __shared__ int wsum[8], base;
-  if (!L.ok || L.hdr->err) { if (threadIdx.x == 0) { hdr[0] = n; hdr[1] = 0; hdr[2] = L.ok ? L.hdr->err : GT_ERR_SCRATCH; hdr[3] = 0; } return; }
+  if (!L.okPersist || L.hdr->err) { if (threadIdx.x == 0) { hdr[0] = n; hdr[1] = 0; hdr[2] = L.okPersist ? L.hdr->err : GT_ERR_SCRATCH; hdr[3] = 0; } return; }
   const int nc = L.hdr->ncand;
   if (threadIdx.x == 0) base = 0;
   __syncthreads();

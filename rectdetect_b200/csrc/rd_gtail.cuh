@@ -549,7 +549,7 @@ struct GtChain { int head, m; };
 struct GtCand { int type, idx, m, pad; unsigned long long off; };        // type 0: region, 1: polyline chain; off: byte offset of its work storage
 struct GtLayout {
   GtHdr *hdr; GtPair *pairs; GtRegion *regions; GtChain *chains; int *members; GtCand *cands; GtQuad *quads; GtPoseOut *pose; int *vlist;
-  unsigned char *work; size_t workBytes; int ok;
+  unsigned char *work; size_t workBytes; int ok, okPersist;
 };
 #define GT_ERR_SCRATCH 1        // the frame needs more tail scratch than the arena holds
 #define GT_ERR_RECTS 2          // more rectangles than the read-back record holds
@@ -572,6 +572,7 @@ GT_FN GtLayout gt_layout(unsigned char *scratch, size_t S, unsigned char *persis
   L.members = (int *)(scratch + o); o += gt_align16(np * sizeof(int));
   L.cands = (GtCand *)(scratch + o); o += gt_align16(nc * sizeof(GtCand));
   L.work = scratch + o;
+  L.okPersist = L.ok;                                             // all the pose / finish kernels need
   L.ok = L.ok && o < S;
   L.workBytes = L.ok ? S - o : 0;
   return L;

@@ -213,6 +213,131 @@ void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int 
   RD_LAUNCH(k_iir_pass3, rd_gy(rd_cdiv(n, B1), nb), B1, 0, s, obuf, tmp0, tmp1, r, n, fs);
 }
 
+// ---- operators no configured path of the reference enqueues: the visualisers (packed Lab / float / label planes -> BGR8) and the
+// alternative edge / thinning kernels.  Plain one-thread-per-pixel kernels: they are off the hot path and exist so that the
+// L2 surface (oclimgutil.h:74-100) is complete. ----
+__device__ __forceinline__ int rd_floor_clamp(float v, int lo, int hi) {      // clamp(convert_int_rtn(v), lo, hi); NaN -> lo
+  if (!(v >= (float)lo)) return lo;
+  if (v >= (float)hi) return hi;
+  return (int)floorf(v);
+}
+__device__ __forceinline__ float rd_icfunc(float ft) {                        // oclimgutil.cl:136-142
+  if (ft > 0.20689270648f) return __fmul_rn(__fmul_rn(ft, ft), ft);
+  return __fmul_rn(__fsub_rn(ft, __fdiv_rn(16.0f, 116.0f)), __fdiv_rn(1.0f, 7.787f));
+}
+// plab2bgr (oclimgutil.cl:146-178, 264-273)
+__global__ void k_plab2bgr(uint8_t *out, const uint32_t *in, int iw, int ih, int ws, size_t fs) {
+  rd_batch_z(fs, out, in);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const float xn = 0.950456f, zn = 1.088754f;
+  float l, a, b;
+  rd_unpacklab(in[y * iw + x], l, a, b);
+  l = __fmul_rn(l, 256.0f); a = __fmul_rn(a, 256.0f); b = __fmul_rn(b, 256.0f);
+  float cy;
+  if (l > 0.20689270648f) {
+    cy = __fmul_rn(__fadd_rn(l, 16.0f), __fdiv_rn(1.0f, 116.0f));
+    cy = __fmul_rn(__fmul_rn(cy, cy), cy);
+  } else {
+    cy = __fmul_rn(l, __fdiv_rn(1.0f, 903.3f));
+  }
+  const float fy = __fmul_rn((float)((int)RD_CFUNC[rd_floor_clamp(__fmul_rn(cy, 1024.0f), 0, 1023)] + 9039), __fdiv_rn(1.0f, 65536.0f));
+  const float fz = __fsub_rn(fy, __fmul_rn(__fsub_rn(b, 128.0f), __fdiv_rn(1.0f, 200.0f)));
+  const float fx = __fadd_rn(fy, __fmul_rn(__fsub_rn(a, 128.0f), __fdiv_rn(1.0f, 500.0f)));
+  const float cx = __fmul_rn(rd_icfunc(fx), xn), cz = __fmul_rn(rd_icfunc(fz), zn);
+  const float r = __fadd_rn(__fadd_rn(__fmul_rn(cx, 3.240479f), __fmul_rn(cy, -1.537150f)), __fmul_rn(cz, -0.498535f));
+  const float g = __fadd_rn(__fadd_rn(__fmul_rn(cx, -0.969256f), __fmul_rn(cy, 1.875991f)), __fmul_rn(cz, 0.041556f));
+  const float bl = __fadd_rn(__fadd_rn(__fmul_rn(cx, 0.055648f), __fmul_rn(cy, -0.204043f)), __fmul_rn(cz, 1.057311f));
+  uint8_t *o = out + (size_t)y * ws + x * 3;
+  o[2] = RD_L2S[rd_floor_clamp(__fmul_rn(r, 1024.0f), 0, 1023)];
+  o[1] = RD_L2S[rd_floor_clamp(__fmul_rn(g, 1024.0f), 0, 1023)];
+  o[0] = RD_L2S[rd_floor_clamp(__fmul_rn(bl, 1024.0f), 0, 1023)];
+}
+// oclimgutil.cl:283-289
+__global__ void k_convert_bgr_lumaf(uint8_t *out, const float *in, float f, int iw, int ih, int ws, size_t fs) {
+  rd_batch_z(fs, out, in);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  uint8_t *o = out + (size_t)y * ws + x * 3;
+  o[0] = o[1] = o[2] = (uint8_t)rd_floor_clamp(__fmul_rn(__fmul_rn(in[y * iw + x], f), 255.0f), 0, 255);
+}
+// oclimgutil.cl:291-322
+__global__ void k_convert_bgr_labeli(uint8_t *out, const int *in, int bgc, int iw, int ih, int ws, size_t fs) {
+  rd_batch_z(fs, out, in);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  uint8_t *o = out + (size_t)y * ws + x * 3;
+  const int c = in[y * iw + x];
+  if (c == bgc) { o[0] = o[1] = o[2] = 0; return; }
+  const int g = (int)((uint32_t)c * 1103515245u + 12345u);
+  o[2] = (uint8_t)((((g & (7 << 0)) << 5) | 31) & 255);
+  o[1] = (uint8_t)((((g & (7 << 3)) << 2) | 31) & 255);
+  o[0] = (uint8_t)((((g & (7 << 6)) >> 1) | 31) & 255);
+}
+// oclimgutil.cl:439-452
+__global__ void k_edge_f_f(float *out, const float *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const float n = in[rd_mirror(x, y - 1, iw, ih)], w = in[rd_mirror(x - 1, y, iw, ih)], s_ = in[rd_mirror(x, y + 1, iw, ih)], e = in[rd_mirror(x + 1, y, iw, ih)];
+  const float nw = in[rd_mirror(x - 1, y - 1, iw, ih)], se = in[rd_mirror(x + 1, y + 1, iw, ih)], ne = in[rd_mirror(x + 1, y - 1, iw, ih)], sw = in[rd_mirror(x - 1, y + 1, iw, ih)];
+  float t = __fsub_rn(__fsub_rn(__fadd_rn(n, w), s_), e);
+  float sum = __fadd_rn(0.0f, __fmul_rn(__fsub_rn(nw, se), t));
+  t = __fsub_rn(__fadd_rn(__fsub_rn(n, w), e), s_);
+  sum = __fadd_rn(sum, __fmul_rn(__fsub_rn(ne, sw), t));
+  out[y * iw + x] = __fsqrt_rn(sum > 0.0f ? sum : 0.0f);
+}
+// oclimgutil.cl:473-491
+__global__ void k_thincubic(float *out, const float *in, const float2 *vec, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, in, vec);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  GlobalPlane p = {in, iw, ih};
+  const float2 v = vec[y * iw + x];
+  const float fx = (float)x, fy = (float)y;
+  const float vx2 = __fmul_rn(2.0f, v.x), vy2 = __fmul_rn(2.0f, v.y);
+  const float am2 = rd_bicubic(p, __fsub_rn(fx, vx2), __fsub_rn(fy, vy2));
+  const float am1 = rd_bicubic(p, __fsub_rn(fx, v.x), __fsub_rn(fy, v.y));
+  const float a0 = p.at(x, y);
+  const float ap1 = rd_bicubic(p, __fadd_rn(fx, v.x), __fadd_rn(fy, v.y));
+  const float ap2 = rd_bicubic(p, __fadd_rn(fx, vx2), __fadd_rn(fy, vy2));
+  const float C = 0.99f;
+  const bool keep = __fmul_rn(am2, C) <= a0 && __fmul_rn(am1, C) <= a0 && a0 >= __fmul_rn(ap1, C) && a0 >= __fmul_rn(ap2, C);
+  out[y * iw + x] = keep ? __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(am2, am1), a0), ap1), ap2) : 0.0f;
+}
+// oclimgutil.cl:354-393
+__global__ void k_edgevec_plab(float2 *dst, const uint32_t *in, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, dst, in);
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  float vx3[3] = {0, 0, 0}, vy3[3] = {0, 0, 0};
+  for (int yy = -2; yy <= 2; yy++)
+    for (int xx = -2; xx <= 2; xx++) {
+      float s3[3];
+      rd_unpacklab(in[rd_mirror(x + xx, y + yy, iw, ih)], s3[0], s3[1], s3[2]);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        vx3[c] = __fadd_rn(vx3[c], __fmul_rn(RD_V5C[(xx + 2) + (yy + 2) * 5], s3[c]));
+        vy3[c] = __fadd_rn(vy3[c], __fmul_rn(RD_V5C[(yy + 2) + (xx + 2) * 5], s3[c]));
+      }
+    }
+  float iv3[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) iv3[c] = __fadd_rn(__fmul_rn(vx3[c], vx3[c]), __fmul_rn(vy3[c], vy3[c]));
+  float ivlen, vx, vy;
+  if (iv3[0] >= iv3[1] && iv3[0] >= iv3[2]) { ivlen = iv3[0]; vx = vx3[0]; vy = vy3[0]; }
+  else if (iv3[1] >= iv3[2]) { ivlen = iv3[1]; vx = vx3[1]; vy = vy3[1]; }
+  else { ivlen = iv3[2]; vx = vx3[2]; vy = vy3[2]; }
+  if ((double)iv3[0] >= 1e-6 && __fadd_rn(__fmul_rn(vx3[0], vx), __fmul_rn(vy3[0], vy)) < 0.0f) { vx = -vx; vy = -vy; }
+  if ((double)ivlen > 1e-10) {
+    ivlen = __fdiv_rn(1.0f, __fsqrt_rn(ivlen));
+    vx = __fmul_rn(vx, ivlen); vy = __fmul_rn(vy, ivlen);
+  } else {
+    vx = vy = 0.70710678118f;
+  }
+  dst[y * iw + x] = make_float2(vx, vy);
+}
+
 extern "C" {
 
 oclimgutil_t *init_oclimgutil(cl_device_id device, cl_context) {             // oclimgutil.c:20-98
@@ -338,15 +463,49 @@ cl_event oclimgutil_filterStrength(oclimgutil_t *thiz, cl_mem labelinout, cl_mem
   return NULL;
 }
 
-// Operators of the reference that no configured path enqueues (debug visualisers and dead kernels).
-// They are exported so that programs link; calling one ends the process the way every reference error does.
-#define RD_UNSUPPORTED(name) exitf(-1, "rectdetect_b200: " name " is not on the rectangle-detection path and is not implemented\n"); return NULL
-cl_event oclimgutil_convert_bgr_luminancef(oclimgutil_t *, cl_mem, cl_mem, int, int, int, cl_command_queue, const cl_event *) { RD_UNSUPPORTED("oclimgutil_convert_bgr_luminancef"); }
-cl_event oclimgutil_convert_bgr_lumaf(oclimgutil_t *, cl_mem, cl_mem, float, int, int, int, cl_command_queue, const cl_event *) { RD_UNSUPPORTED("oclimgutil_convert_bgr_lumaf"); }
-cl_event oclimgutil_convert_bgr_labeli(oclimgutil_t *, cl_mem, cl_mem, int, int, int, int, cl_command_queue, const cl_event *) { RD_UNSUPPORTED("oclimgutil_convert_bgr_labeli"); }
-cl_event oclimgutil_edge_f_f(oclimgutil_t *, cl_mem, cl_mem, int, int, cl_command_queue, const cl_event *) { RD_UNSUPPORTED("oclimgutil_edge_f_f"); }
-cl_event oclimgutil_thincubic_f_f_f2(oclimgutil_t *, cl_mem, cl_mem, cl_mem, int, int, cl_command_queue, const cl_event *) { RD_UNSUPPORTED("oclimgutil_thincubic_f_f_f2"); }
-cl_event oclimgutil_convert_bgr_plab(oclimgutil_t *, cl_mem, cl_mem, int, int, int, cl_command_queue, const cl_event *) { RD_UNSUPPORTED("oclimgutil_convert_bgr_plab"); }
-cl_event oclimgutil_edgevec_f2_plab(oclimgutil_t *, cl_mem, cl_mem, int, int, cl_command_queue, const cl_event *) { RD_UNSUPPORTED("oclimgutil_edgevec_f2_plab"); }
+// Operators no configured path of the reference enqueues (visualisers and alternative kernels).
+cl_event oclimgutil_convert_bgr_lumaf(oclimgutil_t *thiz, cl_mem out, cl_mem in, float f, int iw, int ih, int ws, cl_command_queue queue, const cl_event *events) {
+  OP_PROLOGUE;                                                                // oclimgutil.c:191
+  rd_need(out, (size_t)ws * ih, "convert_bgr_lumaf"); rd_need(in, (size_t)iw * ih * 4, "convert_bgr_lumaf");
+  RD_LAUNCH(k_convert_bgr_lumaf, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<uint8_t>(out), rd_ptr<float>(in), f, iw, ih, ws, fs);
+  return rd_make_event(s, events);
+}
+cl_event oclimgutil_convert_bgr_labeli(oclimgutil_t *thiz, cl_mem out, cl_mem in, int bgc, int iw, int ih, int ws, cl_command_queue queue, const cl_event *events) {
+  OP_PROLOGUE;                                                                // oclimgutil.c:197
+  rd_need(out, (size_t)ws * ih, "convert_bgr_labeli"); rd_need(in, (size_t)iw * ih * 4, "convert_bgr_labeli");
+  RD_LAUNCH(k_convert_bgr_labeli, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<uint8_t>(out), rd_ptr<int>(in), bgc, iw, ih, ws, fs);
+  return rd_make_event(s, events);
+}
+cl_event oclimgutil_edge_f_f(oclimgutil_t *thiz, cl_mem out, cl_mem in, int iw, int ih, cl_command_queue queue, const cl_event *events) {
+  OP_PROLOGUE;                                                                // oclimgutil.c:203
+  rd_need(out, (size_t)iw * ih * 4, "edge_f_f"); rd_need(in, (size_t)iw * ih * 4, "edge_f_f");
+  RD_LAUNCH(k_edge_f_f, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<float>(out), rd_ptr<float>(in), iw, ih, fs);
+  return rd_make_event(s, events);
+}
+cl_event oclimgutil_thincubic_f_f_f2(oclimgutil_t *thiz, cl_mem out, cl_mem in, cl_mem vec, int iw, int ih, cl_command_queue queue, const cl_event *events) {
+  OP_PROLOGUE;                                                                // oclimgutil.c:221
+  rd_need(out, (size_t)iw * ih * 4, "thincubic"); rd_need(in, (size_t)iw * ih * 4, "thincubic"); rd_need(vec, (size_t)iw * ih * 8, "thincubic");
+  RD_LAUNCH(k_thincubic, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<float>(out), rd_ptr<float>(in), rd_ptr<float2>(vec), iw, ih, fs);
+  return rd_make_event(s, events);
+}
+cl_event oclimgutil_convert_bgr_plab(oclimgutil_t *thiz, cl_mem out, cl_mem in, int iw, int ih, int ws, cl_command_queue queue, const cl_event *events) {
+  OP_PROLOGUE;                                                                // oclimgutil.c:281-285 runs plab2bgr (names swapped)
+  rd_need(out, (size_t)ws * ih, "convert_bgr_plab"); rd_need(in, (size_t)iw * ih * 4, "convert_bgr_plab");
+  RD_LAUNCH(k_plab2bgr, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<uint8_t>(out), rd_ptr<uint32_t>(in), iw, ih, ws, fs);
+  return rd_make_event(s, events);
+}
+cl_event oclimgutil_edgevec_f2_plab(oclimgutil_t *thiz, cl_mem out, cl_mem in, int iw, int ih, cl_command_queue queue, const cl_event *events) {
+  OP_PROLOGUE;
+  rd_need(out, (size_t)iw * ih * 8, "edgevec_f2_plab"); rd_need(in, (size_t)iw * ih * 4, "edgevec_f2_plab");
+  RD_LAUNCH(k_edgevec_plab, rd_gz(rd_grid2d(iw, ih, B2), nb), B2, 0, s, rd_ptr<float2>(out), rd_ptr<uint32_t>(in), iw, ih, fs);
+  return rd_make_event(s, events);
+}
+// oclimgutil_convert_bgr_luminancef cannot run in the reference either: its wrapper sets five kernel arguments ("MMiii", oclimgutil.c:187)
+// for a kernel that takes six (out, in, float f, iw, ih, ws; oclimgutil.cl:275), so clEnqueueNDRangeKernel fails with
+// CL_INVALID_KERNEL_ARGS and ce() ends the process.  Same outcome here.
+cl_event oclimgutil_convert_bgr_luminancef(oclimgutil_t *, cl_mem, cl_mem, int, int, int, cl_command_queue, const cl_event *) {
+  exitf(-1, "rectdetect_b200: oclimgutil_convert_bgr_luminancef: CL_INVALID_KERNEL_ARGS (the reference's wrapper passes 5 of the kernel's 6 arguments, oclimgutil.c:187)\n");
+  return NULL;
+}
 
 }  // extern "C"

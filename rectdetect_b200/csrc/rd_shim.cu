@@ -6,6 +6,7 @@
 #include <unistd.h>
 #include <vector>
 #include <mutex>
+#include <ctype.h>
 #include "rd_common.cuh"
 
 std::atomic<int> g_rd_launches{0};
@@ -83,6 +84,62 @@ void **ArrayMap_valueArray(ArrayMap *thiz) {
   return a;
 }
 
+uint64_t ArrayMap_getKey(ArrayMap *thiz, int idx) {        // helper.h:30 (declared by the reference, defined nowhere in it): idx-th entry in
+  for (int j = 0; j < 1024; j++) {                        // keyArray order
+    if (idx < (int)thiz->bucket[j].size()) return thiz->bucket[j][idx].key;
+    idx -= (int)thiz->bucket[j].size();
+  }
+  return 0;
+}
+void *ArrayMap_getValue(ArrayMap *thiz, int idx) {         // helper.h:31
+  for (int j = 0; j < 1024; j++) {
+    if (idx < (int)thiz->bucket[j].size()) return thiz->bucket[j][idx].value;
+    idx -= (int)thiz->bucket[j].size();
+  }
+  return NULL;
+}
+// helper.c:40-62 : a whole text file as a malloc()ed string; larger than maxSize or unreadable ends the process
+char *readFileAsStr(const char *fn, int maxSize) {
+  FILE *fp = fopen(fn, "r");
+  if (!fp) exitf(-1, "Couldn't open file %s\n", fn);
+  fseek(fp, 0, SEEK_END);
+  long size = ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  if (size > maxSize) exitf(-1, "readFileAsStr : file too large (%d bytes)\n", (int)size);
+  char *buf = (char *)malloc((size_t)size + 10);
+  if (!buf) exitf(-1, "readFileAsStr : malloc failed\n");
+  size = (long)fread(buf, 1, (size_t)size, fp);
+  buf[size] = '\0';
+  fclose(fp);
+  return buf;
+}
+// helper.c:64-88 : the files of a NULL-terminated name list, concatenated (1 MB limit)
+char *readFileAsStrN(const char **fn) {
+  size_t total = 0;
+  char *buf = (char *)malloc(10);
+  buf[0] = '\0';
+  for (int i = 0; fn[i] != NULL; i++) {
+    char *one = readFileAsStr(fn[i], 1000000);
+    const size_t len = strlen(one);
+    if (total + len > 1000000) exitf(-1, "readFileAsStrN : total file size %d bytes is too large\n", (int)(total + len));
+    buf = (char *)realloc(buf, total + len + 10);
+    if (!buf) exitf(-1, "readFileAsStrN : realloc failed\n");
+    memcpy(buf + total, one, len + 1);
+    total += len;
+    free(one);
+  }
+  return buf;
+}
+void String_trim(char *str) {                             // helper.c:90-101 : strip leading and trailing white space in place
+  char *dst = str, *src = str, *end = str;
+  while (*src != '\0' && isspace((unsigned char)*src)) src++;
+  for (; *src != '\0'; src++) {
+    *dst++ = *src;
+    if (!isspace((unsigned char)*src)) end = dst;
+  }
+  *end = '\0';
+}
+
 // ---------------------------------------------------------------- oclhelper.h
 const char *clStrError(int c) {                           // oclhelper.c:31-111 (only the codes this library can produce)
   switch (c) {
@@ -146,6 +203,19 @@ cl_context simpleCreateContext(cl_device_id device) {     // oclhelper.c:225-233
   c->ordinal = device->ordinal;
   return c;
 }
+// oclhelper.h:20-25 : the program-build / argument / launch helpers the reference's three host layers use internally.  There
+// are no OpenCL program or kernel objects in this library (the kernels are sm_100a code linked into it, and no exported call
+// creates a cl_program / cl_kernel), so these exist for link completeness and end the process if something calls them.
+int simpleBuildProgram(cl_program, cl_device_id, const char *) {
+  exitf(-1, "rectdetect_b200: simpleBuildProgram: there is no OpenCL program to build (kernels are precompiled CUDA)\n");
+  return -1;
+}
+void simpleSetKernelArg(cl_kernel, const char *, ...) { exitf(-1, "rectdetect_b200: simpleSetKernelArg: no OpenCL kernel objects exist in this library\n"); }
+cl_event runKernel1D(cl_command_queue, cl_kernel, int, size_t, int, ...) { exitf(-1, "rectdetect_b200: runKernel1D: no OpenCL kernel objects exist in this library\n"); return NULL; }
+cl_event runKernel2D(cl_command_queue, cl_kernel, int, size_t, size_t, int, ...) { exitf(-1, "rectdetect_b200: runKernel2D: no OpenCL kernel objects exist in this library\n"); return NULL; }
+cl_event runKernel1Dx(cl_command_queue, cl_kernel, int, size_t, const cl_event *) { exitf(-1, "rectdetect_b200: runKernel1Dx: no OpenCL kernel objects exist in this library\n"); return NULL; }
+cl_event runKernel2Dx(cl_command_queue, cl_kernel, int, size_t, size_t, const cl_event *) { exitf(-1, "rectdetect_b200: runKernel2Dx: no OpenCL kernel objects exist in this library\n"); return NULL; }
+
 void waitForEvent(cl_event ev) {                          // oclhelper.c:799-817, without the 15 ms poll (Q22)
   if (!ev) return;
   RD_CUDA(cudaEventSynchronize(ev->ev));

@@ -59,7 +59,10 @@ def oracle():
             "ora_unpack_f_f_f_plab": (None, [vp, vp, vp, vp, i, i]), "ora_pack_plab_f_f_f": (None, [vp, vp, vp, vp, i, i]),
             "ora_iirblur_f_f": (None, [vp, vp, vp, vp, i, i, i]),
             "ora_edgevec_f2_f": (None, [vp, vp, i, i]), "ora_edge_f_plab": (None, [vp, vp, i, i]),
-            "ora_thinthres_f_f_f2": (None, [vp, vp, vp, i, i]),
+            "ora_thinthres_f_f_f2": (None, [vp, vp, vp, i, i]), "ora_thincubic_f_f_f2": (None, [vp, vp, vp, i, i]),
+            "ora_edgevec_f2_plab": (None, [vp, vp, i, i]), "ora_edge_f_f": (None, [vp, vp, i, i]),
+            "ora_convert_bgr_plab": (None, [vp, vp, i, i, i]), "ora_convert_bgr_lumaf": (None, [vp, vp, f, i, i, i]),
+            "ora_convert_bgr_labeli": (None, [vp, vp, i, i, i, i]),
             "ora_label8x_int_int": (i, [vp, vp, vp, i, i, i]),
             "ora_calcStrength": (None, [vp, vp, vp, i, i]), "ora_filterStrength": (None, [vp, vp, i, i, i]),
             "ora_rect_simpleJunction": (None, [vp, vp, i, i]), "ora_rect_simpleConnect": (None, [vp, vp, i, i]),

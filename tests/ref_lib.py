@@ -59,7 +59,10 @@ def lib():
             "oclimgutil_pack_plab_f_f_f": (vp, [vp, vp, vp, vp, vp, ci, ci, vp, vp]),
             "oclimgutil_iirblur_f_f": (vp, [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp]),
             "oclimgutil_edgevec_f2_f": (vp, [vp, vp, vp, ci, ci, vp, vp]), "oclimgutil_edge_f_plab": (vp, [vp, vp, vp, ci, ci, vp, vp]),
-            "oclimgutil_thinthres_f_f_f2": (vp, [vp, vp, vp, vp, ci, ci, vp, vp]),
+            "oclimgutil_thinthres_f_f_f2": (vp, [vp, vp, vp, vp, ci, ci, vp, vp]), "oclimgutil_thincubic_f_f_f2": (vp, [vp, vp, vp, vp, ci, ci, vp, vp]),
+            "oclimgutil_edgevec_f2_plab": (vp, [vp, vp, vp, ci, ci, vp, vp]), "oclimgutil_edge_f_f": (vp, [vp, vp, vp, ci, ci, vp, vp]),
+            "oclimgutil_convert_bgr_plab": (vp, [vp, vp, vp, ci, ci, ci, vp, vp]), "oclimgutil_convert_bgr_lumaf": (vp, [vp, vp, vp, cf, ci, ci, ci, vp, vp]),
+            "oclimgutil_convert_bgr_labeli": (vp, [vp, vp, vp, ci, ci, ci, ci, vp, vp]),
             "oclimgutil_label8x_int_int": (vp, [vp, vp, vp, vp, ci, ci, ci, vp, vp]),
             "oclimgutil_calcStrength": (vp, [vp, vp, vp, vp, ci, ci, vp, vp]),
             "oclimgutil_filterStrength": (vp, [vp, vp, vp, ci, ci, ci, vp, vp]),

@@ -36,6 +36,65 @@ def test_library_exports_every_declared_symbol(rd):
         assert must in declared
 
 
+# every function the reference's five public headers declare (oclhelper.h, helper.h, oclimgutil.h, oclpolyline.h, oclrect.h), pinned
+# here so that the check also runs where /root/reference is absent; when it is present the list itself is checked against the headers
+REFERENCE_API = """clStrError checkError ce getDeviceName simpleGetDevice simpleGetDevices simpleCreateContext simpleBuildProgram simpleSetKernelArg
+runKernel1D runKernel2D runKernel1Dx runKernel2Dx waitForEvent clearPlan loadPlan savePlan startProfiling finishProfiling showPlan allocatePinnedMemory
+freePinnedMemory getNextKernelID exitf readFileAsStr readFileAsStrN currentTimeMillis sleepMillis String_trim initArrayMap ArrayMap_dispose ArrayMap_size
+ArrayMap_remove ArrayMap_put ArrayMap_get ArrayMap_keyArray ArrayMap_valueArray ArrayMap_getKey ArrayMap_getValue init_oclimgutil dispose_oclimgutil
+oclimgutil_clear oclimgutil_copy oclimgutil_cast_i_f oclimgutil_cast_c_i oclimgutil_threshold_i_i oclimgutil_threshold_f_f oclimgutil_rand
+oclimgutil_convert_bgr_luminancef oclimgutil_convert_bgr_lumaf oclimgutil_convert_bgr_labeli oclimgutil_edge_f_f oclimgutil_edgevec_f2_f
+oclimgutil_thinthres_f_f_f2 oclimgutil_thincubic_f_f_f2 oclimgutil_label8x_int_int oclimgutil_iirblur_f_f oclimgutil_convert_plab_bgr
+oclimgutil_convert_bgr_plab oclimgutil_unpack_f_f_f_plab oclimgutil_pack_plab_f_f_f oclimgutil_edgevec_f2_plab oclimgutil_edge_f_plab
+oclimgutil_calcStrength oclimgutil_filterStrength init_oclpolyline dispose_oclpolyline oclpolyline_execute init_oclrect dispose_oclrect
+oclrect_executeOnce oclrect_enqueueTask oclrect_pollTask""".split()
+
+
+def test_library_exports_the_reference_headers_completely(rd):
+    L = rd.lib()
+    missing = [n for n in REFERENCE_API if not hasattr(L, n)]
+    assert not missing, "declared by the reference's headers but not exported: %s" % missing
+    ref = "/root/reference"
+    if os.path.exists(os.path.join(ref, "oclrect.h")):
+        found = set()
+        for hdr in ("oclhelper.h", "helper.h", "oclimgutil.h", "oclpolyline.h", "oclrect.h"):
+            src = open(os.path.join(ref, hdr)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            src = re.sub(r"//[^\n]*", "", src)
+            for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}()]*\)\s*;", src):
+                found.add(m.group(1))
+        assert found == set(REFERENCE_API), (sorted(found - set(REFERENCE_API)), sorted(set(REFERENCE_API) - found))
+
+
+def test_helper_h_text_utilities(rd, tmp_path):                                # helper.c:40-101
+    L = rd.lib()
+    L.readFileAsStr.restype, L.readFileAsStr.argtypes = C.c_void_p, [C.c_char_p, C.c_int]
+    L.readFileAsStrN.restype, L.readFileAsStrN.argtypes = C.c_void_p, [C.POINTER(C.c_char_p)]
+    L.String_trim.argtypes = [C.c_char_p]
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    a.write_text("first\nfile\n")
+    b.write_text("second")
+    p = L.readFileAsStr(str(a).encode(), 1000)
+    assert C.string_at(p) == b"first\nfile\n"
+    L.rd_free(p)
+    names = (C.c_char_p * 3)(str(a).encode(), str(b).encode(), None)
+    p = L.readFileAsStrN(names)
+    assert C.string_at(p) == b"first\nfile\nsecond"
+    L.rd_free(p)
+    buf = C.create_string_buffer(b"  \t padded text \n ")
+    L.String_trim(buf)
+    assert buf.value == b"padded text"
+    L.ArrayMap_getKey.restype, L.ArrayMap_getKey.argtypes = C.c_uint64, [C.c_void_p, C.c_int]
+    L.initArrayMap.restype = C.c_void_p
+    L.ArrayMap_put.restype, L.ArrayMap_put.argtypes = C.c_void_p, [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.ArrayMap_keyArray.restype, L.ArrayMap_keyArray.argtypes = C.POINTER(C.c_uint64), [C.c_void_p]
+    m = L.initArrayMap()
+    for k in (5, 1029, 77, 2053):
+        L.ArrayMap_put(m, k, 1000 + k)
+    keys = L.ArrayMap_keyArray(m)
+    assert [L.ArrayMap_getKey(m, i) for i in range(4)] == [keys[i] for i in range(4)]
+
+
 def test_library_is_built_for_sm_100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "rectdetect_b200", "librectdetect_b200.so")], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))

@@ -289,3 +289,55 @@ def test_label8x_on_blobs(ctx, iw, ih):
         LO.ora_label8x_int_int(P(out), P(np.ascontiguousarray(src)), P(tmp), bgc, iw, ih)
         assert np.array_equal(ctx.view(mo, n), out), bgc
         ctx.release()
+
+
+@pytest.mark.parametrize("iw,ih", SIZES)
+def test_operators_off_the_configured_paths(ctx, iw, ih):
+    """the L2 operators no program of the reference enqueues (oclimgutil.h:85-94): packed Lab -> BGR (every 10th of the 2^32 codes would
+    be too many: random codes + the code-space corners), float / label planes -> BGR, edge_f_f, thincubic, edgevec_f2_plab -
+    the oracle against the reference's kernels, bit-exact"""
+    L, LO, u, q = ctx.L, ol.oracle(), ctx.imgutil, ctx.queue
+    rng = np.random.default_rng(iw * 77 + ih)
+    n = iw * ih
+    ws = 3 * iw + 7
+    plab = rand_plab(rng, n)
+    plab[:8] = [0, 0xffffffff, 4095, 1023 << 12, 1023 << 22, 2048 | (512 << 12) | (512 << 22), 1, 0x80000000]
+    m_out, m_in = ctx.mem(ws * ih + 16), ctx.mem(4 * n, plab)
+    L.oclimgutil_convert_bgr_plab(u, m_out, m_in, iw, ih, ws, q, None)            # plab2bgr (Q9)
+    out = np.zeros(ws * ih, np.uint8)
+    LO.ora_convert_bgr_plab(P(out), P(plab), iw, ih, ws)
+    got = ctx.view(m_out, ws * ih, np.uint8).reshape(ih, ws)[:, :3 * iw]
+    assert np.array_equal(got, out.reshape(ih, ws)[:, :3 * iw]) and got.max() > 200 and got.min() == 0
+    # round trip through the forward conversion stays close in Lab (a sanity check of the restated formula, not of rounding)
+    fsrc = (rng.random(n, dtype=np.float32) * 1.6 - 0.3).astype(np.float32)
+    m_f = ctx.mem(4 * n, fsrc)
+    for f in (1.0, 0.37, 3.0):
+        L.oclimgutil_convert_bgr_lumaf(u, m_out, m_f, f, iw, ih, ws, q, None)
+        LO.ora_convert_bgr_lumaf(P(out), P(fsrc), f, iw, ih, ws)
+        assert np.array_equal(ctx.view(m_out, ws * ih, np.uint8).reshape(ih, ws)[:, :3 * iw], out.reshape(ih, ws)[:, :3 * iw]), f
+    lab = rng.integers(-3, 1 << 20, n, dtype=np.int32)
+    lab[::9] = 5
+    m_l = ctx.mem(4 * n, lab)
+    L.oclimgutil_convert_bgr_labeli(u, m_out, m_l, 5, iw, ih, ws, q, None)
+    LO.ora_convert_bgr_labeli(P(out), P(lab), 5, iw, ih, ws)
+    assert np.array_equal(ctx.view(m_out, ws * ih, np.uint8).reshape(ih, ws)[:, :3 * iw], out.reshape(ih, ws)[:, :3 * iw])
+    # edge_f_f on noise (negative sums -> 0), thincubic with vectors pointing everywhere, edgevec_f2_plab on noise and on a flat plane
+    src = (rng.random(n, dtype=np.float32) * 2 - 0.5).astype(np.float32)
+    a, b = ctx.mem(4 * n), ctx.mem(4 * n, src)
+    L.oclimgutil_edge_f_f(u, a, b, iw, ih, q, None)
+    o = np.zeros(n, np.float32)
+    LO.ora_edge_f_f(P(o), P(src), iw, ih)
+    assert np.array_equal(bits(ctx.view(a, n, np.float32)), bits(o)) and (o == 0).any() and (o > 0).any()
+    ang = rng.random(n) * 2 * np.pi
+    vec = np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32) * rng.choice([0.0, 0.5, 1.0, 1.7], n)[:, None].astype(np.float32)
+    mv = ctx.mem(8 * n, vec)
+    L.oclimgutil_thincubic_f_f_f2(u, a, b, mv, iw, ih, q, None)
+    LO.ora_thincubic_f_f_f2(P(o), P(src), P(vec), iw, ih)
+    assert np.array_equal(bits(ctx.view(a, n, np.float32)), bits(o)) and (o != 0).any()
+    for pl in (plab, smooth_plab(rng, iw, ih), np.full(n, 2048 | (512 << 12) | (512 << 22), np.uint32)):
+        mp, mo = ctx.mem(4 * n, pl), ctx.mem(8 * n)
+        L.oclimgutil_edgevec_f2_plab(u, mo, mp, iw, ih, q, None)
+        ov = np.zeros(2 * n, np.float32)
+        LO.ora_edgevec_f2_plab(P(ov), P(pl), iw, ih)
+        assert np.array_equal(bits(ctx.view(mo, 2 * n, np.float32)), bits(ov))
+    ctx.release()
