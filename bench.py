@@ -5,12 +5,15 @@ metric  : Mpix/s = frames/s x iw x ih, BGR frame -> rect_t list (BASELINE.json)
 step    : one batch of --frames (default 256) 1280x720 synthetic frames per GPU (config "vidrect 1280x720 synthetic stream, AOV 72,
           batched on 1xB200"); frames of a batch are independent and are sharded across ranks (weak scaling, no data-path
           collective; one gather of the rect lists to rank 0 per step).
-value   : frames already resident in HBM; every device stage, the compact read-back and the host tail run (rect lists
-          are produced on the host), plus the rect-list gather for N > 1.
+value   : frames already resident in HBM; every device stage incl. the device tail (executeCPUTask on the GPU) and the read-back of
+          the rect lists, plus the rect-list gather for N > 1.
 e2e     : the same through the C-ABI batch call with frames in pinned HOST memory (H2D copies inside the timed region).
 roofline: the kernel with the largest share of device time against the measured HBM copy bandwidth.  Per-kernel times come
           from CUDA events around every launch on the launching stream (in the library), in a separate pass through ONE
           pipeline object so that each kernel is timed alone; per-stage (A/B/C/D) totals of the same pass are reported too.
+sub-records of the same JSON line: config4 (1920x1080, 512 frames per step over all ranks: strong scaling), config5 (one 3840x2160 frame,
+          per-stage roofline), api_stream (the reference's enqueue/poll API, unchanged caller), parity_checked_frames (frames of the
+          timed batch compared with the CPU oracle after the timed region).
 --impl reference : THE REFERENCE ITSELF on the host cores - oracle/_ref/librd_ref.so = its unmodified host code and its OpenCL C
           kernels compiled as C++ (oracle/Makefile target _ref), one instance per core on a bounded sample of the stream per step;
           the CPU oracle port is timed beside it (cpu_port).
@@ -56,13 +59,16 @@ def ncu_traffic(kernel):
 
 
 def synth_batch(iw, ih, first_seed, count, pinned):
+    """`count` frames of the synthetic stream (seeds first_seed + i) in one (pinned) host tensor; generated on all host cores"""
     import torch
-    from rectdetect_b200.synth import synth_frame
+    from concurrent.futures import ThreadPoolExecutor
+    from rectdetect_b200.synth import synth_frame, synth_lib
+    synth_lib()
     ws = 3 * iw
     t = torch.empty((count, ih, ws), dtype=torch.uint8, pin_memory=pinned)
     a = t.numpy()
-    for i in range(count):
-        synth_frame(iw, ih, first_seed + i, out=a[i])
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:      # the generator is C++ behind ctypes: the GIL is released
+        list(ex.map(lambda i: synth_frame(iw, ih, first_seed + i, out=a[i]), range(count)))
     return t
 
 
@@ -221,6 +227,9 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=os.cpu_count() or 8, help="frames per step of the CPU reference arm (default: one per host core)")
     ap.add_argument("--cpu-frames", type=int, default=2 * (os.cpu_count() or 8), help="frames of the cpu_baseline sample (default: two per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only: no config4 / config5 / api_stream sub-records")
+    ap.add_argument("--config4-frames", type=int, default=512, help="global frames per step of the 1920x1080 sub-record (BASELINE.json config 4)")
+    ap.add_argument("--parity-frames", type=int, default=4, help="frames of the timed batch checked against the CPU oracle after the timed region")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -229,6 +238,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
     import torch
     import torch.distributed as dist
     import rectdetect_b200 as rd
@@ -240,14 +250,6 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    iw, ih, F = args.w, args.h, args.frames
-    ws = 3 * iw
-    total_frames = F * world
-    lo, hi = rdist.shard_range(total_frames, world, rank)
-    host_frames = synth_batch(iw, ih, 1000 + lo, hi - lo, pinned=True)           # seeds 1000+i (config 3)
-    dev_frames = host_frames.to("cuda", non_blocking=False)
-    frame_bytes = ih * ws
-    batch = rd.Batch(local_rank, iw, ih, nctx=args.nctx, frames_per_launch=args.fpl)
     dev = "cuda"
 
     def barrier():
@@ -255,77 +257,196 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(on_device):
-        ptr = dev_frames.data_ptr() if on_device else host_frames.data_ptr()
-        rects = batch.run(ptr, frame_bytes, ws, hi - lo, TAN_AOV, on_device=on_device)
-        return rdist.gather_rect_lists(lo, rects, total_frames, device=dev)
+    def run_workload(iw, ih, total_frames, first_seed, steps, warmup):
+        """one workload: `total_frames` frames per step over all ranks (rank r owns a contiguous shard), value (frames resident
+        in HBM) and e2e (pinned host frames, H2D inside the timed region); -> dict (timings are max over ranks)"""
+        ws = 3 * iw
+        lo, hi = rdist.shard_range(total_frames, world, rank)
+        host_frames = synth_batch(iw, ih, first_seed + lo, hi - lo, pinned=True)
+        dev_frames = host_frames.to("cuda", non_blocking=False)
+        frame_bytes = ih * ws
+        batch = rd.Batch(local_rank, iw, ih, nctx=args.nctx, frames_per_launch=args.fpl)
 
-    def timed(on_device, steps, profile=False):
-        barrier()
-        l0 = rd.kernel_launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if profile:
-            rd.api.profile_start(None)
-        e0.record()
-        out = None
-        for _ in range(steps):
-            out = step(on_device)
-        barrier()
-        e1.record()
-        torch.cuda.synchronize()
-        prof = rd.api.profile_stop() if profile else None
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        launches = torch.tensor([rd.kernel_launches() - l0], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-        return float(t.item()), int(launches.item()), out, prof
+        def step(on_device):
+            ptr = dev_frames.data_ptr() if on_device else host_frames.data_ptr()
+            rects = batch.run(ptr, frame_bytes, ws, hi - lo, TAN_AOV, on_device=on_device)
+            return rdist.gather_rect_lists(lo, rects, total_frames, device=dev)
 
-    for _ in range(args.warmup):
-        step(True)
-        step(False)
+        def timed(on_device, nsteps):
+            barrier()
+            l0 = rd.kernel_launches()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = None
+            for _ in range(nsteps):
+                out = step(on_device)
+            barrier()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            launches = torch.tensor([rd.kernel_launches() - l0], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+            return float(t.item()), int(launches.item()), out
 
+        for _ in range(warmup):
+            step(True)
+            step(False)
+        ms_val, launches, rects = timed(True, steps)
+        ms_e2e, _, rects_e2e = timed(False, steps)
+        wait_ms, list_ms = batch.stage_ms()
+        pix = total_frames * iw * ih
+        res = {"iw": iw, "ih": ih, "ws": ws, "lo": lo, "hi": hi, "total_frames": total_frames, "frame_bytes": frame_bytes, "host_frames": host_frames, "dev_frames": dev_frames,
+               "value": pix * steps / (ms_val * 1e-3) / 1e6, "e2e": pix * steps / (ms_e2e * 1e-3) / 1e6, "ms_val": ms_val / steps, "ms_e2e": ms_e2e / steps,
+               "launches": launches, "rects": rects, "rects_e2e": rects_e2e, "wait_ms": wait_ms, "list_ms": list_ms,
+               "d2h_bytes": (16 * 1024 * total_frames) if rects is None else sum(max(16 * 1024, 64 + 176 * len(r)) for r in rects)}
+        batch.close()
+        return res
+
+    iw, ih, F = args.w, args.h, args.frames
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_val, launches, rects, _ = timed(True, args.steps)
-    ms_e2e, _, rects_e2e, _ = timed(False, args.steps)
+    main_run = run_workload(iw, ih, F * world, 1000, args.steps, args.warmup)            # config 3: seeds 1000+i, weak scaling
     clocks = sampler.finish() if sampler else None
-    wait_ms, tail_ms = batch.stage_ms()
+    value, e2e = main_run["value"], main_run["e2e"]
+    total_frames, frame_bytes, ws = main_run["total_frames"], main_run["frame_bytes"], main_run["ws"]
+    lo, hi = main_run["lo"], main_run["hi"]
+    dev_frames = main_run["dev_frames"]
+    rects, rects_e2e = main_run["rects"], main_run["rects_e2e"]
+
     # per-kernel device time for the roofline of the top kernel: CUDA events around every launch on the launching stream
     # (rd_profile_*), in a separate pass over the same frames through ONE pipeline object, so that each kernel is timed
     # alone on the device (in the headline passes the streams of the pipeline objects overlap) and the event records do not
     # sit inside the headline timings
+    def staged_profile(run_once, nframes):
+        for _ in range(2):
+            run_once()
+        torch.cuda.synchronize()
+        rd.api.profile_start(None, stages=True)
+        run_once()
+        torch.cuda.synchronize()
+        prof, stage_ms = {}, {}
+        for k, (c, ms) in rd.api.profile_stop().items():
+            st, name = k.split("/", 1)
+            pc, pm = prof.get(name, (0, 0.0))
+            prof[name] = (pc + c, pm + ms)
+            stage_ms[st] = stage_ms.get(st, 0.0) + ms
+        return prof, stage_ms
+
     solo = rd.Batch(local_rank, iw, ih, nctx=1, frames_per_launch=args.fpl)
     nsolo = min(hi - lo, 4 * args.fpl)
-    for _ in range(2):
-        solo.run(dev_frames.data_ptr(), frame_bytes, ws, nsolo, TAN_AOV, on_device=True, want_rects=False)
-    torch.cuda.synchronize()
-    rd.api.profile_start(None, stages=True)
-    solo.run(dev_frames.data_ptr(), frame_bytes, ws, nsolo, TAN_AOV, on_device=True, want_rects=False)
-    torch.cuda.synchronize()
-    prof_staged = rd.api.profile_stop()
+    prof, stage_ms = staged_profile(lambda: solo.run(dev_frames.data_ptr(), frame_bytes, ws, nsolo, TAN_AOV, on_device=True, want_rects=False), nsolo)
     solo.close()
-    prof, stage_ms = {}, {}
-    for k, (c, ms) in prof_staged.items():
-        st, name = k.split("/", 1)
-        pc, pm = prof.get(name, (0, 0.0))
-        prof[name] = (pc + c, pm + ms)
-        stage_ms[st] = stage_ms.get(st, 0.0) + ms
 
-    pix_per_step = total_frames * iw * ih
-    value = pix_per_step * args.steps / (ms_val * 1e-3) / 1e6
-    e2e = pix_per_step * args.steps / (ms_e2e * 1e-3) / 1e6
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    # per-stage roofline (SURVEY.md 8d): algorithmic bytes per pixel A 11, B 16, C 8 (+56 B per segment), D 8 (+20 B per vote pair);
+    # the list terms are <1 % of a frame and are left out.  T = the device tail (executeCPUTask: FP64 compute on lists, no plane traffic)
+    stage_bpp = {"A": 11, "B": 16, "C": 8, "D": 8, "T": 0}
+
+    def stage_table(stage_ms, nframes, w, h):
+        out = {}
+        for st in sorted(stage_ms):
+            us = stage_ms[st] * 1e3 / nframes
+            gbs = stage_bpp.get(st, 0) * w * h / (us * 1e-6) / 1e9 if us > 0 and stage_bpp.get(st) else None
+            out[st] = {"us_per_frame": round(us, 2), "algorithmic_bytes_per_px": stage_bpp.get(st), "achieved_gbs": round(gbs, 1) if gbs else None,
+                       "frac_of_hbm_peak": round(gbs / peak, 4) if gbs else None}
+        return out
+
+    # ---- sub-records (BASELINE.json configs 4 and 5, the reference's streaming API, parity of the timed batch) ----
+    del main_run["host_frames"], main_run["dev_frames"]
+    dev_frames = None
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.no_extras:
+        c4 = run_workload(1920, 1080, args.config4_frames, 2000, 3, 1)                   # config 4: seeds 2000+i, contiguous shards, STRONG scaling
+        extras["config4"] = {"workload": "vidrect 1920x1080 synthetic frame batch (seeds 2000+i), %d frames per step over all GPUs in contiguous shards, rect lists gathered to rank 0" % args.config4_frames,
+                             "scaling": "strong", "value": c4["value"], "unit": "Mpix/s", "ms_per_step": c4["ms_val"],
+                             "e2e": {"value": c4["e2e"], "unit": "Mpix/s", "ms_per_step": c4["ms_e2e"], "h2d_bytes_per_step": c4["total_frames"] * c4["frame_bytes"], "d2h_bytes_per_step": c4["d2h_bytes"]},
+                             "pipeline_frac": (43.0 * c4["value"] * 1e6 / 1e9) / (peak * world), "rects_per_step": sum(len(r) for r in c4["rects"]) if c4["rects"] else None, "steps": 3, "warmup": 1}
+        del c4
+        torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_extras:
+        import oracle_lib as ol
+        import parity
+        # config 5: one 3840x2160 frame through oclrect_executeOnce (pageable host frame in, rect list out), per-stage roofline
+        w5, h5 = 3840, 2160
+        f5 = ol.synth_frame(w5, h5, 5)
+        d5 = rd.Device(local_rank)
+        g5 = rd.OclRect(d5, w5, h5)
+        lat = []
+        for _ in range(6):
+            t0 = time.perf_counter()
+            r5 = g5.execute_once(f5, TAN_AOV)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        prof5, stage5 = staged_profile(lambda: g5.run_device(f5, stop_step=0), 1)
+        k5 = sum(v[1] for v in prof5.values())
+        ms5 = float(np.median(lat[1:]))
+        extras["config5"] = {"workload": "rect 3840x2160 single synthetic frame (seed 5), oclrect_executeOnce: host frame in, rect list out", "ms_per_frame": ms5,
+                             "value": w5 * h5 / (ms5 * 1e-3) / 1e6, "unit": "Mpix/s", "kernel_ms_per_frame": k5, "rects": len(r5),
+                             "pipeline_frac": 43.0 * w5 * h5 / (ms5 * 1e-3) / 1e9 / peak, "stages": stage_table(stage5, 1, w5, h5),
+                             "top5_us": [[k, round(v[1] * 1e3, 1)] for k, v in sorted(prof5.items(), key=lambda kv: -kv[1][1])[:5]]}
+        g5.close()
+        d5.close()
+        # the reference's own streaming API, unchanged caller (vidrect.cpp:159-172: enqueue N+1, poll N): one object, and one object per core
+        from concurrent.futures import ThreadPoolExecutor
+        nstream = 64
+        sf = [np.ascontiguousarray(main_frames) for main_frames in synth_batch(iw, ih, 1000, nstream, pinned=False).numpy()]
+
+        def stream(frames, did):
+            d = rd.Device(did)
+            g = rd.OclRect(d, iw, ih)
+            g.execute_once(frames[0], TAN_AOV)                                           # warm-up (first-touch, tanAOV known to the object)
+            t0 = time.perf_counter()
+            n = 0
+            g.enqueue_task(frames[0])
+            for i in range(1, len(frames)):
+                g.enqueue_task(frames[i])
+                n += len(g.poll_task(TAN_AOV))
+            n += len(g.poll_task(TAN_AOV))
+            dt = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            g.execute_once(frames[1], TAN_AOV)
+            once = time.perf_counter() - t1
+            g.close()
+            d.close()
+            return dt, n, once
+
+        dt1, n1, once1 = stream(sf, local_rank)
+        nobj = min(16, os.cpu_count() or 4)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=nobj) as ex:
+            list(ex.map(lambda k: stream(sf[: nstream // 2], local_rank), range(nobj)))
+        dtn = time.perf_counter() - t0
+        extras["api_stream"] = {"workload": "vidrect 1280x720: oclrect_enqueueTask / oclrect_pollTask, unchanged caller, pageable host frames, carry-over between frames",
+                                "one_object": {"value": nstream * iw * ih / dt1 / 1e6, "unit": "Mpix/s", "ms_per_frame": dt1 / nstream * 1e3, "frames": nstream, "rects": n1},
+                                "execute_once_ms": once1 * 1e3,
+                                "objects_%d" % nobj: {"value": nobj * (nstream // 2 + 2) * iw * ih / dtn / 1e6, "unit": "Mpix/s", "frames_per_object": nstream // 2 + 2,
+                                                      "note": "one oclrect_t + queue per host thread, object creation and warm-up inside the timing"}}
+        # parity of the timed batch: the first frames of the batch against fresh oracle objects (outside every timed region)
+        bad = []
+        k = min(args.parity_frames, len(rects) if rects else 0)
+        for i in range(k):
+            o = ol.OracleRect(iw, ih)
+            want = o.execute_once(ol.synth_frame(iw, ih, 1000 + i), TAN_AOV)
+            o.close()
+            ok, why = parity.rects_close(want, rects[i])
+            if not ok:
+                bad.append((i, why))
+        extras["parity_checked_frames"] = k
+        extras["parity_ok"] = not bad
+        if bad:
+            extras["parity_failures"] = bad[:4]
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         top = max(prof.items(), key=lambda kv: kv[1][1])
         tname, (tcnt, tms) = top
         total_kernel_ms = sum(v[1] for v in prof.values())
@@ -340,17 +461,9 @@ def main():
                     "algorithmic_bytes_per_launch": alg_bytes, "frames_per_launch": fpl_eff, "avg_launch_us": per_launch_ms * 1e3,
                     "share_of_kernel_time": tms / total_kernel_ms, "kernel_time_us_per_frame": total_kernel_ms * 1e3 / nsolo,
                     "top5_us_per_frame": [[k, round(v[1] * 1e3 / nsolo, 2)] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:5]],
-                    "pipeline_algorithmic_bytes_per_px": 43, "pipeline_frac": (43.0 * value * 1e6 / 1e9) / peak}
-        # per-stage roofline: algorithmic bytes per pixel A 11, B 16, C 8 (+56 B per segment), D 8 (+20 B per
-        # vote pair); the list terms are <1 % of a frame and are left out, so the fractions are slightly conservative
-        stage_bpp = {"A": 11, "B": 16, "C": 8, "D": 8, "T": 0}
-        stages = {}
-        for st in sorted(stage_ms):
-            us = stage_ms[st] * 1e3 / nsolo
-            gbs = stage_bpp.get(st, 0) * iw * ih / (us * 1e-6) / 1e9 if us > 0 else None
-            stages[st] = {"us_per_frame": round(us, 2), "algorithmic_bytes_per_px": stage_bpp.get(st), "achieved_gbs": round(gbs, 1) if gbs else None,
-                          "frac_of_hbm_peak": round(gbs / peak, 4) if gbs else None}
-        roofline["stages"] = stages
+                    "pipeline_algorithmic_bytes_per_px": 43, "pipeline_frac": (43.0 * value * 1e6 / 1e9) / (peak * world),
+                    "pipeline_frac_note": "whole-job algorithmic bytes per second over the HBM peak of the %d GPU(s) used" % world}
+        roofline["stages"] = stage_table(stage_ms, nsolo, iw, ih)
         cpu = None
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is timed at N = 1 only
             if os.path.exists(REF_SO):
@@ -362,24 +475,26 @@ def main():
                        "sample": "%d frames of the same stream, %.1f s (CPU oracle = OpenMP restatement of the reference's OpenCL kernels + schedule + host tail)" % (args.cpu_frames, secs)}
             pv, pc, ps = cpu_oracle_mpix(iw, ih, [1000 + i for i in range(min(args.cpu_frames, 16))])
             cpu["port"] = {"value": pv, "unit": "Mpix/s", "cores": pc, "kind": "port", "sample": "CPU oracle (OpenMP restatement) on %d frames, %.1f s" % (min(args.cpu_frames, 16), ps)}
+            cpu["build"] = "g++ -O2 for baseline x86-64 (no -march), -ffp-contract=off: the bit-exactness build of the reference, not a tuned one"
         nrect = sum(len(r) for r in rects) if rects else 0
         same = rects is not None and rects_e2e is not None and all(a.tobytes() == b.tobytes() for a, b in zip(rects, rects_e2e))
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": main_run["ms_val"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i32 (f64 device tail)", "data": "synthetic",
-            "config": {"workload": "vidrect %dx%d synthetic stream (seeds 1000+i), AOV 72, full imgutil->polyline->rect pipeline, batched" % (iw, ih),
+            "config": {"workload": "vidrect %dx%d synthetic stream (seeds 1000+i), AOV 72, full imgutil->polyline->rect pipeline incl. executeCPUTask on the device, independent-frame batch "
+                                   "(every frame as by a fresh oclrect_t: no carry-over between frames)" % (iw, ih),
                        "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "frames_per_launch": args.fpl, "parallelism": "frames x%d" % world,
-                       "l2": "inputs larger than L2 (%d MB of frames + %d x 81 MB working sets per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx * args.fpl)},
-            "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": total_frames * 16 * 1024,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                       "l2": "inputs larger than L2 (%d MB of frames + %d working sets of 24 planes per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx * args.fpl)},
+            "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": main_run["d2h_bytes"],
+                    "ms_per_step": main_run["ms_e2e"]},
+            "gpu_launches": main_run["launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "rects_per_step": nrect, "value_and_e2e_rects_identical": bool(same),
-            "host": {"driver_threads": args.nctx, "wait_for_device_ms_last_step": wait_ms, "host_list_copy_ms_last_step": tail_ms, "host_cores": os.cpu_count(),
+            "host": {"driver_threads": args.nctx, "wait_for_device_ms_last_step": main_run["wait_ms"], "host_list_copy_ms_last_step": main_run["list_ms"], "host_cores": os.cpu_count(),
                      "host_tail": "none: executeCPUTask runs on the device (rd_gtail.cu)"},
         }
+        line.update(extras)
         emit(line)
-    batch.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
