@@ -216,6 +216,11 @@ typedef struct rd_batch rd_batch;
 rd_batch *rd_batch_create(int device, int iw, int ih, int nctx, int frames_per_launch);
 void rd_batch_destroy(rd_batch *b);
 void rd_batch_run(rd_batch *b, const uint8_t *frames, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out);
+/* NV12 input: decoded-video frames - Y plane with a row stride of ystride bytes, the interleaved half-resolution UV
+ * plane behind it - in host or device memory (detected).  The YUV -> BGR step of the reference's video front end
+ * (cv::VideoCapture, vidrect.cpp:160-166; integer BT.601 as OpenCV's COLOR_YUV2BGR_NV12) is fused into the first kernel. */
+void rd_batch_run_nv12(rd_batch *b, const void *frames, size_t frame_stride, int ystride, int nframes, double tanAOV, rect_t **out);
+rect_t *rd_oclrect_executeOnceNV12(struct oclrect_t *thiz, const uint8_t *nv12, int ystride, double tanAOV);
 /* device-resident variant: frames already in device memory (read in place).  out == NULL runs everything on the device but
  * builds no host lists. */
 void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out);

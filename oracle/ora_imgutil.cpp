@@ -546,6 +546,21 @@ void ora_iirblur_f_f(float *obuf, const float *ibuf, float *tmp0, float *tmp1, i
 }
 
 void ora_edgevec_f2_f(float *out_xy, const float *in, int iw, int ih) { k_edgevec_f(out_xy, in, iw, ih); }
+// NV12 (Y plane, row stride ys; interleaved UV plane behind it) -> BGR8 rows of ws bytes: the integer BT.601 limited-range conversion
+// of OpenCV's cvtColor(COLOR_YUV2BGR_NV12) (modules/imgproc/src/color_yuv.simd.hpp: ITUR_BT_601_CY 1220542, CUB 2116026, CUG -409993,
+// CVG -852492, CVR 1673527, shift 20) - the step cv::VideoCapture performs in front of the reference's programs (vidrect.cpp:160-166).
+// Pinned to OpenCV itself by tests/golden/nv12_golden.json (tools/make_nv12_golden.py).
+void ora_nv12_to_bgr(uint8_t *bgr, const uint8_t *nv12, int iw, int ih, int ws, int ys) {
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const uint8_t *uv = nv12 + (size_t)ih * ys + (size_t)(y >> 1) * ys + (x & ~1);
+      const int Y = nv12[(size_t)y * ys + x], u = (int)uv[0] - 128, v = (int)uv[1] - 128;
+      const int yy = (Y - 16 > 0 ? Y - 16 : 0) * 1220542 + (1 << 19);
+      const int r = (yy + 1673527 * v) >> 20, g = (yy - 852492 * v - 409993 * u) >> 20, b = (yy + 2116026 * u) >> 20;
+      uint8_t *o = bgr + (size_t)y * ws + 3 * x;
+      o[0] = (uint8_t)(b < 0 ? 0 : b > 255 ? 255 : b); o[1] = (uint8_t)(g < 0 ? 0 : g > 255 ? 255 : g); o[2] = (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+    }
+}
 void ora_edgevec_f2_plab(float *out_xy, const uint32_t *in, int iw, int ih) { k_edgevec_plab(out_xy, in, iw, ih); }
 void ora_edge_f_f(float *out, const float *in, int iw, int ih) { k_edge_f_f(out, in, iw, ih); }
 void ora_thincubic_f_f_f2(float *out, const float *in, const float *vxy, int iw, int ih) { k_thincubic(out, in, vxy, iw, ih); }

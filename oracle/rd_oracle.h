@@ -80,6 +80,8 @@ void ora_unpack_f_f_f_plab(float *o0, float *o1, float *o2, const uint32_t *in, 
 void ora_pack_plab_f_f_f(uint32_t *out, const float *i0, const float *i1, const float *i2, int iw, int ih);
 void ora_iirblur_f_f(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih);
 void ora_edgevec_f2_f(float *out_xy, const float *in, int iw, int ih);
+/* NV12 -> BGR8 as OpenCV's COLOR_YUV2BGR_NV12 (the video front end of vidrect.cpp:160-166); ys = row stride of the Y / UV planes */
+void ora_nv12_to_bgr(uint8_t *bgr, const uint8_t *nv12, int iw, int ih, int ws, int ys);
 /* operators no configured path enqueues (oclimgutil.h:86-94): visualisers, alternative edge / thinning kernels */
 void ora_edgevec_f2_plab(float *out_xy, const uint32_t *in, int iw, int ih);                      /* oclimgutil.cl:354 */
 void ora_edge_f_f(float *out, const float *in, int iw, int ih);                                   /* oclimgutil.cl:439 */

@@ -93,6 +93,7 @@ def lib():
         "rd_rect_calcSize": (None, [vp, vp, i, i, vp]), "rd_rect_despeckle2": (None, [vp, vp, vp, i, i, i, vp]),
         "rd_rect_markBoundary": (None, [vp, vp, i, i, vp]), "rd_rect_reduceLS": (None, [vp, vp, vp, i, i, i, vp]),
         "rd_oclrect_buffer": (vp, [vp, C.c_char_p]), "rd_oclrect_run_device": (None, [vp, vp, i, i]),
+        "rd_batch_run_nv12": (None, [vp, vp, C.c_size_t, i, i, d, vp]), "rd_oclrect_executeOnceNV12": (vp, [vp, vp, i, d]),
         "rd_rect_tail": (vp, [vp, vp, vp, i, i, d]), "rd_rect_tail_device": (vp, [vp, vp, vp, i, i, d, vp]),
         "rd_batch_create": (vp, [i, i, i, i, i]), "rd_batch_destroy": (None, [vp]),
         "rd_batch_run": (None, [vp, vp, sz, i, i, d, vp]), "rd_batch_run_device": (None, [vp, vp, sz, i, i, d, vp]),
@@ -220,6 +221,11 @@ class OclRect:
         img = np.ascontiguousarray(img)
         return rects_from_ptr(lib().oclrect_executeOnce(self.h, _p(img), ws or img.shape[-1], tan_aov))
 
+    def execute_once_nv12(self, nv12, tan_aov, ystride=None):
+        """nv12: (ih * 3 // 2, ystride) uint8 array - Y plane, then the interleaved UV plane"""
+        nv12 = np.ascontiguousarray(nv12)
+        return rects_from_ptr(lib().rd_oclrect_executeOnceNV12(self.h, _p(nv12), ystride or nv12.shape[-1], tan_aov))
+
     def enqueue_task(self, img, ws=None):
         img = np.ascontiguousarray(img)
         lib().oclrect_enqueueTask(self.h, _p(img), ws or img.shape[-1])
@@ -270,6 +276,12 @@ class Batch:
             L.rd_batch_run(self.h, frames_ptr, frame_stride, ws, nframes, tan_aov, out)
         if out is None:
             return None
+        return [rects_from_ptr(p) for p in out]
+
+    def run_nv12(self, frames_ptr, frame_stride, ystride, nframes, tan_aov):
+        """NV12 frames in host or device memory (rd_batch_run_nv12)"""
+        out = (C.c_void_p * nframes)()
+        lib().rd_batch_run_nv12(self.h, frames_ptr, frame_stride, ystride, nframes, tan_aov, out)
         return [rects_from_ptr(p) for p in out]
 
     def stage_ms(self):

@@ -59,18 +59,11 @@ __device__ __forceinline__ void d2_cp_async4(void *smem, const void *gmem) {
 __device__ __forceinline__ void d2_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void d2_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(D2_RING - 1) : "memory"); }
 
-// rowbuf_g != NULL: the two-row buffer lives in global memory (frames too wide for shared memory)
-__global__ void __launch_bounds__(32) kd2_seq(int *dst, const int *list, const int *recL, const int *recS, const int *rowcnt, int2 *rowbuf_g, int iw, int ih,
-                                              size_t fs) {
-  rd_batch_x(fs, dst, list, recL, recS, rowcnt);
-  if (rowbuf_g) rd_batch_x(fs, rowbuf_g);
-  extern __shared__ __align__(16) int d2_smem[];
-  int *ring = d2_smem;                                        // [D2_RING][3][32]
-  int *cnt = ring + D2_RING * 3 * 32;                         // [ih]
-  int2 *rowbuf = rowbuf_g ? rowbuf_g : (int2 *)(cnt + ((ih + 1) & ~1));   // [2][iw]
+// the plain form of the walk: cursors over the per-row lists, one chunk per iteration.  ring [D2_RING][3][32], cnt [ih] (filled), rowbuf [2][iw]
+__device__ __noinline__ void d2_seq_generic(int *dst, const int *list, const int *recL, const int *recS, int *ring, const int *cnt, int2 *rowbuf, bool rowbuf_global,
+                                            int iw, int ih) {
   const int lane = threadIdx.x;
-  for (int i = lane; i < ih; i += 32) cnt[i] = rowcnt[i];
-  __syncwarp();
+  int2 *rowbuf_g = rowbuf_global ? rowbuf : (int2 *)NULL;
   // fetch cursor (warp-uniform): the next chunk to stream in is entries [fc, fc + 32) of row fy
   int fy = 0, fc = 0;
   while (fy < ih && cnt[fy] == 0) fy++;
@@ -131,6 +124,124 @@ __global__ void __launch_bounds__(32) kd2_seq(int *dst, const int *list, const i
     __syncwarp();
   }
 }
+// rowbuf_g != NULL: the two-row buffer lives in global memory (frames too wide for shared memory)
+__global__ void __launch_bounds__(32) kd2_seq(int *dst, const int *list, const int *recL, const int *recS, const int *rowcnt, int2 *rowbuf_g, int iw, int ih,
+                                              size_t fs) {
+  rd_batch_x(fs, dst, list, recL, recS, rowcnt);
+  if (rowbuf_g) rd_batch_x(fs, rowbuf_g);
+  extern __shared__ __align__(16) int d2_smem[];
+  int *ring = d2_smem;                                        // [D2_RING][3][32]
+  int *cnt = ring + D2_RING * 3 * 32;                         // [ih]
+  int2 *rowbuf = rowbuf_g ? rowbuf_g : (int2 *)(cnt + ((ih + 1) & ~1));   // [2][iw]
+  for (int i = threadIdx.x; i < ih; i += 32) cnt[i] = rowcnt[i];
+  __syncwarp();
+  d2_seq_generic(dst, list, recL, recS, ring, cnt, rowbuf, rowbuf_g != NULL, iw, ih);
+}
+
+// The same walk, software-pipelined (the version the schedule runs; kd2_seq above stays as the fall-back for frames with more
+// chunks than the descriptor table holds).  A chunk's critical path is: the previous chunk's row-buffer stores -> __syncwarp ->
+// row-buffer loads -> merge -> vote (-> scan) -> stores; everything else is taken off it:
+//   * a table of chunk descriptors (row | chunk-in-row << 16) is built once, in parallel, in shared memory, so the cursors need
+//     no loops or row-count look-ups;
+//   * the records of chunk k+1 are moved from the cp.async ring to registers while chunk k computes; the ring is filled
+//     D2_RING chunks ahead.
+#define D2_NCH_MAX 12288
+__global__ void __launch_bounds__(32) kd2_seq_pipe(int *dst, const int *list, const int *recL, const int *recS, const int *rowcnt, int iw, int ih, int nch_cap,
+                                                   size_t fs) {
+  rd_batch_x(fs, dst, list, recL, recS, rowcnt);
+  extern __shared__ __align__(16) int d2_smem[];
+  int *ring = d2_smem;                                        // [D2_RING][3][32]
+  int *cnt = ring + D2_RING * 3 * 32;                         // [ih]
+  int2 *rowbuf = (int2 *)(cnt + ((ih + 1) & ~1));             // [2][iw]
+  int *desc = (int *)(rowbuf + 2 * (size_t)iw);               // [nch_cap]
+  const int lane = threadIdx.x;
+  // descriptors: row y contributes ceil(cnt[y] / 32) chunks
+  int nch = 0;
+  for (int y0 = 0; y0 < ih; y0 += 32) {
+    const int y = y0 + lane;
+    const int c = y < ih ? rowcnt[y] : 0;
+    if (y < ih) cnt[y] = c;
+    const int k = (c + 31) >> 5;
+    int incl = k;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    const int base = nch + incl - k;
+    for (int j = 0; j < k; j++) if (base + j < nch_cap) desc[base + j] = y | (j << 16);
+    nch += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  if (nch > nch_cap) { d2_seq_generic(dst, list, recL, recS, ring, cnt, rowbuf, false, iw, ih); return; }   // more chunks than the table holds
+  auto fetch = [&](int k) {                                   // chunk k -> ring stage k % D2_RING
+    if (k < nch) {
+      const int d = desc[k], y = d & 0xffff, j = ((d >> 16) << 5) + lane;
+      if (j < cnt[y]) {
+        const size_t o = (size_t)y * iw + j;
+        int *r = ring + (k % D2_RING) * 96 + lane;
+        d2_cp_async4(r, list + o); d2_cp_async4(r + 32, recL + o); d2_cp_async4(r + 64, recS + o);
+      }
+    }
+    d2_cp_commit();
+  };
+  for (int k = 0; k < D2_RING; k++) fetch(k);
+  // chunk 0 -> registers
+  d2_cp_wait();
+  __syncwarp();
+  int n_y = 0, n_rec = 0, n_bl = 0, n_bs = 0;
+  bool n_valid = false;
+  auto stage_in = [&](int k) {
+    n_valid = false; n_rec = 0; n_bl = 0; n_bs = 0;
+    if (k < nch) {
+      const int d = desc[k];
+      n_y = d & 0xffff;
+      n_valid = ((d >> 16) << 5) + lane < cnt[n_y];
+      const int *r = ring + (k % D2_RING) * 96 + lane;
+      if (n_valid) { n_rec = r[0]; n_bl = r[32]; n_bs = r[64]; }
+    }
+  };
+  stage_in(0);
+  int carryL = 0, carryS = 0;
+  for (int k = 0; k < nch; k++) {
+    const int py = n_y, rec = n_rec;
+    int bl = n_bl, bs = n_bs;
+    const bool valid = n_valid;
+    const int x = rec & 0xffff, dyn = (rec >> 20) & 15;
+    int code = (rec >> 16) & 15;
+    // critical path, part 1: what the row above ended up with
+    const int2 *above = rowbuf + (size_t)((py + 1) & 1) * iw;
+    int2 v0 = make_int2(0, 0), v1 = v0, v2 = v0;
+    if (dyn & 1) v0 = above[x - 1];
+    if (dyn & 2) v1 = above[x];
+    if (dyn & 4) v2 = above[x + 1];
+    // off the critical path: chunk k+1 -> registers, chunk k+D2_RING -> ring
+    asm volatile("cp.async.wait_group %0;" ::"n"(D2_RING - 2) : "memory");
+    __syncwarp();
+    stage_in(k + 1);
+    __syncwarp();
+    fetch(k + D2_RING);
+    // critical path, part 2
+    if (dyn & 1) d2_take(bl, bs, code, v0.x, v0.y, 1);
+    if (dyn & 2) d2_take(bl, bs, code, v1.x, v1.y, 2);
+    if (dyn & 4) d2_take(bl, bs, code, v2.x, v2.y, 3);
+    int T = D2_HEAD;
+    if (dyn & 8) T = d2_threshold(bs, code);
+    if (lane == 0 && T != D2_HEAD) {                          // the run continues from the previous chunk
+      if (carryS >= T) { bl = carryL; bs = carryS; }
+      T = D2_HEAD;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      if (__all_sync(0xffffffffu, T == D2_HEAD)) break;
+      const int lL = __shfl_up_sync(0xffffffffu, bl, d), lS = __shfl_up_sync(0xffffffffu, bs, d), lT = __shfl_up_sync(0xffffffffu, T, d);
+      if (lane >= d && T != D2_HEAD) d2_compose(bl, bs, T, lL, lS, lT);
+    }
+    if (valid) {
+      rowbuf[(size_t)(py & 1) * iw + x] = make_int2(bl, bs);
+      dst[(size_t)py * iw + x] = bl;
+    }
+    carryL = __shfl_sync(0xffffffffu, bl, 31); carryS = __shfl_sync(0xffffffffu, bs, 31);
+    __syncwarp();
+  }
+}
 
 // markBoundary (oclrect.cl:373-390): a pixel keeps its region label if its 5x5 window holds another label; 2-px frame -> -1
 #define MB_T 32
@@ -172,20 +283,31 @@ void rd_despeckle2_run(int *dst, const int *label, const int *size, int *list, i
   if (iw > 0xffff) exitf(-1, "rectdetect_b200: despeckle2: frames wider than 65535 pixels are not supported\n");
   RD_LAUNCH(kd2_pre, dim3(ih, nb), D2P_THREADS, 0, s, dst, list, recL, recS, rowcnt, label, size, thre, iw, ih, fs);
   const size_t fixed = (size_t)D2_RING * 96 * 4 + (size_t)((ih + 1) & ~1) * 4, full = fixed + (size_t)2 * iw * sizeof(int2);
-  const bool in_smem = full <= D2_SMEM_MAX;
-  const size_t smem = in_smem ? full : fixed;
-  if (smem > D2_SMEM_MAX) exitf(-1, "rectdetect_b200: despeckle2: frame too tall (%d rows)\n", ih);
-  if (smem > 48 * 1024) {                             // opt in once per device
-    static std::mutex mu;
-    static bool ready[64] = {false};
+  static std::mutex mu;
+  static bool ready[64] = {false};
+  {                                                   // opt in to large dynamic shared memory once per device
     int dev = 0;
     RD_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> g(mu);
     if (dev >= 64 || !ready[dev]) {
       RD_CUDA(cudaFuncSetAttribute(kd2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_MAX));
+      RD_CUDA(cudaFuncSetAttribute(kd2_seq_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_MAX));
       if (dev < 64) ready[dev] = true;
     }
   }
+  // descriptor table: room for every row plus a generous share of extra chunks; a frame that turns out to need more (decided on the
+  // device) takes the plain walk inside the same kernel; frames too wide / tall for shared memory take kd2_seq
+  int nch_cap = 2 * ih + 1024;
+  if (nch_cap > D2_NCH_MAX) nch_cap = D2_NCH_MAX;
+  const size_t pipe = full + (size_t)nch_cap * 4;
+  static const bool generic_only = getenv("RD_D2_GENERIC") != NULL;
+  if (!generic_only && pipe <= D2_SMEM_MAX) {
+    RD_LAUNCH(kd2_seq_pipe, nb, 32, pipe, s, dst, list, recL, recS, rowcnt, iw, ih, nch_cap, fs);
+    return;
+  }
+  const bool in_smem = full <= D2_SMEM_MAX;
+  const size_t smem = in_smem ? full : fixed;
+  if (smem > D2_SMEM_MAX) exitf(-1, "rectdetect_b200: despeckle2: frame too tall (%d rows)\n", ih);
   RD_LAUNCH(kd2_seq, nb, 32, smem, s, dst, list, recL, recS, rowcnt, in_smem ? (int2 *)NULL : rowbuf, iw, ih, fs);
 }
 void rd_markBoundary_run(int *out, const int *in, int iw, int ih, int nb, size_t fs, cudaStream_t s) {

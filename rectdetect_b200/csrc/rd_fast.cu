@@ -11,6 +11,7 @@
 //   rd_iirblur3_run   : the three recursive-Gaussian blurs of oclrect.c:248-250 (oclimgutil.cl:542-637) straight
 //                       from the packed Lab plane: one thread runs the three channel chains of a row (column)
 //                       and direction, the pass1 / pass3 combinations are folded into the consumers.
+#include <cuda.h>
 #include "rd_common.cuh"
 #include "rd_stageA.cuh"
 #include "rd_bits.cuh"
@@ -774,8 +775,47 @@ __global__ void kf_bgr2plab1(uint32_t *out, const uint8_t *in, size_t in_fs, int
   const uint8_t *p = in + (size_t)y * ws + x * 3;
   out[(size_t)y * iw + x] = rd_srgb2plab(p[0], p[1], p[2], RD_S2L, RD_CFUNC, RD_CFUNC2);
 }
+// NV12 input (decoded-video frames straight into Stage A): Y plane (row stride ys) followed by the interleaved
+// half-resolution UV plane (same stride).  YUV -> BGR is the integer BT.601 limited-range conversion of OpenCV's
+// cvtColor(COLOR_YUV2BGR_NV12) - what cv::VideoCapture hands the reference's programs (vidrect.cpp:160-166) - fused with bgr2plab:
+// the BGR frame never exists.  Pinned bit-exactly to OpenCV by tests/golden/nv12_golden.json.
+__device__ __forceinline__ uint32_t nv12_px(int Y, int u, int v) {                 // u, v already minus 128
+  const int y = max(0, Y - 16) * 1220542 + (1 << 19);
+  const int r = (y + 1673527 * v) >> 20, g = (y - 852492 * v - 409993 * u) >> 20, b = (y + 2116026 * u) >> 20;
+  return rd_srgb2plab(min(max(b, 0), 255), min(max(g, 0), 255), min(max(r, 0), 255), RD_S2L, RD_CFUNC, RD_CFUNC2);
+}
+__global__ void __launch_bounds__(256) kf_nv12_plab4(uint32_t *out, const uint8_t *in, size_t in_fs, int iw, int ih, int ys, size_t fs) {
+  rd_batch_z(fs, out);
+  rd_batch_z(in_fs, in);
+  const int x4 = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x4 * 4 >= iw || y >= ih) return;
+  const uint32_t yy = *(const uint32_t *)(in + (size_t)y * ys + x4 * 4);
+  const uint32_t uv = *(const uint32_t *)(in + (size_t)ih * ys + (size_t)(y >> 1) * ys + x4 * 4);     // U0 V0 U1 V1
+  const int u0 = (int)(uv & 255) - 128, v0 = (int)((uv >> 8) & 255) - 128, u1 = (int)((uv >> 16) & 255) - 128, v1 = (int)(uv >> 24) - 128;
+  uint4 r;
+  r.x = nv12_px(yy & 255, u0, v0); r.y = nv12_px((yy >> 8) & 255, u0, v0);
+  r.z = nv12_px((yy >> 16) & 255, u1, v1); r.w = nv12_px(yy >> 24, u1, v1);
+  *(uint4 *)(out + (size_t)y * iw + x4 * 4) = r;
+}
+__global__ void kf_nv12_plab1(uint32_t *out, const uint8_t *in, size_t in_fs, int iw, int ih, int ys, size_t fs) {
+  rd_batch_z(fs, out);
+  rd_batch_z(in_fs, in);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const uint8_t *uv = in + (size_t)ih * ys + (size_t)(y >> 1) * ys + (x & ~1);
+  out[(size_t)y * iw + x] = nv12_px(in[(size_t)y * ys + x], (int)uv[0] - 128, (int)uv[1] - 128);
+}
+// ws > 0: BGR8 rows of ws bytes; ws < 0: NV12 with a row stride of -ws bytes
 void rd_bgr2plab_run(uint32_t *out, const uint8_t *in, size_t in_fs, int iw, int ih, int ws, int nb, size_t fs, cudaStream_t s) {
   const dim3 b(32, 8);
+  if (ws < 0) {
+    const int ys = -ws;
+    if ((iw & 3) == 0 && (ys & 3) == 0 && (in_fs & 3) == 0 && ((uintptr_t)in & 3) == 0)
+      RD_LAUNCH(kf_nv12_plab4, dim3(rd_cdiv(iw / 4, 32), rd_cdiv(ih, 8), nb), b, 0, s, out, in, in_fs, iw, ih, ys, fs);
+    else
+      RD_LAUNCH(kf_nv12_plab1, dim3(rd_cdiv(iw, 32), rd_cdiv(ih, 8), nb), b, 0, s, out, in, in_fs, iw, ih, ys, fs);
+    return;
+  }
   if ((iw & 3) == 0 && (ws & 3) == 0 && (in_fs & 3) == 0 && ((uintptr_t)in & 3) == 0)
     RD_LAUNCH(kf_bgr2plab4, dim3(rd_cdiv(iw / 4, 32), rd_cdiv(ih, 8), nb), b, 0, s, out, in, in_fs, iw, ih, ws, fs);
   else
@@ -822,18 +862,62 @@ struct TileMag {                     // Plane interface of rd_bicubic: the tile 
 //    the warps, so they are queued (over the then dead Lab tiles) and finished densely, one per thread.
 struct EtQueued { unsigned short idx, pad; float vx, vy, am1, ap1; };
 #define ET_NPOS (ET_T * ET_T)
-__global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, size_t fs) {
+// TMA variant (USE_TMA): CTAs whose aproned tiles lie inside the frame fetch them with two tensor-map tile loads
+// (cp.async.bulk.tensor.3d -> UTMALDG, completion on an mbarrier) issued by one thread: the packed-Lab tile as a raw 42 x 44 box that
+// a second pass unpacks into the three float tiles, the L tile straight into place.  CTAs on the frame border keep the plain
+// staging below: the reference mirrors coordinates there, the copy engine can only fill zeros.  Measured A/B: profiles/r04*_tma_ab.txt.
+#define ET_RAWW 44                   // box width of the packed tile: 42 columns rounded up to a multiple of 16 bytes
+__device__ __forceinline__ void et_mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void et_mbar_expect(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void et_mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+      ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void et_tma_load3(void *smem, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+struct EtMaps { CUtensorMap p, l; };
+template <bool USE_TMA>
+__global__ void __launch_bounds__(256) kf_edge_thin_t(float *thin, const float *blurL, const uint32_t *blurP, const __grid_constant__ EtMaps maps, int iw, int ih, size_t fs) {
   rd_batch_z(fs, thin, blurL, blurP);
   // phase 1-2: three unpacked Lab tiles (apron 5); phase 3-4: the queue of local maxima
   __shared__ __align__(16) unsigned char lab_or_queue[(3 * ET_PW * ET_PW * 4 > ET_NPOS * (int)sizeof(EtQueued)) ? 3 * ET_PW * ET_PW * 4 : ET_NPOS * (int)sizeof(EtQueued)];
   __shared__ float sm[ET_MW * ET_MW];
-  __shared__ float sl[ET_LW * ET_LW];
+  __shared__ __align__(128) float sl[ET_LW * ET_LW];
+  __shared__ __align__(128) uint32_t rawP[USE_TMA ? ET_PW * ET_RAWW : 4];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ int nq;
   float (*lab)[ET_PW * ET_PW] = (float (*)[ET_PW * ET_PW])lab_or_queue;
   EtQueued *queue = (EtQueued *)lab_or_queue;
   const int bx = blockIdx.x * ET_T, by = blockIdx.y * ET_T;
   const int tx = threadIdx.x, ty = threadIdx.y;
   if (tx == 0 && ty == 0) nq = 0;
+  const bool interior = USE_TMA && bx - ET_PA >= 0 && by - ET_PA >= 0 && bx + ET_T + ET_PA <= iw && by + ET_T + ET_PA <= ih;
+  if (interior) {
+    if (tx == 0 && ty == 0) et_mbar_init(&bar, 1);
+    __syncthreads();
+    if (tx == 0 && ty == 0) {
+      et_mbar_expect(&bar, (unsigned)(ET_PW * ET_RAWW * 4 + ET_LW * ET_LW * 4));
+      et_tma_load3(rawP, &maps.p, bx - ET_PA, by - ET_PA, (int)blockIdx.z, &bar);
+      et_tma_load3(sl, &maps.l, bx - ET_LA, by - ET_LA, (int)blockIdx.z, &bar);
+    }
+    et_mbar_wait(&bar, 0);
+    for (int i = ty * 32 + tx; i < ET_PW * ET_PW; i += 256) {
+      const int r = i / ET_PW, c = i - r * ET_PW;
+      float l, a, b;
+      rd_unpacklab(rawP[r * ET_RAWW + c], l, a, b);
+      lab[0][i] = l; lab[1][i] = a; lab[2][i] = b;
+    }
+  } else {
   // stage the packed-Lab tile (apron 5), unpacked, and the L tile (apron 2) at mirrored coordinates
   for (int r = ty; r < ET_PW; r += 8) {
     const size_t rb = (size_t)mirror_safe(by - ET_PA + r, ih) * iw;
@@ -850,6 +934,7 @@ __global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *bl
     const size_t rb = (size_t)mirror_safe(by - ET_LA + r, ih) * iw;
     sl[r * ET_LW + tx] = blurL[rb + mirror_safe(bx - ET_LA + tx, iw)];
     if (tx < ET_LW - 32) sl[r * ET_LW + 32 + tx] = blurL[rb + mirror_safe(bx - ET_LA + 32 + tx, iw)];
+  }
   }
   __syncthreads();
   // edge magnitude (oclimgutil.cl:422-437) on the apron-4 tile.  Position (gx, gy) of the tile stands for the image position
@@ -933,8 +1018,34 @@ __global__ void __launch_bounds__(256) kf_edge_thin(float *thin, const float *bl
     thin[(size_t)y * iw + x] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(am2, e.am1), mag.at(x, y)), e.ap1), ap2);
   }
 }
+// tensor maps of one plane of the arenas: rank 3 = (x, y, frame), frame stride fs
+static bool et_make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int iw, int ih, int nb, size_t fs, int boxw, int boxh) {
+  typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_t enc = NULL;
+  if (!enc) {
+    void *fn = NULL;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+    enc = (encode_t)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)nb};
+  const cuuint64_t strides[2] = {(cuuint64_t)iw * 4, fs ? (cuuint64_t)fs : (cuuint64_t)iw * ih * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1}, es[3] = {1, 1, 1};
+  return enc(m, dt, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 void rd_edge_thin_run(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_LAUNCH(kf_edge_thin, dim3(rd_cdiv(iw, ET_T), rd_cdiv(ih, ET_T), nb), dim3(32, 8), 0, s, thin, blurL, blurP, iw, ih, fs);
+  static const bool want_tma = getenv("RD_TMA") && atoi(getenv("RD_TMA")) != 0;      // off by default: see the A/B in profiles/ (staging is not what this kernel waits for)
+  EtMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (want_tma && (iw & 3) == 0 && (fs & 15) == 0 && ((uintptr_t)blurP & 15) == 0 && ((uintptr_t)blurL & 15) == 0 &&
+      et_make_map(&maps.p, blurP, CU_TENSOR_MAP_DATA_TYPE_UINT32, iw, ih, nb, fs, ET_RAWW, ET_PW) &&
+      et_make_map(&maps.l, blurL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, iw, ih, nb, fs, ET_LW, ET_LW)) {
+    RD_LAUNCH(kf_edge_thin_t<true>, dim3(rd_cdiv(iw, ET_T), rd_cdiv(ih, ET_T), nb), dim3(32, 8), 0, s, thin, blurL, blurP, maps, iw, ih, fs);
+    return;
+  }
+  RD_LAUNCH(kf_edge_thin_t<false>, dim3(rd_cdiv(iw, ET_T), rd_cdiv(ih, ET_T), nb), dim3(32, 8), 0, s, thin, blurL, blurP, maps, iw, ih, fs);
 }
 
 // =============================================================================================== Stage B, string clean-up

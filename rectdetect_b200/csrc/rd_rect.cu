@@ -309,10 +309,16 @@ __device__ __forceinline__ void rls_pixel(int *out, const int *boundaryin, const
           }
           if (!twice) continue;
         }
-        atomicMax(e + 1, iw - x);
-        atomicMax(e + 2, x);
-        atomicMax(e + 3, ih - y);
-        atomicMax(e + 4, y);
+        // warp-aggregated: the lanes of a warp walk neighbouring string pixels, so several of them usually vote for the same
+        // (segment, region) slot in the same step - they combine their boxes (redux.sync) and one lane issues the atomics
+        const unsigned peers = __match_any_sync(__activemask(), hash);
+        const int m1 = __reduce_max_sync(peers, iw - x), m2 = __reduce_max_sync(peers, x), m3 = __reduce_max_sync(peers, ih - y), m4 = __reduce_max_sync(peers, y);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+          atomicMax(e + 1, m1);
+          atomicMax(e + 2, m2);
+          atomicMax(e + 3, m3);
+          atomicMax(e + 4, m4);
+        }
       } else {
         const int k = *(volatile int *)e;                 // several pixels may finalise one slot: all write the same value
         if (k > 0x3fffffff) *(volatile int *)e = lsidin[RLS_KEY(k)];
@@ -372,6 +378,13 @@ struct oclrect_t {
   double lastTan;                       // tanAOV of the last poll: oclrect_enqueueTask has no tanAOV argument (oclrect.h:21-22), so the pose
                                         // phase runs ahead with this one and is repeated at poll time if the caller asks for another
   double wait_ms, tail_ms;              // host time spent waiting for the device / assembling the lists since the last reset
+  // CUDA graphs of the single-frame task: the reference's streaming API hands over ONE frame per call, so the ~85
+  // launches of a task are latency-, not throughput-bound.  One graph per page: H2D of the staged frame, the whole schedule, the
+  // device tail, D2H of the record.  Captured on the second task of a page (the first one runs eagerly and sets the kernels'
+  // attributes), re-captured when ws / tanAOV change.
+  cudaGraphExec_t graph[2];
+  double graphTan[2];
+  int graphWs[2], graphLaunches[2], graphSeen[2];
 };
 #define FIRST_CHUNK ((size_t)16 * 1024)  // header + 90 rectangles; longer lists take a second copy
 
@@ -640,27 +653,54 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
 // processed as by a newly created object.  tanAOV = NaN: not known yet (oclrect_enqueueTask before the first poll).
 static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, int ws, int page, int src_kind, int fresh, int count, double tanAOV) {
   const int iw = o->iw, ih = o->ih;
-  if (ws < 3 * iw || (size_t)ws * ih > (size_t)iw * ih * 4) exitf(-1, "rectdetect_b200: row stride %d not in [3*iw, 4*iw]\n", ws);
+  // ws > 0: BGR8 rows of ws bytes (the reference's format); ws < 0: an NV12 frame with a row stride of -ws bytes (Y plane, then the UV plane)
+  const bool nv12 = ws < 0;
+  if (!nv12 && (ws < 3 * iw || (size_t)ws * ih > (size_t)iw * ih * 4)) exitf(-1, "rectdetect_b200: row stride %d not in [3*iw, 4*iw]\n", ws);
+  if (nv12 && ((iw | ih) & 1 || -ws < iw || (size_t)(-ws) * ih * 3 / 2 > (size_t)iw * ih * 4)) exitf(-1, "rectdetect_b200: NV12 needs even dimensions and a row stride in [iw, 8*iw/3] (got %d)\n", -ws);
   if (count < 1 || count > o->nb) exitf(-1, "rectdetect_b200: %d frames do not fit an object built for %d\n", count, o->nb);
   cudaStream_t s = rd_stream(o->queue);
   RD_CUDA(cudaSetDevice(o->ordinal));
-  const size_t fbytes = (size_t)ws * ih;
+  const size_t fbytes = nv12 ? (size_t)(-ws) * ih * 3 / 2 : (size_t)ws * ih, hstride = (size_t)iw * ih * 4;
   const uint8_t *din = (const uint8_t *)o->iobuf[0]->dptr;
   size_t din_fs = o->fs;
-  if (src_kind == 0) {
-    const size_t hstride = (size_t)iw * ih * 4;
+  static const bool use_graphs = !(getenv("RD_GRAPH") && atoi(getenv("RD_GRAPH")) == 0);
+  const bool graphable = use_graphs && o->nb == 1 && src_kind == 0 && !fresh && g_rd_prof_mode.load(std::memory_order_relaxed) == 0;
+  if (src_kind == 0)
     for (int i = 0; i < count; i++) memcpy(o->hostImg[page] + i * hstride, img + i * frame_stride, fbytes);
-    RD_CUDA(cudaMemcpy2DAsync(o->iobuf[0]->dptr, o->fs, o->hostImg[page], hstride, fbytes, count, cudaMemcpyHostToDevice, s));   // oclrect.c:241
-  } else if (src_kind == 1) {
-    RD_CUDA(cudaMemcpy2DAsync(o->iobuf[0]->dptr, o->fs, img, count > 1 ? frame_stride : fbytes, fbytes, count, cudaMemcpyHostToDevice, s));
+  if (graphable && o->graph[page] && o->graphWs[page] == ws && memcmp(&o->graphTan[page], &tanAOV, sizeof(double)) == 0) {
+    RD_CUDA(cudaGraphLaunch(o->graph[page], s));              // its H2D node reads the staging page filled above
+    g_rd_launches.fetch_add(o->graphLaunches[page], std::memory_order_relaxed);
   } else {
-    din = img;
-    din_fs = frame_stride;
+    const bool capture = graphable && o->graphSeen[page]++ >= 1;     // the first task of a page runs eagerly (it sets the kernels' attributes)
+    int launches0 = 0;
+    if (capture) {
+      if (o->graph[page]) { RD_CUDA(cudaGraphExecDestroy(o->graph[page])); o->graph[page] = NULL; }
+      launches0 = g_rd_launches.load(std::memory_order_relaxed);
+      RD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    }
+    if (src_kind == 0) {
+      RD_CUDA(cudaMemcpy2DAsync(o->iobuf[0]->dptr, o->fs, o->hostImg[page], hstride, fbytes, count, cudaMemcpyHostToDevice, s));   // oclrect.c:241
+    } else if (src_kind == 1) {
+      RD_CUDA(cudaMemcpy2DAsync(o->iobuf[0]->dptr, o->fs, img, count > 1 ? frame_stride : fbytes, fbytes, count, cudaMemcpyHostToDevice, s));
+    } else {
+      din = img;
+      din_fs = frame_stride;
+    }
+    if (fresh) RD_CUDA(cudaMemset2DAsync(o->buf[3]->dptr, o->fs, 0, (size_t)iw * ih * 4, count, s));
+    gpu_task_fast(o, din, din_fs, ws, count, s, 0, page, tanAOV);
+    if (tanAOV == tanAOV) RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], FIRST_CHUNK, o->dblob[page], o->fs, FIRST_CHUNK, count, cudaMemcpyDeviceToHost, s));
+    if (capture) {
+      cudaGraph_t g = NULL;
+      RD_CUDA(cudaStreamEndCapture(s, &g));
+      RD_CUDA(cudaGraphInstantiate(&o->graph[page], g, 0));
+      RD_CUDA(cudaGraphDestroy(g));
+      o->graphLaunches[page] = g_rd_launches.load(std::memory_order_relaxed) - launches0;    // (a statistic: other threads' launches may slip in)
+      o->graphWs[page] = ws;
+      o->graphTan[page] = tanAOV;
+      RD_CUDA(cudaGraphLaunch(o->graph[page], s));            // the capture recorded the task; this runs it
+    }
   }
-  if (fresh) RD_CUDA(cudaMemset2DAsync(o->buf[3]->dptr, o->fs, 0, (size_t)iw * ih * 4, count, s));
-  gpu_task_fast(o, din, din_fs, ws, count, s, 0, page, tanAOV);
   o->pageTan[page] = tanAOV;
-  if (tanAOV == tanAOV) RD_CUDA(cudaMemcpy2DAsync(o->hostBlob[page], FIRST_CHUNK, o->dblob[page], o->fs, FIRST_CHUNK, count, cudaMemcpyDeviceToHost, s));
   RD_CUDA(cudaEventRecord(o->events[page], s));
   o->pending[page] = count;
 }
@@ -721,6 +761,7 @@ void dispose_oclrect(struct oclrect_t *o) {
   RD_CUDA(cudaFree(o->dbase));
   for (int p = 0; p < 2; p++) { freePinnedMemory(o->hostImg[p], NULL, NULL); freePinnedMemory(o->hostBlob[p], NULL, NULL); RD_CUDA(cudaEventDestroy(o->events[p])); }
   RD_CUDA(cudaStreamDestroy(o->copyq));
+  for (int p = 0; p < 2; p++) if (o->graph[p]) RD_CUDA(cudaGraphExecDestroy(o->graph[p]));
   o->magic = 0;
   free(o);
 }
@@ -919,6 +960,22 @@ void rd_batch_run(rd_batch *b, const uint8_t *frames, size_t frame_stride, int w
   int kind = host_ptr_kind(frames);
   if (kind == 2) exitf(-1, "rectdetect_b200: rd_batch_run expects host frames (use rd_batch_run_device)\n");
   batch_run(b, frames, frame_stride, ws, nframes, tanAOV, out, kind, 1);
+}
+
+// NV12 frames (Y plane with row stride ystride, UV plane behind it), in host (pageable or pinned) or device memory
+void rd_batch_run_nv12(rd_batch *b, const void *frames, size_t frame_stride, int ystride, int nframes, double tanAOV, rect_t **out) {
+  if (ystride <= 0) exitf(-1, "rectdetect_b200: rd_batch_run_nv12: bad row stride %d\n", ystride);
+  batch_run(b, (const uint8_t *)frames, frame_stride, -ystride, nframes, tanAOV, out, host_ptr_kind(frames), 1);
+}
+rect_t *rd_oclrect_executeOnceNV12(struct oclrect_t *o, const uint8_t *nv12, int ystride, double tanAOV) {
+  chk(o);
+  if (o->pending[0]) exitf(-1, "rectdetect_b200: rd_oclrect_executeOnceNV12 while a task is pending on page 0\n");
+  if (ystride <= 0) exitf(-1, "rectdetect_b200: rd_oclrect_executeOnceNV12: bad row stride %d\n", ystride);
+  enqueue_page(o, nv12, 0, -ystride, 0, 0, 0, 1, tanAOV);
+  o->lastTan = tanAOV;
+  rect_t *r = NULL;
+  finish_page(o, 0, tanAOV, &r, 1);
+  return r;
 }
 
 void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out) {

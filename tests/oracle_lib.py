@@ -62,7 +62,7 @@ def oracle():
             "ora_thinthres_f_f_f2": (None, [vp, vp, vp, i, i]), "ora_thincubic_f_f_f2": (None, [vp, vp, vp, i, i]),
             "ora_edgevec_f2_plab": (None, [vp, vp, i, i]), "ora_edge_f_f": (None, [vp, vp, i, i]),
             "ora_convert_bgr_plab": (None, [vp, vp, i, i, i]), "ora_convert_bgr_lumaf": (None, [vp, vp, f, i, i, i]),
-            "ora_convert_bgr_labeli": (None, [vp, vp, i, i, i, i]),
+            "ora_convert_bgr_labeli": (None, [vp, vp, i, i, i, i]), "ora_nv12_to_bgr": (None, [vp, vp, i, i, i, i]),
             "ora_label8x_int_int": (i, [vp, vp, vp, i, i, i]),
             "ora_calcStrength": (None, [vp, vp, vp, i, i]), "ora_filterStrength": (None, [vp, vp, i, i, i]),
             "ora_rect_simpleJunction": (None, [vp, vp, i, i]), "ora_rect_simpleConnect": (None, [vp, vp, i, i]),
@@ -107,6 +107,31 @@ def dense_frame(iw, ih, seed, tiles_x=4, tiles_y=4):
             t = synth_frame(tw, th, seed * 100 + ty * tiles_x + tx)
             img[ty * th:(ty + 1) * th, 3 * tx * tw:3 * (tx + 1) * tw] = t[:, :3 * tw]
     return img
+
+
+def bgr_to_nv12(img, iw, ih, ys=None):
+    """a plausible NV12 rendition of a BGR frame (BT.601 limited range, 2x2 chroma average): workload input for the NV12 path; any byte
+    pattern is a valid NV12 frame, so nothing depends on how faithful this is.  -> (ih * 3 // 2, ys) uint8"""
+    ys = ys or iw
+    bgr = np.ascontiguousarray(img)[:, : 3 * iw].reshape(ih, iw, 3).astype(np.float32)
+    b, g, r = bgr[..., 0], bgr[..., 1], bgr[..., 2]
+    y = 16 + 0.257 * r + 0.504 * g + 0.098 * b
+    u = 128 - 0.148 * r - 0.291 * g + 0.439 * b
+    v = 128 + 0.439 * r - 0.368 * g - 0.071 * b
+    out = np.zeros((ih * 3 // 2, ys), np.uint8)
+    out[:ih, :iw] = np.clip(np.rint(y), 0, 255)
+    uv = np.stack([u.reshape(ih // 2, 2, iw // 2, 2).mean((1, 3)), v.reshape(ih // 2, 2, iw // 2, 2).mean((1, 3))], -1)
+    out[ih:, :iw] = np.clip(np.rint(uv), 0, 255).reshape(ih // 2, iw)
+    return out
+
+
+def nv12_to_bgr(nv12, iw, ih, ws=None):
+    """the oracle's NV12 -> BGR (= OpenCV's COLOR_YUV2BGR_NV12) -> (ih, ws) uint8"""
+    ws = ws or 3 * iw
+    nv12 = np.ascontiguousarray(nv12)
+    out = np.zeros((ih, ws), np.uint8)
+    oracle().ora_nv12_to_bgr(_ptr(out), _ptr(nv12), iw, ih, ws, nv12.shape[-1])
+    return out
 
 
 def rects_from_ptr(p, free=True):

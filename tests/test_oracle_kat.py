@@ -261,3 +261,31 @@ def test_oracle_detects_the_planted_quads():
     assert hits >= len(quads) // 3, "only %d of %d planted quadrilaterals were found" % (hits, len(quads))
     st = ol.stats()
     assert st["ls_overflow"] == 0 and st["mkpl_ties"] == 0
+
+
+def test_nv12_to_bgr_equals_opencv_golden():
+    """the NV12 front end against OpenCV-generated vectors (tools/make_nv12_golden.py), and against cv2 itself where
+    it can be imported"""
+    import hashlib
+    import json
+    import os
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nv12_golden.json")))
+    for g in golden:
+        rng = np.random.default_rng(g["seed"])
+        iw, ih = g["iw"], g["ih"]
+        yuv = rng.integers(0, 256, (ih * 3 // 2, iw), dtype=np.uint8)
+        if g["corners"]:
+            yuv[:] = rng.choice(np.array([0, 15, 16, 17, 128, 234, 235, 236, 255], np.uint8), yuv.shape)
+        bgr = ol.nv12_to_bgr(yuv, iw, ih)
+        assert [int(v) for v in bgr.reshape(-1)[:24]] == g["bgr_head"]
+        assert hashlib.sha256(bgr.tobytes()).hexdigest() == g["bgr_sha"]
+        try:
+            import cv2
+        except ImportError:
+            continue
+        assert np.array_equal(bgr.reshape(ih, iw, 3), cv2.cvtColor(yuv, cv2.COLOR_YUV2BGR_NV12))
+    # a row stride wider than the frame
+    yuv = np.random.default_rng(9).integers(0, 256, (48 * 3 // 2, 80), dtype=np.uint8)
+    a = ol.nv12_to_bgr(yuv, 64, 48)
+    b = ol.nv12_to_bgr(np.ascontiguousarray(yuv[:, :64]), 64, 48)
+    assert np.array_equal(a, b)
