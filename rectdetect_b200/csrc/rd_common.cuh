@@ -52,8 +52,14 @@ int rd_prof_begin(const char *name, cudaStream_t s);
 void rd_prof_end(int slot, cudaStream_t s);
 void rd_prof_stage(const char *tag);      // stage tag of the calling thread (string literal), used by profile mode 3
 
+// the stream behind a queue; also makes the queue's device current for the calling thread (a queue may belong to another device
+// than the thread's current one: kernel launches and async allocations go to the current device)
 static inline cudaStream_t rd_stream(cl_command_queue q) {
   if (!q) exitf(-1, "rectdetect_b200: NULL command queue\n");
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != q->ordinal) {
+    if (cudaSetDevice(q->ordinal) != cudaSuccess) exitf(-1, "rectdetect_b200: cannot select device %d of the command queue\n", q->ordinal);
+  }
   return q->stream;
 }
 template <typename T> static inline T *rd_ptr(cl_mem m) {

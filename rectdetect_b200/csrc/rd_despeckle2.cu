@@ -13,6 +13,7 @@
 //   kf_markBoundary : tile kernel on the final labels.
 #include "rd_common.cuh"
 #include "rd_despeckle2.cuh"
+#include "rd_tma.cuh"
 #include <mutex>
 
 #define D2P_THREADS 256
@@ -247,16 +248,33 @@ __global__ void __launch_bounds__(32) kd2_seq_pipe(int *dst, const int *list, co
 #define MB_T 32
 #define MB_A 2
 #define MB_W (MB_T + 2 * MB_A)
-__global__ void __launch_bounds__(256) kf_markBoundary(int *out, const int *in, int iw, int ih, size_t fs) {
+// USE_TMA: interior CTAs fetch the tile as one box of MB_RAWW columns starting at bx - 4 (a multiple of four: rd_tma.cuh)
+#define MB_RAWW 40
+#define MB_RAWX 4
+template <bool USE_TMA>
+__global__ void __launch_bounds__(256) kf_markBoundary_t(int *out, const int *in, const __grid_constant__ CUtensorMap map, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, in);
-  __shared__ int sd[MB_W * MB_W];
+  __shared__ __align__(128) int sd[USE_TMA ? MB_W * MB_RAWW : MB_W * MB_W];
+  __shared__ __align__(8) uint64_t bar;
   const int bx = blockIdx.x * MB_T - MB_A, by = blockIdx.y * MB_T - MB_A;
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < MB_W * MB_W; i += 256) {
-    const int gx = bx + i % MB_W, gy = by + i / MB_W;
-    sd[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih) ? in[(size_t)gy * iw + gx] : -1;
+  const bool interior = USE_TMA && bx + MB_A - MB_RAWX >= 0 && by >= 0 && bx + MB_W <= iw && by + MB_W <= ih;
+  const int pitch = interior ? MB_RAWW : MB_W, xoff = interior ? MB_RAWX - MB_A : 0;      // tile column t lives at sd[row * pitch + t + xoff]
+  if (interior) {
+    if (tid == 0) rd_mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      rd_mbar_expect(&bar, (unsigned)(MB_W * MB_RAWW * 4));
+      rd_tma_load3(sd, &map, bx + MB_A - MB_RAWX, by, (int)blockIdx.z, &bar);
+    }
+    rd_mbar_wait(&bar, 0);
+  } else {
+    for (int i = tid; i < MB_W * MB_W; i += 256) {
+      const int gx = bx + i % MB_W, gy = by + i / MB_W;
+      sd[i] = (gx >= 0 && gx < iw && gy >= 0 && gy < ih) ? in[(size_t)gy * iw + gx] : -1;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int tx = MB_A + threadIdx.x, ty = MB_A + threadIdx.y + k * 8;
@@ -264,12 +282,12 @@ __global__ void __launch_bounds__(256) kf_markBoundary(int *out, const int *in, 
     if (gx >= iw || gy >= ih) continue;
     int r = -1;
     if (!(gx <= 1 || gy <= 1 || gx >= iw - 2 || gy >= ih - 2)) {
-      const int i = ty * MB_W + tx, c0 = sd[i];
+      const int i = ty * pitch + tx + xoff, c0 = sd[i];
       bool nearEdge = false;
 #pragma unroll
       for (int yy = -2; yy <= 2; yy++)
 #pragma unroll
-        for (int xx = -2; xx <= 2; xx++) nearEdge |= sd[i + yy * MB_W + xx] != c0;
+        for (int xx = -2; xx <= 2; xx++) nearEdge |= sd[i + yy * pitch + xx] != c0;
       if (nearEdge) r = c0;
     }
     out[(size_t)gy * iw + gx] = r;
@@ -311,5 +329,11 @@ void rd_despeckle2_run(int *dst, const int *label, const int *size, int *list, i
   RD_LAUNCH(kd2_seq, nb, 32, smem, s, dst, list, recL, recS, rowcnt, in_smem ? (int2 *)NULL : rowbuf, iw, ih, fs);
 }
 void rd_markBoundary_run(int *out, const int *in, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_LAUNCH(kf_markBoundary, dim3(rd_cdiv(iw, MB_T), rd_cdiv(ih, MB_T), nb), dim3(32, 8), 0, s, out, in, iw, ih, fs);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (rd_tma_ok(in, iw, fs) && rd_tma_make_map(&map, in, CU_TENSOR_MAP_DATA_TYPE_INT32, iw, ih, nb, fs, MB_RAWW, MB_W)) {
+    RD_LAUNCH(kf_markBoundary_t<true>, dim3(rd_cdiv(iw, MB_T), rd_cdiv(ih, MB_T), nb), dim3(32, 8), 0, s, out, in, map, iw, ih, fs);
+    return;
+  }
+  RD_LAUNCH(kf_markBoundary_t<false>, dim3(rd_cdiv(iw, MB_T), rd_cdiv(ih, MB_T), nb), dim3(32, 8), 0, s, out, in, map, iw, ih, fs);
 }

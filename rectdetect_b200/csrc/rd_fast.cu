@@ -11,8 +11,8 @@
 //   rd_iirblur3_run   : the three recursive-Gaussian blurs of oclrect.c:248-250 (oclimgutil.cl:542-637) straight
 //                       from the packed Lab plane: one thread runs the three channel chains of a row (column)
 //                       and direction, the pass1 / pass3 combinations are folded into the consumers.
-#include <cuda.h>
 #include "rd_common.cuh"
+#include "rd_tma.cuh"
 #include "rd_stageA.cuh"
 #include "rd_bits.cuh"
 #include <mutex>
@@ -866,25 +866,13 @@ struct EtQueued { unsigned short idx, pad; float vx, vy, am1, ap1; };
 // (cp.async.bulk.tensor.3d -> UTMALDG, completion on an mbarrier) issued by one thread: the packed-Lab tile as a raw 42 x 44 box that
 // a second pass unpacks into the three float tiles, the L tile straight into place.  CTAs on the frame border keep the plain
 // staging below: the reference mirrors coordinates there, the copy engine can only fill zeros.  Measured A/B: profiles/r04*_tma_ab.txt.
-#define ET_RAWW 44                   // box width of the packed tile: 42 columns rounded up to a multiple of 16 bytes
-__device__ __forceinline__ void et_mbar_init(uint64_t *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void et_mbar_expect(uint64_t *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void et_mbar_wait(uint64_t *bar, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
-      ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void et_tma_load3(void *smem, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
+// The copy engine wants the first element of a box 16-byte aligned (measured: tools/probes/tma_probe.cu - a box starting at x = 27 raises
+// "illegal instruction", x = 28 is fine), so the boxes start at the multiple of four left of the apron: packed tile bx-8 .. bx+39 (48 wide,
+// the kernel uses bx-5 .. bx+36), L tile bx-4 .. bx+35 (40 wide, used: bx-2 .. bx+33).
+#define ET_RAWW 48
+#define ET_RAWX 8                    // the raw packed box starts ET_RAWX columns left of the tile
+#define ET_LTW 40                    // pitch of the L tile when the copy engine fills it
+#define ET_LTX 4
 struct EtMaps { CUtensorMap p, l; };
 template <bool USE_TMA>
 __global__ void __launch_bounds__(256) kf_edge_thin_t(float *thin, const float *blurL, const uint32_t *blurP, const __grid_constant__ EtMaps maps, int iw, int ih, size_t fs) {
@@ -892,7 +880,7 @@ __global__ void __launch_bounds__(256) kf_edge_thin_t(float *thin, const float *
   // phase 1-2: three unpacked Lab tiles (apron 5); phase 3-4: the queue of local maxima
   __shared__ __align__(16) unsigned char lab_or_queue[(3 * ET_PW * ET_PW * 4 > ET_NPOS * (int)sizeof(EtQueued)) ? 3 * ET_PW * ET_PW * 4 : ET_NPOS * (int)sizeof(EtQueued)];
   __shared__ float sm[ET_MW * ET_MW];
-  __shared__ __align__(128) float sl[ET_LW * ET_LW];
+  __shared__ __align__(128) float sl[USE_TMA ? ET_LW * ET_LTW : ET_LW * ET_LW];
   __shared__ __align__(128) uint32_t rawP[USE_TMA ? ET_PW * ET_RAWW : 4];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int nq;
@@ -901,20 +889,21 @@ __global__ void __launch_bounds__(256) kf_edge_thin_t(float *thin, const float *
   const int bx = blockIdx.x * ET_T, by = blockIdx.y * ET_T;
   const int tx = threadIdx.x, ty = threadIdx.y;
   if (tx == 0 && ty == 0) nq = 0;
-  const bool interior = USE_TMA && bx - ET_PA >= 0 && by - ET_PA >= 0 && bx + ET_T + ET_PA <= iw && by + ET_T + ET_PA <= ih;
+  const bool interior = USE_TMA && bx - ET_RAWX >= 0 && by - ET_PA >= 0 && bx + ET_T + ET_PA <= iw && by + ET_T + ET_PA <= ih;
+  const int lpitch = interior ? ET_LTW : ET_LW, lx0 = interior ? bx - ET_LTX : bx - ET_LA;      // layout of the L tile
   if (interior) {
-    if (tx == 0 && ty == 0) et_mbar_init(&bar, 1);
+    if (tx == 0 && ty == 0) rd_mbar_init(&bar, 1);
     __syncthreads();
     if (tx == 0 && ty == 0) {
-      et_mbar_expect(&bar, (unsigned)(ET_PW * ET_RAWW * 4 + ET_LW * ET_LW * 4));
-      et_tma_load3(rawP, &maps.p, bx - ET_PA, by - ET_PA, (int)blockIdx.z, &bar);
-      et_tma_load3(sl, &maps.l, bx - ET_LA, by - ET_LA, (int)blockIdx.z, &bar);
+      rd_mbar_expect(&bar, (unsigned)(ET_PW * ET_RAWW * 4 + ET_LW * ET_LTW * 4));
+      rd_tma_load3(rawP, &maps.p, bx - ET_RAWX, by - ET_PA, (int)blockIdx.z, &bar);
+      rd_tma_load3(sl, &maps.l, bx - ET_LTX, by - ET_LA, (int)blockIdx.z, &bar);
     }
-    et_mbar_wait(&bar, 0);
+    rd_mbar_wait(&bar, 0);
     for (int i = ty * 32 + tx; i < ET_PW * ET_PW; i += 256) {
       const int r = i / ET_PW, c = i - r * ET_PW;
       float l, a, b;
-      rd_unpacklab(rawP[r * ET_RAWW + c], l, a, b);
+      rd_unpacklab(rawP[r * ET_RAWW + c + (ET_RAWX - ET_PA)], l, a, b);
       lab[0][i] = l; lab[1][i] = a; lab[2][i] = b;
     }
   } else {
@@ -977,12 +966,12 @@ __global__ void __launch_bounds__(256) kf_edge_thin_t(float *thin, const float *
     float am1 = 0.0f, ap1 = 0.0f;
     if (x < iw && y < ih) {
       float vx = 0, vy = 0;
-      const float *lc = sl + (y - (by - ET_LA)) * ET_LW + (x - (bx - ET_LA));
+      const float *lc = sl + (y - (by - ET_LA)) * lpitch + (x - lx0);
 #pragma unroll
       for (int yy = -2; yy <= 2; yy++)
 #pragma unroll
         for (int xx = -2; xx <= 2; xx++) {
-          const float s = lc[yy * ET_LW + xx];
+          const float s = lc[yy * lpitch + xx];
           if (V5[(xx + 2) + (yy + 2) * 5] != 0.0f) vx = __fadd_rn(vx, __fmul_rn(V5[(xx + 2) + (yy + 2) * 5], s));
           if (V5[(yy + 2) + (xx + 2) * 5] != 0.0f) vy = __fadd_rn(vy, __fmul_rn(V5[(yy + 2) + (xx + 2) * 5], s));
         }
@@ -1018,30 +1007,12 @@ __global__ void __launch_bounds__(256) kf_edge_thin_t(float *thin, const float *
     thin[(size_t)y * iw + x] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(am2, e.am1), mag.at(x, y)), e.ap1), ap2);
   }
 }
-// tensor maps of one plane of the arenas: rank 3 = (x, y, frame), frame stride fs
-static bool et_make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int iw, int ih, int nb, size_t fs, int boxw, int boxh) {
-  typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_t enc = NULL;
-  if (!enc) {
-    void *fn = NULL;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
-    enc = (encode_t)fn;
-  }
-  const cuuint64_t dims[3] = {(cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)nb};
-  const cuuint64_t strides[2] = {(cuuint64_t)iw * 4, fs ? (cuuint64_t)fs : (cuuint64_t)iw * ih * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1}, es[3] = {1, 1, 1};
-  return enc(m, dt, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 void rd_edge_thin_run(float *thin, const float *blurL, const uint32_t *blurP, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  static const bool want_tma = getenv("RD_TMA") && atoi(getenv("RD_TMA")) != 0;      // off by default: see the A/B in profiles/ (staging is not what this kernel waits for)
   EtMaps maps;
   memset(&maps, 0, sizeof(maps));
-  if (want_tma && (iw & 3) == 0 && (fs & 15) == 0 && ((uintptr_t)blurP & 15) == 0 && ((uintptr_t)blurL & 15) == 0 &&
-      et_make_map(&maps.p, blurP, CU_TENSOR_MAP_DATA_TYPE_UINT32, iw, ih, nb, fs, ET_RAWW, ET_PW) &&
-      et_make_map(&maps.l, blurL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, iw, ih, nb, fs, ET_LW, ET_LW)) {
+  if (rd_tma_ok(blurP, iw, fs) && rd_tma_ok(blurL, iw, fs) &&
+      rd_tma_make_map(&maps.p, blurP, CU_TENSOR_MAP_DATA_TYPE_UINT32, iw, ih, nb, fs, ET_RAWW, ET_PW) &&
+      rd_tma_make_map(&maps.l, blurL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, iw, ih, nb, fs, ET_LTW, ET_LW)) {
     RD_LAUNCH(kf_edge_thin_t<true>, dim3(rd_cdiv(iw, ET_T), rd_cdiv(ih, ET_T), nb), dim3(32, 8), 0, s, thin, blurL, blurP, maps, iw, ih, fs);
     return;
   }
@@ -1157,15 +1128,39 @@ __global__ void kq_tables() {
 __device__ __forceinline__ uint32_t quant24(uint32_t v) {
   return ((uint32_t)g_quantA[v >> 22] << 22) | ((uint32_t)g_quantA[(v >> 12) & 1023u] << 12) | (uint32_t)g_quantL[v & 4095u];
 }
-__global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, size_t fs) {
+// USE_TMA: interior CTAs fetch the two 34-row tiles as boxes of QD_RAWW columns starting at bx - 3 (a multiple of four: rd_tma.cuh)
+#define QD_RAWW 40
+#define QD_RAWX 3                    // the boxes start QD_RAWX columns left of the aproned tile (tile origin = block origin - 1)
+struct QdMaps { CUtensorMap in, thin; };
+template <bool USE_TMA>
+__global__ void __launch_bounds__(256) kf_quant_despeckle_t(uint32_t *out, const uint32_t *in, const float *thin, const __grid_constant__ QdMaps maps, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, in, thin);
   __shared__ uint32_t q[QD_W * QD_W];
   __shared__ uint8_t e[QD_W * QD_W];                          // 1: edge pixel (thinned strength >= 1e-6), 2: outside the image
   __shared__ unsigned short queue[QD_T * QD_T];
+  __shared__ __align__(128) uint32_t rawI[USE_TMA ? QD_W * QD_RAWW : 4];
+  __shared__ __align__(128) float rawT[USE_TMA ? QD_W * QD_RAWW : 4];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ int nq;
   const int bx = blockIdx.x * QD_T - 1, by = blockIdx.y * QD_T - 1;
   const int lane = threadIdx.x, wy = threadIdx.y;
   if (lane == 0 && wy == 0) nq = 0;
+  const bool interior = USE_TMA && bx - QD_RAWX >= 0 && by >= 0 && bx + QD_W <= iw && by + QD_W <= ih;
+  if (interior) {
+    if (lane == 0 && wy == 0) rd_mbar_init(&bar, 1);
+    __syncthreads();
+    if (lane == 0 && wy == 0) {
+      rd_mbar_expect(&bar, (unsigned)(2 * QD_W * QD_RAWW * 4));
+      rd_tma_load3(rawI, &maps.in, bx - QD_RAWX, by, (int)blockIdx.z, &bar);
+      rd_tma_load3(rawT, &maps.thin, bx - QD_RAWX, by, (int)blockIdx.z, &bar);
+    }
+    rd_mbar_wait(&bar, 0);
+    for (int i = wy * 32 + lane; i < QD_W * QD_W; i += 256) {
+      const int ty = i / QD_W, tx = i - ty * QD_W, r = ty * QD_RAWW + tx + QD_RAWX;
+      q[i] = quant24(rawI[r]);
+      e[i] = rawT[r] >= 1e-6f ? 1 : 0;
+    }
+  } else {
   // warp -> tile rows wy, wy + 8, ...; lane -> column lane, lanes 0 / 1 also columns 32 / 33
   for (int ty = wy; ty < QD_W; ty += 8) {
     const int gy = by + ty;
@@ -1180,6 +1175,7 @@ __global__ void __launch_bounds__(256) kf_quant_despeckle(uint32_t *out, const u
         e[i] = thin[p] >= 1e-6f ? 1 : 0;
       } else { q[i] = 0; e[i] = 2; }
     }
+  }
   }
   __syncthreads();
   // non-edge pixels keep their quantised colour; the edge pixels (a third of the frame, scattered over every warp) are
@@ -1252,7 +1248,14 @@ void rd_quant_tables_init() {
   if (dev < 64) ready[dev] = true;
 }
 void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_LAUNCH(kf_quant_despeckle, dim3(rd_cdiv(iw, QD_T), rd_cdiv(ih, QD_T), nb), dim3(32, 8), 0, s, out, in, thin, iw, ih, fs);
+  QdMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (rd_tma_ok(in, iw, fs) && rd_tma_ok(thin, iw, fs) && rd_tma_make_map(&maps.in, in, CU_TENSOR_MAP_DATA_TYPE_UINT32, iw, ih, nb, fs, QD_RAWW, QD_W) &&
+      rd_tma_make_map(&maps.thin, thin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, iw, ih, nb, fs, QD_RAWW, QD_W)) {
+    RD_LAUNCH(kf_quant_despeckle_t<true>, dim3(rd_cdiv(iw, QD_T), rd_cdiv(ih, QD_T), nb), dim3(32, 8), 0, s, out, in, thin, maps, iw, ih, fs);
+    return;
+  }
+  RD_LAUNCH(kf_quant_despeckle_t<false>, dim3(rd_cdiv(iw, QD_T), rd_cdiv(ih, QD_T), nb), dim3(32, 8), 0, s, out, in, thin, maps, iw, ih, fs);
 }
 
 // simpleJunction of the strong edges + clear + mkMergeMask0 + mkMergeMask1 (oclrect.cl:74, 246-287, oclrect.c:314-321).

@@ -622,6 +622,12 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   bb = (bb + 255) & ~(size_t)255;
   o->blobBytes = bb;
   o->fs = 24 * P + 2 * bb;
+  if ((iw & 3) == 0) {                                  // tensor maps (rd_tma.cuh) want the frame stride to be a multiple of the row stride
+    size_t a = (size_t)iw * 4, b = 256;
+    while (b) { const size_t t = a % b; a = b; b = t; }                          // a = gcd(row stride, 256)
+    const size_t unit = (size_t)iw * 4 / a * 256;                                // lcm: the arenas stay 256-byte aligned
+    o->fs = (o->fs + unit - 1) / unit * unit;
+  }
   o->lastTan = o->pageTan[0] = o->pageTan[1] = NAN;
   o->P = P;
   RD_CUDA(cudaMalloc((void **)&o->dbase, o->fs * nb));
