@@ -224,6 +224,9 @@ rect_t *rd_oclrect_executeOnceNV12(struct oclrect_t *thiz, const uint8_t *nv12, 
 /* device-resident variant: frames already in device memory (read in place).  out == NULL runs everything on the device but
  * builds no host lists. */
 void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, int ws, int nframes, double tanAOV, rect_t **out);
+/* n lists as returned above -> one malloc()ed array holding all their entries (headers dropped, list order), counts[i] = entries of
+ * list i; the lists are freed */
+rect_t *rd_rect_lists_flatten(rect_t **lists, int n, int32_t *counts);
 /* host-side accounting of the last rd_batch_run, summed over the pipeline objects' driver threads: out_ms[0] = time spent
  * waiting for the device, out_ms[4] = wall time spent copying the read-back records into rect_t lists; [1..3] are reserved (0) */
 void rd_batch_stage_ms(rd_batch *b, double out_ms[5]);

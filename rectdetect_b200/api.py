@@ -94,6 +94,7 @@ def lib():
         "rd_rect_markBoundary": (None, [vp, vp, i, i, vp]), "rd_rect_reduceLS": (None, [vp, vp, vp, i, i, i, vp]),
         "rd_oclrect_buffer": (vp, [vp, C.c_char_p]), "rd_oclrect_run_device": (None, [vp, vp, i, i]),
         "rd_batch_run_nv12": (None, [vp, vp, C.c_size_t, i, i, d, vp]), "rd_oclrect_executeOnceNV12": (vp, [vp, vp, i, d]),
+        "rd_rect_lists_flatten": (vp, [vp, i, vp]),
         "rd_rect_tail": (vp, [vp, vp, vp, i, i, d]), "rd_rect_tail_device": (vp, [vp, vp, vp, i, i, d, vp]),
         "rd_batch_create": (vp, [i, i, i, i, i]), "rd_batch_destroy": (None, [vp]),
         "rd_batch_run": (None, [vp, vp, sz, i, i, d, vp]), "rd_batch_run_device": (None, [vp, vp, sz, i, i, d, vp]),
@@ -136,6 +137,17 @@ def profile_stop():
         name, cnt, ms = line.rsplit(" ", 2)
         out[name] = (int(cnt), float(ms))
     return out
+
+
+def rect_lists_from_ptrs(ptrs, n):
+    """n malloc()ed rect_t lists (a ctypes array of pointers) -> n numpy arrays (views of ONE flat copy); frees the lists"""
+    L = lib()
+    counts = np.zeros(n, np.int32)
+    flat_p = L.rd_rect_lists_flatten(ptrs, n, _p(counts))
+    total = int(counts.sum())
+    flat = np.frombuffer(C.string_at(flat_p, 176 * total), dtype=RECT_DTYPE) if total else np.zeros(0, RECT_DTYPE)
+    L.rd_free(flat_p)
+    return np.split(flat, np.cumsum(counts)[:-1]) if n else []
 
 
 def rects_from_ptr(p):
@@ -276,13 +288,13 @@ class Batch:
             L.rd_batch_run(self.h, frames_ptr, frame_stride, ws, nframes, tan_aov, out)
         if out is None:
             return None
-        return [rects_from_ptr(p) for p in out]
+        return rect_lists_from_ptrs(out, nframes)
 
     def run_nv12(self, frames_ptr, frame_stride, ystride, nframes, tan_aov):
         """NV12 frames in host or device memory (rd_batch_run_nv12)"""
         out = (C.c_void_p * nframes)()
         lib().rd_batch_run_nv12(self.h, frames_ptr, frame_stride, ystride, nframes, tan_aov, out)
-        return [rects_from_ptr(p) for p in out]
+        return rect_lists_from_ptrs(out, nframes)
 
     def stage_ms(self):
         """host-side accounting of the last run: (ms the driver threads waited for the device, ms of host-tail phases)"""

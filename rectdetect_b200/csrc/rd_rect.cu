@@ -988,6 +988,22 @@ void rd_batch_run_device(rd_batch *b, const void *dframes, size_t frame_stride, 
   batch_run(b, (const uint8_t *)dframes, frame_stride, ws, nframes, tanAOV, out, 2, out != NULL);
 }
 
+// n rect_t lists (as the run functions return them) -> one malloc()ed array of all their entries, headers dropped, in list order;
+// counts[i] = entries of list i.  The lists are freed.  (For callers that handle thousands of lists per second: bench.py, the gather.)
+rect_t *rd_rect_lists_flatten(rect_t **lists, int n, int32_t *counts) {
+  size_t total = 0;
+  for (int i = 0; i < n; i++) { counts[i] = lists[i] ? lists[i][0].nItems - 1 : 0; total += (size_t)counts[i]; }
+  rect_t *flat = (rect_t *)malloc((total ? total : 1) * sizeof(rect_t));
+  size_t o = 0;
+  for (int i = 0; i < n; i++) {
+    if (counts[i] > 0) memcpy(flat + o, lists[i] + 1, (size_t)counts[i] * sizeof(rect_t));
+    o += (size_t)counts[i];
+    free(lists[i]);
+    lists[i] = NULL;
+  }
+  return flat;
+}
+
 void rd_batch_stage_ms(rd_batch *b, double out_ms[5]) {
   for (int i = 0; i < 5; i++) out_ms[i] = 0;
   for (oclrect_t *o : b->ctx) { out_ms[0] += o->wait_ms; out_ms[4] += o->tail_ms; }

@@ -27,17 +27,13 @@ def pack_rect_lists(first_frame, rect_lists):
 
 
 def unpack_rect_lists(blob):
-    """inverse of pack_rect_lists -> (first_frame, [rect arrays])"""
+    """inverse of pack_rect_lists -> (first_frame, [rect arrays]); the arrays are views of one copy of the payload"""
     blob = np.ascontiguousarray(blob, np.uint8)
     nframes, first = (int(v) for v in blob[:16].view(np.int64))
     counts = blob[16: 16 + 8 * nframes].view(np.int64)
     off = 16 + 8 * nframes
-    out = []
-    for c in counts:
-        nb = int(c) * RECT_DTYPE.itemsize
-        out.append(blob[off: off + nb].view(RECT_DTYPE).copy())
-        off += nb
-    return first, out
+    flat = blob[off: off + int(counts.sum()) * RECT_DTYPE.itemsize].copy().view(RECT_DTYPE)
+    return first, (np.split(flat, np.cumsum(counts)[:-1]) if nframes else [])
 
 
 def gather_rect_lists(first_frame, rect_lists, nframes_total, device=None):
