@@ -28,6 +28,9 @@ for r in rows[2:]:
     # the profiler facility of the library names template instantiations by their source spelling
     name = re.sub(r"^k_ccl_tile<.*>$", "k_ccl_tile<LinkFn>", name)
     name = re.sub(r"^kf_blb_stream4<.*>$", "kf_blb_stream4<npx>", name)
+    name = re.sub(r"<\(bool\)1>$", "<true>", name)
+    name = re.sub(r"<\(bool\)0>$", "<false>", name)
+    name = re.sub(r"^(kr_reduceLS_list|kr_reduceLS)<\(int\)(\d)>$", r"\1<\2>", name)
     b = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
     t = float(r[h.index("gpu__time_duration.sum")].replace(",", ""))
     a = acc.setdefault(name, [0, 0.0, 0.0])
