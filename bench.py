@@ -485,7 +485,7 @@ def main():
             "config": {"workload": "vidrect %dx%d synthetic stream (seeds 1000+i), AOV 72, full imgutil->polyline->rect pipeline incl. executeCPUTask on the device, independent-frame batch "
                                    "(every frame as by a fresh oclrect_t: no carry-over between frames)" % (iw, ih),
                        "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "frames_per_launch": args.fpl, "parallelism": "frames x%d" % world,
-                       "l2": "inputs larger than L2 (%d MB of frames + %d working sets of 24 planes per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx * args.fpl)},
+                       "l2": "inputs larger than L2 (%d MB of frames + %d working sets of 31 planes per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx * args.fpl)},
             "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": main_run["d2h_bytes"],
                     "ms_per_step": main_run["ms_e2e"]},
             "gpu_launches": main_run["launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -139,15 +139,42 @@ def profile_stop():
     return out
 
 
+class RectLists:
+    """n per-frame rect_t lists held as ONE flat array + offsets (a sequence of numpy views, made on demand): what a caller that
+    handles thousands of lists per second wants instead of n small arrays"""
+
+    def __init__(self, flat, counts):
+        self.flat = flat
+        self.offsets = np.concatenate([[0], np.cumsum(np.asarray(counts, np.int64))])
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self.flat[self.offsets[i]: self.offsets[i + 1]]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def counts(self):
+        return np.diff(self.offsets)
+
+
 def rect_lists_from_ptrs(ptrs, n):
-    """n malloc()ed rect_t lists (a ctypes array of pointers) -> n numpy arrays (views of ONE flat copy); frees the lists"""
+    """n malloc()ed rect_t lists (a ctypes array of pointers) -> RectLists (views of ONE flat copy); frees the lists"""
     L = lib()
     counts = np.zeros(n, np.int32)
     flat_p = L.rd_rect_lists_flatten(ptrs, n, _p(counts))
     total = int(counts.sum())
     flat = np.frombuffer(C.string_at(flat_p, 176 * total), dtype=RECT_DTYPE) if total else np.zeros(0, RECT_DTYPE)
     L.rd_free(flat_p)
-    return np.split(flat, np.cumsum(counts)[:-1]) if n else []
+    return RectLists(flat, counts)
 
 
 def rects_from_ptr(p):

@@ -244,6 +244,114 @@ __global__ void __launch_bounds__(32) kd2_seq_pipe(int *dst, const int *list, co
   }
 }
 
+// The walk with a producer warp (the version the schedule runs).  A single in-order warp pays every dependent latency of its
+// instruction stream, also those that are not on the data-dependent path (cursor look-ups, ring bookkeeping, cp.async issue):
+// kd2_seq_pipe still needs ~830 cycles per chunk.  Here warp 1 streams the records of chunk k into a ring of D2_STAGES stages
+// (cp.async, D2_RING groups in flight, invalid lanes marked -1) and publishes a sequence number; warp 0 only does the dependent part:
+// records -> registers, row-buffer look-ups, merge, vote / scan, stores.  Sequence numbers in shared memory (release: fence + store by
+// lane 0, acquire: volatile load + fence) - no CTA barrier inside the loop.
+#define D2_STAGES 16
+__global__ void __launch_bounds__(64) kd2_seq_pc(int *dst, const int *list, const int *recL, const int *recS, const int *rowcnt, int iw, int ih, int nch_cap,
+                                                 size_t fs) {
+  rd_batch_x(fs, dst, list, recL, recS, rowcnt);
+  extern __shared__ __align__(16) int d2_smem[];
+  int *ring = d2_smem;                                        // [D2_STAGES][3][32]  (the generic walk uses the first D2_RING stages)
+  int *cnt = ring + D2_STAGES * 96;                           // [ih]
+  int2 *rowbuf = (int2 *)(cnt + ((ih + 1) & ~1));             // [2][iw]
+  int *desc = (int *)(rowbuf + 2 * (size_t)iw);               // [nch_cap]
+  __shared__ volatile int prod, cons;
+  __shared__ int nch_s;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (wp == 0) {
+    int nch = 0;
+    for (int y0 = 0; y0 < ih; y0 += 32) {
+      const int y = y0 + lane;
+      const int c = y < ih ? rowcnt[y] : 0;
+      if (y < ih) cnt[y] = c;
+      const int k = (c + 31) >> 5;
+      int incl = k;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      const int base = nch + incl - k;
+      for (int j = 0; j < k; j++) if (base + j < nch_cap) desc[base + j] = y | (j << 16);
+      nch += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { nch_s = nch; prod = 0; cons = 0; }
+  }
+  __syncthreads();
+  const int nch = nch_s;
+  if (nch > nch_cap) {                                        // more chunks than the table holds: the plain walk
+    if (wp == 0) d2_seq_generic(dst, list, recL, recS, ring, cnt, rowbuf, false, iw, ih);
+    return;
+  }
+  if (wp == 1) {
+    // ---------------- producer
+    for (int k = 0; k < nch + D2_RING - 1; k++) {
+      if (k < nch) {
+        while (k - cons >= D2_STAGES) { }                    // stage still in use
+        const int d = desc[k], y = d & 0xffff, j = ((d >> 16) << 5) + lane;
+        int *r = ring + (k % D2_STAGES) * 96 + lane;
+        if (j < cnt[y]) {
+          const size_t o = (size_t)y * iw + j;
+          d2_cp_async4(r, list + o); d2_cp_async4(r + 32, recL + o); d2_cp_async4(r + 64, recS + o);
+        } else {
+          r[0] = -1;
+        }
+      }
+      d2_cp_commit();
+      if (k >= D2_RING - 1) {                                 // the group of chunk k - (D2_RING - 1) has landed
+        d2_cp_wait();
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) prod = k - (D2_RING - 1) + 1;
+      }
+    }
+    return;
+  }
+  // ---------------- consumer
+  int carryL = 0, carryS = 0;
+  for (int k = 0; k < nch; k++) {
+    while (prod <= k) { }
+    __threadfence_block();
+    const int *r = ring + (k % D2_STAGES) * 96 + lane;
+    const int rec = r[0];
+    int bl = r[32], bs = r[64];
+    const int py = desc[k] & 0xffff;
+    __syncwarp();
+    if (lane == 0) cons = k + 1;                              // the records are in registers: the stage may be refilled
+    const bool valid = rec >= 0;
+    const int x = rec & 0xffff, dyn = valid ? (rec >> 20) & 15 : 0;
+    int code = (rec >> 16) & 15;
+    const int2 *above = rowbuf + (size_t)((py + 1) & 1) * iw;
+    int2 v0 = make_int2(0, 0), v1 = v0, v2 = v0;
+    if (dyn & 1) v0 = above[x - 1];
+    if (dyn & 2) v1 = above[x];
+    if (dyn & 4) v2 = above[x + 1];
+    if (!valid) { bl = 0; bs = 0; }
+    if (dyn & 1) d2_take(bl, bs, code, v0.x, v0.y, 1);
+    if (dyn & 2) d2_take(bl, bs, code, v1.x, v1.y, 2);
+    if (dyn & 4) d2_take(bl, bs, code, v2.x, v2.y, 3);
+    int T = D2_HEAD;
+    if (dyn & 8) T = d2_threshold(bs, code);
+    if (lane == 0 && T != D2_HEAD) {                          // the run continues from the previous chunk
+      if (carryS >= T) { bl = carryL; bs = carryS; }
+      T = D2_HEAD;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      if (__all_sync(0xffffffffu, T == D2_HEAD)) break;
+      const int lL = __shfl_up_sync(0xffffffffu, bl, d), lS = __shfl_up_sync(0xffffffffu, bs, d), lT = __shfl_up_sync(0xffffffffu, T, d);
+      if (lane >= d && T != D2_HEAD) d2_compose(bl, bs, T, lL, lS, lT);
+    }
+    if (valid) {
+      rowbuf[(size_t)(py & 1) * iw + x] = make_int2(bl, bs);
+      dst[(size_t)py * iw + x] = bl;
+    }
+    carryL = __shfl_sync(0xffffffffu, bl, 31); carryS = __shfl_sync(0xffffffffu, bs, 31);
+    __syncwarp();
+  }
+}
+
 // markBoundary (oclrect.cl:373-390): a pixel keeps its region label if its 5x5 window holds another label; 2-px frame -> -1
 #define MB_T 32
 #define MB_A 2
@@ -310,6 +418,7 @@ void rd_despeckle2_run(int *dst, const int *label, const int *size, int *list, i
     if (dev >= 64 || !ready[dev]) {
       RD_CUDA(cudaFuncSetAttribute(kd2_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_MAX));
       RD_CUDA(cudaFuncSetAttribute(kd2_seq_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_MAX));
+      RD_CUDA(cudaFuncSetAttribute(kd2_seq_pc, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_MAX));
       if (dev < 64) ready[dev] = true;
     }
   }
@@ -317,8 +426,12 @@ void rd_despeckle2_run(int *dst, const int *label, const int *size, int *list, i
   // device) takes the plain walk inside the same kernel; frames too wide / tall for shared memory take kd2_seq
   int nch_cap = 2 * ih + 1024;
   if (nch_cap > D2_NCH_MAX) nch_cap = D2_NCH_MAX;
-  const size_t pipe = full + (size_t)nch_cap * 4;
-  static const bool generic_only = getenv("RD_D2_GENERIC") != NULL;
+  const size_t pipe = full + (size_t)nch_cap * 4, pc = pipe + (size_t)(D2_STAGES - D2_RING) * 96 * 4;
+  static const bool generic_only = getenv("RD_D2_GENERIC") != NULL, one_warp = getenv("RD_D2_PIPE") != NULL;
+  if (!generic_only && !one_warp && pc <= D2_SMEM_MAX) {
+    RD_LAUNCH(kd2_seq_pc, nb, 64, pc, s, dst, list, recL, recS, rowcnt, iw, ih, nch_cap, fs);
+    return;
+  }
   if (!generic_only && pipe <= D2_SMEM_MAX) {
     RD_LAUNCH(kd2_seq_pipe, nb, 32, pipe, s, dst, list, recL, recS, rowcnt, iw, ih, nch_cap, fs);
     return;

@@ -475,7 +475,8 @@ void rd_blblur_run(uint32_t *dst, uint32_t *pong, const uint32_t *src, const int
     static bool attr = false;
     const size_t smem = S4_WARPS * sizeof(S4Smem<npx>);
     if (!attr) { RD_CUDA(cudaFuncSetAttribute(kf_blb_stream4<npx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    const int strips = rd_cdiv(iw, 32 * npx), ch = rd_strip_height(strips, nb, ih, 16, nb >= 8 ? 48 : 8 + 5 * nb, 1 << 20), chunks = rd_cdiv(ih, ch);
+    static const int minch_env = getenv("RD_BLB_MINCH") ? atoi(getenv("RD_BLB_MINCH")) : 0;     // (experiments)
+    const int strips = rd_cdiv(iw, 32 * npx), ch = rd_strip_height(strips, nb, ih, 16, minch_env > 0 && nb < 8 ? minch_env : (nb >= 8 ? 48 : 8 + 5 * nb), 1 << 20), chunks = rd_cdiv(ih, ch);
     const int blocks = rd_cdiv(strips * chunks * nb, S4_WARPS);
     for (int i = 0; i < iters; i++) {
       uint32_t *o = ((iters - i) & 1) ? dst : pong;     // the last iteration lands in dst
@@ -601,11 +602,15 @@ __device__ __forceinline__ void iir_h_chain(float *q, const uint32_t *row, const
     const int nblk = iw >> 3;
     // block b covers pixels [8b, 8b+8) walking forward, [iw-8-8b, iw-8b) walking backward
     const uint4 *src = (const uint4 *)row;
+    // two blocks of look-ahead: a step8 is ~250 dependent instructions, an HBM/L2 round trip for 32 scattered sectors is longer
     uint4 v0 = src[DIR == 0 ? 0 : 2 * nblk - 2], v1 = src[DIR == 0 ? 1 : 2 * nblk - 1];
+    uint4 u0 = v0, u1 = v1;
+    if (nblk > 1) { u0 = src[DIR == 0 ? 2 : 2 * nblk - 4]; u1 = src[DIR == 0 ? 3 : 2 * nblk - 3]; }
     for (int b = 0; b < nblk; b++) {
       const int base = DIR == 0 ? 2 * b : 2 * (nblk - 1 - b);
       const uint4 c0 = v0, c1 = v1;
-      if (b + 1 < nblk) { const int nb2 = DIR == 0 ? base + 2 : base - 2; v0 = src[nb2]; v1 = src[nb2 + 1]; }
+      v0 = u0; v1 = u1;
+      if (b + 2 < nblk) { const int nb2 = DIR == 0 ? base + 4 : base - 4; u0 = src[nb2]; u1 = src[nb2 + 1]; }
       const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
       float in[8], out[8];
 #pragma unroll

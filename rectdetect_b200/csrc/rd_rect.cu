@@ -363,6 +363,10 @@ struct oclrect_t {
   unsigned char *dbase;                 // nb arenas, fs bytes apart
   size_t fs, P;                         // arena stride, plane pitch (bytes)
   cl_mem buf[6], tmp[6], iobuf[2], ioBig[2];   // non-owning handles on the buffers of arena 0
+  cl_mem aux[7];                        // planes of the production schedule beyond the reference's plan: packed Lab (aux0), the polyline stage's
+                                        // temporaries (aux1..6) - so that stage C can run beside stage B on a second stream
+  cudaStream_t side;                    // the second branch of a task (stage C)
+  cudaEvent_t evFork, evJoin;
   unsigned char *dblob[2];              // read-back records of arena 0, one per pipeline page: 64-byte header + rect_t list (first half), the
                                         // quadrilaterals / pose results of the device tail (second half, rd_gtail.cu).  A record may be read
                                         // - or its pose phase re-run - while the next task already runs, so the pages do not share one
@@ -492,7 +496,7 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
 
 // The production schedule: same results as gpu_task (the step-by-step replay above, kept for the intermediate-parity
 // tests), but with the fused kernels of rd_fast.cu and a buffer plan of its own.  Plane roles:
-//   buf0 packed Lab -> (later) segment-id map     buf1 blurred packed Lab -> string labels      buf2 thinned strength
+//   aux0 packed Lab   buf0 segment-id map   aux1..6 temporaries of the polyline stage   buf1 blurred packed Lab -> string labels      buf2 thinned strength
 //   buf3 strength accumulator / strong-edge bitmap (carried to the next frame)      buf4 smoothed colours -> region labels
 //   tmp1..3 blurred L, a, b -> weak mask + walk extents (tmp1), flat colours (tmp2), blur ping-pong / merge mask (tmp3)
 //   tmp0 string bytes -> junction map + region sizes   tmp4 CCL link bytes   tmp5 strong-edge bitmap of this frame
@@ -503,12 +507,24 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
 #define STAGE(k) do { if (stop_stage == (k)) return; } while (0)
   const int iw = o->iw, ih = o->ih, n = iw * ih;
   const size_t fs = o->fs;
-  cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig;
+  cl_mem *buf = o->buf, *tmp = o->tmp, *iobuf = o->iobuf, *ioBig = o->ioBig, *aux = o->aux;
+  // Stage C (oclrect.c:361) needs nothing but the strong-edge bitmap of stage 6, so it runs BESIDE stages 7-12 on the object's second
+  // stream (fork / join by events; inside a graph capture they become two branches).  Its clean-up kernel also copies the bitmap
+  // into buf3, where the next frame's strengths accumulate.  Sequential when a test stops the schedule at a stage or
+  // the per-kernel profiler is on (kernels are then timed alone).
+  static const bool use_fork = !(getenv("RD_FORK") && atoi(getenv("RD_FORK")) == 0);
+  const bool fork = use_fork && stop_stage == 0 && g_rd_prof_mode.load(std::memory_order_relaxed) == 0;
+  auto stage_c = [&](cudaStream_t sc) {
+    rd_prof_stage("C");
+    rd_polyline_fast((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(tmp[5]), PI(buf[3]), PI(ioBig[1]), PI(aux[1]), PI(aux[2]), PI(aux[3]), PI(aux[4]), PI(aux[5]),
+                     PI(aux[6]), 4.0f, 20, iw, ih, nb, fs, sc);
+    rd_prof_stage("B");
+  };
   // Stage A (oclrect.c:245-263)
   rd_prof_stage("A");
-  rd_bgr2plab_run(PU(buf[0]), din, din_fs, iw, ih, ws, nb, fs, s);
+  rd_bgr2plab_run(PU(aux[0]), din, din_fs, iw, ih, ws, nb, fs, s);
   STAGE(1);
-  rd_iirblur3_run(PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), PU(buf[1]), PU(buf[0]), PF(ioBig[1]), PF(ioBig[0]), o->P / 4, 2, iw, ih, nb, fs, s);
+  rd_iirblur3_run(PF(tmp[1]), PF(tmp[2]), PF(tmp[3]), PU(buf[1]), PU(aux[0]), PF(ioBig[1]), PF(ioBig[0]), o->P / 4, 2, iw, ih, nb, fs, s);
   STAGE(2);
   rd_edge_thin_run(PF(buf[2]), PF(tmp[1]), PU(buf[1]), iw, ih, nb, fs, s);
   STAGE(3);
@@ -521,7 +537,13 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   RD_LAUNCH(kr_calcStrength, rd_gz(G2, nb), RB, 0, s, PI(buf[3]), PF(buf[2]), PI(buf[1]), iw, ih, fs);
   rd_filter_masks_run((int8_t *)tmp[1]->dptr, PI(tmp[5]), PI(buf[1]), PI(buf[3]), iw, ih, nb, fs, s);
   STAGE(6);
-  rd_blblur_run(PU(buf[4]), PU(tmp[3]), PU(buf[0]), (const int8_t *)tmp[1]->dptr, (uint8_t *)tmp[1]->dptr + (size_t)n, 10, iw, ih, nb, fs, s);
+  if (fork) {
+    RD_CUDA(cudaEventRecord(o->evFork, s));
+    RD_CUDA(cudaStreamWaitEvent(o->side, o->evFork, 0));
+    stage_c(o->side);
+    RD_CUDA(cudaEventRecord(o->evJoin, o->side));
+  }
+  rd_blblur_run(PU(buf[4]), PU(tmp[3]), PU(aux[0]), (const int8_t *)tmp[1]->dptr, (uint8_t *)tmp[1]->dptr + (size_t)n, 10, iw, ih, nb, fs, s);
   STAGE(7);
   rd_quant_despeckle_run(PU(tmp[2]), PU(buf[4]), PF(buf[2]), iw, ih, nb, fs, s);
   STAGE(8);
@@ -530,24 +552,22 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   rd_labelMerge_u8(PI(buf[4]), PI(buf[5]), PU(tmp[2]), (const uint8_t *)tmp[3]->dptr, PI(tmp[5]), tmp[4]->dptr, iw, ih, nb, fs, s);
   STAGE(10);
   rd_calcSize_run(PI(tmp[0]), PI(buf[4]), iw, ih, nb, fs, s);
-  // despeckle2 in raster order: final labels -> buf5; list planes buf1 / buf2 / tmp2, row counts tmp3 (all dead here)
-  rd_despeckle2_run(PI(buf[5]), PI(buf[4]), PI(tmp[0]), PI(buf[1]), PI(buf[2]), PI(tmp[2]), PI(tmp[3]), (int2 *)ioBig[0]->dptr, 16, iw, ih, nb, fs, s);
+  // despeckle2 in raster order: final labels -> buf5; list planes buf1 / buf2 / tmp2, row counts + wide-frame row buffer tmp3 (all dead here)
+  rd_despeckle2_run(PI(buf[5]), PI(buf[4]), PI(tmp[0]), PI(buf[1]), PI(buf[2]), PI(tmp[2]), PI(tmp[3]), (int2 *)(PI(tmp[3]) + ((ih + 2) & ~1)), 16, iw, ih, nb, fs, s);
   rd_markBoundary_run(PI(tmp[1]), PI(buf[5]), iw, ih, nb, fs, s);
   STAGE(11);
   rd_label8x(PI(iobuf[1]), PI(tmp[1]), tmp[4]->dptr, -1, iw, ih, nb, fs, s);
   STAGE(12);
-  // Stage C (oclrect.c:361).  The clean-up kernel also copies the bitmap into buf3, where the next frame's strengths accumulate.
-  rd_prof_stage("C");
-  rd_polyline_fast((LS_t *)ioBig[0]->dptr, n * 16, PI(buf[0]), PI(tmp[5]), PI(buf[3]), PI(ioBig[1]), PI(tmp[0]), PI(tmp[1]), PI(tmp[2]), PI(tmp[3]), PI(tmp[4]),
-                   PI(buf[5]), 4.0f, 20, iw, ih, nb, fs, s);
+  if (fork) RD_CUDA(cudaStreamWaitEvent(s, o->evJoin, 0));
+  else stage_c(s);
   STAGE(13);
-  // Stage D (oclrect.c:365-367) and the compact read-back record
+  // Stage D (oclrect.c:365-367) and the device tail
   rd_prof_stage("D");
   const int nentry = n * 4 / 5;
   rd_k_clear(PI(ioBig[1]), n * 4, nb, fs, s);
-  RD_LAUNCH(kr_reduceLS_list<0>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);   // tmp2: the polyline stage's pixel list
-  RD_LAUNCH(kr_reduceLS_list<1>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
-  RD_LAUNCH(kr_reduceLS_list<2>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(tmp[2]), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS_list<0>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(aux[3]), iw, ih, nentry, fs);   // aux3: the polyline stage's pixel list
+  RD_LAUNCH(kr_reduceLS_list<1>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(aux[3]), iw, ih, nentry, fs);
+  RD_LAUNCH(kr_reduceLS_list<2>, dim3(160, nb), 128, 0, s, PI(ioBig[1]), PI(iobuf[1]), PI(buf[0]), PI(aux[3]), iw, ih, nentry, fs);
   rd_prof_stage("T");
   device_tail(o, page, tanAOV, nb, s);
 }
@@ -621,7 +641,7 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   if (bb < ((size_t)1 << 20)) bb = (size_t)1 << 20;
   bb = (bb + 255) & ~(size_t)255;
   o->blobBytes = bb;
-  o->fs = 24 * P + 2 * bb;
+  o->fs = 31 * P + 2 * bb;
   if ((iw & 3) == 0) {                                  // tensor maps (rd_tma.cuh) want the frame stride to be a multiple of the row stride
     size_t a = (size_t)iw * 4, b = 256;
     while (b) { const size_t t = a % b; a = b; b = t; }                          // a = gcd(row stride, 256)
@@ -638,10 +658,14 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
   for (int i = 0; i < 6; i++) { o->tmp[i] = rd_wrap_device_memory(q, P); q += P; }
   for (int i = 0; i < 2; i++) { o->iobuf[i] = rd_wrap_device_memory(q, P); q += P; }
   for (int i = 0; i < 2; i++) { o->ioBig[i] = rd_wrap_device_memory(q, 4 * P); q += 4 * P; }
+  for (int i = 0; i < 7; i++) { o->aux[i] = rd_wrap_device_memory(q, P); q += P; }
   o->tailTable = (int *)q; q += 2 * P;
   o->dblob[0] = q;
   o->dblob[1] = q + bb;
   RD_CUDA(cudaStreamCreateWithFlags(&o->copyq, cudaStreamNonBlocking));
+  RD_CUDA(cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking));
+  RD_CUDA(cudaEventCreateWithFlags(&o->evFork, cudaEventDisableTiming));
+  RD_CUDA(cudaEventCreateWithFlags(&o->evJoin, cudaEventDisableTiming));
   for (int p = 0; p < 2; p++) {
     o->hostImg[p] = (uint8_t *)allocatePinnedMemory((size_t)iw * ih * 4 * nb, NULL, NULL);
     o->hostBlob[p] = (unsigned char *)allocatePinnedMemory(FIRST_CHUNK * nb, NULL, NULL);
@@ -767,6 +791,11 @@ void dispose_oclrect(struct oclrect_t *o) {
   RD_CUDA(cudaFree(o->dbase));
   for (int p = 0; p < 2; p++) { freePinnedMemory(o->hostImg[p], NULL, NULL); freePinnedMemory(o->hostBlob[p], NULL, NULL); RD_CUDA(cudaEventDestroy(o->events[p])); }
   RD_CUDA(cudaStreamDestroy(o->copyq));
+  RD_CUDA(cudaStreamSynchronize(o->side));
+  RD_CUDA(cudaStreamDestroy(o->side));
+  RD_CUDA(cudaEventDestroy(o->evFork));
+  RD_CUDA(cudaEventDestroy(o->evJoin));
+  for (int i = 0; i < 7; i++) clReleaseMemObject(o->aux[i]);
   for (int p = 0; p < 2; p++) if (o->graph[p]) RD_CUDA(cudaGraphExecDestroy(o->graph[p]));
   o->magic = 0;
   free(o);
@@ -807,6 +836,7 @@ cl_mem rd_oclrect_buffer(struct oclrect_t *o, const char *name) {
   if (!strncmp(name, "tmp", 3) && name[3] >= '0' && name[3] < '6') return o->tmp[name[3] - '0'];
   if (!strncmp(name, "iobuf", 5) && name[5] >= '0' && name[5] < '2') return o->iobuf[name[5] - '0'];
   if (!strncmp(name, "ioBig", 5) && name[5] >= '0' && name[5] < '2') return o->ioBig[name[5] - '0'];
+  if (!strncmp(name, "aux", 3) && name[3] >= '0' && name[3] < '7') return o->aux[name[3] - '0'];
   return NULL;
 }
 

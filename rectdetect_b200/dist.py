@@ -8,7 +8,7 @@ when the tensors live on the GPU, over gloo in the CPU tests.
 """
 import numpy as np
 
-from .api import RECT_DTYPE
+from .api import RECT_DTYPE, RectLists
 
 
 def shard_range(nframes, world_size, rank):
@@ -19,21 +19,25 @@ def shard_range(nframes, world_size, rank):
 
 
 def pack_rect_lists(first_frame, rect_lists):
-    """per-frame rect arrays -> one uint8 blob: int64 header [nframes, first_frame], int64 counts, then the rect_t bytes"""
-    counts = np.array([len(r) for r in rect_lists], np.int64)
+    """per-frame rect arrays (a list, or a RectLists) -> one uint8 blob: int64 header [nframes, first_frame], int64 counts, then the rect_t bytes"""
     head = np.array([len(rect_lists), first_frame], np.int64)
-    body = np.concatenate([np.ascontiguousarray(r).view(np.uint8).reshape(-1) for r in rect_lists]) if len(rect_lists) and counts.sum() else np.zeros(0, np.uint8)
+    if isinstance(rect_lists, RectLists):
+        counts = rect_lists.counts().astype(np.int64)
+        body = np.ascontiguousarray(rect_lists.flat[: int(counts.sum())]).view(np.uint8).reshape(-1)
+    else:
+        counts = np.array([len(r) for r in rect_lists], np.int64)
+        body = np.concatenate([np.ascontiguousarray(r).view(np.uint8).reshape(-1) for r in rect_lists]) if len(rect_lists) and counts.sum() else np.zeros(0, np.uint8)
     return np.concatenate([head.view(np.uint8), counts.view(np.uint8), body])
 
 
 def unpack_rect_lists(blob):
-    """inverse of pack_rect_lists -> (first_frame, [rect arrays]); the arrays are views of one copy of the payload"""
+    """inverse of pack_rect_lists -> (first_frame, RectLists over one copy of the payload)"""
     blob = np.ascontiguousarray(blob, np.uint8)
     nframes, first = (int(v) for v in blob[:16].view(np.int64))
     counts = blob[16: 16 + 8 * nframes].view(np.int64)
     off = 16 + 8 * nframes
     flat = blob[off: off + int(counts.sum()) * RECT_DTYPE.itemsize].copy().view(RECT_DTYPE)
-    return first, (np.split(flat, np.cumsum(counts)[:-1]) if nframes else [])
+    return first, RectLists(flat, counts)
 
 
 def gather_rect_lists(first_frame, rect_lists, nframes_total, device=None):
@@ -43,7 +47,7 @@ def gather_rect_lists(first_frame, rect_lists, nframes_total, device=None):
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return list(rect_lists)
+        return rect_lists
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device(device) if device is not None else torch.device("cpu")
     blob = torch.from_numpy(pack_rect_lists(first_frame, rect_lists)).to(dev)
@@ -57,9 +61,19 @@ def gather_rect_lists(first_frame, rect_lists, nframes_total, device=None):
     dist.all_gather(parts, padded)
     if rank != 0:
         return None
-    full = [None] * nframes_total
+    # ranks own contiguous shards in rank order (shard_range), so the full list is the concatenation of the parts
+    firsts, flats, counts = [], [], []
     for r in range(world):
         first, lists = unpack_rect_lists(parts[r][: int(sizes[r].item())].cpu().numpy())
-        for i, rl in enumerate(lists):
-            full[first + i] = rl
-    return full
+        firsts.append(first)
+        flats.append(lists.flat)
+        counts.append(lists.counts())
+    order = np.argsort(firsts, kind="stable")
+    pos = 0
+    for r in order:
+        if len(counts[r]) and firsts[r] != pos:
+            raise ValueError("rank shards are not contiguous: shard starting at frame %d arrives at position %d" % (firsts[r], pos))
+        pos += len(counts[r])
+    if pos != nframes_total:
+        raise ValueError("gathered %d frames, expected %d" % (pos, nframes_total))
+    return RectLists(np.concatenate([flats[r] for r in order]), np.concatenate([counts[r] for r in order]))

@@ -96,7 +96,7 @@ def compare_steps(iw, ih, seed, steps, rd, dev, ws=None, frames_before=0):
 # types than the reference's; every entry maps one plane to the oracle step / buffer that holds the same values.
 # stage -> [(cuda buffer, dtype, kind, oracle step, oracle buffer, oracle dtype, oracle kind)]
 FAST_STAGES = {
-    1: [("buf0", np.uint32, "n", 1, "buf0", np.uint32, "n")],
+    1: [("aux0", np.uint32, "n", 1, "buf0", np.uint32, "n")],                         # packed Lab (the production schedule keeps it off the reference's plan)
     2: [("tmp1", np.float32, "n", 3, "tmp1", np.float32, "n"), ("tmp2", np.float32, "n", 3, "tmp2", np.float32, "n"),
         ("tmp3", np.float32, "n", 3, "tmp3", np.float32, "n"), ("buf1", np.uint32, "n", 4, "buf1", np.uint32, "n")],
     3: [("buf2", np.float32, "n", 7, "buf1", np.float32, "n")],                       # thinned edge strength

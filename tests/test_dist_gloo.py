@@ -30,7 +30,13 @@ def test_pack_unpack_roundtrip():
     assert first == 17 and len(back) == len(lists)
     assert all(a.tobytes() == b.tobytes() for a, b in zip(lists, back))
     first, back = rdist.unpack_rect_lists(rdist.pack_rect_lists(0, []))
-    assert first == 0 and back == []
+    assert first == 0 and len(back) == 0 and list(back) == []
+    # a RectLists (what the batch engine returns: one flat array + offsets) packs without touching the per-frame views
+    from rectdetect_b200.api import RectLists
+    rl = RectLists(np.concatenate(lists), [len(r) for r in lists])
+    first, again = rdist.unpack_rect_lists(rdist.pack_rect_lists(3, rl))
+    assert first == 3 and len(again) == len(lists) and again[-1].tobytes() == lists[-1].tobytes() and again[0].size == 0
+    assert [a.tobytes() for a in again[1:3]] == [b.tobytes() for b in lists[1:3]]
 
 
 def _fake_rects(frame):
