@@ -195,15 +195,22 @@ static void k_mkMergeMask1(int32_t *inout, const int32_t *junctionIn, int iw, in
 }
 
 // ---- oclrect.cl:289-334 + oclrect.c:325-331 : labelxPreprocess + 8 x labelMergeMain ----
-// The reference's result is schedule dependent: (i) 8 in-place passes need not converge, (ii) the
-// adopt rule `(pix equal || mask[adopter])` is asymmetric so even the fixed point depends on the order in
-// which trees merge, (iii) pixels of the 1-px image border never run the main pass.
-// CANONICAL: components of the graph made of
-//   - the labelxPreprocess links (every pixel: up neighbour if same colour, else left if same colour), and
-//   - every 4-neighbour pair (a, b) with b = a+1 or a+iw, at least one of the two not on the image border,
-//     with edge[b] <= 0 and (pix[a] == pix[b] || mask[a] != 0 || mask[b] != 0);
-// pixels not on the image border get the smallest index of their component, image-border pixels keep their
-// labelxPreprocess value (as they do in the reference unless an interior pixel happens to point at them).
+// The reference's result is schedule dependent: (i) 8 in-place passes need not converge, (ii) a pixel adopts a neighbour's label only
+// if that label is CURRENTLY smaller, and the test `(pix equal || mask[adopter])` is asymmetric, so which trees merge depends on
+// the order of the work-items and on transient pointer values, (iii) pixels of the 1-px image border never run the main pass.
+// CANONICAL (Q6'): a deterministic fixed point of the same rule.  For a 4-neighbour pair (a, b), b = a+1 or a+iw, with edge[b] <= 0:
+//     b may adopt from a  iff  b is not on the image border and (pix[a] == pix[b] || mask[b] != 0)
+//     a may adopt from b  iff  a is not on the image border and (pix[a] == pix[b] || mask[a] != 0)
+//   - the labelxPreprocess links (every pixel: up neighbour if same colour, else left if same colour) and the pairs that may adopt in
+//     BOTH directions are united unconditionally (whatever the order, one of the two labels is the smaller one);
+//   - a pair that may adopt in ONE direction only is united when the source's component label (smallest index) is smaller than
+//     the adopter's - the reference's `s < g` - evaluated for all such pairs at once on the labels of the round before, for at
+//     most ORA_MERGE_ROUNDS rounds (the second one has never enabled anything on the frames of the sweeps: it confirms the fixed point);
+// pixels not on the image border get the smallest index of their component, image-border pixels keep their labelxPreprocess value
+// (as they do in the reference unless an interior pixel happens to point at them).
+// Against the reference's raster-order run (tests/test_ref_device.py, profiles/r04q_*): 0-220 interior pixels of a 640x480 frame
+// differ (round 1's rule - unite every pair that may adopt in at least one direction - 58-460, always a coarsening).
+#define ORA_MERGE_ROUNDS 2
 static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
   const int n = iw * ih;
   std::vector<int32_t> init(n);
@@ -218,19 +225,29 @@ static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, 
   MinUF uf(label);
   for (int p = 0; p < n; p++) if (init[p] != p) uf.unite(p, init[p]);
   auto interior = [&](int x, int y) { return x > 0 && y > 0 && x < iw - 1 && y < ih - 1; };
+  std::vector<std::pair<int, int>> dir;                    // (adopter, source)
+  auto pair_ab = [&](int a, int b, bool ia, bool ib) {
+    if (!(edge[b] <= 0)) return;
+    const bool same = pix[a] == pix[b];
+    const bool b_from_a = ib && (same || mask[b] != 0), a_from_b = ia && (same || mask[a] != 0);
+    if (b_from_a && a_from_b) uf.unite(a, b);
+    else if (b_from_a) dir.push_back({b, a});
+    else if (a_from_b) dir.push_back({a, b});
+  };
   for (int y = 0; y < ih; y++)
     for (int x = 0; x < iw; x++) {
       const int a = y * iw + x;
-      if (x + 1 < iw && (interior(x, y) || interior(x + 1, y))) {
-        const int b = a + 1;
-        if (edge[b] <= 0 && (pix[a] == pix[b] || mask[a] != 0 || mask[b] != 0)) uf.unite(a, b);
-      }
-      if (y + 1 < ih && (interior(x, y) || interior(x, y + 1))) {
-        const int b = a + iw;
-        if (edge[b] <= 0 && (pix[a] == pix[b] || mask[a] != 0 || mask[b] != 0)) uf.unite(a, b);
-      }
+      if (x + 1 < iw) pair_ab(a, a + 1, interior(x, y), interior(x + 1, y));
+      if (y + 1 < ih) pair_ab(a, a + iw, interior(x, y), interior(x, y + 1));
     }
   std::vector<int32_t> root(n);
+  for (int round = 0; round < ORA_MERGE_ROUNDS; round++) {
+    for (int p = 0; p < n; p++) root[p] = uf.find_compress(p);
+    std::vector<size_t> en;
+    for (size_t i = 0; i < dir.size(); i++) if (root[dir[i].second] < root[dir[i].first]) en.push_back(i);
+    if (en.empty()) break;
+    for (size_t i : en) uf.unite(dir[i].first, dir[i].second);
+  }
   for (int p = 0; p < n; p++) root[p] = uf.find_compress(p);
   for (int y = 0; y < ih; y++)
     for (int x = 0; x < iw; x++) {

@@ -22,9 +22,10 @@
  *   - despeckle2 (Q3) updates its labels in place: the oracle evaluates it in raster order, i.e. exactly as the reference run
  *     does - bit-exact on identical inputs;
  *   - labelMergeMain (Q6') is ORDER DEPENDENT in the reference (directed adopt rule gated on the current labels).  The
- *     oracle fixes a deterministic outcome (components of the symmetric closure of the adopt rule) whose relation to the
- *     sequential schedule is tested (coarsening, < 1 % of the pixels); with that one kernel swapped for the reference's
- *     the oracle reproduces the reference's region map bit-exactly.
+ *     oracle fixes a deterministic fixed point of the same rule (two-directional pairs united, one-directional pairs united
+ *     where the source's component label is smaller; ora_rect.cpp) whose distance from the sequential schedule is tested (a
+ *     handful to a few hundred interior pixels per frame); with that one kernel swapped for the reference's the oracle
+ *     reproduces the reference's region map bit-exactly.
  * Every other place where the reference is schedule-dependent (atomic arrival order, in-place races, vote-slot claims)
  * is resolved the way the raster-order schedule resolves it; each is marked "CANONICAL" in the sources and listed in
  * DESIGN.md section "Canonical semantics".  Vendor-defined OpenCL built-ins (rsqrt, hypot, distance, FP contraction) follow

@@ -64,8 +64,15 @@ struct LinkPl {                       // labelpl_main: numbers (+1) both non-zer
     return m;
   }
 };
+// labelxPreprocess + labelMergeMain in the canonical form of DESIGN.md (Q6'): for a 4-neighbour pair (a, b), b = a+1 or a+iw, with
+// edge[b] <= 0, b may adopt from a iff b is interior and (same colour or mask[b]); a may adopt from b iff a is interior and (same
+// colour or mask[a]).  Preprocess links and pairs that may adopt in both directions are plain links of the labelling below; a
+// pair that may adopt in ONE direction only is marked (L_DW / L_DN: the pixel's pair with its W / N neighbour) and decided by the
+// gating rounds after the labelling (k_merge_gate / k_merge_apply): united when the source's label is smaller than the adopter's.
+#define L_DW 0x10                       // merge only: the pair (W neighbour, this pixel) may adopt in one direction
+#define L_DN 0x20                       // ... the pair (N neighbour, this pixel)
 template <class MASK>
-struct LinkMerge {                    // labelxPreprocess + labelMergeMain, canonical symmetric form (see rd_rect.cu / DESIGN.md)
+struct LinkMerge {
   struct V { uint32_t pix; uint32_t fl; };        // fl bit 0: mask != 0, bit 1: edge <= 0
   const uint32_t *pix; const MASK *mask; const int *edge; int iw, ih;
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix, mask, edge); }
@@ -74,18 +81,25 @@ struct LinkMerge {                    // labelxPreprocess + labelMergeMain, cano
     return v;
   }
   __device__ __forceinline__ bool interior(int x, int y) const { return x > 0 && y > 0 && x < iw - 1 && y < ih - 1; }
+  // pair (a, b), b = this pixel: 3 = both directions, 1 = only b adopts from a, 2 = only a adopts from b, 0 = none
+  __device__ __forceinline__ unsigned pair(V a, V b, bool ia, bool ib) const {
+    if (!(b.fl & 2)) return 0;
+    const bool same = a.pix == b.pix;
+    return ((ib && (same || (b.fl & 1))) ? 1u : 0u) | ((ia && (same || (a.fl & 1))) ? 2u : 0u);
+  }
   __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
     unsigned m = 0;
     const bool upSame = y > 0 && n.pix == c.pix;
-    const bool e = (c.fl & 2) != 0, mb = (c.fl & 1) != 0;
+    const bool ic = interior(x, y);
     if (y > 0) {
-      if (upSame) m |= L_N;                                                     // preprocess link
-      else if ((interior(x, y) || interior(x, y - 1)) && e && (mb || (n.fl & 1))) m |= L_N;
+      const unsigned d = pair(n, c, interior(x, y - 1), ic);
+      if (upSame || d == 3) m |= L_N;                                          // preprocess link / both directions
+      else if (d) m |= L_DN;
     }
     if (x > 0) {
-      const bool same = w.pix == c.pix;
-      if (same && !upSame) m |= L_W;                                            // preprocess link (left only when up differs)
-      else if ((interior(x, y) || interior(x - 1, y)) && e && (same || mb || (w.fl & 1))) m |= L_W;
+      const unsigned d = pair(w, c, interior(x - 1, y), ic);
+      if ((w.pix == c.pix && !upSame) || d == 3) m |= L_W;                      // preprocess link (left only when up differs) / both directions
+      else if (d) m |= L_DW;
     }
     return m;
   }
@@ -362,17 +376,103 @@ void rd_labelpl(int *label, const int *num, void *scratch, int iw, int ih, int n
   ccl_core(label, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
   RD_LAUNCH(k_ccl_flatten, rd_gy(rd_cdiv(iw * ih, 256), nb), 256, 0, s, label, (const uint8_t *)scratch, 0, iw * ih, fs);
 }
-// labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331), converged.  work: iw*ih ints, scratch: iw*ih bytes; out may not alias work
-void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  LinkMerge<int> f = {pix, mask, edge, iw, ih};
+// ---- the gating rounds of the merge labelling.  label[] holds tile roots that point at final roots (after k_ccl_roots), so the
+// component label of a pixel is label[label[p]].  k_merge_gate decides every marked pair on the labels as they are (nothing is
+// modified but bits of the pixel's own link byte: L_NW / L_NE are free here, the merge graph is 4-connected), k_merge_apply then
+// unites.  flags[r] != 0: round r enabled something; the kernels of round r > 0 return at once when flags[r - 1] == 0.
+#define RD_MERGE_ROUNDS 2            // one round applies, the second confirms: no frame of the sweeps enables anything in a second round
+template <class MASK>
+__global__ void k_merge_gate(const int *label, uint8_t *links, LinkMerge<MASK> f, int *flags, int round, int iw, int ih, size_t fs) {
+  rd_batch_y(fs, label, links, flags);
+  f.shift((size_t)blockIdx.y * fs);
+  const int n = iw * ih;
+  if (round > 0 && flags[round - 1] == 0) return;
+  bool any = false;
+  for (int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; p4 < n; p4 += gridDim.x * blockDim.x * 4) {
+  unsigned m4;
+  if (p4 + 3 < n) m4 = *(const uint32_t *)(links + p4);
+  else { m4 = 0; for (int k = 0; p4 + k < n; k++) m4 |= (unsigned)links[p4 + k] << (8 * k); }
+  if (!(m4 & 0x30303030u)) continue;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const unsigned m = (m4 >> (8 * k)) & 255u;
+    if (!(m & (L_DW | L_DN))) continue;
+    const int p = p4 + k, x = p % iw, y = p / iw;
+    const typename LinkMerge<MASK>::V c = f.load(p);
+    const int rc = __ldcg(label + __ldcg(label + p));
+    unsigned en = 0;
+    if (m & L_DW) {
+      const unsigned d = f.pair(f.load(p - 1), c, f.interior(x - 1, y), f.interior(x, y));
+      const int rw = __ldcg(label + __ldcg(label + p - 1));
+      if ((d == 1 && rw < rc) || (d == 2 && rc < rw)) en |= L_NW;               // (adopter = this pixel, source = W) or the other way round
+    }
+    if (m & L_DN) {
+      const unsigned d = f.pair(f.load(p - iw), c, f.interior(x, y - 1), f.interior(x, y));
+      const int rn = __ldcg(label + __ldcg(label + p - iw));
+      if ((d == 1 && rn < rc) || (d == 2 && rc < rn)) en |= L_NE;
+    }
+    if (en) { links[p] = (uint8_t)(m | en); any = true; }
+  }
+  }
+  if (any) flags[round] = 1;
+}
+__global__ void k_merge_apply(int *label, uint8_t *links, const int *flags, int round, int iw, int n, size_t fs) {
+  rd_batch_y(fs, label, links, flags);
+  if (flags[round] == 0) return;
+  for (int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; p4 < n; p4 += gridDim.x * blockDim.x * 4) {
+    unsigned m4;
+    if (p4 + 3 < n) m4 = *(const uint32_t *)(links + p4);
+    else { m4 = 0; for (int k = 0; p4 + k < n; k++) m4 |= (unsigned)links[p4 + k] << (8 * k); }
+    if (!(m4 & 0x0a0a0a0au)) continue;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned m = (m4 >> (8 * k)) & 255u;
+      if (!(m & (L_NW | L_NE))) continue;
+      const int p = p4 + k;
+      if (m & L_NW) rd_uf_unite(label, p, p - 1);
+      if (m & L_NE) rd_uf_unite(label, p, p - iw);
+      links[p] = (uint8_t)(m & ~(L_NW | L_NE));
+    }
+  }
+}
+// k_ccl_roots of a gating round: only when the round united something
+__global__ void k_merge_roots(int *label, const uint8_t *links, const int *flags, int round, int n, size_t fs) {
+  rd_batch_y(fs, label, links, flags);
+  if (flags[round] == 0) return;
+  for (int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; p4 < n; p4 += gridDim.x * blockDim.x * 4) {
+    unsigned m4;
+    if (p4 + 3 < n) m4 = *(const uint32_t *)(links + p4);
+    else { m4 = 0; for (int k = 0; p4 + k < n; k++) m4 |= (unsigned)links[p4 + k] << (8 * k); }
+    if (!(m4 & 0x40404040u)) continue;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if ((m4 >> (8 * k)) & L_ROOT) label[p4 + k] = rd_uf_find(label, p4 + k);
+  }
+}
+template <class MASK>
+static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  RD_CUDA(cudaMemset2DAsync(flags, fs ? fs : RD_MERGE_ROUNDS * sizeof(int), 0, RD_MERGE_ROUNDS * sizeof(int), nb, s));
   ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  const int n = iw * ih, g4 = rd_cdiv(rd_cdiv(n, 4), 256);
+  // round 0 has work on a third of the frames, the kernels behind the gate of a later round practically never: small grids there
+  // (grid-stride loops)
+  const int gs = g4 < 48 ? g4 : 48;
+  for (int r = 0; r < RD_MERGE_ROUNDS; r++) {
+    RD_LAUNCH(k_merge_gate<MASK>, rd_gy(g4, nb), 256, 0, s, (const int *)work, (uint8_t *)scratch, f, flags, r, iw, ih, fs);
+    RD_LAUNCH(k_merge_apply, rd_gy(r == 0 ? g4 : gs, nb), 256, 0, s, work, (uint8_t *)scratch, (const int *)flags, r, iw, n, fs);
+    RD_LAUNCH(k_merge_roots, rd_gy(r == 0 ? g4 : gs, nb), 256, 0, s, work, (const uint8_t *)scratch, (const int *)flags, r, n, fs);
+  }
   const dim3 b(32, 8);
-  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, pix, iw, ih, fs);
+  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, f.pix, iw, ih, fs);
+}
+// labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331) in the canonical form.  work: iw*ih ints, scratch: iw*ih bytes, flags:
+// RD_MERGE_ROUNDS ints; out may not alias work
+void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+  LinkMerge<int> f = {pix, mask, edge, iw, ih};
+  merge_core(out, work, f, scratch, flags, iw, ih, nb, fs, s);
 }
 // same with the merge mask as a byte plane
-void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
+void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   LinkMerge<uint8_t> f = {pix, mask, edge, iw, ih};
-  ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
-  const dim3 b(32, 8);
-  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, pix, iw, ih, fs);
+  merge_core(out, work, f, scratch, flags, iw, ih, nb, fs, s);
 }

@@ -21,7 +21,7 @@
 typedef linesegment_t LS_t;
 
 void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
-void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_k_clear(int *out, int nints, int nb, size_t fs, cudaStream_t s);
 void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream_t s);
 void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, int nb, size_t fs, cudaStream_t s);
@@ -42,7 +42,7 @@ void rd_despeckle2_run(int *dst, const int *label, const int *size, int *list, i
                        int nb, size_t fs, cudaStream_t s);
 void rd_markBoundary_run(int *out, const int *in, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_label8x_u8(int *label, const uint8_t *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
-void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_polyline_fast(LS_t *lsList, int lsListSize, int *lsIdOut, const int *in, int *copyOut, int *tmpBig, int *t0, int *t1, int *t2, int *t3, int *t4, int *t5,
                       float minerror, int sizeThre, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_gtail_run(unsigned char *blob, size_t blobBytes, const linesegment_t *ls, const int *segid, const int *votes, int *table, unsigned char *scratch,
@@ -466,7 +466,7 @@ static void gpu_task(oclrect_t *o, const uint8_t *din, size_t din_fs, int ws, in
   RD_LAUNCH(kr_mkMergeMask1, rd_gz(G2, nb), RB, 0, s, PI(tmp[1]), PI(tmp[0]), iw, ih, fs);
   STEP(16);
   // step 17 : colour regions (work plane tmp4, link bytes tmp5: both dead until the polyline stage rewrites them)
-  rd_labelMerge(PI(buf[5]), PI(tmp[4]), PU(buf[4]), PI(tmp[1]), PI(buf[2]), tmp[5]->dptr, iw, ih, nb, fs, s);
+  rd_labelMerge(PI(buf[5]), PI(tmp[4]), PU(buf[4]), PI(tmp[1]), PI(buf[2]), tmp[5]->dptr, PI(tmp[2]), iw, ih, nb, fs, s);     // round flags: tmp2 (dead)
   STEP(17);
   // step 18 : region sizes on top of the junction map (Q2), small regions absorbed in place in raster order (rd_despeckle2.cu;
   // input snapshot in tmp4, list planes tmp2 / tmp3 / tmp5, row counts tmp1, wide-frame row buffer ioBig0: all dead here)
@@ -549,7 +549,7 @@ static void gpu_task_fast(oclrect_t *o, const uint8_t *din, size_t din_fs, int w
   STAGE(8);
   rd_junction_mask_run((uint8_t *)tmp[3]->dptr, PI(tmp[0]), PI(tmp[5]), iw, ih, nb, fs, s);
   STAGE(9);
-  rd_labelMerge_u8(PI(buf[4]), PI(buf[5]), PU(tmp[2]), (const uint8_t *)tmp[3]->dptr, PI(tmp[5]), tmp[4]->dptr, iw, ih, nb, fs, s);
+  rd_labelMerge_u8(PI(buf[4]), PI(buf[5]), PU(tmp[2]), (const uint8_t *)tmp[3]->dptr, PI(tmp[5]), tmp[4]->dptr, PI(buf[1]), iw, ih, nb, fs, s);   // round flags: buf1 (dead)
   STAGE(10);
   rd_calcSize_run(PI(tmp[0]), PI(buf[4]), iw, ih, nb, fs, s);
   // despeckle2 in raster order: final labels -> buf5; list planes buf1 / buf2 / tmp2, row counts + wide-frame row buffer tmp3 (all dead here)
@@ -863,9 +863,9 @@ void rd_rect_mkMergeMask1(cl_mem io, cl_mem j, int iw, int ih, cl_command_queue 
 void rd_rect_labelMerge(cl_mem label, cl_mem pix, cl_mem mask, cl_mem edge, int iw, int ih, cl_command_queue q) {
   QS;
   int *work = NULL; void *links = NULL;
-  RD_CUDA(cudaMallocAsync((void **)&work, (size_t)iw * ih * 4, s));
+  RD_CUDA(cudaMallocAsync((void **)&work, (size_t)iw * ih * 4 + 64, s));
   RD_CUDA(cudaMallocAsync(&links, (size_t)iw * ih, s));
-  rd_labelMerge(PI(label), work, PU(pix), PI(mask), PI(edge), links, iw, ih, 1, 0, s);
+  rd_labelMerge(PI(label), work, PU(pix), PI(mask), PI(edge), links, work + (size_t)iw * ih, iw, ih, 1, 0, s);
   RD_CUDA(cudaFreeAsync(work, s));
   RD_CUDA(cudaFreeAsync(links, s));
 }

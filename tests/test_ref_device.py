@@ -9,10 +9,12 @@ What is pinned here (CPU tests; the GPU tests pin the CUDA path to the oracle pl
   * oclpolyline_execute steps 1-11 (string clean-up ... relabel, the whole split loop): every plane, the segment-id map and
     the segment list BIT-EXACT, and so is step 12 (refine): the final polyline vertex list, floats included;
   * calcSize, markBoundary, label8x, reduceLS (the vote table) on identical inputs: BIT-EXACT;
-  * the two kernels whose outcome depends on the order of the work-items - labelMergeMain (Q6') and despeckle2 (Q3) - are
-    compared through the relation the canonical choice has to the sequential schedule (coarsening / bounded difference),
-    and with them swapped for the reference's kernels the oracle reproduces the reference's region map bit-exactly;
-  * end to end (oclrect_executeOnce): same rectangles within 1e-4 relative on the frames where the two deviations do not
+  * despeckle2 (Q3: in-place update) is evaluated in raster order, i.e. exactly as the reference run does: BIT-EXACT;
+  * the ONE kernel whose outcome depends on the order of the work-items in a way no deterministic rule reproduces -
+    labelMergeMain (Q6') - is compared through the distance of the canonical choice from the sequential schedule (a handful
+    to a few hundred interior pixels per frame), and with it swapped for the reference's kernel the oracle reproduces the
+    reference's region map bit-exactly;
+  * end to end (oclrect_executeOnce): same rectangles within 1e-4 relative on the frames where that deviation does not
     change a region that carries a rectangle;
   * poly.cpp:104-123 (config 1) replayed through the reference's own L2 operators.
 """
@@ -127,20 +129,23 @@ def _splits(a, b):
     return int((np.unique(pairs[:, 0], return_counts=True)[1] > 1).sum())
 
 
-@pytest.mark.parametrize("iw,ih,seed", [(640, 480, 2), (640, 480, 9)])
-def test_label_merge_canonical_choice_against_the_sequential_schedule(ctx, iw, ih, seed):
-    """labelMergeMain (oclrect.cl:300-334): the adopt rule is directed and gated on the current labels, so which regions
-    merge depends on the order of the work-items.  The canonical result (components of the rule's symmetric closure,
-    DESIGN.md Q6') must be a COARSENING of what the sequential schedule produces and differ in well under 1 % of the frame."""
+@pytest.mark.parametrize("iw,ih,seed,max_px", [(640, 480, 2, 0), (640, 480, 9, 4), (641, 479, 33, 250), (1280, 720, 1000, 100)])
+def test_label_merge_canonical_choice_against_the_sequential_schedule(ctx, iw, ih, seed, max_px):
+    """labelMergeMain (oclrect.cl:300-334): a pixel adopts a neighbour's label only if it is currently smaller, and the adopt test
+    is asymmetric, so which regions merge depends on the order of the work-items.  The canonical result (DESIGN.md Q6': pairs that
+    may adopt in both directions are united, one-directional pairs only where the source's component label is smaller) against the
+    sequential (raster) schedule of the reference: the two partitions of the interior pixels differ in at most `max_px` pixels
+    (measured: 0 / 2 / 217 / 71; round 1's rule - unite every pair that may adopt in at least one direction - 58 / 136 / 459 / 505)."""
     _, d = _oracle_stage_b_inputs(iw, ih, seed)
     ref = _ref_label_merge(d, iw, ih, passes=12)
     assert np.array_equal(ref[7], ref[11])                           # the reference's 8 passes have converged on these frames
     inner = np.zeros((ih, iw), bool)
     inner[1:-1, 1:-1] = True
     inner = inner.ravel()
-    # (image-border pixels never run the main pass: preprocess labels on both sides, except where the reference's
-    # atomic_min on a root lands on a border pixel an interior pixel pointed at - they are part of the < 1 % below)
-    assert _splits(ref[7][inner], d["label"][inner]) == 0            # every reference region lies inside ONE canonical region
+    # compare as partitions: both label every interior pixel with the smallest index of its region once the reference has converged
+    # (image-border pixels never run the main pass: preprocess labels on the canonical side, whatever an atomic_min left on the reference's)
+    diff = int((ref[7][inner] != d["label"][inner]).sum())
+    assert diff <= max_px, diff
     assert (ref[7] != d["label"]).mean() < 0.01
 
 
