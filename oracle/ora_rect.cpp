@@ -207,8 +207,9 @@ static void k_mkMergeMask1(int32_t *inout, const int32_t *junctionIn, int iw, in
 //     the adopter's - the reference's `s < g` - evaluated for all such pairs at once on the labels of the round before, for at
 //     most ORA_MERGE_ROUNDS rounds (the second one has never enabled anything on the frames of the sweeps: it confirms the fixed point);
 // pixels not on the image border get the smallest index of their component, image-border pixels keep their labelxPreprocess value
-// (as they do in the reference unless an interior pixel happens to point at them).
-// Against the reference's raster-order run (tests/test_ref_device.py, profiles/r04q_*): 0-220 interior pixels of a 640x480 frame
+// except on the top row: a top-row pixel whose lower neighbour has its colour and is no edge pixel lands on the start of its run
+// of equal colours (the reference's first pass, row 1 adopting from row 0 left to right, flattens the row-0 chains that way).
+// Against the reference's raster-order run (tests/test_ref_device.py, profiles/r04r_*): 0-220 interior pixels of a 640x480 frame
 // differ (round 1's rule - unite every pair that may adopt in at least one direction - 58-460, always a coarsening).
 #define ORA_MERGE_ROUNDS 2
 static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
@@ -254,6 +255,16 @@ static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, 
       const int p0 = y * iw + x;
       label[p0] = interior(x, y) ? root[p0] : init[p0];
     }
+  // The top row.  An interior pixel q = (x, 1) with the colour of p = (x, 0) starts out pointing at p; when it first adopts - in the
+  // reference's first pass, from p itself, whose preprocess label is its left neighbour - it chases the pointers along the top row
+  // to the start of p's run of equal colours and drags p along (atomic_min(&label[og], g), og = p).  So in the reference's raster
+  // run the top-row pixels sit on the START OF THEIR RUN, not on their left neighbour (99.6 % of the image-frame labels of the
+  // reference follow this rule, 70 % the plain preprocess rule).  Left / right / bottom frame pixels are nobody's first pointer.
+  int start = 0;
+  for (int x = 0; x < iw; x++) {
+    if (x == 0 || pix[x] != pix[x - 1]) start = x;
+    if (x >= 1 && x < iw - 1 && ih > 2 && start != x && pix[iw + x] == pix[x] && edge[iw + x] <= 0) label[x] = start;
+  }
 }
 
 // ---- oclrect.cl:336-346 ----

@@ -449,6 +449,25 @@ __global__ void k_merge_roots(int *label, const uint8_t *links, const int *flags
       if ((m4 >> (8 * k)) & L_ROOT) label[p4 + k] = rd_uf_find(label, p4 + k);
   }
 }
+// The top row of the merge labelling (see the oracle, ora_rect.cpp labelMerge): a pixel of the top row whose lower neighbour has its
+// colour and is no edge pixel ends up on the START of its run of equal colours - that is where the reference's first pass drags
+// it - instead of on its left neighbour.  One warp per frame: run starts by a max-scan over chunks of 32 columns.
+__global__ void __launch_bounds__(32) k_merge_toprow(int *out, const uint32_t *pix, const int *edge, int iw, int ih, size_t fs) {
+  rd_batch_x(fs, out, pix, edge);
+  if (ih <= 2) return;
+  const int lane = threadIdx.x;
+  int carry = 0;
+  for (int x0 = 0; x0 < iw; x0 += 32) {
+    const int x = x0 + lane;
+    const uint32_t c = x < iw ? pix[x] : 0u;
+    int v = (x < iw && (x == 0 || pix[x - 1] != c)) ? x : -1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
+    v = max(v, carry);
+    carry = __shfl_sync(0xffffffffu, v, 31);
+    if (x >= 1 && x < iw - 1 && v != x && pix[iw + x] == c && edge[iw + x] <= 0) out[x] = v;
+  }
+}
 template <class MASK>
 static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   RD_CUDA(cudaMemset2DAsync(flags, fs ? fs : RD_MERGE_ROUNDS * sizeof(int), 0, RD_MERGE_ROUNDS * sizeof(int), nb, s));
@@ -464,6 +483,7 @@ static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, in
   }
   const dim3 b(32, 8);
   RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, f.pix, iw, ih, fs);
+  RD_LAUNCH(k_merge_toprow, nb, 32, 0, s, out, f.pix, f.edge, iw, ih, fs);
 }
 // labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331) in the canonical form.  work: iw*ih ints, scratch: iw*ih bytes, flags:
 // RD_MERGE_ROUNDS ints; out may not alias work
