@@ -212,19 +212,45 @@ static void k_mkMergeMask1(int32_t *inout, const int32_t *junctionIn, int iw, in
 // Against the reference's raster-order run (tests/test_ref_device.py, profiles/r04r_*): 0-220 interior pixels of a 640x480 frame
 // differ (round 1's rule - unite every pair that may adopt in at least one direction - 58-460, always a coarsening).
 #define ORA_MERGE_ROUNDS 2
-static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
-  const int n = iw * ih;
-  std::vector<int32_t> init(n);
+// The first pass of labelMergeMain, replayed in raster order exactly as the reference's kernel runs it (oclrect.cl:300-334 after
+// labelxPreprocess :289-298): image-frame pixels are skipped, a pixel compares the RAW current labels of its neighbours, follows the
+// pointers eight times and lowers label[og] and its own label.
+static void merge_first_pass(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
   for (int y = 0; y < ih; y++)
     for (int x = 0; x < iw; x++) {
       const int p0 = y * iw + x;
-      if (y > 0 && pix[p0] == pix[p0 - iw]) init[p0] = p0 - iw;
-      else if (x > 0 && pix[p0] == pix[p0 - 1]) init[p0] = p0 - 1;
-      else init[p0] = p0;
+      if (y > 0 && pix[p0] == pix[p0 - iw]) label[p0] = p0 - iw;
+      else if (x > 0 && pix[p0] == pix[p0 - 1]) label[p0] = p0 - 1;
+      else label[p0] = p0;
     }
+  for (int y = 1; y < ih - 1; y++)
+    for (int x = 1; x < iw - 1; x++) {
+      const int p0 = y * iw + x;
+      int g = label[p0];
+      const int og = g;
+      const bool m = mask[p0] != 0;
+      int p1 = p0 - iw, s = label[p1];
+      if (s < g && (pix[p0] == pix[p1] || m) && edge[p0] <= 0) g = s;
+      p1 = p0 - 1; s = label[p1];
+      if (s < g && (pix[p0] == pix[p1] || m) && edge[p0] <= 0) g = s;
+      p1 = p0 + 1; s = label[p1];
+      if (s < g && (pix[p0] == pix[p1] || m) && edge[p1] <= 0) g = s;
+      p1 = p0 + iw; s = label[p1];
+      if (s < g && (pix[p0] == pix[p1] || m) && edge[p1] <= 0) g = s;
+      for (int j = 0; j < 8; j++) g = label[g];
+      if (g != og) {
+        if (g < label[og]) label[og] = g;
+        if (g < label[p0]) label[p0] = g;
+      }
+    }
+}
+static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
+  const int n = iw * ih;
+  std::vector<int32_t> first(n);
+  merge_first_pass(first.data(), pix, mask, edge, iw, ih);
   for (int p = 0; p < n; p++) label[p] = p;
   MinUF uf(label);
-  for (int p = 0; p < n; p++) if (init[p] != p) uf.unite(p, init[p]);
+  for (int p = 0; p < n; p++) if (first[p] != p) uf.unite(p, first[p]);
   auto interior = [&](int x, int y) { return x > 0 && y > 0 && x < iw - 1 && y < ih - 1; };
   std::vector<std::pair<int, int>> dir;                    // (adopter, source)
   auto pair_ab = [&](int a, int b, bool ia, bool ib) {
@@ -250,21 +276,14 @@ static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, 
     for (size_t i : en) uf.unite(dir[i].first, dir[i].second);
   }
   for (int p = 0; p < n; p++) root[p] = uf.find_compress(p);
+  // interior pixels: the smallest index of their component.  Image-frame pixels never run the main pass; they keep what the first
+  // pass left in them, except that one that was still the root of its tree after the first pass has been hooked under a smaller
+  // root since: the smallest index of its component.
   for (int y = 0; y < ih; y++)
     for (int x = 0; x < iw; x++) {
       const int p0 = y * iw + x;
-      label[p0] = interior(x, y) ? root[p0] : init[p0];
+      label[p0] = (interior(x, y) || first[p0] == p0) ? root[p0] : first[p0];
     }
-  // The top row.  An interior pixel q = (x, 1) with the colour of p = (x, 0) starts out pointing at p; when it first adopts - in the
-  // reference's first pass, from p itself, whose preprocess label is its left neighbour - it chases the pointers along the top row
-  // to the start of p's run of equal colours and drags p along (atomic_min(&label[og], g), og = p).  So in the reference's raster
-  // run the top-row pixels sit on the START OF THEIR RUN, not on their left neighbour (99.6 % of the image-frame labels of the
-  // reference follow this rule, 70 % the plain preprocess rule).  Left / right / bottom frame pixels are nobody's first pointer.
-  int start = 0;
-  for (int x = 0; x < iw; x++) {
-    if (x == 0 || pix[x] != pix[x - 1]) start = x;
-    if (x >= 1 && x < iw - 1 && ih > 2 && start != x && pix[iw + x] == pix[x] && edge[iw + x] <= 0) label[x] = start;
-  }
 }
 
 // ---- oclrect.cl:336-346 ----
@@ -364,6 +383,7 @@ void ora_rect_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2
 void ora_rect_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih) { k_despeckle(out, in, edge, iw, ih); }
 void ora_rect_mkMergeMask0(int32_t *out, const int32_t *junction, int iw, int ih) { k_mkMergeMask0(out, junction, iw, ih); }
 void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int ih) { k_mkMergeMask1(inout, junction, iw, ih); }
+void ora_rect_labelMerge_first_pass(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { merge_first_pass(label, pix, mask, edge, iw, ih); }
 void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { labelMerge(label, pix, mask, edge, iw, ih); }
 void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih) { k_calcSize(out, label, iw, ih); }
 void ora_rect_despeckle2(int32_t *labelinout, const int32_t *size, int thre, int iw, int ih) { k_despeckle2(labelinout, size, thre, iw, ih); }

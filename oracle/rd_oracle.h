@@ -108,6 +108,8 @@ void ora_rect_despeckle(uint32_t *out, const uint32_t *in, const float *edge, in
 void ora_rect_mkMergeMask0(int32_t *out, const int32_t *junction, int iw, int ih);
 void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int ih);
 /* labelxPreprocess + labelMergeMain x8 -> CANONICAL converged symmetric merge */
+/* labelxPreprocess + the first labelMergeMain pass in raster order (= the reference kernel run sequentially once) */
+void ora_rect_labelMerge_first_pass(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);
 void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);
 void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih);
 /* in place, work-items in raster order (CANONICAL Q3 = the reference run) */

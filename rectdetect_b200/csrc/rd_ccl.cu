@@ -14,6 +14,7 @@
 //   3. k_ccl_flatten: every pixel reads its final root.
 // HBM traffic: predicate inputs once, 1 B/px links write + seam re-reads, label plane written twice and read once.
 #include "rd_common.cuh"
+#include "rd_merge1.cuh"
 
 #define TW 32
 #define TH 32
@@ -64,11 +65,13 @@ struct LinkPl {                       // labelpl_main: numbers (+1) both non-zer
     return m;
   }
 };
-// labelxPreprocess + labelMergeMain in the canonical form of DESIGN.md (Q6'): for a 4-neighbour pair (a, b), b = a+1 or a+iw, with
+// labelxPreprocess + labelMergeMain (DESIGN.md Q6'): the first pass is replayed exactly (rd_merge1.cuh, kernels below); what the seven
+// other passes make of it is the fixed point of the adopt rule, computed here.  For a 4-neighbour pair (a, b), b = a+1 or a+iw, with
 // edge[b] <= 0, b may adopt from a iff b is interior and (same colour or mask[b]); a may adopt from b iff a is interior and (same
-// colour or mask[a]).  Preprocess links and pairs that may adopt in both directions are plain links of the labelling below; a
-// pair that may adopt in ONE direction only is marked (L_DW / L_DN: the pixel's pair with its W / N neighbour) and decided by the
-// gating rounds after the labelling (k_merge_gate / k_merge_apply): united when the source's label is smaller than the adopter's.
+// colour or mask[a]).  Pairs that may adopt in both directions are plain links of the labelling below (whatever the order, one of the
+// two labels is the smaller one), the pointers the first pass left are united with it afterwards (k_merge_seed); a pair that may
+// adopt in ONE direction only is marked (L_DW / L_DN: the pixel's pair with its W / N neighbour) and decided by the gating rounds
+// (k_merge_gate / k_merge_apply): united when the source's label is smaller than the adopter's.
 #define L_DW 0x10                       // merge only: the pair (W neighbour, this pixel) may adopt in one direction
 #define L_DN 0x20                       // ... the pair (N neighbour, this pixel)
 template <class MASK>
@@ -89,16 +92,15 @@ struct LinkMerge {
   }
   __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
     unsigned m = 0;
-    const bool upSame = y > 0 && n.pix == c.pix;
     const bool ic = interior(x, y);
     if (y > 0) {
       const unsigned d = pair(n, c, interior(x, y - 1), ic);
-      if (upSame || d == 3) m |= L_N;                                          // preprocess link / both directions
+      if (d == 3) m |= L_N;                                                     // both directions
       else if (d) m |= L_DN;
     }
     if (x > 0) {
       const unsigned d = pair(w, c, interior(x - 1, y), ic);
-      if ((w.pix == c.pix && !upSame) || d == 3) m |= L_W;                      // preprocess link (left only when up differs) / both directions
+      if (d == 3) m |= L_W;
       else if (d) m |= L_DW;
     }
     return m;
@@ -330,18 +332,15 @@ __global__ void k_ccl_flatten_list(int *label, const uint8_t *links, int *list, 
   base = __shfl_sync(0xffffffffu, base, leader);
   if (fg) list[1 + base + __popc(m & ((1u << lane) - 1))] = p;
 }
-// labelMerge: interior pixels get the root, image-border pixels keep their labelxPreprocess value (oclrect.cl:289-298)
-__global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *pix, int iw, int ih, size_t fs) {
-  rd_batch_z(fs, out, label, pix);
+// labelMerge: interior pixels get the root.  Image-frame pixels never run the main pass: they keep what the first pass left in them
+// (first[]), except that a frame pixel that was still the root of its tree then has been hooked under a smaller root since.
+__global__ void k_ccl_flatten_merge(int *out, const int *label, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, label);
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
   const int p = y * iw + x;
-  if (x > 0 && y > 0 && x < iw - 1 && y < ih - 1) { out[p] = __ldcg(label + __ldcg(label + p)); return; }
-  const uint32_t v = pix[p];
-  int l = p;
-  if (y > 0 && pix[p - iw] == v) l = p - iw;
-  else if (x > 0 && pix[p - 1] == v) l = p - 1;
-  out[p] = l;
+  const int first = out[p];
+  if ((x > 0 && y > 0 && x < iw - 1 && y < ih - 1) || first == p) out[p] = __ldcg(label + __ldcg(label + p));
 }
 
 template <class LinkFn>
@@ -449,30 +448,160 @@ __global__ void k_merge_roots(int *label, const uint8_t *links, const int *flags
       if ((m4 >> (8 * k)) & L_ROOT) label[p4 + k] = rd_uf_find(label, p4 + k);
   }
 }
-// The top row of the merge labelling (see the oracle, ora_rect.cpp labelMerge): a pixel of the top row whose lower neighbour has its
-// colour and is no edge pixel ends up on the START of its run of equal colours - that is where the reference's first pass drags
-// it - instead of on its left neighbour.  One warp per frame: run starts by a max-scan over chunks of 32 columns.
-__global__ void __launch_bounds__(32) k_merge_toprow(int *out, const uint32_t *pix, const int *edge, int iw, int ih, size_t fs) {
-  rd_batch_x(fs, out, pix, edge);
-  if (ih <= 2) return;
-  const int lane = threadIdx.x;
-  int carry = 0;
-  for (int x0 = 0; x0 < iw; x0 += 32) {
-    const int x = x0 + lane;
-    const uint32_t c = x < iw ? pix[x] : 0u;
-    int v = (x < iw && (x == 0 || pix[x - 1] != c)) ? x : -1;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
-    v = max(v, carry);
-    carry = __shfl_sync(0xffffffffu, v, 31);
-    if (x >= 1 && x < iw - 1 && v != x && pix[iw + x] == c && edge[iw + x] <= 0) out[x] = v;
+// ---- the first pass, exactly (rd_merge1.cuh).  k_m1_pre: per-pixel records, A = L0, B = none, all three in the time-major layout
+// of the wavefront.  k_m1_wave: one CTA per frame, lane = row, warp = 32 rows, the warps take the groups of 32 rows round robin; a
+// warp may run step t of its group once the group above has finished step t + 32 * M1_SKEW (its last row is then M1_SKEW pixels
+// ahead of this group's first row) - progress counters in shared memory.  All planes are read and written by this one CTA, so
+// plain (L1) accesses are coherent.  k_m1_fold: back to the image layout, label = min(A, B).
+template <class MASK>
+__global__ void k_m1_pre(int *A, int *B, uint8_t *F, LinkMerge<MASK> f, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, A, B, F);
+  f.shift((size_t)blockIdx.z * fs);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const int p = y * iw + x, i = m1_index_xy(x, y, iw, ih);
+  const bool in = x > 0 && y > 0 && x < iw - 1 && y < ih - 1;
+  int L0;
+  const unsigned r = m1_record(x, y, iw, ih, f.pix[p], y > 0 ? f.pix[p - iw] : 0u, x > 0 ? f.pix[p - 1] : 0u, in ? f.pix[p + 1] : 0u, in ? f.pix[p + 1 - iw] : 0u,
+                               in && f.mask[p] != 0, in && f.edge[p] <= 0, in && f.edge[p + 1] <= 0, L0);
+  A[i] = L0;
+  B[i] = M1_NONE;
+  F[i] = (uint8_t)r;
+}
+// Per step a lane needs: its record (fetched a step ahead; one contiguous run of bytes per warp), the label of the pixel above as
+// the row above left it - that row's lane holds it in a register three steps after it did the pixel to the right of it, so it
+// travels by shuffle through a three-deep delay line (a lane whose upper row belongs to another warp, or is the top row of the
+// image, reads it from memory four steps ahead: that row is at least 128 pixels further on) - and whatever the pointer chase
+// touches (gathers; the two roots met last are remembered).  What the lanes store in a step is contiguous in the time-major layout.
+#define M1_POLL 8                      // steps between two looks at the progress of the group above
+template <bool BIG>
+__global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_t *F0, int *err, int iw, int ih, size_t fs) {
+  rd_batch_x(fs, A0, B0, F0, err);
+  int *__restrict__ A = A0, *__restrict__ B = B0;
+  const uint8_t *__restrict__ F = F0;
+  __shared__ volatile int prog[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+  if (threadIdx.x < 32) prog[threadIdx.x] = 0;
+  __syncthreads();
+  const int groups = (ih + 31) >> 5, S = (iw + M1_SKEW * 31 + M1_POLL - 1) & ~(M1_POLL - 1), prev = w == 0 ? W - 1 : w - 1;
+  auto wrap = [&](int v) { if (BIG) return v >= iw ? v - iw : v; return m1_wrap(v, iw); };
+  M1TimeMajor<BIG> mem;
+  mem.A = A; mem.B = B; mem.iw = iw; mem.ih = ih; mem.rcp = 1.0f / (float)iw;
+  for (int G = w; G < groups; G += W) {
+    const int y = G * 32 + lane, R = m1_rows(G, ih), gbase = (G << 5) * iw + lane;
+    const bool rowint = y > 0 && y < ih - 1;
+    const bool memup = rowint && (lane == 0 || y == 1);                           // the row above is not the lane above
+    // where the row above lives: the lane above, or lane 31 of the group above.  Element (x, y - 1) = ubase + wrap(t + ushift) * uR
+    // at the step t = x + M1_SKEW * lane in which this lane does pixel x
+    const int ubase = lane > 0 ? gbase - 1 : ((G - 1) << 5) * iw + 31, uR = lane > 0 ? R : 32;
+    const int ushift = lane > 0 ? wrap(iw - wrap(M1_SKEW)) : wrap(M1_SKEW * 31);
+    M1Row r;
+    r.gleft = 0; r.croot[0] = r.croot[1] = -1;
+    int d0 = 0, d1 = 0, d2 = 0;
+    int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    auto wait_for = [&](int t0) {                                                  // the group above has finished what steps t0 .. t0 + M1_POLL - 1 read
+      const int need = (G - 1) * (S + 1) + min(t0 + 2 * M1_POLL + 32 * M1_SKEW, S);
+      unsigned spins = 0;
+      while (prog[prev] < need) {
+        __nanosleep(1500);                                                          // (a step takes some hundred ns, progress is published every M1_POLL steps)
+        if (++spins > (1u << 18)) { *err = 1; __trap(); }                          // (never: a stuck wavefront ends the process loudly instead of hanging the device)
+      }
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
+    };
+    if (G > 0) wait_for(0);
+    // running positions (time-major indices) of: this lane's pixel, the pixel above it, the pixel above four steps ahead
+    int tm = 0, pos = gbase, posL = gbase;
+    int utm = ushift, posU = ubase + utm * uR;
+    int qtm = wrap(utm + wrap(4)), qpos = ubase + qtm * uR;
+    if (memup) {
+      q3 = A[posU];
+      if (1 < iw) q2 = A[ubase + wrap(utm + 1) * uR];
+      if (2 < iw) q1 = A[ubase + wrap(utm + wrap(2)) * uR];
+      if (3 < iw) q0 = A[ubase + wrap(utm + wrap(3)) * uR];
+    }
+    // records two steps ahead: fn = of the pixel of this step, fn1 = of the next
+    unsigned fn = 0, fn1 = 0;
+    if (rowint && lane == 0) { fn = F[gbase]; if (1 < iw) fn1 = F[gbase + R]; }   // x = 0 of lane 0 is step 0
+    int x = -M1_SKEW * lane, p = y * iw + x;
+    const int iwR = iw * R, iwuR = iw * uR;
+    int pos2 = gbase + wrap(2) * R, tm2 = wrap(2);                                 // position two steps ahead
+    int aupn = 0;                                                                  // (the shuffle of the next step's operand is issued a step early)
+    for (int t = 0; t < S; t++) {
+      if (G > 0 && t > 0 && (t & (M1_POLL - 1)) == 0) wait_for(t);
+      int aup = aupn;
+      if (memup) {
+        aup = q3;
+        q3 = q2; q2 = q1; q1 = q0;
+        q0 = (unsigned)(x + 4) < (unsigned)iw ? A[qpos] : 0;
+      }
+      int fin = r.gleft;
+      if (rowint && (unsigned)x < (unsigned)iw) {
+        const unsigned f = fn;
+        if (!(f & M1_INT)) r.gleft = A[pos];
+        else {
+          mem.pos = pos; mem.posL = posL; mem.posU = posU;
+          fin = m1_pixel(p, iw, f, aup, mem, r);
+        }
+      }
+      posL = pos;
+      pos += R; posU += uR; qpos += uR;
+      if (++tm == iw) { tm = 0; pos -= iwR; }
+      if (++utm == iw) { utm = 0; posU -= iwuR; }
+      if (++qtm == iw) { qtm = 0; qpos -= iwuR; }
+      x++; p++;
+      fn = fn1;
+      fn1 = (rowint && (unsigned)(x + 1) < (unsigned)iw) ? F[pos2] : 0u;           // the record of the step after the next
+      pos2 += R;
+      if (++tm2 == iw) { tm2 = 0; pos2 -= iwR; }
+      d2 = d1; d1 = d0; d0 = fin;
+      aupn = __shfl_up_sync(0xffffffffu, d2, 1);                                   // what the lane above produced three steps before the next one
+      __syncwarp();
+      if ((t & (M1_POLL - 1)) == M1_POLL - 1) {
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
+        if (lane == 0) prog[w] = G * (S + 1) + t + 1;
+      }
+    }
   }
+}
+// label after the first pass = min(A, B), in the image layout
+__global__ void k_m1_fold(int *out, const int *A, const int *B, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, A, B);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const int i = m1_index_xy(x, y, iw, ih);
+  out[y * iw + x] = min(A[i], B[i]);
+}
+// the pointers of the first pass into the union-find of the pair labelling
+__global__ void k_merge_seed(int *label, const int *first, int n, size_t fs) {
+  rd_batch_y(fs, label, first);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int t = first[p];
+  if (t == p) return;
+  const int a = __ldcg(label + p), b = __ldcg(label + t);                       // tile roots
+  if (a != b) rd_uf_unite(label, a, b);
 }
 template <class MASK>
 static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  RD_CUDA(cudaMemset2DAsync(flags, fs ? fs : RD_MERGE_ROUNDS * sizeof(int), 0, RD_MERGE_ROUNDS * sizeof(int), nb, s));
-  ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  // flags: RD_MERGE_ROUNDS round flags + the guard word of the wavefront
+  RD_CUDA(cudaMemset2DAsync(flags, fs ? fs : (RD_MERGE_ROUNDS + 1) * sizeof(int), 0, (RD_MERGE_ROUNDS + 1) * sizeof(int), nb, s));
   const int n = iw * ih, g4 = rd_cdiv(rd_cdiv(n, 4), 256);
+  const dim3 b(32, 8);
+  // the first pass: A = work, B = scratch (as a plane of ints), records in `out` - whose image-layout content the fold then writes
+  RD_LAUNCH(k_m1_pre<MASK>, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, work, (int *)scratch, (uint8_t *)out, f, iw, ih, fs);
+  // warps per CTA: a group of 32 rows starts 32 * M1_SKEW + 2 * M1_POLL steps after the one above and takes iw + 31 * M1_SKEW steps,
+  // so no more than that many groups (+ 1) are ever under way at once; further warps would only hold registers
+  const int groups = rd_cdiv(ih, 32), live = (iw + M1_SKEW * 31) / (32 * M1_SKEW + 2 * M1_POLL) + 2;
+  const int wv = groups < live ? groups : (live < 32 ? live : 32);
+  if (iw >= M1_BIG && n < (1 << 24))
+    RD_LAUNCH(k_m1_wave<true>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
+  else
+    RD_LAUNCH(k_m1_wave<false>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
+  RD_LAUNCH(k_m1_fold, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, (const int *)scratch, iw, ih, fs);
+  // pairs that may adopt in both directions, then the pointers of the first pass
+  ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
+  RD_LAUNCH(k_merge_seed, rd_gy(rd_cdiv(n, 256), nb), 256, 0, s, work, (const int *)out, n, fs);
+  RD_LAUNCH(k_ccl_roots, rd_gy(g4, nb), 256, 0, s, work, (const uint8_t *)scratch, n, fs);
   // round 0 has work on a third of the frames, the kernels behind the gate of a later round practically never: small grids there
   // (grid-stride loops)
   const int gs = g4 < 48 ? g4 : 48;
@@ -481,12 +610,10 @@ static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, in
     RD_LAUNCH(k_merge_apply, rd_gy(r == 0 ? g4 : gs, nb), 256, 0, s, work, (uint8_t *)scratch, (const int *)flags, r, iw, n, fs);
     RD_LAUNCH(k_merge_roots, rd_gy(r == 0 ? g4 : gs, nb), 256, 0, s, work, (const uint8_t *)scratch, (const int *)flags, r, n, fs);
   }
-  const dim3 b(32, 8);
-  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, f.pix, iw, ih, fs);
-  RD_LAUNCH(k_merge_toprow, nb, 32, 0, s, out, f.pix, f.edge, iw, ih, fs);
+  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, iw, ih, fs);
 }
-// labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331) in the canonical form.  work: iw*ih ints, scratch: iw*ih bytes, flags:
-// RD_MERGE_ROUNDS ints; out may not alias work
+// labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331).  work: iw*ih ints, scratch: iw*ih ints, flags: RD_MERGE_ROUNDS + 1 ints;
+// out may not alias work
 void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
   LinkMerge<int> f = {pix, mask, edge, iw, ih};
   merge_core(out, work, f, scratch, flags, iw, ih, nb, fs, s);

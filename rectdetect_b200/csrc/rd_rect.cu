@@ -864,7 +864,7 @@ void rd_rect_labelMerge(cl_mem label, cl_mem pix, cl_mem mask, cl_mem edge, int 
   QS;
   int *work = NULL; void *links = NULL;
   RD_CUDA(cudaMallocAsync((void **)&work, (size_t)iw * ih * 4 + 64, s));
-  RD_CUDA(cudaMallocAsync(&links, (size_t)iw * ih, s));
+  RD_CUDA(cudaMallocAsync(&links, (size_t)iw * ih * 4, s));
   rd_labelMerge(PI(label), work, PU(pix), PI(mask), PI(edge), links, work + (size_t)iw * ih, iw, ih, 1, 0, s);
   RD_CUDA(cudaFreeAsync(work, s));
   RD_CUDA(cudaFreeAsync(links, s));

@@ -71,6 +71,7 @@ def oracle():
             "ora_rect_quantize": (None, [vp, vp, i, i, i, i, i]), "ora_rect_despeckle": (None, [vp, vp, vp, i, i]),
             "ora_rect_mkMergeMask0": (None, [vp, vp, i, i]), "ora_rect_mkMergeMask1": (None, [vp, vp, i, i]),
             "ora_rect_labelMerge": (None, [vp, vp, vp, vp, i, i]),
+            "ora_rect_labelMerge_first_pass": (None, [vp, vp, vp, vp, i, i]),
             "ora_rect_calcSize": (None, [vp, vp, i, i]), "ora_rect_despeckle2": (None, [vp, vp, i, i, i]),
             "ora_rect_markBoundary": (None, [vp, vp, i, i]), "ora_rect_reduceLS": (None, [vp, vp, vp, i, i, i]),
             "ora_polyline_execute": (None, [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, f, i, i, i, i]),

@@ -11,7 +11,12 @@ needs no GPU (the -m gpu tests then check the kernels themselves).
 2. The device tail (executeCPUTask on the GPU, rectdetect_b200/csrc/rd_gtail.cu): its logic is rd_gtail.cuh; tests/emu_gtail.cpp runs
 the per-item kernels as loops and the warp-per-candidate kernel with its 32 lanes as fibers (every ballot / shuffle / syncwarp
 is a rendezvous, so a missing synchronisation shows up as a wrong answer).  The rect_t lists must equal the oracle's tail - and
-through it the reference's own executeCPUTask (tests/test_ref_tail.py) - byte for byte, in the same order."""
+through it the reference's own executeCPUTask (tests/test_ref_tail.py) - byte for byte, in the same order.
+
+3. The first pass of labelMergeMain as a row wavefront (rd_merge1.cuh, kernels k_m1_pre / k_m1_wave of rd_ccl.cu):
+tests/emu_merge1.cpp runs every row as a lane, all rows in lock step M1_SKEW pixels apart, with the A / B split of the label
+plane and the one-step operand prefetch of the kernel.  Result = the oracle's sequential pass (= the reference kernel,
+tests/test_ref_device.py), and no address is touched by two lanes in one step when one of them writes."""
 import ctypes as C
 import os
 import subprocess
@@ -141,3 +146,56 @@ def test_device_tail_replay_with_vote_collisions_and_dead_segments(emu_tail):
     ls[0] = 0
     got, _ = _emu_tail(emu_tail, ls, seg, votes, iw, ih, tan)
     assert len(got) == 0
+
+
+# ---- 3. first pass of the merge labelling as a wavefront ----
+SO_M1 = os.path.join(ROOT, "tests", "_emu", "libemu_m1.so")
+
+
+@pytest.fixture(scope="module")
+def emu_m1():
+    os.makedirs(os.path.dirname(SO_M1), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", SO_M1, os.path.join(ROOT, "tests", "emu_merge1.cpp")])
+    E = C.CDLL(SO_M1)
+    E.emu_merge1.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4
+    E.emu_merge1.restype = C.c_long
+    return E
+
+
+def _m1_both(E, pix, mask, edge, iw, ih, check):
+    want, got = np.zeros(iw * ih, np.int32), np.zeros(iw * ih, np.int32)
+    ol.oracle().ora_rect_labelMerge_first_pass(P(want), P(pix), P(mask), P(edge), iw, ih)
+    hazards = E.emu_merge1(P(got), P(pix), P(mask), P(edge), iw, ih, 4, check)
+    return want, got, hazards
+
+
+@pytest.mark.parametrize("iw,ih,seed", [(640, 480, 2), (641, 479, 33), (322, 200, 31), (130, 97, 31), (48, 40, 32), (1280, 720, 1000)])
+def test_merge_first_pass_wavefront_on_pipeline_planes(emu_m1, iw, ih, seed):
+    img = ol.synth_frame(iw, ih, seed)
+    o = ol.OracleRect(iw, ih)
+    o.gpu_task(img, img.shape[-1], 16)                               # up to mkMergeMask1: pix = buf4, mask = tmp1, edge = buf2
+    pix, mask, edge = o.buffer("buf4").copy(), o.buffer("tmp1").copy(), o.buffer("buf2").copy()
+    o.close()
+    want, got, hazards = _m1_both(emu_m1, pix, mask, edge, iw, ih, 1 if iw <= 640 else 0)
+    assert np.array_equal(want, got)
+    assert hazards == 0
+
+
+def test_merge_first_pass_wavefront_on_adversarial_planes(emu_m1):
+    """few colours (long pointer chains, deep chases: the 8-step limit of the kernel's chase is exercised), dense masks (every
+    pixel may adopt from every neighbour), dense and sparse edges, frames narrower than the skew and smaller than a warp"""
+    rng = np.random.default_rng(7)
+    for k in range(160):
+        iw, ih = int(rng.integers(3, 100)), int(rng.integers(3, 80))
+        if k % 5 == 0:
+            iw, ih = int(rng.integers(3, 8)), int(rng.integers(30, 120))
+        ncol = int(rng.integers(1, 4))
+        pix = rng.integers(0, ncol + 1, iw * ih).astype(np.int32)
+        if k % 3 == 0:                                               # horizontal / vertical stripes: chains as long as the frame
+            yy, xx = np.divmod(np.arange(iw * ih), iw)
+            pix = (((yy // int(rng.integers(1, 4))) + (xx // int(rng.integers(1, 30))) * (k % 2)) % (ncol + 1)).astype(np.int32)
+        mask = (rng.random(iw * ih) < rng.choice([0.0, 0.02, 0.3, 0.9])).astype(np.int32)
+        edge = (rng.random(iw * ih) < rng.choice([0.0, 0.05, 0.3])).astype(np.int32)
+        want, got, hazards = _m1_both(emu_m1, pix, mask, edge, iw, ih, 1)
+        assert np.array_equal(want, got), (k, iw, ih)
+        assert hazards == 0, (k, iw, ih, hazards)

@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Run on a GPU box: production-schedule parity (every stage plane + rectangle lists) against the CPU oracle over a sweep of
 frame sizes and seeds, including widths that are not multiples of 4 / 32 / 128 and frames smaller than a tile.
-usage: gpu_stress_parity.py [quick]"""
+Every third case is a frame tiled from 3x3 independent scenes (many more segments / regions / candidates: long read-back
+records, long despeckle2 runs, more tail candidates).
+usage: gpu_stress_parity.py [quick | <first seed> <seeds per size>]"""
 import os
 import sys
 import time
@@ -12,16 +14,20 @@ import parity  # noqa: E402
 import oracle_lib as ol  # noqa: E402
 import rectdetect_b200 as rd  # noqa: E402
 
-quick = len(sys.argv) > 1
+quick = len(sys.argv) == 2
 sizes = [(640, 480), (641, 479), (322, 200), (130, 97), (96, 64), (1000, 562), (1284, 724), (1920, 1080), (257, 511), (48, 40), (1276, 716), (800, 600)]
 seeds = [11, 12] if quick else [21, 22, 23, 24]
+if len(sys.argv) > 2:
+    seeds = list(range(int(sys.argv[1]), int(sys.argv[1]) + int(sys.argv[2])))
 dev = rd.Device(0)
 t0 = time.time()
 nbad = 0
+ncase = 0
 for iw, ih in sizes:
     for seed in seeds:
         bad = [r for r in parity.compare_fast_stages(iw, ih, seed, sorted(parity.FAST_STAGES), rd, dev) if r[2] != 0]
-        img = ol.synth_frame(iw, ih, seed)
+        ncase += 1
+        img = ol.dense_frame(iw, ih, seed, 3, 3) if (ncase % 3 == 0 and iw >= 320) else ol.synth_frame(iw, ih, seed)
         o = ol.OracleRect(iw, ih)
         g = rd.OclRect(dev, iw, ih)
         ok, why = True, ""
