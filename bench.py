@@ -12,7 +12,8 @@ roofline: the kernel with the largest share of device time against the measured 
           from CUDA events around every launch on the launching stream (in the library), in a separate pass through ONE
           pipeline object so that each kernel is timed alone; per-stage (A/B/C/D) totals of the same pass are reported too.
 sub-records of the same JSON line: config4 (1920x1080, 512 frames per step over all ranks: strong scaling), config5 (one 3840x2160 frame,
-          per-stage roofline), api_stream (the reference's enqueue/poll API, unchanged caller), parity_checked_frames (frames of the
+          per-stage roofline), api_stream (the reference's enqueue/poll API, unchanged caller), merge_replay (cost of the exact first-pass
+          replay of labelMergeMain, off by default), parity_checked_frames (frames of the
           timed batch compared with the CPU oracle after the timed region).
 --impl reference : THE REFERENCE ITSELF on the host cores - oracle/_ref/librd_ref.so = its unmodified host code and its OpenCL C
           kernels compiled as C++ (oracle/Makefile target _ref), one instance per core on a bounded sample of the stream per step;
@@ -431,6 +432,42 @@ def main():
                                 "execute_once_ms": once1 * 1e3,
                                 "objects_%d" % nobj: {"value": nobj * (nstream // 2 + 2) * iw * ih / dtn / 1e6, "unit": "Mpix/s", "frames_per_object": nstream // 2 + 2,
                                                       "note": "one oclrect_t + queue per host thread, object creation and warm-up inside the timing"}}
+        # the first-pass replay of labelMergeMain (rd_set_merge_replay(1) / RD_MERGE_REPLAY=1: the reference's region map bit for bit,
+        # include/rectdetect_b200.h): what it costs - one frame through executeOnce, a short batch - and a parity check in that mode
+        rd.set_merge_replay(True)
+        ol.oracle().ora_set_merge_replay(1)
+        try:
+            g = rd.OclRect(rd.Device(local_rank), iw, ih)
+            g.execute_once(sf[0], TAN_AOV)
+            ts = []
+            for i in range(6):
+                t1 = time.perf_counter()
+                rr = g.execute_once(sf[1 + i % 2], TAN_AOV)
+                ts.append(time.perf_counter() - t1)
+            g.close()
+            o = ol.OracleRect(iw, ih)
+            o.execute_once(sf[0], TAN_AOV)
+            for i in range(6):
+                want = o.execute_once(sf[1 + i % 2], TAN_AOV)                              # (same carry-over history as the object above)
+            o.close()
+            nrep = min(hi - lo, 128)
+            dev_rep = synth_batch(iw, ih, 1000, nrep, pinned=False).to("cuda")
+            brep = rd.Batch(local_rank, iw, ih, nctx=args.nctx, frames_per_launch=args.fpl)
+            for _ in range(2):
+                brep.run(dev_rep.data_ptr(), frame_bytes, ws, nrep, TAN_AOV, on_device=True, want_rects=False)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(3):
+                brep.run(dev_rep.data_ptr(), frame_bytes, ws, nrep, TAN_AOV, on_device=True, want_rects=False)
+            torch.cuda.synchronize()
+            dtb = (time.perf_counter() - t1) / 3
+            brep.close()
+            del dev_rep
+            extras["merge_replay"] = {"what": "labelMergeMain with the reference's first pass replayed exactly (off by default)", "execute_once_ms": sorted(ts)[len(ts) // 2] * 1e3,
+                                      "batch_value": nrep * iw * ih / dtb / 1e6, "unit": "Mpix/s", "batch_frames": nrep, "rects_identical_to_oracle_in_that_mode": want.tobytes() == rr.tobytes()}
+        finally:
+            rd.set_merge_replay(False)
+            ol.oracle().ora_set_merge_replay(0)
         # parity of the timed batch: the first frames of the batch against fresh oracle objects (outside every timed region)
         bad = []
         k = min(args.parity_frames, len(rects) if rects else 0)

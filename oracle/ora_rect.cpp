@@ -244,7 +244,66 @@ static void merge_first_pass(int32_t *label, const int32_t *pix, const int32_t *
       }
     }
 }
-static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
+// ---- the two forms of the merge labelling.  ora_set_merge_replay(0) (default): the schedule-independent fixed point alone, seeded
+// with the preprocess pointers - what the CUDA path computes by default.  ora_set_merge_replay(1): the first pass replayed exactly,
+// then the fixed point - the CUDA path under RD_MERGE_REPLAY=1 / rd_set_merge_replay(1). ----
+static int g_merge_replay = 0;
+static void labelMerge_fixed_point(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
+  const int n = iw * ih;
+  std::vector<int32_t> init(n);
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      if (y > 0 && pix[p0] == pix[p0 - iw]) init[p0] = p0 - iw;
+      else if (x > 0 && pix[p0] == pix[p0 - 1]) init[p0] = p0 - 1;
+      else init[p0] = p0;
+    }
+  for (int p = 0; p < n; p++) label[p] = p;
+  MinUF uf(label);
+  for (int p = 0; p < n; p++) if (init[p] != p) uf.unite(p, init[p]);
+  auto interior = [&](int x, int y) { return x > 0 && y > 0 && x < iw - 1 && y < ih - 1; };
+  std::vector<std::pair<int, int>> dir;                    // (adopter, source)
+  auto pair_ab = [&](int a, int b, bool ia, bool ib) {
+    if (!(edge[b] <= 0)) return;
+    const bool same = pix[a] == pix[b];
+    const bool b_from_a = ib && (same || mask[b] != 0), a_from_b = ia && (same || mask[a] != 0);
+    if (b_from_a && a_from_b) uf.unite(a, b);
+    else if (b_from_a) dir.push_back({b, a});
+    else if (a_from_b) dir.push_back({a, b});
+  };
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int a = y * iw + x;
+      if (x + 1 < iw) pair_ab(a, a + 1, interior(x, y), interior(x + 1, y));
+      if (y + 1 < ih) pair_ab(a, a + iw, interior(x, y), interior(x, y + 1));
+    }
+  std::vector<int32_t> root(n);
+  for (int round = 0; round < ORA_MERGE_ROUNDS; round++) {
+    for (int p = 0; p < n; p++) root[p] = uf.find_compress(p);
+    std::vector<size_t> en;
+    for (size_t i = 0; i < dir.size(); i++) if (root[dir[i].second] < root[dir[i].first]) en.push_back(i);
+    if (en.empty()) break;
+    for (size_t i : en) uf.unite(dir[i].first, dir[i].second);
+  }
+  for (int p = 0; p < n; p++) root[p] = uf.find_compress(p);
+  for (int y = 0; y < ih; y++)
+    for (int x = 0; x < iw; x++) {
+      const int p0 = y * iw + x;
+      label[p0] = interior(x, y) ? root[p0] : init[p0];
+    }
+  // The top row.  An interior pixel q = (x, 1) with the colour of p = (x, 0) starts out pointing at p; when it first adopts - in the
+  // reference's first pass, from p itself, whose preprocess label is its left neighbour - it chases the pointers along the top row
+  // to the start of p's run of equal colours and drags p along (atomic_min(&label[og], g), og = p).  So in the reference's raster
+  // run the top-row pixels sit on the START OF THEIR RUN, not on their left neighbour (99.6 % of the image-frame labels of the
+  // reference follow this rule, 70 % the plain preprocess rule).  Left / right / bottom frame pixels are nobody's first pointer.
+  int start = 0;
+  for (int x = 0; x < iw; x++) {
+    if (x == 0 || pix[x] != pix[x - 1]) start = x;
+    if (x >= 1 && x < iw - 1 && ih > 2 && start != x && pix[iw + x] == pix[x] && edge[iw + x] <= 0) label[x] = start;
+  }
+}
+
+static void labelMerge_replay(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
   const int n = iw * ih;
   std::vector<int32_t> first(n);
   merge_first_pass(first.data(), pix, mask, edge, iw, ih);
@@ -284,6 +343,11 @@ static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, 
       const int p0 = y * iw + x;
       label[p0] = (interior(x, y) || first[p0] == p0) ? root[p0] : first[p0];
     }
+}
+
+static void labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
+  if (g_merge_replay) labelMerge_replay(label, pix, mask, edge, iw, ih);
+  else labelMerge_fixed_point(label, pix, mask, edge, iw, ih);
 }
 
 // ---- oclrect.cl:336-346 ----
@@ -383,6 +447,8 @@ void ora_rect_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2
 void ora_rect_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih) { k_despeckle(out, in, edge, iw, ih); }
 void ora_rect_mkMergeMask0(int32_t *out, const int32_t *junction, int iw, int ih) { k_mkMergeMask0(out, junction, iw, ih); }
 void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int ih) { k_mkMergeMask1(inout, junction, iw, ih); }
+void ora_set_merge_replay(int on) { g_merge_replay = on != 0; }
+int ora_get_merge_replay(void) { return g_merge_replay; }
 void ora_rect_labelMerge_first_pass(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { merge_first_pass(label, pix, mask, edge, iw, ih); }
 void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { labelMerge(label, pix, mask, edge, iw, ih); }
 void ora_rect_calcSize(int32_t *out, const int32_t *label, int iw, int ih) { k_calcSize(out, label, iw, ih); }

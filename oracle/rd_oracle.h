@@ -108,6 +108,10 @@ void ora_rect_despeckle(uint32_t *out, const uint32_t *in, const float *edge, in
 void ora_rect_mkMergeMask0(int32_t *out, const int32_t *junction, int iw, int ih);
 void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int ih);
 /* labelxPreprocess + labelMergeMain x8 -> CANONICAL converged symmetric merge */
+/* which form of the merge labelling the oracle computes (process-wide): 0 = the schedule-independent fixed point (default, = the CUDA
+ * path by default), 1 = the reference's first pass replayed in raster order, then the fixed point (= the CUDA path with RD_MERGE_REPLAY=1) */
+void ora_set_merge_replay(int on);
+int ora_get_merge_replay(void);
 /* labelxPreprocess + the first labelMergeMain pass in raster order (= the reference kernel run sequentially once) */
 void ora_rect_labelMerge_first_pass(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);
 void ora_rect_labelMerge(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);

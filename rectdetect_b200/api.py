@@ -89,6 +89,8 @@ def lib():
         "rd_rect_blblur0": (None, [vp, vp, vp, i, i, vp]), "rd_rect_blblur1": (None, [vp, vp, vp, i, i, vp]),
         "rd_rect_quantize": (None, [vp, vp, i, i, i, i, i, vp]), "rd_rect_despeckle": (None, [vp, vp, vp, i, i, vp]),
         "rd_rect_mkMergeMask0": (None, [vp, vp, i, i, vp]), "rd_rect_mkMergeMask1": (None, [vp, vp, i, i, vp]),
+        "rd_set_merge_replay": (None, [i]),
+        "rd_get_merge_replay": (i, []),
         "rd_rect_labelMerge": (None, [vp, vp, vp, vp, i, i, vp]),
         "rd_rect_calcSize": (None, [vp, vp, i, i, vp]), "rd_rect_despeckle2": (None, [vp, vp, vp, i, i, i, vp]),
         "rd_rect_markBoundary": (None, [vp, vp, i, i, vp]), "rd_rect_reduceLS": (None, [vp, vp, vp, i, i, i, vp]),
@@ -118,6 +120,16 @@ def device_count():
 
 def kernel_launches():
     return lib().rd_kernel_launches()
+
+
+def set_merge_replay(on):
+    """labelMergeMain: 0 = schedule-independent fixed point (default), 1 = replay the reference's first pass exactly, then the
+    fixed point (include/rectdetect_b200.h); process-wide, set before creating OclRect / Batch objects"""
+    lib().rd_set_merge_replay(1 if on else 0)
+
+
+def get_merge_replay():
+    return bool(lib().rd_get_merge_replay())
 
 
 def _p(a):

@@ -65,8 +65,10 @@ struct LinkPl {                       // labelpl_main: numbers (+1) both non-zer
     return m;
   }
 };
-// labelxPreprocess + labelMergeMain (DESIGN.md Q6'): the first pass is replayed exactly (rd_merge1.cuh, kernels below); what the seven
-// other passes make of it is the fixed point of the adopt rule, computed here.  For a 4-neighbour pair (a, b), b = a+1 or a+iw, with
+// labelxPreprocess + labelMergeMain (DESIGN.md Q6'): the schedule-independent fixed point of the adopt rule, computed here.  By default
+// it starts from the preprocess pointers (they are plain links, LinkMerge::pre); with the first-pass replay on (rd_set_merge_replay /
+// RD_MERGE_REPLAY=1) the reference's first pass is replayed exactly (rd_merge1.cuh, kernels below) and the fixed point starts from
+// what that pass left - the reference's own region map on all but one frame of the sweeps, at ten times the cost of the labelling.  For a 4-neighbour pair (a, b), b = a+1 or a+iw, with
 // edge[b] <= 0, b may adopt from a iff b is interior and (same colour or mask[b]); a may adopt from b iff a is interior and (same
 // colour or mask[a]).  Pairs that may adopt in both directions are plain links of the labelling below (whatever the order, one of the
 // two labels is the smaller one), the pointers the first pass left are united with it afterwards (k_merge_seed); a pair that may
@@ -78,6 +80,7 @@ template <class MASK>
 struct LinkMerge {
   struct V { uint32_t pix; uint32_t fl; };        // fl bit 0: mask != 0, bit 1: edge <= 0
   const uint32_t *pix; const MASK *mask; const int *edge; int iw, ih;
+  int pre;                                        // 1: the preprocess pointers are links of the labelling too (no first-pass replay)
   __device__ __forceinline__ void shift(size_t o) { rd_batch_off(o, pix, mask, edge); }
   __device__ __forceinline__ V load(int p) const {
     V v; v.pix = pix[p]; v.fl = (mask[p] != 0 ? 1u : 0u) | (edge[p] <= 0 ? 2u : 0u);
@@ -92,15 +95,16 @@ struct LinkMerge {
   }
   __device__ __forceinline__ unsigned link(V c, V w, V nw, V n, V ne, int x, int y) const {
     unsigned m = 0;
+    const bool upSame = pre && y > 0 && n.pix == c.pix;
     const bool ic = interior(x, y);
     if (y > 0) {
       const unsigned d = pair(n, c, interior(x, y - 1), ic);
-      if (d == 3) m |= L_N;                                                     // both directions
+      if (upSame || d == 3) m |= L_N;                                           // preprocess link / both directions
       else if (d) m |= L_DN;
     }
     if (x > 0) {
       const unsigned d = pair(w, c, interior(x - 1, y), ic);
-      if (d == 3) m |= L_W;
+      if ((pre && w.pix == c.pix && !upSame) || d == 3) m |= L_W;               // preprocess link (left only when up differs) / both directions
       else if (d) m |= L_DW;
     }
     return m;
@@ -332,9 +336,23 @@ __global__ void k_ccl_flatten_list(int *label, const uint8_t *links, int *list, 
   base = __shfl_sync(0xffffffffu, base, leader);
   if (fg) list[1 + base + __popc(m & ((1u << lane) - 1))] = p;
 }
+// labelMerge: interior pixels get the root, image-border pixels keep their labelxPreprocess value (oclrect.cl:289-298)
+__global__ void k_ccl_flatten_merge(int *out, const int *label, const uint32_t *pix, int iw, int ih, size_t fs) {
+  rd_batch_z(fs, out, label, pix);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= iw || y >= ih) return;
+  const int p = y * iw + x;
+  if (x > 0 && y > 0 && x < iw - 1 && y < ih - 1) { out[p] = __ldcg(label + __ldcg(label + p)); return; }
+  const uint32_t v = pix[p];
+  int l = p;
+  if (y > 0 && pix[p - iw] == v) l = p - iw;
+  else if (x > 0 && pix[p - 1] == v) l = p - 1;
+  out[p] = l;
+}
+
 // labelMerge: interior pixels get the root.  Image-frame pixels never run the main pass: they keep what the first pass left in them
 // (first[]), except that a frame pixel that was still the root of its tree then has been hooked under a smaller root since.
-__global__ void k_ccl_flatten_merge(int *out, const int *label, int iw, int ih, size_t fs) {
+__global__ void k_ccl_flatten_merge1(int *out, const int *label, int iw, int ih, size_t fs) {
   rd_batch_z(fs, out, label);
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= iw || y >= ih) return;
@@ -446,6 +464,25 @@ __global__ void k_merge_roots(int *label, const uint8_t *links, const int *flags
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if ((m4 >> (8 * k)) & L_ROOT) label[p4 + k] = rd_uf_find(label, p4 + k);
+  }
+}
+// The top row of the merge labelling (see the oracle, ora_rect.cpp labelMerge): a pixel of the top row whose lower neighbour has its
+// colour and is no edge pixel ends up on the START of its run of equal colours - that is where the reference's first pass drags
+// it - instead of on its left neighbour.  One warp per frame: run starts by a max-scan over chunks of 32 columns.
+__global__ void __launch_bounds__(32) k_merge_toprow(int *out, const uint32_t *pix, const int *edge, int iw, int ih, size_t fs) {
+  rd_batch_x(fs, out, pix, edge);
+  if (ih <= 2) return;
+  const int lane = threadIdx.x;
+  int carry = 0;
+  for (int x0 = 0; x0 < iw; x0 += 32) {
+    const int x = x0 + lane;
+    const uint32_t c = x < iw ? pix[x] : 0u;
+    int v = (x < iw && (x == 0 || pix[x - 1] != c)) ? x : -1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, t); }
+    v = max(v, carry);
+    carry = __shfl_sync(0xffffffffu, v, 31);
+    if (x >= 1 && x < iw - 1 && v != x && pix[iw + x] == c && edge[iw + x] <= 0) out[x] = v;
   }
 }
 // ---- the first pass, exactly (rd_merge1.cuh).  k_m1_pre: per-pixel records, A = L0, B = none, all three in the time-major layout
@@ -571,15 +608,27 @@ __global__ void k_m1_fold(int *out, const int *A, const int *B, int iw, int ih, 
   const int i = m1_index_xy(x, y, iw, ih);
   out[y * iw + x] = min(A[i], B[i]);
 }
-// the pointers of the first pass into the union-find of the pair labelling
+// the pointers of the first pass into the union-find of the pair labelling.  label[] holds tile roots that point at final roots
+// (k_ccl_roots), so the component of a pixel is label[label[p]]; nearly every pointer stays inside its pixel's component, and along
+// a row most of the rest repeat the union the lane to the left already asks for.
 __global__ void k_merge_seed(int *label, const int *first, int n, size_t fs) {
   rd_batch_y(fs, label, first);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const int t = first[p];
-  if (t == p) return;
-  const int a = __ldcg(label + p), b = __ldcg(label + t);                       // tile roots
-  if (a != b) rd_uf_unite(label, a, b);
+  int a = -1, b = -1;
+  if (p < n) {
+    const int t = first[p];
+    if (t != p) { a = __ldcg(label + __ldcg(label + p)); b = __ldcg(label + __ldcg(label + t)); }
+  }
+  const int pa = __shfl_up_sync(0xffffffffu, a, 1), pb = __shfl_up_sync(0xffffffffu, b, 1);
+  if (a != b && !((threadIdx.x & 31) > 0 && pa == a && pb == b)) rd_uf_unite(label, a, b);
+}
+// 0: the fixed point from the preprocess pointers (default); 1: the first pass replayed exactly, then the fixed point.  Process-wide;
+// read when a labelling is enqueued (a captured CUDA graph keeps the mode it was captured with: set it before creating objects).
+static int g_merge_replay = -1;
+extern "C" void rd_set_merge_replay(int on) { g_merge_replay = on != 0; }
+extern "C" int rd_get_merge_replay(void) {
+  if (g_merge_replay < 0) { const char *e = getenv("RD_MERGE_REPLAY"); g_merge_replay = e && atoi(e) != 0; }
+  return g_merge_replay;
 }
 template <class MASK>
 static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
@@ -587,21 +636,27 @@ static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, in
   RD_CUDA(cudaMemset2DAsync(flags, fs ? fs : (RD_MERGE_ROUNDS + 1) * sizeof(int), 0, (RD_MERGE_ROUNDS + 1) * sizeof(int), nb, s));
   const int n = iw * ih, g4 = rd_cdiv(rd_cdiv(n, 4), 256);
   const dim3 b(32, 8);
-  // the first pass: A = work, B = scratch (as a plane of ints), records in `out` - whose image-layout content the fold then writes
-  RD_LAUNCH(k_m1_pre<MASK>, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, work, (int *)scratch, (uint8_t *)out, f, iw, ih, fs);
-  // warps per CTA: a group of 32 rows starts 32 * M1_SKEW + 2 * M1_POLL steps after the one above and takes iw + 31 * M1_SKEW steps,
-  // so no more than that many groups (+ 1) are ever under way at once; further warps would only hold registers
-  const int groups = rd_cdiv(ih, 32), live = (iw + M1_SKEW * 31) / (32 * M1_SKEW + 2 * M1_POLL) + 2;
-  const int wv = groups < live ? groups : (live < 32 ? live : 32);
-  if (iw >= M1_BIG && n < (1 << 24))
-    RD_LAUNCH(k_m1_wave<true>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
-  else
-    RD_LAUNCH(k_m1_wave<false>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
-  RD_LAUNCH(k_m1_fold, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, (const int *)scratch, iw, ih, fs);
-  // pairs that may adopt in both directions, then the pointers of the first pass
+  const bool replay = rd_get_merge_replay() != 0;
+  f.pre = replay ? 0 : 1;
+  if (replay) {
+    // the first pass: A = work, B = scratch (as a plane of ints), records in `out` - whose image-layout content the fold then writes
+    RD_LAUNCH(k_m1_pre<MASK>, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, work, (int *)scratch, (uint8_t *)out, f, iw, ih, fs);
+    // warps per CTA: a group of 32 rows starts 32 * M1_SKEW + 2 * M1_POLL steps after the one above and takes iw + 31 * M1_SKEW steps,
+    // so no more than that many groups (+ 1) are ever under way at once; further warps would only hold registers
+    const int groups = rd_cdiv(ih, 32), live = (iw + M1_SKEW * 31) / (32 * M1_SKEW + 2 * M1_POLL) + 2;
+    const int wv = groups < live ? groups : (live < 32 ? live : 32);
+    if (iw >= M1_BIG && n < (1 << 24))
+      RD_LAUNCH(k_m1_wave<true>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
+    else
+      RD_LAUNCH(k_m1_wave<false>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
+    RD_LAUNCH(k_m1_fold, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, (const int *)scratch, iw, ih, fs);
+  }
+  // pairs that may adopt in both directions (+ the preprocess pointers, or afterwards the pointers of the first pass)
   ccl_core(work, (uint8_t *)scratch, f, iw, ih, nb, fs, s);
-  RD_LAUNCH(k_merge_seed, rd_gy(rd_cdiv(n, 256), nb), 256, 0, s, work, (const int *)out, n, fs);
-  RD_LAUNCH(k_ccl_roots, rd_gy(g4, nb), 256, 0, s, work, (const uint8_t *)scratch, n, fs);
+  if (replay) {
+    RD_LAUNCH(k_merge_seed, rd_gy(rd_cdiv(n, 256), nb), 256, 0, s, work, (const int *)out, n, fs);
+    RD_LAUNCH(k_ccl_roots, rd_gy(g4, nb), 256, 0, s, work, (const uint8_t *)scratch, n, fs);
+  }
   // round 0 has work on a third of the frames, the kernels behind the gate of a later round practically never: small grids there
   // (grid-stride loops)
   const int gs = g4 < 48 ? g4 : 48;
@@ -610,16 +665,20 @@ static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, in
     RD_LAUNCH(k_merge_apply, rd_gy(r == 0 ? g4 : gs, nb), 256, 0, s, work, (uint8_t *)scratch, (const int *)flags, r, iw, n, fs);
     RD_LAUNCH(k_merge_roots, rd_gy(r == 0 ? g4 : gs, nb), 256, 0, s, work, (const uint8_t *)scratch, (const int *)flags, r, n, fs);
   }
-  RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, iw, ih, fs);
+  if (replay) RD_LAUNCH(k_ccl_flatten_merge1, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, iw, ih, fs);
+  else {
+    RD_LAUNCH(k_ccl_flatten_merge, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, work, f.pix, iw, ih, fs);
+    RD_LAUNCH(k_merge_toprow, nb, 32, 0, s, out, f.pix, f.edge, iw, ih, fs);
+  }
 }
-// labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331).  work: iw*ih ints, scratch: iw*ih ints, flags: RD_MERGE_ROUNDS + 1 ints;
+// labelxPreprocess + 8 x labelMergeMain (oclrect.c:325-331).  work: iw*ih ints, scratch: iw*ih bytes (iw*ih ints with the first-pass replay), flags: RD_MERGE_ROUNDS + 1 ints;
 // out may not alias work
 void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  LinkMerge<int> f = {pix, mask, edge, iw, ih};
+  LinkMerge<int> f = {pix, mask, edge, iw, ih, 1};
   merge_core(out, work, f, scratch, flags, iw, ih, nb, fs, s);
 }
 // same with the merge mask as a byte plane
 void rd_labelMerge_u8(int *out, int *work, const uint32_t *pix, const uint8_t *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s) {
-  LinkMerge<uint8_t> f = {pix, mask, edge, iw, ih};
+  LinkMerge<uint8_t> f = {pix, mask, edge, iw, ih, 1};
   merge_core(out, work, f, scratch, flags, iw, ih, nb, fs, s);
 }

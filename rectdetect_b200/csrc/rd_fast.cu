@@ -1250,7 +1250,7 @@ void rd_quant_tables_init() {
   std::lock_guard<std::mutex> g(mu);
   if (dev < 64 && ready[dev]) return;
   RD_LAUNCH(kq_tables, 16, 256, 0, (cudaStream_t)0);
-  RD_CUDA(cudaDeviceSynchronize());
+  RD_CUDA(cudaStreamSynchronize(cudaStreamLegacy));          // (not a device-wide wait: another thread's stream may be capturing)
   if (dev < 64) ready[dev] = true;
 }
 void rd_quant_despeckle_run(uint32_t *out, const uint32_t *in, const float *thin, int iw, int ih, int nb, size_t fs, cudaStream_t s) {

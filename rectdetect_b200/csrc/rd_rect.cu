@@ -672,7 +672,9 @@ static oclrect_t *rect_create(cl_command_queue queue, int ordinal, int iw, int i
     RD_CUDA(cudaEventCreateWithFlags(&o->events[p], cudaEventDisableTiming | cudaEventBlockingSync));   // waiting host threads sleep: the cores run host tails
   }
   rd_quant_tables_init();
-  RD_CUDA(cudaDeviceSynchronize());
+  // (the memset above ran on the legacy stream.  Not cudaDeviceSynchronize: another thread's object may be capturing its CUDA graph,
+  // and a device-wide wait is not permitted while any stream captures)
+  RD_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
   return o;
 }
 
