@@ -3,7 +3,8 @@
 (incl. widths that are not multiples of 32, frames smaller than the blur / window radii), row strides wider than the image,
 blank frames and many seeds.  Per case: which of the order-independent planes are bit-exact after the full genGPUTask, how far
 the region map is off (labelMergeMain is order dependent: the one remaining canonical substitute), the vote table on identical
-inputs, and how the rectangle lists compare.   usage: ref_vs_oracle_sweep.py [quick|big]   (needs a built librd_ref.so)"""
+inputs, and how the rectangle lists compare.   usage: ref_vs_oracle_sweep.py [quick|big] [replay]   (needs a built librd_ref.so;
+`replay`: the oracle with the first labelMergeMain pass replayed, ora_set_merge_replay(1))"""
 import ctypes as C
 import math
 import os
@@ -18,8 +19,9 @@ import ref_lib as rl  # noqa: E402
 from test_ref_device import _match_rects  # noqa: E402
 
 TAN = math.tan(math.radians(36.0))
-quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-big = len(sys.argv) > 1 and sys.argv[1] == "big"          # configs 4 and 5 of BASELINE.json: 1920x1080 seed 2000, 3840x2160 seed 5
+quick = "quick" in sys.argv[1:]
+big = "big" in sys.argv[1:]
+replay = "replay" in sys.argv[1:]          # configs 4 and 5 of BASELINE.json: 1920x1080 seed 2000, 3840x2160 seed 5
 sizes = [(640, 480), (641, 479), (322, 200), (130, 97), (96, 64), (48, 40), (257, 511), (1000, 562), (1280, 720)]
 seeds = [31] if quick else [31, 32, 33]
 cases = [(iw, ih, s, None, False) for iw, ih in sizes for s in seeds]
@@ -33,6 +35,8 @@ t0 = time.time()
 bad = tot_r = tot_m = 0
 print("%-26s %-58s %-12s %-7s %s" % ("case", "bit-exact planes (plab thin strong quant lsid ls)", "segid off", "votes", "rects ref/ora/matched"))
 LO = ol.oracle()
+LO.ora_set_merge_replay(1 if replay else 0)
+print("oracle: labelMergeMain %s" % ("with the first pass replayed in raster order" if replay else "as the schedule-independent fixed point (default)"))
 
 
 for iw, ih, seed, ws, blank in cases:
