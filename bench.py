@@ -268,10 +268,17 @@ def main():
         frame_bytes = ih * ws
         batch = rd.Batch(local_rank, iw, ih, nctx=args.nctx, frames_per_launch=args.fpl)
 
+        def gather(rects):
+            torch.cuda.set_device(local_rank)
+            return rdist.gather_rect_lists(lo, rects, total_frames, device=dev)
+
         def step(on_device):
             ptr = dev_frames.data_ptr() if on_device else host_frames.data_ptr()
             rects = batch.run(ptr, frame_bytes, ws, hi - lo, TAN_AOV, on_device=on_device)
-            return rdist.gather_rect_lists(lo, rects, total_frames, device=dev)
+            return gather(rects)
+
+        from concurrent.futures import ThreadPoolExecutor as _Pool
+        gather_pool = _Pool(max_workers=1) if world > 1 else None
 
         def timed(on_device, nsteps):
             barrier()
@@ -279,8 +286,19 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = None
-            for _ in range(nsteps):
-                out = step(on_device)
+            if world > 1:
+                # the gather of step k (NCCL, rank 0 unpacks) runs beside the frames of step k + 1; the last one is inside the timed region too
+                fut = None
+                for _ in range(nsteps):
+                    ptr = dev_frames.data_ptr() if on_device else host_frames.data_ptr()
+                    rects = batch.run(ptr, frame_bytes, ws, hi - lo, TAN_AOV, on_device=on_device)
+                    if fut is not None:
+                        out = fut.result()
+                    fut = gather_pool.submit(gather, rects)
+                out = fut.result()
+            else:
+                for _ in range(nsteps):
+                    out = step(on_device)
             barrier()
             e1.record()
             torch.cuda.synchronize()
@@ -304,6 +322,8 @@ def main():
                "launches": launches, "rects": rects, "rects_e2e": rects_e2e, "wait_ms": wait_ms, "list_ms": list_ms,
                "d2h_bytes": (16 * 1024 * total_frames) if rects is None else sum(max(16 * 1024, 64 + 176 * len(r)) for r in rects)}
         batch.close()
+        if gather_pool:
+            gather_pool.shutdown()
         return res
 
     iw, ih, F = args.w, args.h, args.frames
@@ -521,7 +541,7 @@ def main():
             "dtype": "f32+i32 (f64 device tail)", "data": "synthetic",
             "config": {"workload": "vidrect %dx%d synthetic stream (seeds 1000+i), AOV 72, full imgutil->polyline->rect pipeline incl. executeCPUTask on the device, independent-frame batch "
                                    "(every frame as by a fresh oclrect_t: no carry-over between frames)" % (iw, ih),
-                       "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "frames_per_launch": args.fpl, "parallelism": "frames x%d" % world,
+                       "frames_per_gpu_per_step": F, "global_frames_per_step": total_frames, "pipelines_per_gpu": args.nctx, "frames_per_launch": args.fpl, "parallelism": "frames x%d" % world, "gather": "none (1 GPU)" if world == 1 else "rect lists of step k gathered to rank 0 over NCCL beside the frames of step k+1 (the last gather inside the timed region)",
                        "l2": "inputs larger than L2 (%d MB of frames + %d working sets of 31 planes per GPU)" % (F * frame_bytes // 2 ** 20, args.nctx * args.fpl)},
             "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": total_frames * frame_bytes, "d2h_bytes_per_step": main_run["d2h_bytes"],
                     "ms_per_step": main_run["ms_e2e"]},

@@ -52,19 +52,36 @@ def gather_rect_lists(first_frame, rect_lists, nframes_total, device=None):
     dev = torch.device(device) if device is not None else torch.device("cpu")
     blob = torch.from_numpy(pack_rect_lists(first_frame, rect_lists)).to(dev)
     size = torch.tensor([blob.numel()], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, size)
-    mx = int(max(int(s.item()) for s in sizes))
-    padded = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    padded[: blob.numel()] = blob
-    parts = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(parts, padded)
-    if rank != 0:
-        return None
+    if dist.get_backend() == "nccl":
+        # one tensor per collective and one read-back each (a list of per-rank tensors costs a device round trip per rank)
+        allsz = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allsz, size)
+        sizes = [int(v) for v in allsz.cpu().tolist()]
+        mx = max(sizes)
+        padded = torch.zeros(mx, dtype=torch.uint8, device=dev)
+        padded[: blob.numel()] = blob
+        allparts = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allparts, padded)
+        if rank != 0:
+            return None
+        host = allparts.cpu().numpy()
+        parts = [host[r * mx: r * mx + sizes[r]] for r in range(world)]
+    else:
+        szl = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(szl, size)
+        sizes = [int(s.item()) for s in szl]
+        mx = max(sizes)
+        padded = torch.zeros(mx, dtype=torch.uint8, device=dev)
+        padded[: blob.numel()] = blob
+        pl = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(pl, padded)
+        if rank != 0:
+            return None
+        parts = [pl[r][: sizes[r]].cpu().numpy() for r in range(world)]
     # ranks own contiguous shards in rank order (shard_range), so the full list is the concatenation of the parts
     firsts, flats, counts = [], [], []
     for r in range(world):
-        first, lists = unpack_rect_lists(parts[r][: int(sizes[r].item())].cpu().numpy())
+        first, lists = unpack_rect_lists(parts[r])
         firsts.append(first)
         flats.append(lists.flat)
         counts.append(lists.counts())
