@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_
   const int groups = (ih + 31) >> 5, S = (iw + M1_SKEW * 31 + M1_POLL - 1) & ~(M1_POLL - 1), prev = w == 0 ? W - 1 : w - 1;
   auto wrap = [&](int v) { if (BIG) return v >= iw ? v - iw : v; return m1_wrap(v, iw); };
   M1TimeMajor<BIG> mem;
-  mem.A = A; mem.B = B; mem.iw = iw; mem.ih = ih; mem.rcp = 1.0f / (float)iw;
+  mem.A = A; mem.B = B; mem.iw = iw; mem.ih = ih; mem.dv = m1_div_make(iw);
   for (int G = w; G < groups; G += W) {
     const int y = G * 32 + lane, R = m1_rows(G, ih), gbase = (G << 5) * iw + lane;
     const bool rowint = y > 0 && y < ih - 1;

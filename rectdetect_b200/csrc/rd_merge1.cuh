@@ -73,13 +73,30 @@ M1_HD int m1_index(int q, int iw, int ih) {
   const int y = q / iw;
   return m1_index_xy(q - y * iw, y, iw, ih);
 }
-// the same for frames of at least M1_BIG columns and fewer than 2^24 pixels (every video size): the row by a float reciprocal
-// corrected by one, the wrap by one conditional subtraction
+// the same for frames of at least M1_BIG columns and fewer than 2^24 pixels (every video size): the row by a multiply-high,
+// the wrap by one conditional subtraction
 #define M1_BIG 256
-M1_HD int m1_index_big(int q, int iw, int ih, float rcp) {
-  int y = (int)((float)q * rcp);
-  int x = q - y * iw;
-  if (x < 0) { y--; x += iw; } else if (x >= iw) { y++; x -= iw; }
+// q / iw for 0 <= q < 2^24, iw >= 256: (q * M) >> (32 + L) with L = floor(log2 iw), M = ceil(2^(32+L) / iw) (< 2^32 as iw > 2^L or M = 2^32 - ... :
+// for a power of two iw the host passes L - 1).  The error term q * (M * iw - 2^(32+L)) / (iw * 2^(32+L)) < q / 2^(32+L) < 1 / iw.
+struct M1Div { unsigned M; int L; };
+M1_HD M1Div m1_div_make(int iw) {
+  int L = 0;
+  while ((2 << L) < iw) L++;                                        // 2^L < iw <= 2^(L+1)
+  M1Div d;
+  d.L = L;
+  d.M = (unsigned)((((unsigned long long)1 << (32 + L)) + (unsigned)iw - 1) / (unsigned)iw);
+  return d;
+}
+M1_HD int m1_div(int q, M1Div d) {
+#ifdef __CUDA_ARCH__
+  return (int)(__umulhi((unsigned)q, d.M) >> d.L);
+#else
+  return (int)((((unsigned long long)(unsigned)q * d.M) >> 32) >> d.L);
+#endif
+}
+M1_HD int m1_index_big(int q, int iw, int ih, M1Div dv) {
+  const int y = m1_div(q, dv);
+  const int x = q - y * iw;
   const int G = y >> 5, k = y & 31;
   int tm = x + M1_SKEW * k;
   if (tm >= iw) tm -= iw;
@@ -97,9 +114,9 @@ struct M1Linear {
 };
 template <bool BIG>
 struct M1TimeMajor {
-  int *A, *B; int iw, ih, pos, posL, posU; float rcp;
+  int *A, *B; int iw, ih, pos, posL, posU; M1Div dv;
   M1_MEMBER int look(int q, bool withB) const {
-    const int i = BIG ? m1_index_big(q, iw, ih, rcp) : m1_index(q, iw, ih);
+    const int i = BIG ? m1_index_big(q, iw, ih, dv) : m1_index(q, iw, ih);
     int v = A[i];
     if (withB) { const int b = B[i]; if (b < v) v = b; }
     return v;
@@ -120,7 +137,7 @@ struct M1Row {
 template <class Mem>
 M1_HD int m1_pixel(int p, int iw, unsigned f, int aup, Mem &mem, M1Row &r) {
   const unsigned kind = (f >> M1_KIND_SHIFT) & 3u;
-  const int og = kind == 1u ? p - iw : (kind == 2u ? p - 1 : p);
+  const int og = p - ((f & (1u << M1_KIND_SHIFT)) ? iw : 0) - (int)((f >> (M1_KIND_SHIFT + 1)) & 1u);   // kind 1: p - iw, kind 2: p - 1
   int g = og, fin = r.gleft;
   if ((f & M1_U) && aup < g) g = aup;
   if ((f & M1_L) && r.gleft < g) g = r.gleft;

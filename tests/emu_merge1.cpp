@@ -59,8 +59,8 @@ extern "C" long emu_merge1(int32_t *label, const int32_t *pix, const int32_t *ma
       else {
         const int aup = (y == 1 || skew != M1_SKEW) ? A[at(p - iw)] : aups[y];
         if (check) { LogMem m{A.data(), B.data(), iw, p, &log, y}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
-        else if (tmj && iw >= M1_BIG && n < (1 << 24)) { M1TimeMajor<true> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), 1.0f / (float)iw}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
-        else if (tmj) { M1TimeMajor<false> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), 0.f}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
+        else if (tmj && iw >= M1_BIG && n < (1 << 24)) { M1TimeMajor<true> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), m1_div_make(iw)}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
+        else if (tmj) { M1TimeMajor<false> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), M1Div{0u, 0}}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
         else { M1Linear m{A.data(), B.data(), iw, p}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
       }
       dd[2] = dd[1]; dd[1] = dd[0]; dd[0] = fin;
@@ -77,7 +77,11 @@ extern "C" long emu_merge1(int32_t *label, const int32_t *pix, const int32_t *ma
       }
     }
   }
-  // the layout is a bijection
+  // the layout is a bijection; the multiply-high division is exact on the whole frame
+  if (tmj && iw >= M1_BIG && n < (1 << 24)) {
+    const M1Div dv = m1_div_make(iw);
+    for (int q = 0; q < n; q++) if (m1_div(q, dv) != q / iw) return -2;
+  }
   if (tmj) {
     std::vector<uint8_t> seen(n, 0);
     for (int p = 0; p < n; p++) { const int i = m1_index(p, iw, ih); if (i < 0 || i >= n || seen[i]) return -1; seen[i] = 1; }

@@ -3,7 +3,7 @@
 frame sizes and seeds, including widths that are not multiples of 4 / 32 / 128 and frames smaller than a tile.
 Every third case is a frame tiled from 3x3 independent scenes (many more segments / regions / candidates: long read-back
 records, long despeckle2 runs, more tail candidates).
-usage: gpu_stress_parity.py [quick | <first seed> <seeds per size>]"""
+usage: gpu_stress_parity.py [quick | <first seed> <seeds per size> [replay]]   (replay: labelMergeMain with the first pass replayed, both sides)"""
 import os
 import sys
 import time
@@ -19,6 +19,10 @@ sizes = [(640, 480), (641, 479), (322, 200), (130, 97), (96, 64), (1000, 562), (
 seeds = [11, 12] if quick else [21, 22, 23, 24]
 if len(sys.argv) > 2:
     seeds = list(range(int(sys.argv[1]), int(sys.argv[1]) + int(sys.argv[2])))
+if "replay" in sys.argv[1:]:
+    rd.set_merge_replay(True)
+    ol.oracle().ora_set_merge_replay(1)
+    print("labelMergeMain: first-pass replay on (CUDA and oracle)")
 dev = rd.Device(0)
 t0 = time.time()
 nbad = 0
