@@ -7,8 +7,10 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * The product library never links, imports or calls anything in this directory.
  *
- * PARITY STATUS: PINNED TO THE REFERENCE RUNNING HERE, except one kernel (labelMergeMain) whose result depends on the order
- * of the reference's own work-items in a way no deterministic rule reproduces.  The reference ships no tests, golden vectors or fixtures and no
+ * PARITY STATUS: PINNED TO THE REFERENCE RUNNING HERE.  One kernel (labelMergeMain) depends on the order of the reference's own
+ * work-items: by default the oracle computes a schedule-independent fixed point of its adopt rule, with ora_set_merge_replay(1) it
+ * replays the reference's first pass in raster order first (bit-exact to the reference's kernel) and then equals the reference's
+ * sequential run on all rectangles of the sweeps.  The reference ships no tests, golden vectors or fixtures and no
  * OpenCL runtime exists in this image, but the reference itself does run: `make _ref` compiles its host code
  * (helper.c, oclhelper.c, oclimgutil.c, oclpolyline.c, oclrect.c - unmodified, from /root/reference) together with its
  * three OpenCL C kernel files compiled as C++ (cl_translate.py rewrites only the vector-literal syntax, cl_compat.h supplies
@@ -25,7 +27,10 @@
  *     oracle fixes a deterministic fixed point of the same rule (two-directional pairs united, one-directional pairs united
  *     where the source's component label is smaller; ora_rect.cpp) whose distance from the sequential schedule is tested (a
  *     handful to a few hundred interior pixels per frame); with that one kernel swapped for the reference's the oracle
- *     reproduces the reference's region map bit-exactly.
+ *     reproduces the reference's region map bit-exactly.  ora_set_merge_replay(1): labelxPreprocess + the FIRST labelMergeMain pass
+ *     as the reference's kernel runs them in raster order (whole label plane bit-exact), then the same fixed point seeded with
+ *     that plane: label plane identical to the reference's 8 passes on 29 of 30 sweep frames, region map on 31 of 33, all 249
+ *     rectangles identical (profiles/r04t_*).
  * Every other place where the reference is schedule-dependent (atomic arrival order, in-place races, vote-slot claims)
  * is resolved the way the raster-order schedule resolves it; each is marked "CANONICAL" in the sources and listed in
  * DESIGN.md section "Canonical semantics".  Vendor-defined OpenCL built-ins (rsqrt, hypot, distance, FP contraction) follow
