@@ -509,10 +509,12 @@ __global__ void k_m1_pre(int *A, int *B, uint8_t *F, LinkMerge<MASK> f, int iw, 
 // the row above left it - that row's lane holds it in a register three steps after it did the pixel to the right of it, so it
 // travels by shuffle through a three-deep delay line (a lane whose upper row belongs to another warp, or is the top row of the
 // image, reads it from memory four steps ahead: that row is at least 128 pixels further on) - and whatever the pointer chase
-// touches (gathers; the two roots met last are remembered).  What the lanes store in a step is contiguous in the time-major layout.
+// touches (gathers).  A root found below the line p - iw is final (all its writers have passed): the two met last are remembered,
+// and the flag travels with the label to the lane below, so that the look is only repeated where a tree is still growing -
+// 0.9 % of the pixels of a 720p frame instead of 4.9 %.  What the lanes store in a step is contiguous in the time-major layout.
 #define M1_POLL 8                      // steps between two looks at the progress of the group above
 template <bool BIG>
-__global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_t *F0, int *err, int iw, int ih, size_t fs) {
+__global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_t *F0, int *err, int iw, int ih, int slack, size_t fs) {
   rd_batch_x(fs, A0, B0, F0, err);
   int *__restrict__ A = A0, *__restrict__ B = B0;
   const uint8_t *__restrict__ F = F0;
@@ -533,11 +535,11 @@ __global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_
     const int ubase = lane > 0 ? gbase - 1 : ((G - 1) << 5) * iw + 31, uR = lane > 0 ? R : 32;
     const int ushift = lane > 0 ? wrap(iw - wrap(M1_SKEW)) : wrap(M1_SKEW * 31);
     M1Row r;
-    r.gleft = 0; r.croot[0] = r.croot[1] = -1;
-    int d0 = 0, d1 = 0, d2 = 0;
+    r.gleft = 0; r.gleftF = 0u; r.croot[0] = r.croot[1] = -1;
+    unsigned d0 = 0, d1 = 0, d2 = 0;                                               // (label | M1_FINAL)
     int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
     auto wait_for = [&](int t0) {                                                  // the group above has finished what steps t0 .. t0 + M1_POLL - 1 read
-      const int need = (G - 1) * (S + 1) + min(t0 + 2 * M1_POLL + 32 * M1_SKEW, S);
+      const int need = (G - 1) * (S + 1) + min(t0 + slack + 32 * M1_SKEW, S);
       unsigned spins = 0;
       while (prog[prev] < need) {
         __nanosleep(1500);                                                          // (a step takes some hundred ns, progress is published every M1_POLL steps)
@@ -562,19 +564,19 @@ __global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_
     int x = -M1_SKEW * lane, p = y * iw + x;
     const int iwR = iw * R, iwuR = iw * uR;
     int pos2 = gbase + wrap(2) * R, tm2 = wrap(2);                                 // position two steps ahead
-    int aupn = 0;                                                                  // (the shuffle of the next step's operand is issued a step early)
+    unsigned aupn = 0;                                                             // (the shuffle of the next step's operand is issued a step early)
     for (int t = 0; t < S; t++) {
       if (G > 0 && t > 0 && (t & (M1_POLL - 1)) == 0) wait_for(t);
-      int aup = aupn;
+      unsigned aup = aupn;
       if (memup) {
-        aup = q3;
+        aup = (unsigned)q3;                                                        // (from memory: not known to be final)
         q3 = q2; q2 = q1; q1 = q0;
         q0 = (unsigned)(x + 4) < (unsigned)iw ? A[qpos] : 0;
       }
-      int fin = r.gleft;
+      unsigned fin = (unsigned)r.gleft | r.gleftF;
       if (rowint && (unsigned)x < (unsigned)iw) {
         const unsigned f = fn;
-        if (!(f & M1_INT)) r.gleft = A[pos];
+        if (!(f & M1_INT)) { r.gleft = A[pos]; r.gleftF = 0u; }
         else {
           mem.pos = pos; mem.posL = posL; mem.posU = posU;
           fin = m1_pixel(p, iw, f, aup, mem, r);
@@ -643,12 +645,16 @@ static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, in
     RD_LAUNCH(k_m1_pre<MASK>, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, work, (int *)scratch, (uint8_t *)out, f, iw, ih, fs);
     // warps per CTA: a group of 32 rows starts 32 * M1_SKEW + 2 * M1_POLL steps after the one above and takes iw + 31 * M1_SKEW steps,
     // so no more than that many groups (+ 1) are ever under way at once; further warps would only hold registers
-    const int groups = rd_cdiv(ih, 32), live = (iw + M1_SKEW * 31) / (32 * M1_SKEW + 2 * M1_POLL) + 2;
+    // cushion between two groups beyond the 32 * M1_SKEW steps the data flow needs: the smallest the polling allows.  (Measured: the
+    // kernel time is the length of the chain, (groups - 1) * (128 + cushion) + iw + 124 steps, times 0.61 - 0.65 us whatever the
+    // cushion - 2.96 / 3.35 / 3.95 / 4.72 ms at 720p for 16 / 48 / 96 / 160: the warps do not hold each other up, a step is simply slow.)
+    const int slack = 2 * M1_POLL;
+    const int groups = rd_cdiv(ih, 32), live = (iw + M1_SKEW * 31) / (32 * M1_SKEW + slack) + 2;
     const int wv = groups < live ? groups : (live < 32 ? live : 32);
     if (iw >= M1_BIG && n < (1 << 24))
-      RD_LAUNCH(k_m1_wave<true>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
+      RD_LAUNCH(k_m1_wave<true>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, slack, fs);
     else
-      RD_LAUNCH(k_m1_wave<false>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, fs);
+      RD_LAUNCH(k_m1_wave<false>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, slack, fs);
     RD_LAUNCH(k_m1_fold, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, (const int *)scratch, iw, ih, fs);
   }
   // pairs that may adopt in both directions (+ the preprocess pointers, or afterwards the pointers of the first pass)

@@ -126,42 +126,50 @@ struct M1TimeMajor {
   M1_MEMBER void setUp(int v) { B[posU] = v; }
 };
 
+// A label value travels between lanes with a flag in bit 31: M1_FINAL = it was a root when it was produced AND nothing can change
+// that any more.  A node g read at pixel p with g < p - iw has had all three of its writers (g, g+1, g+iw) pass, so a root found
+// below that limit - with B included in the look - stays a root for every later reader: no need to look again.
+#define M1_FINAL 0x80000000u
+
 // per-row state a lane carries along its row
 struct M1Row {
   int gleft;                            // label of the pixel to the left as it is now
-  int croot[2];                         // nodes known to be roots for this reader until the lane itself writes to them, or -1
+  unsigned gleftF;                      // M1_FINAL if that label is a final root
+  int croot[2];                         // final roots met last, or -1
 };
 
-// one interior pixel p (record f, `aup` = A[p - iw] as it is now).  Returns the final value of A[p - 1] (nothing but p itself could
-// still have lowered it) - what the row below will read as its `aup` three steps later.
+// one interior pixel p (record f, `aupx` = A[p - iw] as it is now, | M1_FINAL if the lane above knows it to be a final root).
+// Returns the final value of A[p - 1] (nothing but p itself could still have lowered it), | M1_FINAL if it is a final root -
+// what the row below will read as its `aupx` three steps later.
 template <class Mem>
-M1_HD int m1_pixel(int p, int iw, unsigned f, int aup, Mem &mem, M1Row &r) {
+M1_HD unsigned m1_pixel(int p, int iw, unsigned f, unsigned aupx, Mem &mem, M1Row &r) {
   const unsigned kind = (f >> M1_KIND_SHIFT) & 3u;
   const int og = p - ((f & (1u << M1_KIND_SHIFT)) ? iw : 0) - (int)((f >> (M1_KIND_SHIFT + 1)) & 1u);   // kind 1: p - iw, kind 2: p - 1
-  int g = og, fin = r.gleft;
+  const int aup = (int)(aupx & ~M1_FINAL);
+  const bool aupF = (aupx & M1_FINAL) != 0;
+  int g = og;
+  unsigned fin = (unsigned)r.gleft | r.gleftF;
   if ((f & M1_U) && aup < g) g = aup;
   if ((f & M1_L) && r.gleft < g) g = r.gleft;
   if ((f & M1_R) && p + 1 - iw < g) g = p + 1 - iw;
-  if (g != r.croot[0] && g != r.croot[1]) {
-    const int lim = p - iw;
-    bool fixed = false;
-    for (int j = 0; j < 8; j++) {                                   // for (j < 8) g = label[g]
-      const int v = mem.look(g, g < lim);
-      if (v == g) { fixed = true; break; }
-      g = v;
-    }
-    if (fixed) {
-      if (g != r.croot[0] && g != r.croot[1]) { r.croot[1] = r.croot[0]; r.croot[0] = g; }
-    }
+  const int lim = p - iw;
+  bool final = false;
+  for (int j = 0; j < 8; j++) {                                     // for (j < 8) g = label[g]
+    if ((g == aup && aupF) || (g == r.gleft && r.gleftF) || g == r.croot[0] || g == r.croot[1]) { final = true; break; }
+    // the labels of the pixel itself, of the pixel above and of the pixel to the left are in registers (their B is not visible yet)
+    const int v = g == p ? p : (g == lim ? aup : (g == p - 1 ? r.gleft : mem.look(g, g < lim)));
+    if (v == g) { final = g < lim; break; }
+    g = v;
   }
+  if (final && g != r.croot[0] && g != r.croot[1]) { r.croot[1] = r.croot[0]; r.croot[0] = g; }
+  const unsigned gx = (unsigned)g | (final ? M1_FINAL : 0u);
   if (g != og) {                                                    // atomic_min(&label[og], g); atomic_min(&label[p], g)
     if (kind == 1u) mem.setUp(g);                                   // the only writer of B[p - iw]
-    else if (kind == 2u) { if (g < fin) { mem.setLeft(g); fin = g; } }   // A[p - 1] is r.gleft
+    else if (kind == 2u) { if (g < r.gleft) { mem.setLeft(g); fin = gx; } }   // A[p - 1] is r.gleft
     mem.setSelf(g);
-    if (og == r.croot[0]) r.croot[0] = -1;
-    if (og == r.croot[1]) r.croot[1] = -1;
   }
   r.gleft = g;
+  r.gleftF = final ? M1_FINAL : 0u;
   return fin;
 }
 #endif

@@ -12,11 +12,13 @@
 #include "../rectdetect_b200/csrc/rd_merge1.cuh"
 
 struct Access { int addr; int lane; bool write; };
+static long g_looks = 0;
+extern "C" long emu_merge1_looks(void) { const long v = g_looks; g_looks = 0; return v; }
 struct LogMem {                                  // M1Linear with a log
   int *A, *B; int iw, p; std::vector<Access> *log; int lane;
   void rd(int a) const { log->push_back({a, lane, false}); }
   void wr(int a) const { log->push_back({a, lane, true}); }
-  int look(int q, bool withB) const { rd(2 * q); int v = A[q]; if (withB) { rd(2 * q + 1); const int b = B[q]; if (b < v) v = b; } return v; }
+  int look(int q, bool withB) const { g_looks++; rd(2 * q); int v = A[q]; if (withB) { rd(2 * q + 1); const int b = B[q]; if (b < v) v = b; } return v; }
   void setSelf(int v) { wr(2 * p); A[p] = v; }
   void setLeft(int v) { wr(2 * (p - 1)); A[p - 1] = v; }
   void setUp(int v) { wr(2 * (p - iw) + 1); B[p - iw] = v; }
@@ -38,10 +40,10 @@ extern "C" long emu_merge1(int32_t *label, const int32_t *pix, const int32_t *ma
       A[at(p)] = L0;
     }
   std::vector<M1Row> row(ih);
-  for (auto &r : row) { r.gleft = 0; r.croot[0] = r.croot[1] = -1; }
+  for (auto &r : row) { r.gleft = 0; r.gleftF = 0u; r.croot[0] = r.croot[1] = -1; }
   // d[y][0..2]: the last three values lane y produced for the row below (final A of the pixel left of the one it just did);
   // like the kernel, lane y takes its `aup` from d[y-1][2] at the start of a step (before anybody pushes), row 1 reads row 0 from memory
-  std::vector<int> d(3 * (size_t)ih, 0), aups(ih, 0);
+  std::vector<unsigned> d(3 * (size_t)ih, 0u), aups(ih, 0u);
   std::vector<Access> log;
   long hazards = 0;
   const int steps = iw + skew * ih + 2;
@@ -50,14 +52,14 @@ extern "C" long emu_merge1(int32_t *label, const int32_t *pix, const int32_t *ma
     for (int y = 2; y < ih - 1; y++) aups[y] = d[3 * (y - 1) + 2];
     for (int y = 1; y < ih - 1; y++) {
       const int x = t - skew * y;
-      int *dd = &d[3 * y];
+      unsigned *dd = &d[3 * y];
       if (x < 0 || x >= iw) { dd[2] = dd[1]; dd[1] = dd[0]; continue; }
       const int p = y * iw + x;
       const unsigned f = F[at(p)];
-      int fin = row[y].gleft;
-      if (!(f & M1_INT)) row[y].gleft = A[at(p)];
+      unsigned fin = (unsigned)row[y].gleft | row[y].gleftF;
+      if (!(f & M1_INT)) { row[y].gleft = A[at(p)]; row[y].gleftF = 0u; }
       else {
-        const int aup = (y == 1 || skew != M1_SKEW) ? A[at(p - iw)] : aups[y];
+        const unsigned aup = (y == 1 || skew != M1_SKEW) ? (unsigned)A[at(p - iw)] : aups[y];
         if (check) { LogMem m{A.data(), B.data(), iw, p, &log, y}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
         else if (tmj && iw >= M1_BIG && n < (1 << 24)) { M1TimeMajor<true> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), m1_div_make(iw)}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
         else if (tmj) { M1TimeMajor<false> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), M1Div{0u, 0}}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
