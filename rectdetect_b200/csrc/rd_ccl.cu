@@ -523,17 +523,14 @@ __global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_
   if (threadIdx.x < 32) prog[threadIdx.x] = 0;
   __syncthreads();
   const int groups = (ih + 31) >> 5, S = (iw + M1_SKEW * 31 + M1_POLL - 1) & ~(M1_POLL - 1), prev = w == 0 ? W - 1 : w - 1;
-  auto wrap = [&](int v) { if (BIG) return v >= iw ? v - iw : v; return m1_wrap(v, iw); };
   M1TimeMajor<BIG> mem;
   mem.A = A; mem.B = B; mem.iw = iw; mem.ih = ih; mem.dv = m1_div_make(iw);
   for (int G = w; G < groups; G += W) {
-    const int y = G * 32 + lane, R = m1_rows(G, ih), gbase = (G << 5) * iw + lane;
+    const int y = G * 32 + lane;
     const bool rowint = y > 0 && y < ih - 1;
     const bool memup = rowint && (lane == 0 || y == 1);                           // the row above is not the lane above
-    // where the row above lives: the lane above, or lane 31 of the group above.  Element (x, y - 1) = ubase + wrap(t + ushift) * uR
-    // at the step t = x + M1_SKEW * lane in which this lane does pixel x
-    const int ubase = lane > 0 ? gbase - 1 : ((G - 1) << 5) * iw + 31, uR = lane > 0 ? R : 32;
-    const int ushift = lane > 0 ? wrap(iw - wrap(M1_SKEW)) : wrap(M1_SKEW * 31);
+    m1_row_setup(mem, rowint ? y : (G << 5) + (lane > 0 ? lane : 1));             // (rows that do nothing get harmless values)
+    const int gbase = mem.gbase, R = mem.R, ubase = mem.ubase, uR = mem.uR, ushift = mem.ushift;
     M1Row r;
     r.gleft = 0; r.gleftF = 0u; r.croot[0] = r.croot[1] = -1;
     unsigned d0 = 0, d1 = 0, d2 = 0;                                               // (label | M1_FINAL)
@@ -548,50 +545,39 @@ __global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_
       asm volatile("fence.acq_rel.cta;" ::: "memory");
     };
     if (G > 0) wait_for(0);
-    // running positions (time-major indices) of: this lane's pixel, the pixel above it, the pixel above four steps ahead
-    int tm = 0, pos = gbase, posL = gbase;
-    int utm = ushift, posU = ubase + utm * uR;
-    int qtm = wrap(utm + wrap(4)), qpos = ubase + qtm * uR;
+    // element (x', y - 1) while this lane is at step t: ubase + ((t + (x' - x) + ushift) mod iw) * uR
+    auto up_ahead = [&](int tmv, int ahead) { return ubase + mem.wrap(mem.wrap(tmv + mem.wrap(ahead)) + ushift) * uR; };
+    const int tm0 = mem.wrap(M1_SKEW * lane);                                      // (t mod iw) at the step of this lane's x = 0
     if (memup) {
-      q3 = A[posU];
-      if (1 < iw) q2 = A[ubase + wrap(utm + 1) * uR];
-      if (2 < iw) q1 = A[ubase + wrap(utm + wrap(2)) * uR];
-      if (3 < iw) q0 = A[ubase + wrap(utm + wrap(3)) * uR];
+      q3 = A[up_ahead(tm0, 0)];
+      if (1 < iw) q2 = A[up_ahead(tm0, 1)];
+      if (2 < iw) q1 = A[up_ahead(tm0, 2)];
+      if (3 < iw) q0 = A[up_ahead(tm0, 3)];
     }
     // records two steps ahead: fn = of the pixel of this step, fn1 = of the next
     unsigned fn = 0, fn1 = 0;
-    if (rowint && lane == 0) { fn = F[gbase]; if (1 < iw) fn1 = F[gbase + R]; }   // x = 0 of lane 0 is step 0
+    if (rowint && lane == 0) { fn = F[gbase]; if (1 < iw) fn1 = F[gbase + R]; }    // x = 0 of lane 0 is step 0
     int x = -M1_SKEW * lane, p = y * iw + x;
-    const int iwR = iw * R, iwuR = iw * uR;
-    int pos2 = gbase + wrap(2) * R, tm2 = wrap(2);                                 // position two steps ahead
+    int tm = 0;                                                                    // t mod iw, the same for every lane
+    bool act = rowint && x == 0;
     unsigned aupn = 0;                                                             // (the shuffle of the next step's operand is issued a step early)
     for (int t = 0; t < S; t++) {
       if (G > 0 && t > 0 && (t & (M1_POLL - 1)) == 0) wait_for(t);
-      unsigned aup = aupn;
-      if (memup) {
-        aup = (unsigned)q3;                                                        // (from memory: not known to be final)
-        q3 = q2; q2 = q1; q1 = q0;
-        q0 = (unsigned)(x + 4) < (unsigned)iw ? A[qpos] : 0;
-      }
+      const unsigned aup = memup ? (unsigned)q3 : aupn;                            // (from memory: not known to be final)
+      q3 = q2; q2 = q1; q1 = q0;
+      if (memup && (unsigned)(x + 4) < (unsigned)iw) q0 = A[up_ahead(tm, 4)];
       unsigned fin = (unsigned)r.gleft | r.gleftF;
-      if (rowint && (unsigned)x < (unsigned)iw) {
+      if (act) {
         const unsigned f = fn;
-        if (!(f & M1_INT)) { r.gleft = A[pos]; r.gleftF = 0u; }
-        else {
-          mem.pos = pos; mem.posL = posL; mem.posU = posU;
-          fin = m1_pixel(p, iw, f, aup, mem, r);
-        }
+        mem.tm = tm;
+        if (!(f & M1_INT)) { r.gleft = A[mem.self()]; r.gleftF = 0u; }
+        else fin = m1_pixel(p, iw, f, aup, mem, r);
       }
-      posL = pos;
-      pos += R; posU += uR; qpos += uR;
-      if (++tm == iw) { tm = 0; pos -= iwR; }
-      if (++utm == iw) { utm = 0; posU -= iwuR; }
-      if (++qtm == iw) { qtm = 0; qpos -= iwuR; }
+      tm = tm + 1 == iw ? 0 : tm + 1;
       x++; p++;
+      act = rowint && (unsigned)x < (unsigned)iw;
       fn = fn1;
-      fn1 = (rowint && (unsigned)(x + 1) < (unsigned)iw) ? F[pos2] : 0u;           // the record of the step after the next
-      pos2 += R;
-      if (++tm2 == iw) { tm2 = 0; pos2 -= iwR; }
+      fn1 = (rowint && (unsigned)(x + 1) < (unsigned)iw) ? F[gbase + mem.wrap(tm + 1) * R] : 0u;   // the record of the step after the next
       d2 = d1; d1 = d0; d0 = fin;
       aupn = __shfl_up_sync(0xffffffffu, d2, 1);                                   // what the lane above produced three steps before the next one
       __syncwarp();

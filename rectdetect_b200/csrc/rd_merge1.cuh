@@ -112,19 +112,33 @@ struct M1Linear {
   M1_MEMBER void setLeft(int v) { A[p - 1] = v; }
   M1_MEMBER void setUp(int v) { B[p - iw] = v; }
 };
+// The kernel's policy: positions are derived from the step (tm = t mod iw, the same for every lane) only where they are used.
+// gbase = 32 G iw + k; the row above lives at ubase + ((tm + ushift) mod iw) * uR (the lane above, or lane 31 of the group above).
 template <bool BIG>
 struct M1TimeMajor {
-  int *A, *B; int iw, ih, pos, posL, posU; M1Div dv;
+  int *A, *B; int iw, ih; M1Div dv;
+  int gbase, R, ubase, uR, ushift, tm;
+  M1_MEMBER int wrap(int v) const { if (BIG) return v >= iw ? v - iw : v; return m1_wrap(v, iw); }
   M1_MEMBER int look(int q, bool withB) const {
     const int i = BIG ? m1_index_big(q, iw, ih, dv) : m1_index(q, iw, ih);
     int v = A[i];
     if (withB) { const int b = B[i]; if (b < v) v = b; }
     return v;
   }
-  M1_MEMBER void setSelf(int v) { A[pos] = v; }
-  M1_MEMBER void setLeft(int v) { A[posL] = v; }
-  M1_MEMBER void setUp(int v) { B[posU] = v; }
+  M1_MEMBER int self() const { return gbase + tm * R; }
+  M1_MEMBER void setSelf(int v) { A[gbase + tm * R] = v; }
+  M1_MEMBER void setLeft(int v) { A[gbase + (tm > 0 ? tm - 1 : iw - 1) * R] = v; }
+  M1_MEMBER void setUp(int v) { B[ubase + wrap(tm + ushift) * uR] = v; }
 };
+// the fields of M1TimeMajor for row y (host replay and kernel set-up)
+template <bool BIG>
+M1_HD void m1_row_setup(M1TimeMajor<BIG> &m, int y) {
+  const int G = y >> 5, k = y & 31;
+  m.R = m1_rows(G, m.ih);
+  m.gbase = (G << 5) * m.iw + k;
+  if (k > 0) { m.ubase = m.gbase - 1; m.uR = m.R; m.ushift = m.wrap(m.iw - m.wrap(M1_SKEW)); }
+  else { m.ubase = ((G - 1) << 5) * m.iw + 31; m.uR = 32; m.ushift = m.wrap(M1_SKEW * 31); }
+}
 
 // A label value travels between lanes with a flag in bit 31: M1_FINAL = it was a root when it was produced AND nothing can change
 // that any more.  A node g read at pixel p with g < p - iw has had all three of its writers (g, g+1, g+iw) pass, so a root found

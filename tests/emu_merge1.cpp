@@ -61,8 +61,15 @@ extern "C" long emu_merge1(int32_t *label, const int32_t *pix, const int32_t *ma
       else {
         const unsigned aup = (y == 1 || skew != M1_SKEW) ? (unsigned)A[at(p - iw)] : aups[y];
         if (check) { LogMem m{A.data(), B.data(), iw, p, &log, y}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
-        else if (tmj && iw >= M1_BIG && n < (1 << 24)) { M1TimeMajor<true> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), m1_div_make(iw)}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
-        else if (tmj) { M1TimeMajor<false> m{A.data(), B.data(), iw, ih, at(p), at(p - 1), at(p - iw), M1Div{0u, 0}}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
+        else if (tmj && iw >= M1_BIG && n < (1 << 24)) {
+          M1TimeMajor<true> m; m.A = A.data(); m.B = B.data(); m.iw = iw; m.ih = ih; m.dv = m1_div_make(iw);
+          m1_row_setup(m, y); m.tm = m.wrap(x + M1_SKEW * (y & 31));
+          fin = m1_pixel(p, iw, f, aup, m, row[y]);
+        } else if (tmj) {
+          M1TimeMajor<false> m; m.A = A.data(); m.B = B.data(); m.iw = iw; m.ih = ih; m.dv = M1Div{0u, 0};
+          m1_row_setup(m, y); m.tm = m.wrap(x + M1_SKEW * (y & 31));
+          fin = m1_pixel(p, iw, f, aup, m, row[y]);
+        }
         else { M1Linear m{A.data(), B.data(), iw, p}; fin = m1_pixel(p, iw, f, aup, m, row[y]); }
       }
       dd[2] = dd[1]; dd[1] = dd[0]; dd[0] = fin;
