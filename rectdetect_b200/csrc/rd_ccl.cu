@@ -13,6 +13,10 @@
 //                     atomicMin union-find; ~6 % of the pixels take part);
 //   3. k_ccl_flatten: every pixel reads its final root.
 // HBM traffic: predicate inputs once, 1 B/px links write + seam re-reads, label plane written twice and read once.
+//
+// The merge labelling (labelMergeMain, whose outcome depends on the order of the reference's work-items) adds to this: the gating
+// rounds of its one-directional pairs (k_merge_gate / k_merge_apply / k_merge_roots) and, as a mode (rd_set_merge_replay), the exact
+// replay of the reference's first pass as a row wavefront (k_m1_pre / k_m1_wave / k_m1_fold / k_merge_seed, logic in rd_merge1.cuh).
 #include "rd_common.cuh"
 #include "rd_merge1.cuh"
 
