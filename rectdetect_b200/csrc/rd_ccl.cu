@@ -518,7 +518,7 @@ __global__ void k_m1_pre(int *A, int *B, uint8_t *F, LinkMerge<MASK> f, int iw, 
 // 0.9 % of the pixels of a 720p frame instead of 4.9 %.  What the lanes store in a step is contiguous in the time-major layout.
 #define M1_POLL 8                      // steps between two looks at the progress of the group above
 template <bool BIG>
-__global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_t *F0, int *err, int iw, int ih, int slack, size_t fs) {
+__global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_t *F0, int *err, int iw, int ih, int slack, int sleepns, size_t fs) {
   rd_batch_x(fs, A0, B0, F0, err);
   int *__restrict__ A = A0, *__restrict__ B = B0;
   const uint8_t *__restrict__ F = F0;
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(1024) k_m1_wave(int *A0, int *B0, const uint8_
       const int need = (G - 1) * (S + 1) + min(t0 + slack + 32 * M1_SKEW, S);
       unsigned spins = 0;
       while (prog[prev] < need) {
-        __nanosleep(1500);                                                          // (a step takes some hundred ns, progress is published every M1_POLL steps)
+        __nanosleep(sleepns);                                                       // (a step takes some hundred ns, progress is published every M1_POLL steps)
         if (++spins > (1u << 18)) { *err = 1; __trap(); }                          // (never: a stuck wavefront ends the process loudly instead of hanging the device)
       }
       asm volatile("fence.acq_rel.cta;" ::: "memory");
@@ -639,12 +639,13 @@ static void merge_core(int *out, int *work, LinkMerge<MASK> f, void *scratch, in
     // kernel time is the length of the chain, (groups - 1) * (128 + cushion) + iw + 124 steps, times 0.61 - 0.65 us whatever the
     // cushion - 2.96 / 3.35 / 3.95 / 4.72 ms at 720p for 16 / 48 / 96 / 160: the warps do not hold each other up, a step is simply slow.)
     const int slack = 2 * M1_POLL;
+    const int sleepns = 1500;                     // (measured: 100 ... 5000 ns make no difference, the waiting warps are not on the critical path)
     const int groups = rd_cdiv(ih, 32), live = (iw + M1_SKEW * 31) / (32 * M1_SKEW + slack) + 2;
     const int wv = groups < live ? groups : (live < 32 ? live : 32);
     if (iw >= M1_BIG && n < (1 << 24))
-      RD_LAUNCH(k_m1_wave<true>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, slack, fs);
+      RD_LAUNCH(k_m1_wave<true>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, slack, sleepns, fs);
     else
-      RD_LAUNCH(k_m1_wave<false>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, slack, fs);
+      RD_LAUNCH(k_m1_wave<false>, nb, 32 * wv, 0, s, work, (int *)scratch, (const uint8_t *)out, flags + RD_MERGE_ROUNDS, iw, ih, slack, sleepns, fs);
     RD_LAUNCH(k_m1_fold, rd_gz(rd_grid2d(iw, ih, b), nb), b, 0, s, out, (const int *)work, (const int *)scratch, iw, ih, fs);
   }
   // pairs that may adopt in both directions (+ the preprocess pointers, or afterwards the pointers of the first pass)
