@@ -485,6 +485,8 @@ def main():
             del dev_rep
             extras["merge_replay"] = {"what": "labelMergeMain with the reference's first pass replayed exactly (off by default)", "execute_once_ms": sorted(ts)[len(ts) // 2] * 1e3,
                                       "batch_value": nrep * iw * ih / dtb / 1e6, "unit": "Mpix/s", "batch_frames": nrep, "rects_identical_to_oracle_in_that_mode": want.tobytes() == rr.tobytes()}
+        except Exception as e:                                                          # an optional sub-record must not cost the line
+            extras["merge_replay"] = {"error": repr(e)}
         finally:
             rd.set_merge_replay(False)
             ol.oracle().ora_set_merge_replay(0)
