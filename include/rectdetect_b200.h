@@ -231,8 +231,8 @@ rect_t *rd_rect_lists_flatten(rect_t **lists, int n, int32_t *counts);
 /* labelMergeMain (oclrect.cl:300-334) depends on the order of its work-items.  Default (0): the schedule-independent fixed point of
  * its adopt rule.  1: the reference's FIRST pass is replayed exactly in raster order (a latency-bound row wavefront, ~3 ms per
  * 1280x720 frame) and the fixed point is taken from there - the region map of the reference's sequential run (oracle/_ref) bit
- * for bit on all but one frame of the sweeps.  Process-wide; initial value from the environment variable RD_MERGE_REPLAY; set it
- * before creating oclrect_t / rd_batch objects (a captured CUDA graph keeps the mode it was captured with). */
+ * for bit on all but one frame of the sweeps.  Process-wide; initial value from the environment variable RD_MERGE_REPLAY; read when
+ * a task is enqueued (a captured CUDA graph of another mode is re-captured). */
 void rd_set_merge_replay(int on);
 int rd_get_merge_replay(void);
 /* host-side accounting of the last rd_batch_run, summed over the pipeline objects' driver threads: out_ms[0] = time spent

@@ -615,7 +615,7 @@ __global__ void k_merge_seed(int *label, const int *first, int n, size_t fs) {
   if (a != b && !((threadIdx.x & 31) > 0 && pa == a && pb == b)) rd_uf_unite(label, a, b);
 }
 // 0: the fixed point from the preprocess pointers (default); 1: the first pass replayed exactly, then the fixed point.  Process-wide;
-// read when a labelling is enqueued (a captured CUDA graph keeps the mode it was captured with: set it before creating objects).
+// read when a labelling is enqueued (rd_rect.cu re-captures the CUDA graph of a page when the mode has changed).
 static int g_merge_replay = -1;
 extern "C" void rd_set_merge_replay(int on) { g_merge_replay = on != 0; }
 extern "C" int rd_get_merge_replay(void) {

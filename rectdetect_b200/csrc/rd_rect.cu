@@ -22,6 +22,7 @@ typedef linesegment_t LS_t;
 
 void rd_label8x(int *label, const int *pix, void *scratch, int bgc, int iw, int ih, int nb, size_t fs, cudaStream_t s);
 void rd_labelMerge(int *out, int *work, const uint32_t *pix, const int *mask, const int *edge, void *scratch, int *flags, int iw, int ih, int nb, size_t fs, cudaStream_t s);
+extern "C" int rd_get_merge_replay(void);
 void rd_k_clear(int *out, int nints, int nb, size_t fs, cudaStream_t s);
 void rd_k_copy(int *out, const int *in, int nints, int nb, size_t fs, cudaStream_t s);
 void rd_k_iirblur(float *obuf, const float *ibuf, float *tmp0, float *tmp1, int r, int iw, int ih, int nb, size_t fs, cudaStream_t s);
@@ -388,7 +389,7 @@ struct oclrect_t {
   // attributes), re-captured when ws / tanAOV change.
   cudaGraphExec_t graph[2];
   double graphTan[2];
-  int graphWs[2], graphLaunches[2], graphSeen[2];
+  int graphWs[2], graphLaunches[2], graphSeen[2], graphMode[2];      // graphMode: rd_get_merge_replay() at capture
 };
 #define FIRST_CHUNK ((size_t)16 * 1024)  // header + 90 rectangles; longer lists take a second copy
 
@@ -699,7 +700,7 @@ static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, 
   const bool graphable = use_graphs && o->nb == 1 && src_kind == 0 && !fresh && g_rd_prof_mode.load(std::memory_order_relaxed) == 0;
   if (src_kind == 0)
     for (int i = 0; i < count; i++) memcpy(o->hostImg[page] + i * hstride, img + i * frame_stride, fbytes);
-  if (graphable && o->graph[page] && o->graphWs[page] == ws && memcmp(&o->graphTan[page], &tanAOV, sizeof(double)) == 0) {
+  if (graphable && o->graph[page] && o->graphWs[page] == ws && o->graphMode[page] == rd_get_merge_replay() && memcmp(&o->graphTan[page], &tanAOV, sizeof(double)) == 0) {
     RD_CUDA(cudaGraphLaunch(o->graph[page], s));              // its H2D node reads the staging page filled above
     g_rd_launches.fetch_add(o->graphLaunches[page], std::memory_order_relaxed);
   } else {
@@ -728,6 +729,7 @@ static void enqueue_page(oclrect_t *o, const uint8_t *img, size_t frame_stride, 
       RD_CUDA(cudaGraphDestroy(g));
       o->graphLaunches[page] = g_rd_launches.load(std::memory_order_relaxed) - launches0;    // (a statistic: other threads' launches may slip in)
       o->graphWs[page] = ws;
+      o->graphMode[page] = rd_get_merge_replay();
       o->graphTan[page] = tanAOV;
       RD_CUDA(cudaGraphLaunch(o->graph[page], s));            // the capture recorded the task; this runs it
     }
