@@ -303,10 +303,16 @@ static void labelMerge_fixed_point(int32_t *label, const int32_t *pix, const int
   }
 }
 
+// the fixed point seeded with a label plane `first` (pointers towards smaller indices): the plane after the first pass in the replay
+// mode; any later state of the reference's label plane in tools/merge_seed_experiment.py
+static void merge_fixed_point_from(int32_t *label, const std::vector<int32_t> &first, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);
 static void labelMerge_replay(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
-  const int n = iw * ih;
-  std::vector<int32_t> first(n);
+  std::vector<int32_t> first((size_t)iw * ih);
   merge_first_pass(first.data(), pix, mask, edge, iw, ih);
+  merge_fixed_point_from(label, first, pix, mask, edge, iw, ih);
+}
+static void merge_fixed_point_from(int32_t *label, const std::vector<int32_t> &first, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
+  const int n = iw * ih;
   for (int p = 0; p < n; p++) label[p] = p;
   MinUF uf(label);
   for (int p = 0; p < n; p++) if (first[p] != p) uf.unite(p, first[p]);
@@ -447,6 +453,11 @@ void ora_rect_quantize(uint32_t *out, const uint32_t *in, int n0, int n1, int n2
 void ora_rect_despeckle(uint32_t *out, const uint32_t *in, const float *edge, int iw, int ih) { k_despeckle(out, in, edge, iw, ih); }
 void ora_rect_mkMergeMask0(int32_t *out, const int32_t *junction, int iw, int ih) { k_mkMergeMask0(out, junction, iw, ih); }
 void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int ih) { k_mkMergeMask1(inout, junction, iw, ih); }
+/* label holds a label plane of the reference on entry (after any of its passes), the fixed point seeded with it on return */
+void ora_rect_labelMerge_seeded(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) {
+  std::vector<int32_t> first(label, label + (size_t)iw * ih);
+  merge_fixed_point_from(label, first, pix, mask, edge, iw, ih);
+}
 void ora_set_merge_replay(int on) { g_merge_replay = on != 0; }
 int ora_get_merge_replay(void) { return g_merge_replay; }
 void ora_rect_labelMerge_first_pass(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih) { merge_first_pass(label, pix, mask, edge, iw, ih); }

@@ -29,7 +29,7 @@
  *     handful to a few hundred interior pixels per frame); with that one kernel swapped for the reference's the oracle
  *     reproduces the reference's region map bit-exactly.  ora_set_merge_replay(1): labelxPreprocess + the FIRST labelMergeMain pass
  *     as the reference's kernel runs them in raster order (whole label plane bit-exact), then the same fixed point seeded with
- *     that plane: label plane identical to the reference's 8 passes on 29 of 30 sweep frames, region map on 31 of 33, all 249
+ *     that plane: label plane identical to the reference's 8 passes on 24 of 27 sweep frames (3 / 1 / 87 px on the others), region map on 31 of 33, all 249
  *     rectangles identical (profiles/r04t_*).
  * Every other place where the reference is schedule-dependent (atomic arrival order, in-place races, vote-slot claims)
  * is resolved the way the raster-order schedule resolves it; each is marked "CANONICAL" in the sources and listed in
@@ -116,6 +116,8 @@ void ora_rect_mkMergeMask1(int32_t *inout, const int32_t *junction, int iw, int 
 /* which form of the merge labelling the oracle computes (process-wide): 0 = the schedule-independent fixed point (default, = the CUDA
  * path by default), 1 = the reference's first pass replayed in raster order, then the fixed point (= the CUDA path with RD_MERGE_REPLAY=1) */
 void ora_set_merge_replay(int on);
+/* the fixed point seeded with the label plane found in `label` (a state of the reference's plane after one of its passes) */
+void ora_rect_labelMerge_seeded(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);
 int ora_get_merge_replay(void);
 /* labelxPreprocess + the first labelMergeMain pass in raster order (= the reference kernel run sequentially once) */
 void ora_rect_labelMerge_first_pass(int32_t *label, const int32_t *pix, const int32_t *mask, const int32_t *edge, int iw, int ih);

@@ -73,6 +73,7 @@ def oracle():
             "ora_rect_labelMerge": (None, [vp, vp, vp, vp, i, i]),
             "ora_rect_labelMerge_first_pass": (None, [vp, vp, vp, vp, i, i]),
             "ora_set_merge_replay": (None, [i]),
+            "ora_rect_labelMerge_seeded": (None, [vp, vp, vp, vp, i, i]),
             "ora_get_merge_replay": (i, []),
             "ora_rect_calcSize": (None, [vp, vp, i, i]), "ora_rect_despeckle2": (None, [vp, vp, i, i, i]),
             "ora_rect_markBoundary": (None, [vp, vp, i, i]), "ora_rect_reduceLS": (None, [vp, vp, vp, i, i, i]),
